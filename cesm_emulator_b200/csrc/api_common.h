@@ -1,0 +1,35 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error state, the
+// cuTensorMapEncodeTiled entry point (resolved at run time so the library links without
+// libcuda), and a small cache of encoded TMA descriptors.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+
+#include "../../include/cesm_b200.h"
+
+namespace cesm {
+
+int set_error(int code, const char* fmt, ...);
+#define CESM_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::cesm::set_error(CESM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,            \
+                                     cudaGetErrorString(_e), __FILE__, __LINE__);              \
+    } while (0)
+#define CESM_REQUIRE(cond, ...)                                                 \
+    do {                                                                        \
+        if (!(cond)) return ::cesm::set_error(CESM_ERR_INVALID, __VA_ARGS__);   \
+    } while (0)
+
+// Encode (or fetch from the cache) a bf16 tiled tensor map with SWIZZLE_128B.
+// dims/strides/box follow cuTensorMapEncodeTiled (dim 0 innermost, strides in bytes for dims >= 1).
+int get_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace cesm

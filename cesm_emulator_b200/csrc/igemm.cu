@@ -1,0 +1,237 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for sm_100a.
+//
+// One kernel serves every dense contraction of the space-time U-Net forward and data-gradient
+// passes (reference call sites: video_net.py:215 Block.proj Conv3d(1,3,3); :62/:66 Down/Upsample;
+// :246 res_conv; :322-323 SpatialLinearAttention 1x1 convs; :380-381 Attention linears):
+//
+//     out[pixel, co] = sum_{tap, ci} A[pixel + tap, ci] * Wt[co, tap, ci]   (+ bias) (+ residual)
+//
+// A is one or two NHWC bf16 activation tensors (two = the U-Net skip concat, never materialised),
+// fetched tile by tile with 4-D TMA boxes; conv zero padding comes from TMA out-of-bounds fill.
+// Wt is bf16 [cout][taps*cin] (K-major).  A 128-pixel x BLOCK_N tile is accumulated in TMEM by a
+// single MMA-issuing thread; 4 epilogue warps read TMEM back, fuse bias/residual and store.
+//
+// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+#include "common.cuh"
+#include "igemm.h"
+
+namespace cesm {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+static constexpr int kUmmaK = 16;
+
+struct IgemmMaps {
+    CUtensorMap a[4];
+    CUtensorMap b;
+};
+
+template <int BLOCK_N, int STAGES>
+struct IgemmSmem {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 1024 /*barriers+tmem ptr+bias*/ + 1024 /*align slack*/;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(256)
+igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
+    using S = IgemmSmem<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const uint32_t bar_base = smem_base + S::kBarOffset;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 1);
+    volatile uint32_t* tmem_ptr_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_gen + S::kBarOffset + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- tile coordinates ------------------------------------------------------------------
+    const int tiles_w = (p.ow + p.bw - 1) / p.bw;
+    const int tiles_h = (p.oh + p.bh - 1) / p.bh;
+    int t = blockIdx.x;
+    const int tw = t % tiles_w;
+    t /= tiles_w;
+    const int th = t % tiles_h;
+    const int tn = t / tiles_h;
+    const int ow0 = tw * p.bw, oh0 = th * p.bh, n0 = tn * p.bn;
+    const int col0 = blockIdx.y * BLOCK_N;
+
+    const int cblk0 = p.c0 >> 6;
+    const int cblk = (p.c0 + p.c1) >> 6;
+    const int num_kb = p.num_taps * cblk;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr_addr, BLOCK_N < 32 ? 32 : BLOCK_N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+            const int tap = kb / cblk;
+            const int cb = kb - tap * cblk;
+            int midx = p.tap_map[tap];
+            int c = cb << 6;
+            if (cb >= cblk0) {
+                midx += 1;
+                c = (cb - cblk0) << 6;
+            }
+            const uint32_t sa = smem_base + stage * S::kStageBytes;
+            const uint32_t sb = sa + S::kABytes;
+            mbar_arrive_expect_tx(full_bar(stage), p.a_box_bytes + S::kBBytes);
+            tma_load_4d(sa, &maps.a[midx], full_bar(stage), c, ow0 + p.tap_dw[tap], oh0 + p.tap_dh[tap], n0);
+            tma_load_2d(sb, &maps.b, full_bar(stage), kb * kBlockK, col0);
+            if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full_bar(stage), phase, 2);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * S::kStageBytes;
+            const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // K-major SWIZZLE_128B: 8-row x 128 B atoms, 1024 B apart along M/N; a 16-element
+                // K step is a 32 B advance of the start address inside the atom.
+                const uint64_t da = make_smem_desc_sw128(sa + k * kUmmaK * 2, 0, 1024);
+                const uint64_t db = make_smem_desc_sw128(sb + k * kUmmaK * 2, 0, 1024);
+                umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+            }
+            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+            if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;  // tile row == TMEM lane
+        const int rw = r % p.bw;
+        const int rh = (r / p.bw) % p.bh;
+        const int rn = r / (p.bw * p.bh);
+        const int n = n0 + rn, oh = oh0 + rh, ow = ow0 + rw;
+        const bool valid = (n < p.n) && (oh < p.oh) && (ow < p.ow) && (rn < p.bn);
+        const long long pix = (static_cast<long long>(n) * p.out_h + (oh * p.o_sh + p.o_h0)) * p.out_w +
+                              (ow * p.o_sw + p.o_w0);
+        mbar_wait(tmem_full_bar, 0, 3);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < BLOCK_N; cc += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + cc, v);
+            tmem_ld_wait();
+            if (valid) {
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                const int col = col0 + cc;
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col + i);
+                }
+                if (p.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(
+                        reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u = __ldg(rp + j);
+                        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
+                               d = unpack_bf16x2(u.w);
+                        f[j * 8 + 0] += a.x; f[j * 8 + 1] += a.y; f[j * 8 + 2] += b.x; f[j * 8 + 3] += b.y;
+                        f[j * 8 + 4] += c2.x; f[j * 8 + 5] += c2.y; f[j * 8 + 6] += d.x; f[j * 8 + 7] += d.y;
+                    }
+                }
+                if (p.out_fp32) {
+                    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                        u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                        u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        op[j] = u;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+static cudaError_t launch_igemm(const IgemmMaps& maps, const IgemmParams& p, int m_tiles, cudaStream_t stream) {
+    using S = IgemmSmem<BLOCK_N, STAGES>;
+    static bool configured = false;  // benign race: attribute set is idempotent
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BLOCK_N, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(m_tiles, p.cout / BLOCK_N, 1);
+    igemm_kernel<BLOCK_N, STAGES><<<grid, 256, S::kTotal, stream>>>(maps, p);
+    return cudaGetLastError();
+}
+
+cudaError_t igemm_launch(const CUtensorMap* amaps, int n_amaps, const CUtensorMap& bmap, const IgemmParams& p,
+                         int block_n, cudaStream_t stream) {
+    IgemmMaps maps;
+    for (int i = 0; i < 4; ++i) maps.a[i] = amaps[i < n_amaps ? i : 0];
+    maps.b = bmap;
+    const int tiles = ((p.ow + p.bw - 1) / p.bw) * ((p.oh + p.bh - 1) / p.bh) * ((p.n + p.bn - 1) / p.bn);
+    switch (block_n) {
+        case 64: return launch_igemm<64, 4>(maps, p, tiles, stream);
+        case 128: return launch_igemm<128, 3>(maps, p, tiles, stream);
+        case 256: return launch_igemm<256, 2>(maps, p, tiles, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace cesm
