@@ -35,6 +35,24 @@ class IgemmArgs(Structure):
     ]
 
 
+class WgradArgs(Structure):
+    """Mirror of `cesm_wgrad_args` (include/cesm_b200.h)."""
+
+    _fields_ = [
+        ("x0", c_void_p), ("x1", c_void_p),
+        ("c0", c_int32), ("c1", c_int32),
+        ("n", c_int32), ("h", c_int32), ("w", c_int32),
+        ("stride", c_int32),
+        ("num_taps", c_int32),
+        ("tap_dh", c_int32 * CESM_MAX_TAPS), ("tap_dw", c_int32 * CESM_MAX_TAPS),
+        ("dy", c_void_p), ("cout", c_int32),
+        ("oh", c_int32), ("ow", c_int32),
+        ("y_h", c_int32), ("y_w", c_int32),
+        ("y_sh", c_int32), ("y_sw", c_int32), ("y_h0", c_int32), ("y_w0", c_int32),
+        ("dw", c_void_p),
+    ]
+
+
 class CesmError(RuntimeError):
     pass
 
@@ -60,8 +78,33 @@ def load() -> ctypes.CDLL:
 
 
 # name -> argtypes; every function returns int (cesm_status)
+_P, _I, _L, _F = c_void_p, ctypes.c_int, ctypes.c_longlong, c_float
 _SIGNATURES: dict[str, list] = {
-    "cesm_igemm": [POINTER(IgemmArgs), c_void_p],
+    "cesm_igemm": [POINTER(IgemmArgs), _P],
+    "cesm_wgrad": [POINTER(WgradArgs), _P],
+    "cesm_pack_weight": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _P],
+    "cesm_unpack_wgrad": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _I, _P],
+    "cesm_colsum": [_P, _P, _L, _I, _P],
+    "cesm_gn_stats": [_P, _P, _I, _L, _I, _I, _P],
+    "cesm_gn_apply_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
+    "cesm_gn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
+    "cesm_ln_fwd": [_P, _P, _P, _L, _I, _F, _P],
+    "cesm_ln_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "cesm_tattn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "cesm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "cesm_linattn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "cesm_linattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "cesm_input_conv_fwd": [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cesm_input_conv_wgrad": [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cesm_out_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _L, _I, _P],
+    "cesm_out_conv_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P],
+    "cesm_sinusoidal": [_P, _P, _I, _I, _P],
+    "cesm_small_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "cesm_small_linear_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "cesm_q_sample": [_P, _P, _P, _P, _P, _P, _I, _L, _P],
+    "cesm_mse_fwd": [_P, _P, _P, _P, _L, _P],
+    "cesm_scale_by_scalar": [_P, _P, _F, _P, _L, _P],
+    "cesm_p_sample": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _P],
 }
 
 

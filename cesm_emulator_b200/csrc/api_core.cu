@@ -235,3 +235,103 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
     CESM_CHECK_CUDA(igemm_launch(amaps, n_amaps, bmap, p, block_n, as_stream(stream)));
     return CESM_OK;
 }
+
+// 64-pixel K tile for the weight gradient: powers of two with bw*bh*bn == 64, fewest tiles
+static void choose_tile64(int n, int oh, int ow, int* bw, int* bh, int* bn) {
+    long long best = -1;
+    for (int w = 1; w <= 64; w <<= 1)
+        for (int h = 1; h * w <= 64; h <<= 1) {
+            const int nn = 64 / (w * h);
+            const long long tiles = 1LL * ceil_div(ow, w) * ceil_div(oh, h) * ceil_div(n, nn);
+            if (best < 0 || tiles < best || (tiles == best && w > *bw)) {
+                best = tiles;
+                *bw = w;
+                *bh = h;
+                *bn = nn;
+            }
+        }
+}
+
+extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
+    CESM_REQUIRE(a != nullptr, "args is NULL");
+    CESM_REQUIRE(a->c0 > 0 && a->c0 % 64 == 0 && a->c1 >= 0 && a->c1 % 64 == 0,
+                 "channel counts must be multiples of 64 (c0=%d c1=%d)", a->c0, a->c1);
+    CESM_REQUIRE(a->cout > 0 && a->cout % 64 == 0, "cout=%d must be a multiple of 64", a->cout);
+    CESM_REQUIRE(a->num_taps >= 1 && a->num_taps <= CESM_MAX_TAPS, "num_taps=%d out of range", a->num_taps);
+    CESM_REQUIRE(a->stride == 1 || a->stride == 2, "stride=%d unsupported", a->stride);
+    CESM_REQUIRE(a->stride == 1 || (a->c1 == 0 && a->h % 2 == 0 && a->w % 2 == 0),
+                 "stride 2 needs a single source with even h, w");
+    CESM_REQUIRE((a->c1 == 0) == (a->x1 == nullptr), "x1 / c1 mismatch");
+    cudaStream_t st = as_stream(stream);
+
+    WgradParams p{};
+    p.c0 = a->c0;
+    p.c1 = a->c1;
+    p.num_taps = a->num_taps;
+    p.n = a->n;
+    p.oh = a->oh;
+    p.ow = a->ow;
+    choose_tile64(a->n, a->oh, a->ow, &p.bw, &p.bh, &p.bn);
+    p.box_bytes = 64u * 2u * 64u;
+    p.cout = a->cout;
+    p.dw = a->dw;
+    const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+
+    CUtensorMap xmaps[4];
+    int n_xmaps = 0;
+    if (a->stride == 1) {
+        const void* src[2] = {a->x0, a->x1};
+        const int cs[2] = {a->c0, a->c1};
+        for (int s = 0; s < 2; ++s) {
+            if (!src[s]) continue;
+            const uint64_t dims[4] = {(uint64_t)cs[s], (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+            const uint64_t str[3] = {(uint64_t)cs[s] * 2, (uint64_t)a->w * cs[s] * 2, (uint64_t)a->h * a->w * cs[s] * 2};
+            int rc = get_tensor_map_bf16(&xmaps[s], src[s], 4, dims, str, box);
+            if (rc) return rc;
+            n_xmaps = s + 1;
+        }
+        for (int t = 0; t < a->num_taps; ++t) {
+            p.tap_map[t] = 0;
+            p.tap_dh[t] = a->tap_dh[t];
+            p.tap_dw[t] = a->tap_dw[t];
+        }
+    } else {
+        const int c = a->c0;
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                const char* base = static_cast<const char*>(a->x0) + (size_t)(ph * a->w + pw) * c * 2;
+                const uint64_t dims[4] = {(uint64_t)c, (uint64_t)a->w / 2, (uint64_t)a->h / 2, (uint64_t)a->n};
+                const uint64_t str[3] = {(uint64_t)c * 4, (uint64_t)a->w * c * 4, (uint64_t)a->h * a->w * c * 2};
+                int rc = get_tensor_map_bf16(&xmaps[ph * 2 + pw], base, 4, dims, str, box);
+                if (rc) return rc;
+            }
+        n_xmaps = 4;
+        for (int t = 0; t < a->num_taps; ++t) {
+            const int ph = a->tap_dh[t] & 1, pw = a->tap_dw[t] & 1;
+            p.tap_map[t] = ph * 2 + pw;
+            p.tap_dh[t] = (a->tap_dh[t] - ph) / 2;
+            p.tap_dw[t] = (a->tap_dw[t] - pw) / 2;
+        }
+    }
+    CUtensorMap ymap;
+    {
+        const int co = a->cout;
+        const char* base = static_cast<const char*>(a->dy) + ((size_t)a->y_h0 * a->y_w + a->y_w0) * co * 2;
+        const uint64_t dims[4] = {(uint64_t)co, (uint64_t)a->ow, (uint64_t)a->oh, (uint64_t)a->n};
+        const uint64_t str[3] = {(uint64_t)a->y_sw * co * 2, (uint64_t)a->y_sh * a->y_w * co * 2,
+                                 (uint64_t)a->y_h * a->y_w * co * 2};
+        int rc = get_tensor_map_bf16(&ymap, base, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    const int ctot = a->c0 + a->c1;
+    CESM_CHECK_CUDA(cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * a->num_taps * ctot, st));
+    const int block_n = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
+    const int units = a->num_taps * (ctot / 64);
+    const int base_ctas = ((units + 1) / 2) * (a->cout / block_n);
+    const int tiles = ceil_div(a->ow, p.bw) * ceil_div(a->oh, p.bh) * ceil_div(a->n, p.bn);
+    int ksplit = ceil_div(148 * 2, base_ctas);
+    if (ksplit > tiles) ksplit = tiles;
+    if (ksplit < 1) ksplit = 1;
+    CESM_CHECK_CUDA(wgrad_launch(xmaps, n_xmaps, ymap, p, block_n, ksplit, st));
+    return CESM_OK;
+}

@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: a protocol bug must never hang the GPU (a hung box is a lost lease), so after
 // ~2 s of spinning the kernel reports where it stuck and traps.
-__device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity, int site) {
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity, int site) {
     printf("[cesm_b200] mbarrier wait timed out: block (%d,%d,%d) thread %d site %d bar 0x%x parity %u\n",
            blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, site, bar, parity);
     __trap();

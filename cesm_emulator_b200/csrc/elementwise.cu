@@ -1,0 +1,516 @@
+// Small and bandwidth-bound kernels around the tensor-core path:
+//   weight re-layout (fp32 parameter -> bf16 GEMM operand, and fp32 GEMM-layout gradient -> parameter)
+//   7x7 input conv with fused concat / frame broadcast (video_net.py:808-815, model.py:110-121)
+//   1x1x1 output conv fused with centre-frame selection (video_net.py:763, model.py:129-130)
+//   time embedding + small fp32 linears (video_net.py:101-113, 651-656, 238-241)
+//   DDPM q_sample / MSE / p_sample update (model.py:168-208)
+//   column sums (bias gradients)
+#include "api_common.h"
+#include "common.cuh"
+
+namespace cesm {
+
+struct TapOffsets {
+    int32_t off[CESM_MAX_TAPS];
+};
+
+// dst[o][t][i] (bf16) = src[o*so + i*si + off[t]] (fp32)
+__global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int O, int T, int I,
+                                   long long so, long long si, TapOffsets taps) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)O * T * I) return;
+    const int i = idx % I;
+    const int t = (idx / I) % T;
+    const int o = idx / ((long long)I * T);
+    dst[idx] = __float2bfloat16(src[o * so + i * si + taps.off[t]]);
+}
+// dst[o*so + i*si + off[t]] (+)= src[o][t][i]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int T, int I,
+                                    long long so, long long si, TapOffsets taps, int accumulate) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)O * T * I) return;
+    const int i = idx % I;
+    const int t = (idx / I) % T;
+    const int o = idx / ((long long)I * T);
+    float* d = dst + o * so + i * si + taps.off[t];
+    *d = accumulate ? (*d + src[idx]) : src[idx];
+}
+
+// out[c] = sum_rows x[row][c]; block handles a strip of rows, thread owns 8 channels
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long M, int C) {
+    const int vec = C >> 3;
+    const int slot = threadIdx.x % vec;
+    const int rows_per_iter = 256 / vec;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (long long r = (long long)blockIdx.x * rows_per_iter + threadIdx.x / vec; r < M;
+         r += (long long)gridDim.x * rows_per_iter) {
+        uint4 u = *reinterpret_cast<const uint4*>(x + r * C + slot * 8);
+        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+    __shared__ float red[256][9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;
+        for (int t = c >> 3; t < 256; t += vec) s += red[t][c & 7];
+        atomicAdd(&out[c], s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 7x7 input conv, 2 input planes (noisy target, condition) -> COUT channels, bf16 NHWC output.
+// Plane p of image (b, f) lives at in_p + (b*fp + (fp == 1 ? 0 : f)) * H*W  (frame broadcast).
+// ------------------------------------------------------------------------------------------------
+template <int KS, int COUT>
+__global__ void __launch_bounds__(256)
+input_conv_fwd_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
+                      const float* __restrict__ w /* [COUT][2][KS][KS] */, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ out, int F, int H, int W) {
+    constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1;
+    __shared__ float sw[2 * KS * KS][COUT];
+    __shared__ float sin_[2][PW][PW + 1];
+    const int img = blockIdx.z, b = img / F, f = img % F;
+    const int h0 = blockIdx.y * T, w0 = blockIdx.x * T;
+    for (int x = threadIdx.x; x < 2 * KS * KS * COUT; x += 256) {
+        const int co = x % COUT, tap = x / COUT;
+        sw[tap][co] = w[co * 2 * KS * KS + tap];
+    }
+    const float* p0 = in0 + ((size_t)b * f0 + (f0 == 1 ? 0 : f)) * H * W;
+    const float* p1 = in1 + ((size_t)b * f1 + (f1 == 1 ? 0 : f)) * H * W;
+    for (int x = threadIdx.x; x < 2 * PW * PW; x += 256) {
+        const int ci = x / (PW * PW), rr = (x / PW) % PW, cc = x % PW;
+        const int hh = h0 + rr - PAD, ww = w0 + cc - PAD;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = (ci ? p1 : p0)[(size_t)hh * W + ww];
+        sin_[ci][rr][cc] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / T, tx = threadIdx.x % T;
+    const int h = h0 + ty, ww = w0 + tx;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = bias[c];
+    for (int ci = 0; ci < 2; ++ci)
+        for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < KS; ++kw) {
+                const float v = sin_[ci][ty + kh][tx + kw];
+                const float4* wr = reinterpret_cast<const float4*>(sw[(ci * KS + kh) * KS + kw]);
+#pragma unroll
+                for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                    const float4 q = wr[c4];
+                    acc[4 * c4 + 0] = fmaf(v, q.x, acc[4 * c4 + 0]);
+                    acc[4 * c4 + 1] = fmaf(v, q.y, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(v, q.z, acc[4 * c4 + 2]);
+                    acc[4 * c4 + 3] = fmaf(v, q.w, acc[4 * c4 + 3]);
+                }
+            }
+    if (h < H && ww < W) {
+        uint4* op = reinterpret_cast<uint4*>(out + (((size_t)img * H + h) * W + ww) * COUT);
+#pragma unroll
+        for (int j = 0; j < COUT / 8; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]);
+            u.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
+            u.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
+            u.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+            op[j] = u;
+        }
+    }
+}
+
+// dW[co][ci][kh][kw] += sum dy[img][h][w][co] * in_ci[img][h+kh-PAD][w+kw-PAD];  db[co] += sum dy
+// Persistent blocks loop over 16x16 tiles; thread owns channel co = tid % COUT and every 4th tap.
+template <int KS, int COUT>
+__global__ void __launch_bounds__(256)
+input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
+                        const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db, int NI,
+                        int F, int H, int W) {
+    constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS, Q = 256 / COUT;
+    constexpr int TPT = (NT + Q - 1) / Q;  // taps per thread
+    __shared__ float sin_[2][PW][PW + 1];
+    __shared__ __nv_bfloat16 sdy[T * T][COUT + 8];
+    const int co = threadIdx.x % COUT, q = threadIdx.x / COUT;
+    float acc[TPT], accb = 0.f;
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) acc[i] = 0.f;
+    const int tiles_w = (W + T - 1) / T, tiles_h = (H + T - 1) / T;
+    const int ntiles = tiles_w * tiles_h * NI;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int img = tile / (tiles_w * tiles_h), b = img / F, f = img % F;
+        const int h0 = ((tile / tiles_w) % tiles_h) * T, w0 = (tile % tiles_w) * T;
+        const float* p0 = in0 + ((size_t)b * f0 + (f0 == 1 ? 0 : f)) * H * W;
+        const float* p1 = in1 + ((size_t)b * f1 + (f1 == 1 ? 0 : f)) * H * W;
+        __syncthreads();
+        for (int x = threadIdx.x; x < 2 * PW * PW; x += 256) {
+            const int ci = x / (PW * PW), rr = (x / PW) % PW, cc = x % PW;
+            const int hh = h0 + rr - PAD, ww = w0 + cc - PAD;
+            float v = 0.f;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = (ci ? p1 : p0)[(size_t)hh * W + ww];
+            sin_[ci][rr][cc] = v;
+        }
+        for (int x = threadIdx.x; x < T * T * (COUT / 8); x += 256) {
+            const int px = x / (COUT / 8), v8 = x % (COUT / 8);
+            const int h = h0 + px / T, ww = w0 + px % T;
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (h < H && ww < W) u = *reinterpret_cast<const uint4*>(dy + (((size_t)img * H + h) * W + ww) * COUT + v8 * 8);
+            *reinterpret_cast<uint4*>(&sdy[px][v8 * 8]) = u;
+        }
+        __syncthreads();
+        for (int px = 0; px < T * T; ++px) {
+            const float g = __bfloat162float(sdy[px][co]);
+            const int ty = px / T, tx = px % T;
+            if (q == 0) accb += g;
+#pragma unroll
+            for (int i = 0; i < TPT; ++i) {
+                const int tap = q + i * Q;
+                if (tap < NT) {
+                    const int ci = tap / (KS * KS), kh = (tap / KS) % KS, kw = tap % KS;
+                    acc[i] = fmaf(g, sin_[ci][ty + kh][tx + kw], acc[i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+        const int tap = q + i * Q;
+        if (tap < NT) atomicAdd(&dw[co * NT + tap], acc[i]);
+    }
+    if (q == 0) atomicAdd(&db[co], accb);
+}
+
+// eps[b][h][w] = bias + sum_c a[(b*F + mid)][h][w][c] * w[c]   ; 8 lanes per pixel (C == 64)
+__global__ void __launch_bounds__(256)
+out_conv_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ eps, int B, int F, int mid, long long HW) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pix = t >> 3;
+    const int sub = t & 7;
+    float s = 0.f;
+    if (pix < (long long)B * HW) {
+        const long long b = pix / HW, p = pix % HW;
+        uint4 u = *reinterpret_cast<const uint4*>(a + (((size_t)b * F + mid) * HW + p) * 64 + sub * 8);
+        float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+        const float* ww = w + sub * 8;
+        s = x0.x * ww[0] + x0.y * ww[1] + x1.x * ww[2] + x1.y * ww[3] + x2.x * ww[4] + x2.y * ww[5] + x3.x * ww[6] + x3.y * ww[7];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0 && pix < (long long)B * HW) eps[pix] = s + bias[0];
+}
+// da[(b,f)][p][c] = (f == mid) ? deps[b][p]*w[c] : 0 ; dw[c] += sum deps*a ; db += sum deps
+__global__ void __launch_bounds__(256)
+out_conv_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ deps,
+                    __nv_bfloat16* __restrict__ da, float* __restrict__ dw, float* __restrict__ db, int B, int F, int mid,
+                    long long HW) {
+    const int sub = threadIdx.x & 7;
+    float wv[8], acc[8], accb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        wv[i] = w[sub * 8 + i];
+        acc[i] = 0.f;
+    }
+    const long long total = (long long)B * F * HW;
+    for (long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < total;
+         pix += ((long long)gridDim.x * blockDim.x) >> 3) {
+        const long long img = pix / HW, p = pix % HW;
+        const int f = img % F;
+        const long long b = img / F;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (f == mid) {
+            const float g = deps[b * HW + p];
+            uint4 u = *reinterpret_cast<const uint4*>(a + pix * 64 + sub * 8);
+            float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+            acc[0] += g * x0.x; acc[1] += g * x0.y; acc[2] += g * x1.x; acc[3] += g * x1.y;
+            acc[4] += g * x2.x; acc[5] += g * x2.y; acc[6] += g * x3.x; acc[7] += g * x3.y;
+            if (sub == 0) accb += g;
+            o.x = pack_bf16x2(g * wv[0], g * wv[1]);
+            o.y = pack_bf16x2(g * wv[2], g * wv[3]);
+            o.z = pack_bf16x2(g * wv[4], g * wv[5]);
+            o.w = pack_bf16x2(g * wv[6], g * wv[7]);
+        }
+        *reinterpret_cast<uint4*>(da + pix * 64 + sub * 8) = o;
+    }
+    __shared__ float red[256][9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+    red[threadIdx.x][8] = accb;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        float s = 0.f;
+        for (int t = c >> 3; t < 256; t += 8) s += red[t][c & 7];
+        atomicAdd(&dw[c], s);
+    } else if (threadIdx.x == 64) {
+        float s = 0.f;
+        for (int t = 0; t < 256; t += 8) s += red[t][8];
+        atomicAdd(db, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// time embedding + small fp32 linears (batch <= a few hundred rows)
+// ------------------------------------------------------------------------------------------------
+__global__ void sinusoidal_kernel(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * dim) return;
+    const int b = idx / dim, i = idx % dim, half = dim / 2;
+    const int k = i % half;
+    const float freq = expf((float)k * -(logf(10000.f) / (float)(half - 1)));
+    const float arg = (float)t[b] * freq;
+    out[idx] = i < half ? sinf(arg) : cosf(arg);
+}
+// y[b][n] = sum_k act(x[b][k]) W[n][k] + bias[n]; warp per n
+__global__ void __launch_bounds__(256)
+small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                        float* __restrict__ y, int B, int K, int N, int act) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    for (int b = 0; b < B; ++b) {
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            float v = x[(size_t)b * K + k];
+            if (act) v = silu_f(v);
+            s = fmaf(v, W[(size_t)n * K + k], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) y[(size_t)b * N + n] = s + (bias ? bias[n] : 0.f);
+    }
+}
+// dW[n][k] = sum_b dy[b][n] act(x[b][k]) ; db[n] = sum_b dy[b][n]
+__global__ void small_linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                          float* __restrict__ dW, float* __restrict__ db, int B, int K, int N, int act) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * K) return;
+    const int k = idx % K, n = idx / K;
+    float s = 0.f, sb = 0.f;
+    for (int b = 0; b < B; ++b) {
+        float v = x[(size_t)b * K + k];
+        if (act) v = silu_f(v);
+        const float g = dy[(size_t)b * N + n];
+        s = fmaf(g, v, s);
+        sb += g;
+    }
+    dW[idx] = s;
+    if (k == 0 && db) db[n] = sb;
+}
+// dx[b][k] = act'(x[b][k]) * sum_n dy[b][n] W[n][k]
+__global__ void small_linear_dgrad_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                          const float* __restrict__ dy, float* __restrict__ dx, int B, int K, int N,
+                                          int act) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * K) return;
+    const int k = idx % K, b = idx / K;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dy[(size_t)b * N + n], W[(size_t)n * K + k], s);
+    if (act) s *= dsilu_f(x[idx]);
+    dx[idx] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DDPM elementwise
+// ------------------------------------------------------------------------------------------------
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const long long* __restrict__ t, const float* __restrict__ sqrt_ac,
+                                const float* __restrict__ sqrt_1mac, float* __restrict__ xt, long long per, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long tb = t[idx / per];
+    xt[idx] = sqrt_ac[tb] * x0[idx] + sqrt_1mac[tb] * noise[idx];
+}
+// loss += sum (eps-noise)^2 / total ; diff = eps - noise
+__global__ void __launch_bounds__(256)
+mse_fwd_kernel(const float* __restrict__ eps, const float* __restrict__ noise, float* __restrict__ diff,
+               float* __restrict__ loss, long long total) {
+    float s = 0.f;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const float d = eps[idx] - noise[idx];
+        diff[idx] = d;
+        s = fmaf(d, d, s);
+    }
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        atomicAdd(loss, tot / (float)total);
+    }
+}
+// out = in * factor * (*gscale)
+__global__ void scale_by_device_scalar_kernel(const float* __restrict__ in, const float* __restrict__ gscale,
+                                              float factor, float* __restrict__ out, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    out[idx] = in[idx] * factor * gscale[0];
+}
+// x_{t-1} = sqrt_recip_alpha[t] * (x_t - beta[t]/sqrt_1mac[t] * eps) + sqrt(post_var[t]) * z
+// (post_var[0] == 0, so t == 0 adds no noise: identical to model.py:178-183)
+__global__ void p_sample_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
+                                const float* __restrict__ z, const long long* __restrict__ t,
+                                const float* __restrict__ betas, const float* __restrict__ sqrt_1mac,
+                                const float* __restrict__ sqrt_recip_a, const float* __restrict__ post_var,
+                                float* __restrict__ out, long long per, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long tb = t[idx / per];
+    const float mean = sqrt_recip_a[tb] * (xt[idx] - betas[tb] / sqrt_1mac[tb] * eps[idx]);
+    out[idx] = mean + sqrtf(post_var[tb]) * z[idx];
+}
+
+}  // namespace cesm
+
+using namespace cesm;
+
+static inline int nblk(long long total, int threads) { return (int)((total + threads - 1) / threads); }
+
+extern "C" int cesm_pack_weight(const float* src, void* dst, int O, int T, int I, long long so, long long si,
+                                const int32_t* tap_off, void* stream) {
+    CESM_REQUIRE(T >= 1 && T <= CESM_MAX_TAPS, "T=%d out of range", T);
+    TapOffsets taps{};
+    for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
+    const long long total = (long long)O * T * I;
+    pack_weight_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, O, T, I, so, si, taps);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int I, long long so, long long si,
+                                 const int32_t* tap_off, int accumulate, void* stream) {
+    CESM_REQUIRE(T >= 1 && T <= CESM_MAX_TAPS, "T=%d out of range", T);
+    TapOffsets taps{};
+    for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
+    const long long total = (long long)O * T * I;
+    unpack_wgrad_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(src, dst, O, T, I, so, si, taps, accumulate);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, void* stream) {
+    CESM_REQUIRE(C % 8 == 0 && C <= 2048 && 2048 % C == 0, "colsum needs C dividing 2048 (C=%d)", C);
+    cudaStream_t st = as_stream(stream);
+    CESM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+    long long blocks = (M + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    colsum_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, M, C);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_input_conv_fwd(const float* in0, const float* in1, int f0, int f1, const float* w,
+                                   const float* bias, void* out, int B, int F, int H, int W, int ks, int cout,
+                                   void* stream) {
+    CESM_REQUIRE(ks == 7 && cout == 64, "input conv kernel is specialised for 7x7, 64 channels (ks=%d cout=%d)", ks, cout);
+    CESM_REQUIRE((f0 == 1 || f0 == F) && (f1 == 1 || f1 == F), "frame counts must be 1 or F");
+    dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B * F);
+    input_conv_fwd_kernel<7, 64><<<grid, 256, 0, as_stream(stream)>>>(in0, in1, f0, f1, w, bias, (__nv_bfloat16*)out, F, H, W);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_input_conv_wgrad(const float* in0, const float* in1, int f0, int f1, const void* dy, float* dw,
+                                     float* db, int B, int F, int H, int W, int ks, int cout, void* stream) {
+    CESM_REQUIRE(ks == 7 && cout == 64, "input conv kernel is specialised for 7x7, 64 channels (ks=%d cout=%d)", ks, cout);
+    cudaStream_t st = as_stream(stream);
+    CESM_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * cout * 2 * ks * ks, st));
+    CESM_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * cout, st));
+    const int ntiles = ceil_div(W, 16) * ceil_div(H, 16) * B * F;
+    const int grid = ntiles < 148 * 2 ? ntiles : 148 * 2;
+    input_conv_wgrad_kernel<7, 64><<<grid, 256, 0, st>>>(in0, in1, f0, f1, (const __nv_bfloat16*)dy, dw, db, B * F, F, H, W);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_out_conv_fwd(const void* a, const float* w, const float* bias, float* eps, int B, int F, int mid,
+                                 long long HW, int C, void* stream) {
+    CESM_REQUIRE(C == 64, "output conv kernel needs 64 input channels (C=%d)", C);
+    const long long threads = (long long)B * HW * 8;
+    out_conv_fwd_kernel<<<nblk(threads, 256), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)a, w, bias, eps, B, F, mid, HW);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_out_conv_bwd(const void* a, const float* w, const float* deps, void* da, float* dw, float* db,
+                                 int B, int F, int mid, long long HW, int C, void* stream) {
+    CESM_REQUIRE(C == 64, "output conv kernel needs 64 input channels (C=%d)", C);
+    cudaStream_t st = as_stream(stream);
+    CESM_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, st));
+    CESM_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
+    long long blocks = ((long long)B * F * HW * 8 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    out_conv_bwd_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)a, w, deps, (__nv_bfloat16*)da, dw, db, B, F, mid, HW);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_sinusoidal(const long long* t, float* out, int B, int dim, void* stream) {
+    CESM_REQUIRE(dim >= 4 && dim % 2 == 0, "dim=%d must be even and >= 4", dim);
+    sinusoidal_kernel<<<nblk((long long)B * dim, 128), 128, 0, as_stream(stream)>>>(t, out, B, dim);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_small_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
+                                     int act_silu_in, void* stream) {
+    small_linear_fwd_kernel<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(x, W, bias, y, B, K, N, act_silu_in);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_small_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
+                                     int B, int K, int N, int act_silu_in, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    small_linear_wgrad_kernel<<<nblk((long long)N * K, 256), 256, 0, st>>>(x, dy, dW, db, B, K, N, act_silu_in);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    if (dx) {
+        small_linear_dgrad_kernel<<<nblk((long long)B * K, 256), 256, 0, st>>>(x, W, dy, dx, B, K, N, act_silu_in);
+        CESM_CHECK_CUDA(cudaGetLastError());
+    }
+    return CESM_OK;
+}
+
+extern "C" int cesm_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
+                             const float* sqrt_1mac, float* xt, int B, long long per_sample, void* stream) {
+    const long long total = (long long)B * per_sample;
+    q_sample_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(x0, noise, t, sqrt_ac, sqrt_1mac, xt, per_sample, total);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_mse_fwd(const float* eps, const float* noise, float* diff, float* loss, long long total,
+                            void* stream) {
+    cudaStream_t st = as_stream(stream);
+    CESM_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    mse_fwd_kernel<<<(int)blocks, 256, 0, st>>>(eps, noise, diff, loss, total);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_scale_by_scalar(const float* in, const float* gscale, float factor, float* out, long long total,
+                                    void* stream) {
+    scale_by_device_scalar_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(in, gscale, factor, out, total);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}
+
+extern "C" int cesm_p_sample(const float* xt, const float* eps, const float* z, const long long* t, const float* betas,
+                             const float* sqrt_1mac, const float* sqrt_recip_a, const float* post_var, float* out,
+                             int B, long long per_sample, void* stream) {
+    const long long total = (long long)B * per_sample;
+    p_sample_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(xt, eps, z, t, betas, sqrt_1mac, sqrt_recip_a,
+                                                                    post_var, out, per_sample, total);
+    CESM_CHECK_CUDA(cudaGetLastError());
+    return CESM_OK;
+}

@@ -29,6 +29,22 @@ struct IgemmParams {
     int32_t ldr;
 };
 
+struct WgradParams {
+    int32_t c0, c1;
+    int32_t num_taps;
+    int32_t tap_map[16];
+    int32_t tap_dh[16];
+    int32_t tap_dw[16];
+    int32_t n, oh, ow;      // pixel grid contracted over
+    int32_t bw, bh, bn;     // 64-pixel K tile box (bw*bh*bn == 64)
+    uint32_t box_bytes;     // bytes of one 64-channel x 64-pixel TMA box
+    int32_t cout;
+    float* dw;              // fp32 [cout][num_taps][c0+c1], accumulated with red.add
+};
+
+cudaError_t wgrad_launch(const CUtensorMap* xmaps, int n_xmaps, const CUtensorMap& ymap, const WgradParams& p,
+                         int block_n, int ksplit, cudaStream_t stream);
+
 cudaError_t igemm_launch(const CUtensorMap* amaps, int n_amaps, const CUtensorMap& bmap, const IgemmParams& p,
                          int block_n, cudaStream_t stream);
 

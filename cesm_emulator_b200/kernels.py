@@ -78,3 +78,263 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
         assert residual.dtype == BF16 and residual.shape[:3] == out.shape[:3]
     _lib.call("cesm_igemm", ctypes.byref(args), _stream())
     return out
+
+
+def wgrad(x0: torch.Tensor, dy: torch.Tensor, *, taps: Sequence[Tuple[int, int]] = TAPS_1x1,
+          x1: Optional[torch.Tensor] = None, stride: int = 1, grid_hw: Optional[Tuple[int, int]] = None,
+          dy_place: Tuple[int, int, int, int] = (1, 1, 0, 0)) -> torch.Tensor:
+    """dw[co, t, ci] = sum_pixels dy[n,oh,ow,co] * X[n, oh*stride+dh_t, ow*stride+dw_t, ci]  -> fp32 [cout, T, C0+C1]."""
+    _req_cuda(x0, x1, dy)
+    assert x0.dtype == BF16 and dy.dtype == BF16 and x0.dim() == 4 and dy.dim() == 4
+    n, h, w, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    cout = dy.shape[-1]
+    oh, ow = grid_hw if grid_hw is not None else (h // stride, w // stride)
+    dw_ = torch.empty((cout, len(taps), c0 + c1), dtype=torch.float32, device=x0.device)
+    a = _lib.WgradArgs()
+    a.x0, a.x1, a.c0, a.c1 = _ptr(x0), _ptr(x1), c0, c1
+    a.n, a.h, a.w, a.stride = n, h, w, stride
+    a.num_taps = len(taps)
+    for i, (dh, dw) in enumerate(taps):
+        a.tap_dh[i], a.tap_dw[i] = dh, dw
+    a.dy, a.cout, a.oh, a.ow = _ptr(dy), cout, oh, ow
+    a.y_h, a.y_w = dy.shape[1], dy.shape[2]
+    a.y_sh, a.y_sw, a.y_h0, a.y_w0 = dy_place
+    a.dw = _ptr(dw_)
+    _lib.call("cesm_wgrad", ctypes.byref(a), _stream())
+    return dw_
+
+
+def _tap_array(offs: Sequence[int]):
+    arr = (ctypes.c_int32 * _lib.CESM_MAX_TAPS)()
+    for i, o in enumerate(offs):
+        arr[i] = int(o)
+    return arr
+
+
+def pack_weight(src: torch.Tensor, O: int, T: int, I: int, so: int, si: int, tap_off: Sequence[int],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dst[o][t][i] (bf16) = src.flatten()[o*so + i*si + tap_off[t]]."""
+    _req_cuda(src)
+    assert src.dtype == torch.float32
+    if out is None:
+        out = torch.empty((O, T * I), dtype=BF16, device=src.device)
+    _lib.call("cesm_pack_weight", _ptr(src), _ptr(out), O, T, I, so, si, _tap_array(tap_off), _stream())
+    return out
+
+
+def unpack_wgrad(src: torch.Tensor, dst: torch.Tensor, O: int, T: int, I: int, so: int, si: int,
+                 tap_off: Sequence[int], accumulate: bool = False) -> torch.Tensor:
+    _req_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.float32
+    _lib.call("cesm_unpack_wgrad", _ptr(src), _ptr(dst), O, T, I, so, si, _tap_array(tap_off), int(accumulate), _stream())
+    return dst
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    _req_cuda(x)
+    C = x.shape[-1]
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    _lib.call("cesm_colsum", _ptr(x), _ptr(out), x.numel() // C, C, _stream())
+    return out
+
+
+# ---- GroupNorm / LayerNorm ----------------------------------------------------------------------
+def gn_stats(x: torch.Tensor, B: int, G: int) -> torch.Tensor:
+    _req_cuda(x)
+    C = x.shape[-1]
+    P = x.numel() // (B * C)
+    sums = torch.empty((B, G, 2), dtype=torch.float32, device=x.device)
+    _lib.call("cesm_gn_stats", _ptr(x), _ptr(sums), B, P, C, G, _stream())
+    return sums
+
+
+def gn_apply_fwd(x, sums, gamma, beta, film, residual, B: int, G: int, eps: float) -> torch.Tensor:
+    _req_cuda(x, sums, gamma, beta, film, residual)
+    C = x.shape[-1]
+    P = x.numel() // (B * C)
+    out = torch.empty_like(x)
+    _lib.call("cesm_gn_apply_fwd", _ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(film), _ptr(residual), _ptr(out),
+              B, P, C, G, eps, _stream())
+    return out
+
+
+def gn_bwd(x, dout, sums, gamma, beta, film, B: int, G: int, eps: float):
+    _req_cuda(x, dout, sums, gamma, beta, film)
+    C = x.shape[-1]
+    P = x.numel() // (B * C)
+    dev = x.device
+    csum = torch.empty((B, C, 4), dtype=torch.float32, device=dev)
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+    dfilm = torch.empty((B, 2 * C), dtype=torch.float32, device=dev) if film is not None else None
+    _lib.call("cesm_gn_bwd", _ptr(x), _ptr(dout), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(film), _ptr(csum), _ptr(dx),
+              _ptr(dgamma), _ptr(dbeta), _ptr(dfilm), B, P, C, G, eps, _stream())
+    return dx, dgamma, dbeta, dfilm
+
+
+def ln_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
+    _req_cuda(x, gamma)
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    _lib.call("cesm_ln_fwd", _ptr(x), _ptr(gamma), _ptr(out), x.numel() // C, C, eps, _stream())
+    return out
+
+
+def ln_bwd(x, gamma, dy, dres, eps: float):
+    _req_cuda(x, gamma, dy, dres)
+    C = x.shape[-1]
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+    _lib.call("cesm_ln_bwd", _ptr(x), _ptr(gamma), _ptr(dy), _ptr(dres), _ptr(dx), _ptr(dgamma), x.numel() // C, C, eps,
+              _stream())
+    return dx, dgamma
+
+
+# ---- attention cores ----------------------------------------------------------------------------
+def tattn_fwd(qkv, bias, cs, sn, B: int, F: int, HW: int, H: int, D: int, scale: float):
+    _req_cuda(qkv, bias, cs, sn)
+    rows = B * F * HW
+    out = torch.empty((rows, H * D), dtype=BF16, device=qkv.device)
+    lse = torch.empty((rows, H), dtype=torch.float32, device=qkv.device)
+    _lib.call("cesm_tattn_fwd", _ptr(qkv), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse), B, F, HW, H, D, scale,
+              _stream())
+    return out, lse
+
+
+def tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B: int, F: int, HW: int, H: int, D: int, scale: float):
+    _req_cuda(qkv, bias, cs, sn, out, lse, dout)
+    dqkv = torch.empty_like(qkv)
+    dbias = torch.empty((H, F, F), dtype=torch.float32, device=qkv.device)
+    _lib.call("cesm_tattn_bwd", _ptr(qkv), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse), _ptr(dout), _ptr(dqkv),
+              _ptr(dbias), B, F, HW, H, D, scale, _stream())
+    return dqkv, dbias
+
+
+def linattn_fwd(qkv, NI: int, n: int, H: int, D: int, scale: float):
+    _req_cuda(qkv)
+    dev = qkv.device
+    HD = H * D
+    part = torch.empty((NI, 64, HD, 2), dtype=torch.float32, device=dev)
+    kstat = torch.empty((NI, HD, 2), dtype=torch.float32, device=dev)
+    qk = torch.empty((NI * n, 2 * HD), dtype=BF16, device=dev)
+    ctx = torch.empty((NI, H, D, D), dtype=torch.float32, device=dev)
+    out = torch.empty((NI * n, HD), dtype=BF16, device=dev)
+    _lib.call("cesm_linattn_fwd", _ptr(qkv), _ptr(part), _ptr(kstat), _ptr(qk), _ptr(ctx), _ptr(out), NI, n, H, D, scale,
+              _stream())
+    return out, qk, ctx
+
+
+def linattn_bwd(qkv, qk, ctx, dout, NI: int, n: int, H: int, D: int, scale: float):
+    _req_cuda(qkv, qk, ctx, dout)
+    dev = qkv.device
+    dctx = torch.empty((NI, H, D, D), dtype=torch.float32, device=dev)
+    delta = torch.empty((NI, H, D), dtype=torch.float32, device=dev)
+    dqkv = torch.empty_like(qkv)
+    _lib.call("cesm_linattn_bwd", _ptr(qkv), _ptr(qk), _ptr(ctx), _ptr(dout), _ptr(dctx), _ptr(delta), _ptr(dqkv), NI, n,
+              H, D, scale, _stream())
+    return dqkv
+
+
+# ---- boundary convs -----------------------------------------------------------------------------
+def input_conv_fwd(in0, in1, w, bias, B: int, F: int, H: int, W: int, ks: int):
+    _req_cuda(in0, in1, w, bias)
+    cout = w.shape[0]
+    f0, f1 = in0.numel() // (B * H * W), in1.numel() // (B * H * W)
+    out = torch.empty((B * F, H, W, cout), dtype=BF16, device=in0.device)
+    _lib.call("cesm_input_conv_fwd", _ptr(in0), _ptr(in1), f0, f1, _ptr(w), _ptr(bias), _ptr(out), B, F, H, W, ks, cout,
+              _stream())
+    return out
+
+
+def input_conv_wgrad(in0, in1, dy, B: int, F: int, H: int, W: int, ks: int):
+    _req_cuda(in0, in1, dy)
+    cout = dy.shape[-1]
+    f0, f1 = in0.numel() // (B * H * W), in1.numel() // (B * H * W)
+    dw = torch.empty((cout, 2, 1, ks, ks), dtype=torch.float32, device=dy.device)
+    db = torch.empty(cout, dtype=torch.float32, device=dy.device)
+    _lib.call("cesm_input_conv_wgrad", _ptr(in0), _ptr(in1), f0, f1, _ptr(dy), _ptr(dw), _ptr(db), B, F, H, W, ks, cout,
+              _stream())
+    return dw, db
+
+
+def out_conv_fwd(a, w, bias, B: int, F: int, H: int, W: int):
+    _req_cuda(a, w, bias)
+    eps = torch.empty((B, 1, H, W), dtype=torch.float32, device=a.device)
+    _lib.call("cesm_out_conv_fwd", _ptr(a), _ptr(w), _ptr(bias), _ptr(eps), B, F, F // 2, H * W, a.shape[-1], _stream())
+    return eps
+
+
+def out_conv_bwd(a, w, deps, B: int, F: int, H: int, W: int):
+    _req_cuda(a, w, deps)
+    da = torch.empty_like(a)
+    dw = torch.empty_like(w)
+    db = torch.empty(1, dtype=torch.float32, device=a.device)
+    _lib.call("cesm_out_conv_bwd", _ptr(a), _ptr(w), _ptr(deps), _ptr(da), _ptr(dw), _ptr(db), B, F, F // 2, H * W,
+              a.shape[-1], _stream())
+    return da, dw, db
+
+
+# ---- time embedding / small linears -------------------------------------------------------------
+def sinusoidal(t: torch.Tensor, dim: int) -> torch.Tensor:
+    _req_cuda(t)
+    assert t.dtype == torch.int64
+    out = torch.empty((t.numel(), dim), dtype=torch.float32, device=t.device)
+    _lib.call("cesm_sinusoidal", _ptr(t), _ptr(out), t.numel(), dim, _stream())
+    return out
+
+
+def small_linear_fwd(x, W, bias, act_silu_in: bool):
+    _req_cuda(x, W, bias)
+    B, K = x.shape
+    N = W.shape[0]
+    y = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    _lib.call("cesm_small_linear_fwd", _ptr(x), _ptr(W), _ptr(bias), _ptr(y), B, K, N, int(act_silu_in), _stream())
+    return y
+
+
+def small_linear_bwd(x, W, dy, act_silu_in: bool, need_dx: bool):
+    _req_cuda(x, W, dy)
+    B, K = x.shape
+    N = W.shape[0]
+    dW = torch.empty_like(W)
+    db = torch.empty(N, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x) if need_dx else None
+    _lib.call("cesm_small_linear_bwd", _ptr(x), _ptr(W), _ptr(dy), _ptr(dx), _ptr(dW), _ptr(db), B, K, N,
+              int(act_silu_in), _stream())
+    return dx, dW, db
+
+
+# ---- DDPM ---------------------------------------------------------------------------------------
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
+    _req_cuda(x0, noise, t, sqrt_ac, sqrt_1mac)
+    xt = torch.empty_like(x0)
+    B = x0.shape[0]
+    _lib.call("cesm_q_sample", _ptr(x0), _ptr(noise), _ptr(t), _ptr(sqrt_ac), _ptr(sqrt_1mac), _ptr(xt), B,
+              x0.numel() // B, _stream())
+    return xt
+
+
+def mse_fwd(eps, noise):
+    _req_cuda(eps, noise)
+    diff = torch.empty_like(eps)
+    loss = torch.empty((), dtype=torch.float32, device=eps.device)
+    _lib.call("cesm_mse_fwd", _ptr(eps), _ptr(noise), _ptr(diff), _ptr(loss), eps.numel(), _stream())
+    return loss, diff
+
+
+def scale_by_scalar(x, gscale, factor: float):
+    _req_cuda(x, gscale)
+    out = torch.empty_like(x)
+    _lib.call("cesm_scale_by_scalar", _ptr(x), _ptr(gscale), factor, _ptr(out), x.numel(), _stream())
+    return out
+
+
+def p_sample(xt, eps, z, t, betas, sqrt_1mac, sqrt_recip_a, post_var):
+    _req_cuda(xt, eps, z, t, betas, sqrt_1mac, sqrt_recip_a, post_var)
+    out = torch.empty_like(xt)
+    B = xt.shape[0]
+    _lib.call("cesm_p_sample", _ptr(xt), _ptr(eps), _ptr(z), _ptr(t), _ptr(betas), _ptr(sqrt_1mac), _ptr(sqrt_recip_a),
+              _ptr(post_var), _ptr(out), B, xt.numel() // B, _stream())
+    return out

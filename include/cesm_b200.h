@@ -82,6 +82,133 @@ typedef struct cesm_igemm_args {
 
 int cesm_igemm(const cesm_igemm_args* args, void* stream);
 
+/*
+ * Weight gradient of the implicit GEMM above, contracted over pixels on tcgen05 tensor cores:
+ *     dw[co, t, ci] = sum_{n, oh, ow}  dy[n, oh, ow, co] * X[n, oh*stride + tap_dh[t], ow*stride + tap_dw[t], ci]
+ * X = concat(x0, x1) as in cesm_igemm.  dy pixel (n, oh, ow) is row
+ * ((n*y_h + oh*y_sh + y_h0)*y_w + ow*y_sw + y_w0) of a bf16 [*, cout] matrix (sub-pixel phases of
+ * a transposed conv).  dw is fp32 [cout, num_taps, c0+c1] and is overwritten.
+ *
+ * Replaces the weight-gradient halves of cuDNN/cuBLAS backward for the call sites listed above.
+ */
+typedef struct cesm_wgrad_args {
+    const void* x0;
+    const void* x1;
+    int32_t c0, c1;
+    int32_t n, h, w;
+    int32_t stride;
+    int32_t num_taps;
+    int32_t tap_dh[CESM_MAX_TAPS];
+    int32_t tap_dw[CESM_MAX_TAPS];
+    const void* dy;
+    int32_t cout;
+    int32_t oh, ow;
+    int32_t y_h, y_w, y_sh, y_sw, y_h0, y_w0;
+    float* dw;
+} cesm_wgrad_args;
+
+int cesm_wgrad(const cesm_wgrad_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight re-layout.  dst[o][t][i] (bf16) = src[o*so + i*si + tap_off[t]] (fp32): turns a PyTorch
+ * conv / linear parameter into the [cout][taps][cin] operand of cesm_igemm (forward, or flipped /
+ * transposed for the data gradient).  cesm_unpack_wgrad is the inverse scatter for fp32 gradients
+ * produced by cesm_wgrad (accumulate != 0 adds into dst).
+ * ---------------------------------------------------------------------------------------------- */
+int cesm_pack_weight(const float* src, void* dst, int O, int T, int I, long long so, long long si,
+                     const int32_t* tap_off, void* stream);
+int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int I, long long so, long long si,
+                      const int32_t* tap_off, int accumulate, void* stream);
+/* out[c] = sum over rows of bf16 x[M][C] (bias gradients). */
+int cesm_colsum(const void* x, float* out, long long M, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm + FiLM + SiLU (+ residual), video_net.py:216-227 and :265.   x: bf16 [B][P][C],
+ * P = frames*H*W (statistics couple the frames of a sample, as nn.GroupNorm on a 5-D tensor does).
+ *   sums  : fp32 [B][G][2]  (sum, sum of squares), written by cesm_gn_stats
+ *   film  : fp32 [B][2C] = (scale | shift) from the time-embedding MLP, or NULL
+ *   out   = silu(((x-mean)*rstd*gamma+beta)*(scale+1)+shift) (+ residual)
+ * cesm_gn_bwd returns dx (bf16), dgamma/dbeta [C], dfilm [B][2C] (if film); csum is fp32 scratch [B][C][4].
+ * ---------------------------------------------------------------------------------------------- */
+int cesm_gn_stats(const void* x, float* sums, int B, long long P, int C, int G, void* stream);
+int cesm_gn_apply_fwd(const void* x, const float* sums, const float* gamma, const float* beta, const float* film,
+                      const void* residual, void* out, int B, long long P, int C, int G, float eps, void* stream);
+int cesm_gn_bwd(const void* x, const void* dout, const float* sums, const float* gamma, const float* beta,
+                const float* film, float* csum, void* dx, float* dgamma, float* dbeta, float* dfilm, int B,
+                long long P, int C, int G, float eps, void* stream);
+
+/* Channel LayerNorm with gain only, video_net.py:78-87.  x, out, dy, dres, dx: bf16 [M][C].
+ * bwd: dx = LN'(dy) (+ dres if not NULL); dgamma fp32 [C] is overwritten. */
+int cesm_ln_fwd(const void* x, const float* gamma, void* out, long long M, int C, float eps, void* stream);
+int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, const void* dres, void* dx, float* dgamma,
+                long long M, int C, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Temporal attention core, video_net.py:413-453 + rotary_embedding.py:29-48, fused:
+ * q*scale -> RoPE(q), RoPE(k) -> q.k + rel-pos bias -> online softmax over frames -> .v
+ *   qkv : bf16 [B*F*HW][3*H*32] (q | k | v), row = (b*F + f)*HW + pixel
+ *   bias: fp32 [H][F][F];  cs, sn: fp32 [F][16] rotary cos / sin;  out: bf16 [B*F*HW][H*32]
+ *   lse : fp32 [B*F*HW][H] log-sum-exp saved for the backward
+ * ---------------------------------------------------------------------------------------------- */
+int cesm_tattn_fwd(const void* qkv, const float* bias, const float* cs, const float* sn, void* out, float* lse,
+                   int B, int F, int HW, int H, int dim_head, float scale, void* stream);
+int cesm_tattn_bwd(const void* qkv, const float* bias, const float* cs, const float* sn, const void* out,
+                   const float* lse, const void* dout, void* dqkv, float* dbias, int B, int F, int HW, int H,
+                   int dim_head, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spatial linear attention core, video_net.py:338-344, per image (frame) of n pixels:
+ * softmax(q) over d, softmax(k) over n, ctx = k^T v, out = ctx^T q*scale.
+ *   qkv: bf16 [NI*n][3*H*32];  part: fp32 scratch [NI][64][H*32][2];  kstat: fp32 [NI][H*32][2];
+ *   qk : bf16 [NI*n][2*H*32] (scale*softmax(q) | softmax(k)), saved for the backward;
+ *   ctx: fp32 [NI][H][32][32];  out: bf16 [NI*n][H*32]
+ * bwd: dctx [NI][H][32][32] and delta [NI][H][32] are fp32 scratch; dqkv: bf16 [NI*n][3*H*32].
+ * ---------------------------------------------------------------------------------------------- */
+int cesm_linattn_fwd(const void* qkv, float* part, float* kstat, void* qk, float* ctx, void* out, int NI, int n,
+                     int H, int dim_head, float scale, void* stream);
+int cesm_linattn_bwd(const void* qkv, const void* qk, const float* ctx, const void* dout, float* dctx, float* delta,
+                     void* dqkv, int NI, int n, int H, int dim_head, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Network boundary convs.
+ * Input conv (video_net.py:808-815 + model.py:110-121): 7x7, the two fp32 input planes (noisy
+ * target, condition) are read in place -- channel concat and frame broadcast (f0/f1 = 1 or F frames
+ * per sample) are folded into the kernel.  out: bf16 [B*F][H][W][64].  Only the weight gradient
+ * exists (network inputs need no gradient).
+ * Output conv (video_net.py:763 + model.py:129-130): 1x1x1, 64 -> 1, evaluated on the centre
+ * frame only (the reference computes every frame and then selects frame F//2).
+ * ---------------------------------------------------------------------------------------------- */
+int cesm_input_conv_fwd(const float* in0, const float* in1, int f0, int f1, const float* w, const float* bias,
+                        void* out, int B, int F, int H, int W, int ks, int cout, void* stream);
+int cesm_input_conv_wgrad(const float* in0, const float* in1, int f0, int f1, const void* dy, float* dw, float* db,
+                          int B, int F, int H, int W, int ks, int cout, void* stream);
+int cesm_out_conv_fwd(const void* a, const float* w, const float* bias, float* eps, int B, int F, int mid,
+                      long long HW, int C, void* stream);
+int cesm_out_conv_bwd(const void* a, const float* w, const float* deps, void* da, float* dw, float* db, int B, int F,
+                      int mid, long long HW, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Time embedding and small fp32 linears (video_net.py:101-113, 651-656, 238-241).
+ * small_linear: y[b][n] = sum_k act(x[b][k]) W[n][k] + bias[n], act = SiLU if act_silu_in.
+ * ---------------------------------------------------------------------------------------------- */
+int cesm_sinusoidal(const long long* t, float* out, int B, int dim, void* stream);
+int cesm_small_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
+                          int act_silu_in, void* stream);
+int cesm_small_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db, int B,
+                          int K, int N, int act_silu_in, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DDPM elementwise steps (model.py:168-208); t is an int64 device vector, schedule buffers fp32 [T].
+ * ---------------------------------------------------------------------------------------------- */
+int cesm_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
+                  const float* sqrt_1mac, float* xt, int B, long long per_sample, void* stream);
+int cesm_mse_fwd(const float* eps, const float* noise, float* diff, float* loss, long long total, void* stream);
+int cesm_scale_by_scalar(const float* in, const float* gscale, float factor, float* out, long long total,
+                         void* stream);
+int cesm_p_sample(const float* xt, const float* eps, const float* z, const long long* t, const float* betas,
+                  const float* sqrt_1mac, const float* sqrt_recip_a, const float* post_var, float* out, int B,
+                  long long per_sample, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

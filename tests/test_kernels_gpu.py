@@ -1,0 +1,313 @@
+"""GPU parity of every non-GEMM kernel and of the tcgen05 weight-gradient kernel, through the C ABI.
+
+Each check feeds the CUDA kernel and a torch fp32 restatement (oracle functions where they exist)
+the SAME bf16-rounded inputs.  Tolerances (relative to max|ref|): 1e-2 for bf16 outputs (one or
+two bf16 roundings of 2^-9 each plus fp32 reassociation), 2e-3 for fp32 outputs.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cesm_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def err(a, b):
+    a, b = a.float(), b.float()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-20)
+
+
+def rnd(shape, dev, scale=1.0, dtype=BF):
+    return (torch.randn(shape, device=dev) * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight gradients (tcgen05, MN-major operands)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 32, 64, 64), (3, 64, 64, 128, 128), (2, 16, 16, 256, 256),
+                                             (6, 8, 8, 512, 512), (2, 48, 72, 64, 128), (1, 24, 36, 128, 64),
+                                             (2, 128, 128, 64, 64)])
+def test_wgrad_conv3x3(cuda, n, h, w, cin, cout):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(0)
+    x, dy = rnd((n, h, w, cin), cuda), rnd((n, h, w, cout), cuda, 0.1)
+    dw = K.wgrad(x, dy, taps=K.TAPS_3x3)  # [cout, 9, cin]
+    wt = torch.zeros(cout, cin, 3, 3, device=cuda, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=1)
+    (ref,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    assert err(dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2), ref) < 2e-3
+
+
+def test_wgrad_concat_and_1x1(cuda):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(1)
+    n, h, w, c0, c1, cout = 2, 32, 32, 128, 64, 128
+    x0, x1, dy = rnd((n, h, w, c0), cuda), rnd((n, h, w, c1), cuda), rnd((n, h, w, cout), cuda, 0.1)
+    dw = K.wgrad(x0, dy, x1=x1, taps=K.TAPS_3x3)
+    wt = torch.zeros(cout, c0 + c1, 3, 3, device=cuda, requires_grad=True)
+    y = F.conv2d(torch.cat([x0, x1], -1).float().permute(0, 3, 1, 2), wt, padding=1)
+    (ref,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    assert err(dw.view(cout, 3, 3, c0 + c1).permute(0, 3, 1, 2), ref) < 2e-3
+    # plain linear: dW = dy^T x
+    m, k, nn = 5000, 256, 768
+    a, g = rnd((1, 1, m, k), cuda), rnd((1, 1, m, nn), cuda, 0.1)
+    dwl = K.wgrad(a, g)
+    assert err(dwl.view(nn, k), g.float().view(m, nn).t() @ a.float().view(m, k)) < 2e-3
+
+
+def test_wgrad_strided_and_transposed(cuda):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(2)
+    n, h, w, c = 2, 32, 32, 128
+    # Downsample conv 4x4 s2 p1
+    x, dy = rnd((n, h, w, c), cuda), rnd((n, h // 2, w // 2, c), cuda, 0.1)
+    taps = [(kh - 1, kw - 1) for kh in range(4) for kw in range(4)]
+    dw = K.wgrad(x, dy, taps=taps, stride=2)
+    wt = torch.zeros(c, c, 4, 4, device=cuda, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, stride=2, padding=1)
+    (ref,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    assert err(dw.view(c, 4, 4, c).permute(0, 3, 1, 2), ref) < 2e-3
+    # Upsample ConvTranspose 4x4 s2 p1: weight [cin, cout, kh, kw]
+    x, dy = rnd((n, h, w, c), cuda), rnd((n, 2 * h, 2 * w, c), cuda, 0.1)
+    wt = torch.zeros(c, c, 4, 4, device=cuda, requires_grad=True)
+    y = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt, stride=2, padding=1)
+    (ref,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    got = torch.zeros_like(ref)
+    sel = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}
+    for ph in (0, 1):
+        for pw in (0, 1):
+            taps, khw = [], []
+            for dh, kh in sel[ph]:
+                for dw_, kw in sel[pw]:
+                    taps.append((dh, dw_))
+                    khw.append((kh, kw))
+            d = K.wgrad(x, dy, taps=taps, grid_hw=(h, w), dy_place=(2, 2, ph, pw))  # [cout, 4, cin]
+            for t, (kh, kw) in enumerate(khw):
+                got[:, :, kh, kw] = d[:, t, :].t()
+    assert err(got, ref) < 2e-3
+
+
+def test_pack_unpack_weight(cuda):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(3)
+    co, ci = 128, 64
+    w = torch.randn(co, ci, 1, 3, 3, device=cuda)
+    offs = [kh * 3 + kw for kh in range(3) for kw in range(3)]
+    p = K.pack_weight(w, co, 9, ci, ci * 9, 9, offs)
+    assert torch.equal(p.view(co, 9, ci), w.view(co, ci, 9).permute(0, 2, 1).to(BF))
+    # dgrad layout: [ci][flipped tap][co]
+    pd = K.pack_weight(w, ci, 9, co, 9, ci * 9, [8 - o for o in offs])
+    assert torch.equal(pd.view(ci, 9, co), w.view(co, ci, 9).flip(-1).permute(1, 2, 0).to(BF))
+    g = torch.randn(co, 9, ci, device=cuda)
+    dst = torch.zeros_like(w)
+    K.unpack_wgrad(g, dst, co, 9, ci, ci * 9, 9, offs)
+    assert torch.equal(dst.view(co, ci, 9), g.permute(0, 2, 1))
+    K.unpack_wgrad(g, dst, co, 9, ci, ci * 9, 9, offs, accumulate=True)
+    assert torch.equal(dst.view(co, ci, 9), 2 * g.permute(0, 2, 1))
+    x = rnd((777, 256), cuda)
+    assert err(K.colsum(x), x.float().sum(0)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm + FiLM + SiLU (+ residual) and channel LayerNorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,P,C,film,res", [(2, 3 * 16 * 16, 64, True, False), (2, 3 * 8 * 8, 128, False, True),
+                                            (1, 1000, 256, True, True), (3, 65, 512, False, False)])
+def test_groupnorm_fwd_bwd(cuda, B, P, C, film, res):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(4)
+    G = 8
+    x = rnd((B, P, C), cuda, 2.0) + 0.5
+    gamma = torch.randn(C, device=cuda) * 0.5 + 1
+    beta = torch.randn(C, device=cuda) * 0.2
+    fl = torch.randn(B, 2 * C, device=cuda) * 0.3 if film else None
+    r = rnd((B, P, C), cuda) if res else None
+    dout = rnd((B, P, C), cuda)
+    sums = K.gn_stats(x, B, G)
+    out = K.gn_apply_fwd(x, sums, gamma, beta, fl, r, B, G, 1e-5)
+    dx, dg, db, dfl = K.gn_bwd(x, dout, sums, gamma, beta, fl, B, G, 1e-5)
+
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    flr = fl.clone().requires_grad_(True) if film else None
+    y = F.group_norm(xr.transpose(1, 2), G, gr, br, 1e-5)  # [B, C, P]
+    if film:
+        y = y * (flr[:, :C, None] + 1) + flr[:, C:, None]
+    y = F.silu(y).transpose(1, 2)
+    ref = y + (r.float() if res else 0)
+    assert err(out, ref) < 1e-2
+    grads = torch.autograd.grad(y, [xr, gr, br] + ([flr] if film else []), dout.float())
+    assert err(dx, grads[0]) < 1e-2
+    assert err(dg, grads[1]) < 2e-3 and err(db, grads[2]) < 2e-3
+    if film:
+        assert err(dfl, grads[3]) < 2e-3
+
+
+@pytest.mark.parametrize("M,C", [(1000, 64), (513, 128), (300, 256), (77, 512)])
+def test_layernorm_fwd_bwd(cuda, M, C):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(5)
+    x = rnd((M, C), cuda, 2.0) + 0.3
+    gamma = torch.randn(C, device=cuda) * 0.5 + 1
+    dy, dres = rnd((M, C), cuda), rnd((M, C), cuda)
+    out = K.ln_fwd(x, gamma, 1e-5)
+    dx, dg = K.ln_bwd(x, gamma, dy, dres, 1e-5)
+    xr, gr = x.float().requires_grad_(True), gamma.clone().requires_grad_(True)
+    y = O.channel_layer_norm(xr.t()[None], gr[None, :, None])[0].t()
+    assert err(out, y) < 1e-2
+    gx, gg = torch.autograd.grad(y, [xr, gr], dy.float())
+    assert err(dx, gx + dres.float()) < 1e-2
+    assert err(dg, gg) < 2e-3
+    dx2, _ = K.ln_bwd(x, gamma, dy, None, 1e-5)
+    assert err(dx2, gx) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# attention cores
+# ------------------------------------------------------------------------------------------------
+def _tattn_ref(qkv, bias, freqs, B, Fr, HW, H, D):
+    """oracle.attention without the projections: qkv [B*F*HW, 3HD] -> out [B*F*HW, HD]."""
+    x = qkv.view(B, Fr, HW, 3 * H * D).permute(0, 2, 1, 3)  # b hw f c
+    q, k, v = (t.reshape(B, HW, Fr, H, D).transpose(-2, -3) for t in x.chunk(3, dim=-1))
+    q = q * D ** -0.5
+    ang = O.rotary_angles(freqs, Fr)
+    q, k = O.apply_rotary(q, ang), O.apply_rotary(k, ang)
+    sim = torch.einsum("...hid,...hjd->...hij", q, k) + bias
+    attn = (sim - sim.amax(-1, keepdim=True).detach()).softmax(-1)
+    out = torch.einsum("...hij,...hjd->...hid", attn, v)
+    out = out.transpose(-2, -3).reshape(B, HW, Fr, H * D)
+    return out.permute(0, 2, 1, 3).reshape(B * Fr * HW, H * D)
+
+
+@pytest.mark.parametrize("B,Fr,HW,H", [(2, 3, 64, 8), (1, 1, 100, 8), (2, 12, 33, 8), (1, 40, 16, 4)])
+def test_temporal_attention_core(cuda, B, Fr, HW, H):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(6)
+    D = 32
+    qkv = rnd((B * Fr * HW, 3 * H * D), cuda)
+    bias = torch.randn(H, Fr, Fr, device=cuda)
+    freqs = (1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))).to(cuda)
+    ang = torch.arange(Fr, device=cuda, dtype=torch.float32)[:, None] * freqs[None]
+    cs, sn = ang.cos().contiguous(), ang.sin().contiguous()
+    dout = rnd((B * Fr * HW, H * D), cuda)
+    out, lse = K.tattn_fwd(qkv, bias, cs, sn, B, Fr, HW, H, D, D ** -0.5)
+    dqkv, dbias = K.tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B, Fr, HW, H, D, D ** -0.5)
+    qr, br = qkv.float().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = _tattn_ref(qr, br, freqs, B, Fr, HW, H, D)
+    assert err(out, ref) < 1e-2
+    gq, gb = torch.autograd.grad(ref, [qr, br], dout.float())
+    assert err(dqkv, gq) < 1.5e-2
+    assert err(dbias, gb) < 1e-2
+
+
+def _linattn_ref(qkv, NI, n, H, D):
+    q, k, v = (t.reshape(NI, n, H, D).permute(0, 2, 3, 1) for t in qkv.view(NI, n, 3 * H * D).chunk(3, dim=-1))
+    q = q.softmax(dim=-2) * D ** -0.5
+    k = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    out = torch.einsum("bhde,bhdn->bhen", ctx, q)
+    return out.permute(0, 3, 1, 2).reshape(NI * n, H * D)
+
+
+@pytest.mark.parametrize("NI,n,H", [(2, 256, 8), (3, 1024, 8), (1, 4096, 8), (6, 64, 8), (2, 24 * 36, 8)])
+def test_linear_attention_core(cuda, NI, n, H):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(7)
+    D = 32
+    qkv = rnd((NI * n, 3 * H * D), cuda, 1.5)
+    dout = rnd((NI * n, H * D), cuda)
+    out, qk, ctx = K.linattn_fwd(qkv, NI, n, H, D, D ** -0.5)
+    dqkv = K.linattn_bwd(qkv, qk, ctx, dout, NI, n, H, D, D ** -0.5)
+    qr = qkv.float().requires_grad_(True)
+    ref = _linattn_ref(qr, NI, n, H, D)
+    assert err(out, ref) < 1.5e-2
+    (g,) = torch.autograd.grad(ref, qr, dout.float())
+    assert err(dqkv, g) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# boundary convs, small linears, DDPM elementwise
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Fr,H,W,f0", [(2, 3, 32, 32, 1), (1, 1, 48, 72, 1), (2, 3, 20, 36, 3)])
+def test_input_conv(cuda, B, Fr, H, W, f0):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(8)
+    x = torch.randn(B, 1, f0, H, W, device=cuda)
+    c = torch.randn(B, 1, Fr, H, W, device=cuda)
+    w = torch.randn(64, 2, 1, 7, 7, device=cuda) * 0.1
+    b = torch.randn(64, device=cuda)
+    out = K.input_conv_fwd(x, c, w, b, B, Fr, H, W, 7)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    xin = torch.cat([x.expand(-1, -1, Fr, -1, -1), c], dim=1)
+    ref = F.conv3d(xin, wr, br, padding=(0, 3, 3))  # [B,64,F,H,W]
+    ref_cl = ref.permute(0, 2, 3, 4, 1).reshape(B * Fr, H, W, 64)
+    assert err(out, ref_cl) < 1e-2
+    dy = rnd((B * Fr, H, W, 64), cuda)
+    dw, db = K.input_conv_wgrad(x, c, dy, B, Fr, H, W, 7)
+    gw, gb = torch.autograd.grad(ref_cl, [wr, br], dy.float())
+    assert err(dw, gw) < 2e-3 and err(db, gb) < 2e-3
+
+
+def test_output_conv(cuda):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(9)
+    B, Fr, H, W = 2, 3, 16, 24
+    a = rnd((B * Fr, H, W, 64), cuda)
+    w = torch.randn(1, 64, 1, 1, 1, device=cuda) * 0.2
+    b = torch.randn(1, device=cuda)
+    eps = K.out_conv_fwd(a, w, b, B, Fr, H, W)
+    ar, wr, br = a.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    full = (ar.view(B, Fr, H, W, 64) * wr.view(64)).sum(-1) + br
+    ref = full[:, Fr // 2][:, None]
+    assert err(eps, ref) < 2e-3
+    de = torch.randn(B, 1, H, W, device=cuda)
+    da, dw, db = K.out_conv_bwd(a, w, de, B, Fr, H, W)
+    ga, gw, gb = torch.autograd.grad(ref, [ar, wr, br], de)
+    assert err(da, ga) < 1e-2 and err(dw, gw) < 2e-3 and err(db, gb) < 2e-3
+
+
+def test_time_embedding_and_small_linear(cuda):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(10)
+    t = torch.tensor([0, 1, 17, 999], device=cuda)
+    assert err(K.sinusoidal(t, 64), O.sinusoidal_pos_emb(t, 64)) < 1e-5
+    for act in (False, True):
+        x = torch.randn(4, 256, device=cuda)
+        W = torch.randn(512, 256, device=cuda) * 0.1
+        b = torch.randn(512, device=cuda)
+        y = K.small_linear_fwd(x, W, b, act)
+        xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        ref = F.linear(F.silu(xr) if act else xr, Wr, br)
+        assert err(y, ref) < 1e-4
+        dy = torch.randn_like(y)
+        dx, dW, db = K.small_linear_bwd(x, W, dy, act, True)
+        gx, gW, gb = torch.autograd.grad(ref, [xr, Wr, br], dy)
+        assert err(dx, gx) < 1e-4 and err(dW, gW) < 1e-4 and err(db, gb) < 1e-4
+
+
+def test_ddpm_elementwise(cuda):
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(11)
+    buf = {k: v.to(cuda) for k, v in O.diffusion_buffers(1000).items()}
+    B, H, W = 3, 16, 24
+    x0, noise = torch.randn(B, 1, H, W, device=cuda), torch.randn(B, 1, H, W, device=cuda)
+    t = torch.tensor([0, 500, 999], device=cuda)
+    xt = K.q_sample(x0, noise, t, buf["sqrt_alphas_cumprod"], buf["sqrt_one_minus_alphas_cumprod"])
+    assert err(xt, O.q_sample(buf, x0, t, noise)) < 1e-6
+    eps = torch.randn_like(x0)
+    loss, diff = K.mse_fwd(eps, noise)
+    assert abs(loss.item() - F.mse_loss(eps, noise).item()) < 1e-5
+    g = torch.tensor([0.5], device=cuda)
+    assert err(K.scale_by_scalar(diff, g, 2.0 / eps.numel()), (eps - noise) * 2 / eps.numel() * 0.5) < 1e-6
+    z = torch.randn_like(x0)
+    got = K.p_sample(xt, eps, z, t, buf["betas"], buf["sqrt_one_minus_alphas_cumprod"], buf["sqrt_recip_alphas"],
+                     buf["posterior_variance"])
+    beta = buf["betas"][t].view(-1, 1, 1, 1)
+    mean = buf["sqrt_recip_alphas"][t].view(-1, 1, 1, 1) * (xt - beta / buf["sqrt_one_minus_alphas_cumprod"][t].view(-1, 1, 1, 1) * eps)
+    ref = mean + torch.sqrt(buf["posterior_variance"][t].view(-1, 1, 1, 1)) * z
+    assert err(got, ref) < 1e-6
+    assert torch.equal(got[0], mean[0])  # t == 0 adds no noise (model.py:178-179)
