@@ -310,4 +310,5 @@ def test_ddpm_elementwise(cuda):
     mean = buf["sqrt_recip_alphas"][t].view(-1, 1, 1, 1) * (xt - beta / buf["sqrt_one_minus_alphas_cumprod"][t].view(-1, 1, 1, 1) * eps)
     ref = mean + torch.sqrt(buf["posterior_variance"][t].view(-1, 1, 1, 1)) * z
     assert err(got, ref) < 1e-6
-    assert torch.equal(got[0], mean[0])  # t == 0 adds no noise (model.py:178-179)
+    assert err(got[0], mean[0]) < 1e-6  # t == 0 adds no noise (model.py:178-179): posterior_variance[0] == 0
+    assert buf["posterior_variance"][0].item() == 0.0
