@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: data-parallel training of the config/baseline space-time U-Net.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's B200 path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference algorithm on host cores
+
+A "step" is one training step (Diffusion.loss forward + backward, gradient all-reduce when N > 1,
+global-norm clip, AdamW) on one synthetic batch.  Workload (BASELINE.json configs[1]): the
+config/baseline model, K=3 condition frames, full 192x288 grid, per-GPU batch 2 (train.batch_size),
+bf16 activations with fp32 accumulation and fp32 master weights.  One JSON line is printed by rank 0.
+
+  value    : samples/s over all N GPUs, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e      : the same metric through the public API (TrainEngine.step) with pinned HOST batches
+             copied in and the loss read back every step
+  roofline : the dominant kernel (the tcgen05 implicit GEMM, all its launches in one step):
+             algorithmic FLOPs / summed CUDA-event durations from an untimed instrumented step,
+             against the measured bf16 peak in MEASURED_PEAKS.json; `step_frac` does the same
+             for the whole step (algorithmic FLOPs per sample from SURVEY.md section 8(d))
+  cpu_baseline : the CPU oracle (a port of the reference's fp32 algorithm) timed on this box's
+             host cores on a bounded sample, N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BASELINE_KW = dict(in_channels=2, out_channels=1, base_ch=64, ch_mults=(1, 2, 4), num_res_blocks=2, time_dim=124,
+                   groups=8, dropout=0.0, use_checkpoint=False)          # config/baseline "unet"
+MORE_BLOCKS_KW = dict(in_channels=2, out_channels=1, base_ch=64, ch_mults=(1, 2, 4, 8), num_res_blocks=6,
+                      time_dim=124, groups=8, dropout=0.0, use_checkpoint=False)  # config/more_blocks "unet"
+# algorithmic GFLOP per sample, forward + backward, K = 3 (linear in pixels)
+GFLOP_PER_PIXEL = {"baseline": 476.45 / (128 * 128), "more_blocks": 137.5 / (64 * 64)}
+METRIC = "train samples/s (baseline cfg)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="baseline", choices=["baseline", "more_blocks"])
+    ap.add_argument("--batch", type=int, default=2, help="per-GPU batch (config/baseline train.batch_size = 2)")
+    ap.add_argument("--hw", default="192x288", help="grid (lat x lon); 192x288 = full CESM2 f09 grid")
+    ap.add_argument("--frames", type=int, default=3, help="dataset.K condition frames")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--kernel-table", default="", help="write the per-kernel breakdown to this file")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm_sorted = sorted(sm)
+            out.update(sm_mhz=sm_sorted[len(sm_sorted) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(arch_kw, frames, H, W, threads, steps, warmup):
+    """Seconds per fwd+bwd of one sample (B=1) at H x W on `threads` host threads (fp32)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _parity import make_inputs
+    from oracle import cesm_oracle as O
+    from cesm_emulator_b200.model import UNet
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    unet = UNet(**arch_kw)  # parameter container only: the oracle consumes its state_dict on the CPU
+    sd = {k: v.detach().float() for k, v in unet.state_dict().items()}
+    cfg = O.OracleConfig.from_unet_kwargs(**arch_kw)
+    buf = O.diffusion_buffers(1000)
+    x0, cond, t, noise = make_inputs(1, frames, H, W, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(sd, cfg, buf, x0, cond, t, noise)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def pick_cpu_sample(H, W, budget_s, n_steps, arch_kw, frames, threads):
+    """Choose a crop (a power-of-two fraction of the grid) so that n_steps oracle steps fit the budget."""
+    probe_h, probe_w = max(16, H // 8), max(16, W // 8)
+    # 2 probe steps: first is cold
+    t_probe = cpu_reference_step_time(arch_kw, frames, probe_h, probe_w, threads, steps=1, warmup=1)
+    per_pixel = t_probe / (probe_h * probe_w)
+    frac = 1
+    while per_pixel * (H // frac) * (W // frac) * n_steps > budget_s and frac < 8:
+        frac *= 2
+    return H // frac, W // frac, frac
+
+
+def run_reference(args, H, W, arch_kw):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_steps = args.steps + args.warmup
+    h, w, frac = pick_cpu_sample(H, W, budget_s=150.0, n_steps=n_steps, arch_kw=arch_kw, frames=args.frames,
+                                 threads=threads)
+    sec = cpu_reference_step_time(arch_kw, args.frames, h, w, threads, steps=args.steps, warmup=args.warmup)
+    sec_full = sec * (H * W) / (h * w)  # cost is linear in pixels (convs, linear attention, per-pixel temporal attention)
+    value = 1.0 / sec_full
+    sample = (f"oracle port of the reference fp32 algorithm, fwd+bwd of 1 sample at {h}x{w}"
+              + (f" (1/{frac * frac} of the {H}x{W} grid, time scaled by pixel count)" if frac > 1 else "")
+              + f", {args.steps} timed steps after {args.warmup} warm-up")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, H, W, 1),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, H, W, per_gpu_batch):
+    return {"workload": f"config/{args.arch} training step (Diffusion.loss fwd+bwd + grad all-reduce + clip + AdamW), "
+                        f"K={args.frames} frames, {H}x{W} grid",
+            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "frames": args.frames,
+            "grid": [H, W], "parallelism": f"dp{args.gpus}"}
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, H, W, arch_kw):
+    import torch
+    import torch.distributed as dist
+    from cesm_emulator_b200 import _lib
+    from cesm_emulator_b200.engine import TrainEngine
+    from cesm_emulator_b200.model import Diffusion, UNet
+    from cesm_emulator_b200.synthetic import SyntheticEnsemble
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs `python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py ...`")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    B, Kf = args.batch, args.frames
+
+    torch.manual_seed(0)
+    diff = Diffusion(UNet(**arch_kw), timesteps=1000).to(dev)
+    diff.train()
+    eng = TrainEngine(diff, (B, 1, H, W), (B, 1, Kf, H, W), use_graph=not args.no_graph)
+
+    # synthetic (member, time, lat, lon, channel) ensemble; a small pool of pinned host batches
+    ds = SyntheticEnsemble(members=4, times=8, lat=H, lon=W, seed=1234 + rank, K=Kf)
+    idx = ds.shard_indices(0, rank, world)
+    pool = [ds.batch(idx[(i * B + torch.arange(B).numpy()) % len(idx)], pin=True) for i in range(4)]
+    torch.manual_seed(1234 + rank)
+    eng.x0.copy_(pool[0][1])
+    eng.cond.copy_(pool[0][0])
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: engine-internal eager steps + capture, then W replays
+    for _ in range(3 + args.warmup):
+        eng.step_resident()
+    barrier()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        n0 = _lib.launch_count()
+        e0.record()
+        for i in range(args.steps):
+            flush.zero_()
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.launch_count() - n0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, eager_launches = timed(lambda i: eng.step_resident())
+    losses = []
+
+    def e2e_step(i):
+        cond, x0 = pool[i % len(pool)]
+        losses.append(eng.step(x0, cond).item())  # D2H read of the loss: syncs every step, as train.py:898 does
+
+    ms_e2e, _ = timed(e2e_step)
+    clocks = sampler.stop() if rank == 0 else None
+
+    samples = B * world * args.steps
+    value = samples / (ms_res * 1e-3)
+    e2e_value = samples / (ms_e2e * 1e-3)
+    launches = eng.launches_per_step * args.steps  # graph replays re-issue the captured kernels
+    h2d = pool[0][0].numel() * 4 + pool[0][1].numel() * 4
+
+    # ---- untimed instrumented step: per-kernel breakdown and the dominant kernel's roofline --------
+    roofline, table = None, None
+    gflop_sample = GFLOP_PER_PIXEL[args.arch] * H * W if Kf == 3 else None
+    step_tf = (gflop_sample * B / (ms_res / args.steps)) if gflop_sample else None  # GFLOP/ms == TFLOP/s
+    if not args.no_kernel_pass:
+        # every rank runs the step (it contains the all-reduce); rank 0 reports
+        prof_eng = TrainEngine(diff, (B, 1, H, W), (B, 1, Kf, H, W), use_graph=False)
+        prof_eng.x0.copy_(eng.x0)
+        prof_eng.cond.copy_(eng.cond)
+        prof_eng.step_resident()
+        torch.cuda.synchronize()
+        _lib.PROFILER = _lib.KernelProfiler()
+        prof_eng.step_resident()
+        table = _lib.PROFILER.summary()
+        _lib.PROFILER = None
+    if rank == 0 and table is not None:
+        ig = [v for k, v in table.items() if k.startswith("cesm_igemm")]
+        ig_ms, ig_fl, ig_calls = sum(v["ms"] for v in ig), sum(v["flops"] for v in ig), sum(v["calls"] for v in ig)
+        total_ms = sum(v["ms"] for v in table.values())
+        peak = peaks["bf16_tflops_sustained"]
+        ach = ig_fl / (ig_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv fwd + dgrad + projections)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "launches_per_step": ig_calls, "share_of_kernel_time": ig_ms / total_ms, "traffic": None,
+                    "step_achieved": step_tf, "step_frac": (step_tf / peak) if step_tf else None}
+        lines = [f"{'kernel':40s} {'calls':>6s} {'ms':>9s} {'share':>7s} {'TFLOP/s':>9s} {'GB/s':>9s}"]
+        for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
+            tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else 0.0
+            gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] else 0.0
+            lines.append(f"{k:40s} {v['calls']:6d} {v['ms']:9.3f} {v['ms'] / total_ms:7.1%} {tf:9.1f} {gb:9.1f}")
+        lines.append(f"{'total (instrumented eager step)':40s} {sum(v['calls'] for v in table.values()):6d} {total_ms:9.3f}")
+        text = "\n".join(lines)
+        sys.stderr.write(text + "\n")
+        if args.kernel_table:
+            with open(args.kernel_table, "w") as f:
+                f.write(f"# bench.py kernel pass: arch={args.arch} B={B} K={Kf} grid={H}x{W}\n" + text + "\n")
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        h, w, frac = pick_cpu_sample(H, W, budget_s=25.0, n_steps=1, arch_kw=arch_kw, frames=Kf, threads=threads)
+        sec = cpu_reference_step_time(arch_kw, Kf, h, w, threads, steps=1, warmup=0)
+        sec_full = sec * (H * W) / (h * w)
+        cpu_baseline = {"value": 1.0 / sec_full, "unit": "samples/s", "cores": threads, "kind": "port",
+                        "sample": f"oracle port (fp32 torch CPU) fwd+bwd of 1 sample at {h}x{w}"
+                                  + (f", 1/{frac * frac} of the grid, time scaled by pixel count" if frac > 1 else "")
+                                  + ", 1 timed step after a small-grid warm-up"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {**workload_config(args, H, W, B), "cuda_graph": not args.no_graph,
+                       "l2": "256 MiB buffer zeroed between steps (L2 is 126 MB); per-step activations >> L2"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "launches_per_step": eng.launches_per_step,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "loss_first_last": [losses[0], losses[-1]] if losses else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    H, W = (int(v) for v in args.hw.lower().split("x"))
+    arch_kw = BASELINE_KW if args.arch == "baseline" else MORE_BLOCKS_KW
+    if args.impl == "reference":
+        run_reference(args, H, W, arch_kw)
+    else:
+        run_b200(args, H, W, arch_kw)
+
+
+if __name__ == "__main__":
+    main()

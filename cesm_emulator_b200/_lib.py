@@ -72,6 +72,7 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(str(LIB_PATH))
     lib.cesm_last_error.restype = c_char_p
     lib.cesm_version.restype = c_char_p
+    lib.cesm_launch_count.restype = ctypes.c_longlong
     _declare(lib)
     _lib = lib
     return lib
@@ -116,7 +117,12 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 
 def exported_symbols() -> list[str]:
-    return ["cesm_last_error", "cesm_version", *sorted(_SIGNATURES)]
+    return ["cesm_last_error", "cesm_version", "cesm_launch_count", *sorted(_SIGNATURES)]
+
+
+def launch_count() -> int:
+    """Kernels launched by libcesm_b200.so in this process so far."""
+    return int(load().cesm_launch_count())
 
 
 def check(rc: int, what: str) -> None:
@@ -125,6 +131,42 @@ def check(rc: int, what: str) -> None:
         raise CesmError(f"{what} failed (status {rc}): {msg}")
 
 
-def call(name: str, *args) -> None:
+class KernelProfiler:
+    """Per-C-ABI-call device timing with CUDA events on the calling stream (bench.py's kernel
+    breakdown and roofline pass).  Only usable outside graph capture; every call is bracketed by
+    two events, so use it in a dedicated, untimed pass."""
+
+    def __init__(self):
+        self.records = []  # (name, meta, start_event, end_event)
+
+    def summary(self):
+        """-> {key: {"calls", "ms", "flops", "bytes"}} with key = name or name + '/' + meta['kind']."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, meta, e0, e1 in self.records:
+            key = name if not meta or "kind" not in meta else f"{name}/{meta['kind']}"
+            d = out.setdefault(key, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            if meta:
+                d["flops"] += meta.get("flops", 0.0)
+                d["bytes"] += meta.get("bytes", 0.0)
+        return out
+
+
+PROFILER = None  # set to a KernelProfiler to time every call
+
+
+def call(name: str, *args, _meta=None) -> None:
     lib = load()
+    prof = PROFILER
+    if prof is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib, name)(*args), name)
+    e1.record()
+    prof.records.append((name, _meta, e0, e1))

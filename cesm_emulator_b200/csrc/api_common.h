@@ -19,6 +19,13 @@ int set_error(int code, const char* fmt, ...);
             return ::cesm::set_error(CESM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,            \
                                      cudaGetErrorString(_e), __FILE__, __LINE__);              \
     } while (0)
+// Every kernel launch goes through this: counts it (cesm_launch_count) and checks the launch.
+void note_launch();
+#define CESM_CHECK_LAUNCH()            \
+    do {                               \
+        ::cesm::note_launch();         \
+        CESM_CHECK_CUDA(cudaGetLastError()); \
+    } while (0)
 #define CESM_REQUIRE(cond, ...)                                                 \
     do {                                                                        \
         if (!(cond)) return ::cesm::set_error(CESM_ERR_INVALID, __VA_ARGS__);   \

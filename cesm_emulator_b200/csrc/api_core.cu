@@ -1,5 +1,6 @@
 // C-ABI core: error reporting, TMA descriptor cache, and the cesm_igemm entry point
 // (tile-shape selection + tensor-map construction for igemm.cu).
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -10,6 +11,8 @@
 namespace cesm {
 
 static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
     char buf[1024];
@@ -146,6 +149,7 @@ using namespace cesm;
 
 extern "C" const char* cesm_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* cesm_version(void) { return "cesm_b200 0.1 sm_100a"; }
+extern "C" long long cesm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
     CESM_REQUIRE(a != nullptr, "args is NULL");
@@ -232,6 +236,7 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
         int rc = get_tensor_map_bf16(&bmap, a->wt, 2, dims, str, bbox);
         if (rc) return rc;
     }
+    note_launch();
     CESM_CHECK_CUDA(igemm_launch(amaps, n_amaps, bmap, p, block_n, as_stream(stream)));
     return CESM_OK;
 }
@@ -332,6 +337,7 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
     int ksplit = ceil_div(148 * 2, base_ctas);
     if (ksplit > tiles) ksplit = tiles;
     if (ksplit < 1) ksplit = 1;
+    note_launch();
     CESM_CHECK_CUDA(wgrad_launch(xmaps, n_xmaps, ymap, p, block_n, ksplit, st));
     return CESM_OK;
 }

@@ -410,7 +410,7 @@ extern "C" int cesm_tattn_fwd(const void* qkv, const float* bias, const float* c
     const int blocks = (int)((total + 127) / 128);
     tattn_fwd_kernel<<<blocks, 128, 0, as_stream(stream)>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out,
                                                             lse, B, F, HW, H, scale);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -426,7 +426,7 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
     tattn_bwd_kernel<<<blocks, 128, sh, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (const __nv_bfloat16*)out, lse,
                                               (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias, B, F, HW, H,
                                               scale);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -441,21 +441,21 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* part, float* kstat, void
     const int HD = H * D;
     const int nstrips = n >= 64 * 64 ? 64 : (n >= 256 ? 16 : 1);
     la_kstats_partial_kernel<<<dim3(nstrips, NI), 256, 0, st>>>((const __nv_bfloat16*)qkv, part, n, HD, nstrips);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     la_kstats_combine_kernel<<<ceil_div(NI * HD, 256), 256, 0, st>>>(part, kstat, HD, nstrips, NI * HD);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     const long long rows = (long long)NI * n;
     la_prep_kernel<<<(int)((rows * H + 127) / 128), 128, 0, st>>>((const __nv_bfloat16*)qkv, kstat, (__nv_bfloat16*)qk,
                                                                   rows, n, H, scale);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     CESM_CHECK_CUDA(cudaMemsetAsync(ctx, 0, sizeof(float) * NI * H * D * D, st));
     const int chunk = la_chunk(n);
     dim3 grid(ceil_div(n, chunk), H, NI);
     const __nv_bfloat16* qkp = (const __nv_bfloat16*)qk;
     la_context_kernel<<<grid, 256, 0, st>>>(qkp + HD, 2 * HD, (const __nv_bfloat16*)qkv + 2 * HD, 3 * HD, ctx, n, H, chunk);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     la_apply_kernel<<<grid, 128, 0, st>>>(qkp, ctx, (__nv_bfloat16*)out, n, H, chunk);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -472,12 +472,12 @@ extern "C" int cesm_linattn_bwd(const void* qkv, const void* qk, const float* ct
     // dctx[d][e] = sum_p (scale*softmax(q))[p][d] * dout[p][e]
     la_context_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qk, 2 * HD, (const __nv_bfloat16*)dout, HD, dctx, n, H,
                                             chunk);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     la_delta_kernel<<<ceil_div(NI * HD, 128), 128, 0, st>>>(ctx, dctx, delta, NI * HD);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     la_bwd_apply_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qk,
                                               (const __nv_bfloat16*)dout, ctx, dctx, delta, (__nv_bfloat16*)dqkv, n, H,
                                               chunk, scale);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

@@ -380,7 +380,7 @@ extern "C" int cesm_pack_weight(const float* src, void* dst, int O, int T, int I
     for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
     const long long total = (long long)O * T * I;
     pack_weight_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, O, T, I, so, si, taps);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -391,7 +391,7 @@ extern "C" int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int
     for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
     const long long total = (long long)O * T * I;
     unpack_wgrad_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(src, dst, O, T, I, so, si, taps, accumulate);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -403,7 +403,7 @@ extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, void* 
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
     colsum_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, M, C);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -414,7 +414,7 @@ extern "C" int cesm_input_conv_fwd(const float* in0, const float* in1, int f0, i
     CESM_REQUIRE((f0 == 1 || f0 == F) && (f1 == 1 || f1 == F), "frame counts must be 1 or F");
     dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B * F);
     input_conv_fwd_kernel<7, 64><<<grid, 256, 0, as_stream(stream)>>>(in0, in1, f0, f1, w, bias, (__nv_bfloat16*)out, F, H, W);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -427,7 +427,7 @@ extern "C" int cesm_input_conv_wgrad(const float* in0, const float* in1, int f0,
     const int ntiles = ceil_div(W, 16) * ceil_div(H, 16) * B * F;
     const int grid = ntiles < 148 * 2 ? ntiles : 148 * 2;
     input_conv_wgrad_kernel<7, 64><<<grid, 256, 0, st>>>(in0, in1, f0, f1, (const __nv_bfloat16*)dy, dw, db, B * F, F, H, W);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -436,7 +436,7 @@ extern "C" int cesm_out_conv_fwd(const void* a, const float* w, const float* bia
     CESM_REQUIRE(C == 64, "output conv kernel needs 64 input channels (C=%d)", C);
     const long long threads = (long long)B * HW * 8;
     out_conv_fwd_kernel<<<nblk(threads, 256), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)a, w, bias, eps, B, F, mid, HW);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -449,21 +449,21 @@ extern "C" int cesm_out_conv_bwd(const void* a, const float* w, const float* dep
     long long blocks = ((long long)B * F * HW * 8 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     out_conv_bwd_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)a, w, deps, (__nv_bfloat16*)da, dw, db, B, F, mid, HW);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
 extern "C" int cesm_sinusoidal(const long long* t, float* out, int B, int dim, void* stream) {
     CESM_REQUIRE(dim >= 4 && dim % 2 == 0, "dim=%d must be even and >= 4", dim);
     sinusoidal_kernel<<<nblk((long long)B * dim, 128), 128, 0, as_stream(stream)>>>(t, out, B, dim);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
 extern "C" int cesm_small_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
                                      int act_silu_in, void* stream) {
     small_linear_fwd_kernel<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(x, W, bias, y, B, K, N, act_silu_in);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -471,10 +471,10 @@ extern "C" int cesm_small_linear_bwd(const float* x, const float* W, const float
                                      int B, int K, int N, int act_silu_in, void* stream) {
     cudaStream_t st = as_stream(stream);
     small_linear_wgrad_kernel<<<nblk((long long)N * K, 256), 256, 0, st>>>(x, dy, dW, db, B, K, N, act_silu_in);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     if (dx) {
         small_linear_dgrad_kernel<<<nblk((long long)B * K, 256), 256, 0, st>>>(x, W, dy, dx, B, K, N, act_silu_in);
-        CESM_CHECK_CUDA(cudaGetLastError());
+        CESM_CHECK_LAUNCH();
     }
     return CESM_OK;
 }
@@ -483,7 +483,7 @@ extern "C" int cesm_q_sample(const float* x0, const float* noise, const long lon
                              const float* sqrt_1mac, float* xt, int B, long long per_sample, void* stream) {
     const long long total = (long long)B * per_sample;
     q_sample_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(x0, noise, t, sqrt_ac, sqrt_1mac, xt, per_sample, total);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -494,14 +494,14 @@ extern "C" int cesm_mse_fwd(const float* eps, const float* noise, float* diff, f
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
     mse_fwd_kernel<<<(int)blocks, 256, 0, st>>>(eps, noise, diff, loss, total);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
 extern "C" int cesm_scale_by_scalar(const float* in, const float* gscale, float factor, float* out, long long total,
                                     void* stream) {
     scale_by_device_scalar_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(in, gscale, factor, out, total);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -511,6 +511,6 @@ extern "C" int cesm_p_sample(const float* xt, const float* eps, const float* z, 
     const long long total = (long long)B * per_sample;
     p_sample_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(xt, eps, z, t, betas, sqrt_1mac, sqrt_recip_a,
                                                                     post_var, out, per_sample, total);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

@@ -417,7 +417,7 @@ extern "C" int cesm_gn_stats(const void* x, float* sums, int B, long long P, int
     const int per_block = kNormThreads / (C / 8) * 8;
     dim3 grid(norm_grid(P, per_block), B);
     gn_stats_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, sums, P, C, G);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -430,7 +430,7 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
     gn_apply_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)x, sums, gamma, beta, film, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, P, C, G,
         eps);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -445,12 +445,12 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     dim3 grid(norm_grid(P, per_block), B);
     gn_bwd_reduce_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     gn_bwd_apply_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
                                                        beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, dgamma, dbeta, dfilm, B, C);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -467,7 +467,7 @@ extern "C" int cesm_ln_fwd(const void* x, const float* gamma, void* out, long lo
     cudaStream_t st = as_stream(stream);
     const int grid = norm_grid(M, 8 * 4);
     LN_DISPATCH(ln_fwd_kernel, (const __nv_bfloat16*)x, gamma, (__nv_bfloat16*)out, M, C, eps);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
@@ -479,6 +479,6 @@ extern "C" int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, co
     const int grid = norm_grid(M, 8 * 8);
     LN_DISPATCH(ln_bwd_kernel, (const __nv_bfloat16*)x, gamma, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dres,
                 (__nv_bfloat16*)dx, dgamma, M, C, eps);
-    CESM_CHECK_CUDA(cudaGetLastError());
+    CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

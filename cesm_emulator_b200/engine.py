@@ -1,0 +1,233 @@
+"""Training-step and sampling engines: the loop bodies of the reference's train.py / inference.py
+on CUDA streams and graphs.
+
+TrainEngine.step is what `train_one_epoch` does per batch (train.py:829-867) -- loss, backward,
+global-norm clip, AdamW -- with three differences that are deliberate and documented in DESIGN.md:
+  * activations are bf16 (fp32 accumulate) instead of fp16 autocast + GradScaler, so there is no
+    loss scaling;
+  * under torch.distributed the gradients really are averaged over ranks (the reference wraps the
+    model in DDP, train.py:1076, but calls `.module.loss`, so its reducer never fires): static
+    buckets in expected-ready order are all-reduced with NCCL on a side stream as soon as the last
+    gradient of a bucket has been produced, overlapping the rest of the backward pass;
+  * the whole step (RNG draws, forward, backward, all-reduce, clip, AdamW) is captured once into a
+    CUDA graph and replayed: no host syncs, no per-kernel launch latency.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+
+def _ready_order(named_params):
+    """Parameters in the order backward is expected to finish them: reverse registration order,
+    with the tensors every level feeds (time MLP, relative-position table) and the input stage last."""
+    late, normal = [], []
+    for name, p in named_params:
+        if not p.requires_grad:
+            continue
+        if ".time_mlp." in name or ".time_rel_pos_bias." in name or ".input_conv." in name or ".input_temp_op." in name:
+            late.append((name, p))
+        else:
+            normal.append((name, p))
+    return list(reversed(normal)) + list(reversed(late))
+
+
+class GradBuckets:
+    """All gradients live in one flat fp32 buffer (p.grad are views), cut into `n_buckets`
+    contiguous buckets in expected-ready order.  With a process group, each bucket is all-reduced
+    on `comm_stream` from the hook of its last-finished parameter."""
+
+    def __init__(self, module: torch.nn.Module, n_buckets: int = 4, process_group=None):
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        order = _ready_order(module.named_parameters())
+        self.params = [p for _, p in order]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        self.bounds: List[int] = [0]
+        per_bucket = -(-total // max(1, n_buckets))
+        self._bucket_of = {}
+        self._pending_init: List[int] = []
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            b = len(self.bounds) - 1
+            self._bucket_of[id(p)] = b
+            if len(self._pending_init) <= b:
+                self._pending_init.append(0)
+            self._pending_init[b] += 1
+            off += n
+            if off - self.bounds[-1] >= per_bucket and off < total:
+                self.bounds.append(off)
+        self.bounds.append(total)
+        self.n_buckets = len(self.bounds) - 1
+        self._pending = list(self._pending_init)
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def begin_step(self):
+        self.flat.zero_()
+        self._pending = list(self._pending_init)
+
+    def _on_grad(self, p):
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            cur = torch.cuda.current_stream()
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.flat[self.bounds[b]:self.bounds[b + 1]], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def finish_step(self):
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def clip_(self, max_norm: float) -> torch.Tensor:
+        """Global-norm clip of every gradient (train.py:865) on the flat buffer: two kernels, no sync."""
+        total = torch.linalg.vector_norm(self.flat)
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        self.flat.mul_(coef)
+        return total
+
+
+class TrainEngine:
+    """One data-parallel training step of `Diffusion.loss` as a replayable CUDA graph."""
+
+    def __init__(self, diffusion, batch_shape, cond_shape, lr: float = 2e-4, betas=(0.9, 0.999),
+                 weight_decay: float = 1e-4, eps: float = 1e-8, max_grad_norm: Optional[float] = 1.0,
+                 n_buckets: int = 4, use_graph: bool = True, process_group=None):
+        self.diffusion = diffusion
+        dev = next(diffusion.parameters()).device
+        self.device = dev
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.pg = process_group
+        if self.world > 1:
+            for t in list(diffusion.parameters()) + list(diffusion.buffers()):
+                dist.broadcast(t.data, src=0, group=process_group)  # what DDP's constructor does
+        self.buckets = GradBuckets(diffusion, n_buckets=n_buckets, process_group=process_group)
+        self.max_grad_norm = max_grad_norm
+        # AdamW as train.py:1078-1083; capturable so that the step lives inside the graph
+        self.opt = torch.optim.AdamW(self.buckets.params, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps,
+                                     capturable=True, fused=True)
+        self.x0 = torch.zeros(batch_shape, dtype=torch.float32, device=dev)
+        self.cond = torch.zeros(cond_shape, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self._warm = 0
+
+    # the captured region ----------------------------------------------------------------------
+    def _step_body(self):
+        self.buckets.begin_step()
+        loss = self.diffusion.loss(self.x0, self.cond)
+        (loss / self.world if self.world > 1 else loss).backward()
+        self.buckets.finish_step()
+        if self.max_grad_norm is not None:
+            self.grad_norm.copy_(self.buckets.clip_(self.max_grad_norm))
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def _run(self):
+        from . import _lib
+        if not self.use_graph:
+            n0 = _lib.launch_count()
+            self._step_body()
+            self.launches_per_step = _lib.launch_count() - n0
+            return
+        if self.graph is None:
+            if self._warm < 2:  # eager warm-up: lazy init of optimizer state, NCCL, kernel attributes
+                self._warm += 1
+                self._step_body()
+                return
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self._step_body()
+            self.launches_per_step = _lib.launch_count() - n0
+        self.graph.replay()
+
+    # public -----------------------------------------------------------------------------------
+    def step_resident(self) -> torch.Tensor:
+        """One step on whatever is in the static device buffers `x0` / `cond`."""
+        self._run()
+        return self.loss
+
+    def step(self, x0: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+        """One step on a host (ideally pinned) or device batch; returns the device loss scalar."""
+        self.x0.copy_(x0, non_blocking=True)
+        self.cond.copy_(cond, non_blocking=True)
+        self._run()
+        return self.loss
+
+
+class SampleEngine:
+    """Ensemble generation (inference.py:217-232 + model.py:186-194): the reverse chain for a batch
+    of independent fields, one UNet call + fused p_sample update per step, replayed as a CUDA graph
+    whose only per-step inputs are the timestep vector and the fresh noise (device RNG)."""
+
+    def __init__(self, diffusion, shape, use_graph: bool = True):
+        self.diffusion = diffusion
+        dev = next(diffusion.parameters()).device
+        self.device = dev
+        self.shape = tuple(shape)
+        self.x = torch.zeros(self.shape, dtype=torch.float32, device=dev)
+        self.cond = torch.zeros(self.shape, dtype=torch.float32, device=dev)
+        self.t = torch.zeros((self.shape[0],), dtype=torch.long, device=dev)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+
+    def _body(self):
+        d = self.diffusion
+        with torch.no_grad():
+            eps = d.model(self.x, self.cond, self.t)
+            z = torch.randn_like(self.x)
+            self.x.copy_(K.p_sample(self.x, eps, z, self.t, d.betas, d.sqrt_one_minus_alphas_cumprod,
+                                    d.sqrt_recip_alphas, d.posterior_variance))
+            self.t.sub_(1)
+
+    def step(self):
+        from . import _lib
+        if not self.use_graph:
+            n0 = _lib.launch_count()
+            self._body()
+            self.launches_per_step = _lib.launch_count() - n0
+            return
+        if self.graph is None:
+            x_keep, t_keep = self.x.clone(), self.t.clone()
+            self._body()  # eager warm-up
+            torch.cuda.synchronize()
+            self.x.copy_(x_keep)
+            self.t.copy_(t_keep)
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.launches_per_step = _lib.launch_count() - n0
+            self.x.copy_(x_keep)
+            self.t.copy_(t_keep)
+        self.graph.replay()
+
+    @torch.no_grad()
+    def sample(self, cond: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
+        """cond: [B,1,H,W] -> generated field [B,1,H,W] after `steps` (default T) reverse steps."""
+        T = self.diffusion.T
+        steps = T if steps is None else steps
+        self.cond.copy_(cond, non_blocking=True)
+        self.x.normal_()
+        self.t.fill_(T - 1)
+        for _ in range(steps):
+            self.step()
+        return self.x.clone()

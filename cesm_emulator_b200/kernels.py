@@ -76,7 +76,13 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
         assert bias.dtype == torch.float32 and bias.numel() == cout
     if residual is not None:
         assert residual.dtype == BF16 and residual.shape[:3] == out.shape[:3]
-    _lib.call("cesm_igemm", ctypes.byref(args), _stream())
+    meta = None
+    if _lib.PROFILER is not None:
+        rows = n * oh * ow
+        ktot = len(taps) * (c0 + c1)
+        meta = {"kind": f"{len(taps)}tap", "flops": 2.0 * rows * cout * ktot,
+                "bytes": 2.0 * (rows * (c0 + c1) * stride * stride + rows * cout + cout * ktot)}
+    _lib.call("cesm_igemm", ctypes.byref(args), _stream(), _meta=meta)
     return out
 
 
@@ -101,7 +107,12 @@ def wgrad(x0: torch.Tensor, dy: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
     a.y_h, a.y_w = dy.shape[1], dy.shape[2]
     a.y_sh, a.y_sw, a.y_h0, a.y_w0 = dy_place
     a.dw = _ptr(dw_)
-    _lib.call("cesm_wgrad", ctypes.byref(a), _stream())
+    meta = None
+    if _lib.PROFILER is not None:
+        rows = n * oh * ow
+        meta = {"kind": f"{len(taps)}tap", "flops": 2.0 * rows * cout * len(taps) * (c0 + c1),
+                "bytes": 2.0 * rows * (c0 + c1 + cout) + 4.0 * cout * len(taps) * (c0 + c1)}
+    _lib.call("cesm_wgrad", ctypes.byref(a), _stream(), _meta=meta)
     return dw_
 
 
@@ -259,19 +270,21 @@ def input_conv_wgrad(in0, in1, dy, B: int, F: int, H: int, W: int, ks: int):
     return dw, db
 
 
-def out_conv_fwd(a, w, bias, B: int, F: int, H: int, W: int):
+def out_conv_fwd(a, w, bias, B: int, F: int, H: int, W: int, mid: Optional[int] = None):
     _req_cuda(a, w, bias)
+    mid = F // 2 if mid is None else mid
     eps = torch.empty((B, 1, H, W), dtype=torch.float32, device=a.device)
-    _lib.call("cesm_out_conv_fwd", _ptr(a), _ptr(w), _ptr(bias), _ptr(eps), B, F, F // 2, H * W, a.shape[-1], _stream())
+    _lib.call("cesm_out_conv_fwd", _ptr(a), _ptr(w), _ptr(bias), _ptr(eps), B, F, mid, H * W, a.shape[-1], _stream())
     return eps
 
 
-def out_conv_bwd(a, w, deps, B: int, F: int, H: int, W: int):
+def out_conv_bwd(a, w, deps, B: int, F: int, H: int, W: int, mid: Optional[int] = None):
     _req_cuda(a, w, deps)
+    mid = F // 2 if mid is None else mid
     da = torch.empty_like(a)
     dw = torch.empty_like(w)
     db = torch.empty(1, dtype=torch.float32, device=a.device)
-    _lib.call("cesm_out_conv_bwd", _ptr(a), _ptr(w), _ptr(deps), _ptr(da), _ptr(dw), _ptr(db), B, F, F // 2, H * W,
+    _lib.call("cesm_out_conv_bwd", _ptr(a), _ptr(w), _ptr(deps), _ptr(da), _ptr(dw), _ptr(db), B, F, mid, H * W,
               a.shape[-1], _stream())
     return da, dw, db
 

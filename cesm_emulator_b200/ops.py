@@ -31,6 +31,35 @@ def _phase(ph: int, pw: int):
     return taps, koff
 
 
+class PackCache:
+    """bf16 GEMM-operand copies of one layer's fp32 parameter, keyed by layout tag and re-made
+    when the parameter changes (optimizer step bumps `_version`).  While a CUDA graph of a TRAINING
+    step is being captured a trainable parameter is always re-packed, so that the pack kernel is
+    part of the graph and replays see the current weights; a no-grad (sampling) capture uses the
+    cached copy, which stays valid as long as the weights are not modified."""
+
+    def __init__(self):
+        self._d = {}
+
+    @staticmethod
+    def must_repack(weight: torch.Tensor) -> bool:
+        """True in the forward of a training step that is being graph-captured."""
+        return weight.requires_grad and torch.is_grad_enabled() and torch.cuda.is_current_stream_capturing()
+
+    def get(self, weight: torch.Tensor, tag, make, force: bool = False):
+        key = (weight.data_ptr(), weight._version)
+        if not force:
+            hit = self._d.get(tag)
+            if hit is not None and hit[0] == key:
+                return hit[1]
+        val = make()
+        self._d[tag] = (key, val)
+        return val
+
+    def __deepcopy__(self, memo):
+        return PackCache()
+
+
 # ------------------------------------------------------------------------------------------------
 # convolutions / linears on the tcgen05 implicit GEMM
 # ------------------------------------------------------------------------------------------------
@@ -43,7 +72,7 @@ class ConvFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x0, x1, weight, bias, residual, ksize: int):
+    def forward(ctx, x0, x1, weight, bias, residual, ksize: int, cache: PackCache):
         x0, x1, residual = _c(x0), _c(x1), _c(residual)
         cout = weight.shape[0]
         c0 = x0.shape[-1]
@@ -52,11 +81,13 @@ class ConvFn(torch.autograd.Function):
         assert weight.numel() == cout * (c0 + c1) * kk, (weight.shape, c0, c1, ksize)
         r = ksize // 2
         taps = [(kh - r, kw - r) for kh in range(ksize) for kw in range(ksize)]
-        wt = K.pack_weight(weight, cout, kk, c0 + c1, (c0 + c1) * kk, kk, list(range(kk)))
+        ctx.force = PackCache.must_repack(weight)
+        wt = cache.get(weight, "fwd",
+                       lambda: K.pack_weight(weight, cout, kk, c0 + c1, (c0 + c1) * kk, kk, list(range(kk))), ctx.force)
         y = K.igemm(x0, wt, a1=x1, taps=taps, bias=bias, residual=residual)
         ctx.save_for_backward(x0, x1, weight)
         ctx.ksize, ctx.has_bias, ctx.has_res = ksize, bias is not None, residual is not None
-        ctx.taps = taps
+        ctx.taps, ctx.cache = taps, cache
         return y
 
     @staticmethod
@@ -71,10 +102,13 @@ class ConvFn(torch.autograd.Function):
         dx0 = dx1 = dwt = db = None
         wflat = weight.reshape(-1)
         if ctx.needs_input_grad[0]:
-            wd = K.pack_weight(wflat, c0, kk, cout, kk, ctot * kk, list(range(kk)))
+            wd = ctx.cache.get(weight, "dgrad0",
+                               lambda: K.pack_weight(wflat, c0, kk, cout, kk, ctot * kk, list(range(kk))), ctx.force)
             dx0 = K.igemm(dy, wd, taps=ntaps)
         if x1 is not None and ctx.needs_input_grad[1]:
-            wd = K.pack_weight(wflat[c0 * kk:], c1, kk, cout, kk, ctot * kk, list(range(kk)))
+            wd = ctx.cache.get(weight, "dgrad1",
+                               lambda: K.pack_weight(wflat[c0 * kk:], c1, kk, cout, kk, ctot * kk, list(range(kk))),
+                               ctx.force)
             dx1 = K.igemm(dy, wd, taps=ntaps)
         if ctx.needs_input_grad[2]:
             g = K.wgrad(x0, dy, x1=x1, taps=ctx.taps)  # [cout, kk, ctot]
@@ -83,7 +117,7 @@ class ConvFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = K.colsum(dy)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
-        return dx0, dx1, dwt, db, dres, None
+        return dx0, dx1, dwt, db, dres, None, None
 
 
 class DownsampleFn(torch.autograd.Function):
@@ -92,12 +126,14 @@ class DownsampleFn(torch.autograd.Function):
     TAPS = [(kh - 1, kw - 1) for kh in range(4) for kw in range(4)]
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, cache: PackCache):
         x = x.contiguous()
         c = x.shape[-1]
-        wt = K.pack_weight(weight, c, 16, c, c * 16, 16, list(range(16)))
+        ctx.force = PackCache.must_repack(weight)
+        wt = cache.get(weight, "fwd", lambda: K.pack_weight(weight, c, 16, c, c * 16, 16, list(range(16))), ctx.force)
         y = K.igemm(x, wt, taps=DownsampleFn.TAPS, stride=2, bias=bias)
         ctx.save_for_backward(x, weight)
+        ctx.cache = cache
         return y
 
     @staticmethod
@@ -111,7 +147,9 @@ class DownsampleFn(torch.autograd.Function):
             for ph in (0, 1):
                 for pw in (0, 1):
                     taps, koff = _phase(ph, pw)
-                    wd = K.pack_weight(weight, c, 4, c, 16, c * 16, koff)  # [ci][t][co] = W[co, ci, kh_t, kw_t]
+                    # [ci][t][co] = W[co, ci, kh_t, kw_t]
+                    wd = ctx.cache.get(weight, ("dgrad", ph, pw),
+                                       lambda: K.pack_weight(weight, c, 4, c, 16, c * 16, koff), ctx.force)
                     K.igemm(dy, wd, taps=taps, out=dx, out_hw=(h // 2, w // 2), out_place=(2, 2, ph, pw))
         if ctx.needs_input_grad[1]:
             g = K.wgrad(x, dy, taps=DownsampleFn.TAPS, stride=2)
@@ -119,23 +157,27 @@ class DownsampleFn(torch.autograd.Function):
             K.unpack_wgrad(g, dwt, c, 16, c, c * 16, 16, list(range(16)))
         if ctx.needs_input_grad[2]:
             db = K.colsum(dy)
-        return dx, dwt, db
+        return dx, dwt, db, None
 
 
 class UpsampleFn(torch.autograd.Function):
     """ConvTranspose3d(dim, dim, (1,4,4), (1,2,2), (0,1,1)) as four sub-pixel 2x2 convs -- video_net.py:65-66."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, cache: PackCache):
         x = x.contiguous()
         n, h, w, c = x.shape
         out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+        ctx.force = PackCache.must_repack(weight)
         for ph in (0, 1):
             for pw in (0, 1):
                 taps, koff = _phase(ph, pw)
-                wt = K.pack_weight(weight, c, 4, c, 16, c * 16, koff)  # [co][t][ci] = W[ci, co, kh_t, kw_t]
+                # [co][t][ci] = W[ci, co, kh_t, kw_t]
+                wt = cache.get(weight, ("fwd", ph, pw), lambda: K.pack_weight(weight, c, 4, c, 16, c * 16, koff),
+                               ctx.force)
                 K.igemm(x, wt, taps=taps, out=out, out_hw=(h, w), out_place=(2, 2, ph, pw), bias=bias)
         ctx.save_for_backward(x, weight)
+        ctx.cache = cache
         return out
 
     @staticmethod
@@ -145,7 +187,9 @@ class UpsampleFn(torch.autograd.Function):
         n, h, w, c = x.shape
         dx = dwt = db = None
         if ctx.needs_input_grad[0]:
-            wd = K.pack_weight(weight, c, 16, c, c * 16, 16, list(range(16)))  # [ci][t][co] = W[ci, co, kh, kw]
+            # [ci][t][co] = W[ci, co, kh, kw]
+            wd = ctx.cache.get(weight, "dgrad", lambda: K.pack_weight(weight, c, 16, c, c * 16, 16, list(range(16))),
+                               ctx.force)
             dx = K.igemm(dy, wd, taps=DownsampleFn.TAPS, stride=2)
         if ctx.needs_input_grad[1]:
             dwt = torch.empty_like(weight)
@@ -156,7 +200,7 @@ class UpsampleFn(torch.autograd.Function):
                     K.unpack_wgrad(g, dwt, c, 4, c, 16, c * 16, koff)
         if ctx.needs_input_grad[2]:
             db = K.colsum(dy)
-        return dx, dwt, db
+        return dx, dwt, db, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -225,6 +269,24 @@ class TemporalAttnCoreFn(torch.autograd.Function):
         return dqkv, dbias, None, None, None, None, None, None, None
 
 
+class RelPosBiasFn(torch.autograd.Function):
+    """Embedding gather of the T5 bucket table -> [heads, n, n] (video_net.py:302-310).  The
+    table has 32 x heads entries; gather and scatter-add are index ops on a few hundred floats."""
+
+    @staticmethod
+    def forward(ctx, weight, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = weight.shape
+        return weight.detach()[idx].permute(2, 0, 1).float().contiguous()
+
+    @staticmethod
+    def backward(ctx, dbias):
+        (idx,) = ctx.saved_tensors
+        dw = torch.zeros(ctx.shape, dtype=dbias.dtype, device=dbias.device)
+        dw.index_add_(0, idx.reshape(-1), dbias.permute(1, 2, 0).reshape(-1, ctx.shape[1]))
+        return dw, None
+
+
 class LinearAttnCoreFn(torch.autograd.Function):
     """softmax(q) over d, softmax(k) over pixels, ctx = k^T v, out = ctx^T q (video_net.py:338-344)."""
 
@@ -274,19 +336,19 @@ class OutConvFn(torch.autograd.Function):
     a: bf16 [B*F, H, W, 64] -> fp32 [B, 1, H, W]."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, B: int, F: int):
+    def forward(ctx, a, weight, bias, B: int, F: int, mid: int):
         a = a.contiguous()
         H, W = a.shape[1], a.shape[2]
         ctx.save_for_backward(a, weight)
-        ctx.dims = (B, F, H, W)
-        return K.out_conv_fwd(a, weight, bias, B, F, H, W)
+        ctx.dims = (B, F, H, W, mid)
+        return K.out_conv_fwd(a, weight, bias, B, F, H, W, mid)
 
     @staticmethod
     def backward(ctx, deps):
         a, weight = ctx.saved_tensors
-        B, F, H, W = ctx.dims
-        da, dw, db = K.out_conv_bwd(a, weight, deps.contiguous().float(), B, F, H, W)
-        return da, dw, db, None, None
+        B, F, H, W, mid = ctx.dims
+        da, dw, db = K.out_conv_bwd(a, weight, deps.contiguous().float(), B, F, H, W, mid)
+        return da, dw, db, None, None, None
 
 
 class SmallLinearFn(torch.autograd.Function):

@@ -1,0 +1,99 @@
+"""Synthetic stand-in for the CESM2-LE NetCDF data and dataset_single_member.py.
+
+`SyntheticEnsemble` generates arrays of the reference's logical shape (member, time, lat, lon,
+channel) and exposes them in the layout the reference's loaders produce, `(T, M, 1, H, W)`
+float32, globally z-scored (train.py:624-646).  `window(idx)` follows
+WindowedAllMembersDataset_random's default "consecutive" indexing (dataset_single_member.py:91-108,
+168-196): idx -> (member = idx % M, start = idx // M), K consecutive condition frames, target at
+the centre frame, optional time-reversal augmentation and random crop.
+
+The fields are not noise: the condition is a smooth emission pattern growing in time, and the
+target is a low-pass response to the cumulative condition plus member-dependent weather noise, so
+the diffusion loss has something to learn.  Sharding over ranks is DistributedSampler's
+(train.py:1002): a seeded permutation of all indices, rank r takes every world-th starting at r.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+
+class SyntheticEnsemble:
+    def __init__(self, members: int = 34, times: int = 251, lat: int = 192, lon: int = 288, seed: int = 1234,
+                 K: int = 3, crop_hw: Optional[Tuple[int, int]] = None, time_reverse_p: float = 0.5):
+        if K < 2:
+            raise ValueError("K must be >= 2")  # dataset_single_member.py:47
+        self.M, self.T, self.H, self.W, self.K = members, times, lat, lon, K
+        self.crop_hw = crop_hw
+        self.time_reverse_p = time_reverse_p
+        rng = np.random.default_rng(seed)
+        self._aug = np.random.default_rng(seed + 1)
+        yy = np.linspace(-1.0, 1.0, lat, dtype=np.float32)[:, None]
+        xx = np.linspace(-1.0, 1.0, lon, dtype=np.float32)[None, :]
+        # a few emission "hot spots" (same for all members: emissions are a scenario, not weather)
+        blobs = np.zeros((lat, lon), np.float32)
+        for _ in range(6):
+            cy, cx, s = rng.uniform(-0.8, 0.8), rng.uniform(-0.9, 0.9), rng.uniform(0.05, 0.25)
+            blobs += rng.uniform(0.5, 1.5) * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
+        growth = np.linspace(0.0, 1.0, times, dtype=np.float32) ** 2
+        cond_tm = growth[:, None, None] * blobs[None]                                    # (T, H, W)
+        cum = np.cumsum(cond_tm, axis=0) / max(1, times)
+        # temperature response: zonal-mean warming + polar amplification + member weather noise
+        resp = cum.mean(axis=(1, 2), keepdims=True) * (1.0 + 0.8 * np.abs(yy)[None]) + 0.3 * cum
+        # logical layout (member, time, lat, lon, channel)
+        self.cond_mtllc = np.broadcast_to(cond_tm[None, ..., None], (members, times, lat, lon, 1))
+        noise = rng.standard_normal((members, times, lat, lon, 1), dtype=np.float32)
+        tgt = resp[None, ..., None] * 4.0 + 0.5 * noise
+        # reference layout (T, M, 1, H, W), globally z-scored (train.py:640-646)
+        self.cond = self._z(np.ascontiguousarray(np.transpose(self.cond_mtllc, (1, 0, 4, 2, 3))))
+        self.tgt = self._z(np.ascontiguousarray(np.transpose(tgt, (1, 0, 4, 2, 3))))
+        self.num_units = max(1, self.T - self.K + 1)
+
+    @staticmethod
+    def _z(a: np.ndarray) -> np.ndarray:
+        a = a.astype(np.float32)
+        return (a - a.mean()) / (a.std() + 1e-8)
+
+    def __len__(self) -> int:
+        return self.num_units * self.M
+
+    def window(self, idx: int, augment: bool = True):
+        """-> (cond_win [1,K,h,w], x0 [1,h,w]) float32 torch tensors."""
+        m, t0 = idx % self.M, idx // self.M
+        anchor = min(t0 + self.K // 2, self.T - 1)
+        times = np.arange(t0, t0 + self.K)
+        cond = self.cond[times, m, 0]            # (K, H, W)
+        x0 = self.tgt[anchor, m]                 # (1, H, W)
+        if augment and self.time_reverse_p > 0 and self._aug.random() < self.time_reverse_p:
+            mid = self.K // 2
+            cond = np.concatenate([cond[:mid][::-1], cond[mid:mid + 1], cond[mid + 1:][::-1]], axis=0)
+        i = j = 0
+        h, w = self.H, self.W
+        if self.crop_hw is not None:
+            h, w = min(self.crop_hw[0], self.H), min(self.crop_hw[1], self.W)
+            if augment:
+                i = 0 if h == self.H else int(self._aug.integers(0, self.H - h + 1))
+                j = 0 if w == self.W else int(self._aug.integers(0, self.W - w + 1))
+            else:
+                i, j = (self.H - h) // 2, (self.W - w) // 2
+        cond = np.ascontiguousarray(cond[:, i:i + h, j:j + w])[None]
+        x0 = np.ascontiguousarray(x0[:, i:i + h, j:j + w])
+        return torch.from_numpy(cond), torch.from_numpy(x0)
+
+    def shard_indices(self, epoch: int, rank: int, world: int, seed: int = 0) -> np.ndarray:
+        """DistributedSampler(shuffle=True, drop_last=False) semantics (train.py:1002,1107)."""
+        g = torch.Generator().manual_seed(seed + epoch)
+        perm = torch.randperm(len(self), generator=g).numpy()
+        total = -(-len(perm) // world) * world
+        perm = np.concatenate([perm, perm[: total - len(perm)]])
+        return perm[rank:total:world]
+
+    def batch(self, indices, augment: bool = True, pin: bool = False):
+        """-> (cond [B,1,K,h,w], x0 [B,1,h,w])."""
+        cs, xs = zip(*(self.window(int(i), augment) for i in indices))
+        cond, x0 = torch.stack(cs), torch.stack(xs)
+        if pin and torch.cuda.is_available():
+            cond, x0 = cond.pin_memory(), x0.pin_memory()
+        return cond, x0

@@ -37,6 +37,8 @@ typedef enum cesm_status {
 const char* cesm_last_error(void);
 /* Library version string, e.g. "cesm_b200 0.1 sm_100a". */
 const char* cesm_version(void);
+/* Number of CUDA kernels this library has launched in this process so far (all threads). */
+long long cesm_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contractions on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
