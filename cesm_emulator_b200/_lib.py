@@ -73,6 +73,8 @@ def load() -> ctypes.CDLL:
     lib.cesm_last_error.restype = c_char_p
     lib.cesm_version.restype = c_char_p
     lib.cesm_launch_count.restype = ctypes.c_longlong
+    lib.cesm_linattn_ws_floats.restype = ctypes.c_size_t
+    lib.cesm_linattn_ws_floats.argtypes = [ctypes.c_int, ctypes.c_int]
     _declare(lib)
     _lib = lib
     return lib
@@ -93,8 +95,8 @@ _SIGNATURES: dict[str, list] = {
     "cesm_ln_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "cesm_tattn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "cesm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
-    "cesm_linattn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
-    "cesm_linattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "cesm_linattn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "cesm_linattn_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "cesm_input_conv_fwd": [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cesm_input_conv_wgrad": [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cesm_out_conv_fwd": [_P, _P, _P, _P, _I, _I, _I, _L, _I, _P],
@@ -117,7 +119,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 
 def exported_symbols() -> list[str]:
-    return ["cesm_last_error", "cesm_version", "cesm_launch_count", *sorted(_SIGNATURES)]
+    return ["cesm_last_error", "cesm_version", "cesm_launch_count", "cesm_linattn_ws_floats", *sorted(_SIGNATURES)]
 
 
 def launch_count() -> int:

@@ -198,205 +198,221 @@ tattn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
     }
 }
 
+
 // ------------------------------------------------------------------------------------------------
-// spatial linear attention
-//   qkv: [NI*n][3*H*D], image ni = rows [ni*n, (ni+1)*n)
+// Small-window specialisation (F <= 4, the training window K=3 and the F=1 sampling call): four
+// lanes share one (pixel column, head), 8 of the 32 features each, so a warp reads one pixel's
+// 512 contiguous bytes of q (then k, then v) per frame; the F x F scores live in registers and
+// are reduced with two quad shuffles.  Nothing but qkv (and dout) is read: the backward recomputes
+// the softmax instead of loading out / lse.
 // ------------------------------------------------------------------------------------------------
-// per (image, k column) partial (max, sum exp) over a strip of pixels; thread = one column
-__global__ void __launch_bounds__(256)
-la_kstats_partial_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ part, int n, int HD, int nstrips) {
-    const int ni = blockIdx.y, strip = blockIdx.x;
-    const int col = threadIdx.x;  // HD == 256 threads (checked on host) or loop
-    const int per = (n + nstrips - 1) / nstrips;
-    const int p0 = strip * per, p1 = min(n, p0 + per);
-    for (int c = col; c < HD; c += blockDim.x) {
-        float m = -INFINITY, z = 0.f;
-        const __nv_bfloat16* base = qkv + ((size_t)ni * n) * (3 * HD) + HD + c;
-        for (int p = p0; p < p1; ++p) {
-            const float v = __bfloat162float(base[(size_t)p * 3 * HD]);
-            const float mn = fmaxf(m, v);
-            z = z * __expf(m - mn) + __expf(v - mn);
-            m = mn;
-        }
-        float* o = part + (((size_t)ni * nstrips + strip) * HD + c) * 2;
-        o[0] = m;
-        o[1] = z;
-    }
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
-__global__ void la_kstats_combine_kernel(const float* __restrict__ part, float* __restrict__ kstat, int HD,
-                                         int nstrips, int total) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // ni*HD + c
-    if (idx >= total) return;
-    const int ni = idx / HD, c = idx % HD;
-    float m = -INFINITY, z = 0.f;
-    for (int s = 0; s < nstrips; ++s) {
-        const float* p = part + (((size_t)ni * nstrips + s) * HD + c) * 2;
-        if (p[1] == 0.f) continue;
-        const float mn = fmaxf(m, p[0]);
-        z = z * __expf(m - mn) + p[1] * __expf(p[0] - mn);
-        m = mn;
-    }
-    kstat[(size_t)idx * 2] = m;
-    kstat[(size_t)idx * 2 + 1] = z;
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
 }
-
-// qk[row][0:HD] = scale*softmax_d(q), qk[row][HD:2HD] = exp(k-m)/Z ; thread per (row, head)
-__global__ void __launch_bounds__(128)
-la_prep_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ kstat, __nv_bfloat16* __restrict__ qk,
-               long long rows, int n, int H, float scale) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= rows * H) return;
-    const int h = t % H;
-    const long long row = t / H;
-    const int ni = row / n;
-    const int HD = H * D;
-    float q[D], k[D];
-    load32(qkv + row * 3 * HD + h * D, q);
-    load32(qkv + row * 3 * HD + HD + h * D, k);
-    float m = q[0];
-#pragma unroll
-    for (int i = 1; i < D; ++i) m = fmaxf(m, q[i]);
-    float z = 0.f;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        q[i] = __expf(q[i] - m);
-        z += q[i];
-    }
-    const float inv = scale / z;
-#pragma unroll
-    for (int i = 0; i < D; ++i) q[i] *= inv;
-    const float* ks = kstat + ((size_t)ni * HD + h * D) * 2;
-#pragma unroll
-    for (int i = 0; i < D; ++i) k[i] = __expf(k[i] - ks[2 * i]) / ks[2 * i + 1];
-    store32(qk + row * 2 * HD + h * D, q);
-    store32(qk + row * 2 * HD + HD + h * D, k);
+__device__ __forceinline__ float qsum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
-
-// ctx[ni][h][d][e] += sum_pixels a[p][h*D+d] * b[p][h*D+e]   (a, b: bf16 with row pitches lda, ldb)
-// block = (pixel chunk, head, image); each warp owns a slice of the chunk, lane = column e.
-__global__ void __launch_bounds__(256)
-la_context_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, int ldb,
-                  float* __restrict__ ctx, int n, int H, int chunk) {
-    const int ni = blockIdx.z, h = blockIdx.y;
-    const int p0 = blockIdx.x * chunk, p1 = min(n, p0 + chunk);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float acc[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.f;
-    const __nv_bfloat16* ab = a + ((size_t)ni * n) * lda + h * D;
-    const __nv_bfloat16* bb = b + ((size_t)ni * n) * ldb + h * D;
-    for (int p = p0 + warp; p < p1; p += 8) {
-        const float av = __bfloat162float(ab[(size_t)p * lda + lane]);  // a[p][d = lane]
-        const float bv = __bfloat162float(bb[(size_t)p * ldb + lane]);  // b[p][e = lane]
-#pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] = fmaf(__shfl_sync(0xffffffffu, av, d), bv, acc[d]);
-    }
-    __shared__ float red[8][D][D + 1];
-#pragma unroll
-    for (int d = 0; d < D; ++d) red[warp][d][lane] = acc[d];
-    __syncthreads();
-    for (int x = threadIdx.x; x < D * D; x += 256) {
-        const int d = x / D, e = x % D;
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][d][e];
-        atomicAdd(&ctx[(((size_t)ni * H + h) * D + d) * D + e], s);
-    }
-}
-
-// out[p][h*D+e] = sum_d ctx[ni][h][d][e] * q[p][h*D+d]   ; thread per (pixel, head)
-__global__ void __launch_bounds__(128)
-la_apply_kernel(const __nv_bfloat16* __restrict__ qk, const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out,
-                int n, int H, int chunk) {
-    __shared__ float sc[D][D];
-    const int ni = blockIdx.z, h = blockIdx.y;
-    const int HD = H * D;
-    for (int x = threadIdx.x; x < D * D; x += blockDim.x) sc[x / D][x % D] = ctx[((size_t)ni * H + h) * D * D + x];
-    __syncthreads();
-    const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
-    for (int p = blockIdx.x * chunk + threadIdx.x; p < p1; p += blockDim.x) {
-        const size_t row = (size_t)ni * n + p;
-        float q[D], o[D];
-        load32(qk + row * 2 * HD + h * D, q);
-#pragma unroll
-        for (int e = 0; e < D; ++e) o[e] = 0.f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-#pragma unroll
-            for (int e = 0; e < D; ++e) o[e] = fmaf(sc[d][e], q[d], o[e]);
-        }
-        store32(out + row * HD + h * D, o);
-    }
-}
-
-// delta[ni][h*D+d] = sum_e dctx[d][e] * ctx[d][e]
-__global__ void la_delta_kernel(const float* __restrict__ ctx, const float* __restrict__ dctx, float* __restrict__ delta,
-                                int total) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (ni*H + h)*D + d
-    if (idx >= total) return;
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) {
     float s = 0.f;
-    for (int e = 0; e < D; ++e) s = fmaf(dctx[(size_t)idx * D + e], ctx[(size_t)idx * D + e], s);
-    delta[idx] = s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[i], b[i], s);
+    return s;
+}
+// rotate the 4 interleaved pairs this lane owns by the angles (c4, s4) of one frame
+__device__ __forceinline__ void rope8(float (&f)[8], const float (&c4)[4], const float (&s4)[4], float scale) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const float x0 = f[2 * m] * scale, x1 = f[2 * m + 1] * scale;
+        f[2 * m] = x0 * c4[m] - x1 * s4[m];
+        f[2 * m + 1] = x1 * c4[m] + x0 * s4[m];
+    }
+}
+__device__ __forceinline__ void rope8_t(float (&f)[8], const float (&c4)[4], const float (&s4)[4], float scale) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const float g0 = f[2 * m], g1 = f[2 * m + 1];
+        f[2 * m] = (g0 * c4[m] + g1 * s4[m]) * scale;
+        f[2 * m + 1] = (g1 * c4[m] - g0 * s4[m]) * scale;
+    }
 }
 
-// Backward of prep+apply for one (pixel, head):
-//   dqh = ctx dout ; dkh = dctx v ; dv = dctx^T kh ; dq = qsm*(g - sum qsm*g), g = scale*dqh ;
-//   dk = kh*(dkh - delta)
-__global__ void __launch_bounds__(128)
-la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ qk,
-                    const __nv_bfloat16* __restrict__ dout, const float* __restrict__ ctx,
-                    const float* __restrict__ dctx, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                    int n, int H, int chunk, float scale) {
-    __shared__ float sc[D][D], sd[D][D], sdel[D];
-    const int ni = blockIdx.z, h = blockIdx.y;
-    const int HD = H * D;
-    for (int x = threadIdx.x; x < D * D; x += blockDim.x) {
-        sc[x / D][x % D] = ctx[((size_t)ni * H + h) * D * D + x];
-        sd[x / D][x % D] = dctx[((size_t)ni * H + h) * D * D + x];
+template <int F>
+__global__ void __launch_bounds__(256)
+tattn_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
+                       const float* __restrict__ cs, const float* __restrict__ sn, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ lse, long long npix /* B*HW */, int HW, int H, float scale) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = idx & 3;
+    const int h = (idx >> 2) % H;
+    long long pix = idx / (4 * H);
+    const bool valid = pix < npix;  // no early return: the quad shuffles below use the full-warp mask
+    if (!valid) pix = 0;
+    const long long b = pix / HW, hw = pix % HW;
+    const int HD = H * D, ld = 3 * HD;
+    float cf[F][4], sf[F][4];
+#pragma unroll
+    for (int f = 0; f < F; ++f)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            cf[f][m] = __ldg(cs + f * (D / 2) + c * 4 + m);
+            sf[f][m] = __ldg(sn + f * (D / 2) + c * 4 + m);
+        }
+    float q[F][8], k[F][8], v[F][8];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        const __nv_bfloat16* row = qkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
+        ld8(row, q[f]);
+        ld8(row + HD, k[f]);
+        ld8(row + 2 * HD, v[f]);
+        rope8(q[f], cf[f], sf[f], scale);
+        rope8(k[f], cf[f], sf[f], 1.f);
     }
-    if (threadIdx.x < D) sdel[threadIdx.x] = delta[((size_t)ni * H + h) * D + threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < F; ++i) {
+        float s[F], m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+            s[j] = qsum(dot8(q[i], k[j])) + __ldg(bias + (h * F + i) * F + j);
+            m = fmaxf(m, s[j]);
+        }
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+            s[j] = __expf(s[j] - m);
+            l += s[j];
+        }
+        const float inv = 1.f / l;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+            const float p = s[j] * inv;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(p, v[j][e], o[e]);
+        }
+        const long long row_i = (b * F + i) * HW + hw;
+        if (valid) {
+            st8(out + row_i * HD + h * D + c * 8, o);
+            if (c == 0 && lse) lse[row_i * H + h] = m + __logf(l);
+        }
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+tattn_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
+                       const float* __restrict__ cs, const float* __restrict__ sn,
+                       const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
+                       float* __restrict__ dbias, long long npix, int HW, int H, float scale) {
+    __shared__ float sbias[8 * F * F];
+    for (int x = threadIdx.x; x < H * F * F; x += blockDim.x) sbias[x] = 0.f;
     __syncthreads();
-    const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
-    for (int p = blockIdx.x * chunk + threadIdx.x; p < p1; p += blockDim.x) {
-        const size_t row = (size_t)ni * n + p;
-        float go[D], t[D], r[D];
-        load32(dout + row * HD + h * D, go);
-        // dq
-        load32(qk + row * 2 * HD + h * D, t);  // scale*softmax(q)
-        float dot = 0.f;
+    const int c = threadIdx.x & 3;
+    const int HD = H * D, ld = 3 * HD;
+    float cf[F][4], sf[F][4];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            float g = 0.f;
+    for (int f = 0; f < F; ++f)
 #pragma unroll
-            for (int e = 0; e < D; ++e) g = fmaf(sc[d][e], go[e], g);
-            r[d] = g;              // dqh[d]
-            dot = fmaf(t[d], g, dot);  // sum_d (scale*sm_d) * dqh_d
+        for (int m = 0; m < 4; ++m) {
+            cf[f][m] = __ldg(cs + f * (D / 2) + c * 4 + m);
+            sf[f][m] = __ldg(sn + f * (D / 2) + c * 4 + m);
         }
-        // t = scale*sm ; dq_d = sm_d*(scale*dqh_d - sum_j sm_j*scale*dqh_j) = t_d*(dqh_d - dot/scale)
-        const float dots = dot / scale;
+    float dbacc[F][F];
 #pragma unroll
-        for (int d = 0; d < D; ++d) r[d] = t[d] * (r[d] - dots);
-        store32(dqkv + row * 3 * HD + h * D, r);
-        // dk, dv
-        float v[D];
-        load32(qkv + row * 3 * HD + 2 * HD + h * D, v);
-        load32(qk + row * 2 * HD + HD + h * D, t);  // kh
-        float dv[D];
+    for (int i = 0; i < F; ++i)
 #pragma unroll
-        for (int e = 0; e < D; ++e) dv[e] = 0.f;
+        for (int j = 0; j < F; ++j) dbacc[i][j] = 0.f;
+    const long long items = npix * H * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;  // multiple of 4*H: (h, c) fixed per thread
+    const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = (idx0 >> 2) % H;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < items; base += stride) {
+        const long long idx = base + threadIdx.x;
+        const bool valid = idx < items;  // warp-uniform trip count: shuffles use the full mask
+        const long long pix = valid ? idx / (4 * H) : 0;
+        const long long b = pix / HW, hw = pix % HW;
+        float q[F][8], k[F][8], v[F][8], go[F][8];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            float g = 0.f;
+        for (int f = 0; f < F; ++f) {
+            const long long r = (b * F + f) * HW + hw;
+            const __nv_bfloat16* row = qkv + r * ld + h * D + c * 8;
+            ld8(row, q[f]);
+            ld8(row + HD, k[f]);
+            ld8(row + 2 * HD, v[f]);
+            ld8(dout + r * HD + h * D + c * 8, go[f]);
+            rope8(q[f], cf[f], sf[f], scale);
+            rope8(k[f], cf[f], sf[f], 1.f);
+        }
+        float p[F][F], ds[F][F];
 #pragma unroll
-            for (int e = 0; e < D; ++e) {
-                g = fmaf(sd[d][e], v[e], g);
-                dv[e] = fmaf(sd[d][e], t[d], dv[e]);
+        for (int i = 0; i < F; ++i) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                p[i][j] = qsum(dot8(q[i], k[j])) + __ldg(bias + (h * F + i) * F + j);
+                m = fmaxf(m, p[i][j]);
             }
-            r[d] = t[d] * (g - sdel[d]);
+            float l = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                p[i][j] = __expf(p[i][j] - m);
+                l += p[i][j];
+            }
+            const float inv = 1.f / l;
+            float Di = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                p[i][j] *= inv;
+                ds[i][j] = qsum(dot8(go[i], v[j]));  // dp_ij
+                Di = fmaf(p[i][j], ds[i][j], Di);
+            }
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                ds[i][j] = p[i][j] * (ds[i][j] - Di);
+                if (valid) dbacc[i][j] += ds[i][j];
+            }
         }
-        store32(dqkv + row * 3 * HD + HD + h * D, r);
-        store32(dqkv + row * 3 * HD + 2 * HD + h * D, dv);
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            float dq[8], dk[8], dv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dq[e] = dk[e] = dv[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; ++j)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    dq[e] = fmaf(ds[f][j], k[j][e], dq[e]);   // query role: f = i
+                    dk[e] = fmaf(ds[j][f], q[j][e], dk[e]);   // key role:   f = j, sum over queries
+                    dv[e] = fmaf(p[j][f], go[j][e], dv[e]);
+                }
+            rope8_t(dq, cf[f], sf[f], scale);
+            rope8_t(dk, cf[f], sf[f], 1.f);
+            __nv_bfloat16* drow = dqkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
+            if (valid) {
+                st8(drow, dq);
+                st8(drow + HD, dk);
+                st8(drow + 2 * HD, dv);
+            }
+        }
     }
+    if (c == 0) {
+#pragma unroll
+        for (int i = 0; i < F; ++i)
+#pragma unroll
+            for (int j = 0; j < F; ++j) atomicAdd(&sbias[(h * F + i) * F + j], dbacc[i][j]);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < H * F * F; x += blockDim.x) atomicAdd(&dbias[x], sbias[x]);
 }
 
 }  // namespace cesm
@@ -406,10 +422,27 @@ using namespace cesm;
 extern "C" int cesm_tattn_fwd(const void* qkv, const float* bias, const float* cs, const float* sn, void* out,
                               float* lse, int B, int F, int HW, int H, int dim_head, float scale, void* stream) {
     CESM_REQUIRE(dim_head == D, "temporal attention kernel needs dim_head == 32 (got %d)", dim_head);
+    CESM_REQUIRE(H >= 1 && H <= 8, "temporal attention kernel supports 1..8 heads (got %d)", H);
+    cudaStream_t st = as_stream(stream);
+    if (F <= 4) {
+        const long long npix = (long long)B * HW, items = npix * H * 4;
+        const int blocks = (int)((items + 255) / 256);
+#define TATTN_FWD(FF)                                                                                              \
+    tattn_small_fwd_kernel<FF><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out, \
+                                                       lse, npix, HW, H, scale)
+        if (F == 1) TATTN_FWD(1);
+        else if (F == 2) TATTN_FWD(2);
+        else if (F == 3) TATTN_FWD(3);
+        else TATTN_FWD(4);
+#undef TATTN_FWD
+        CESM_CHECK_LAUNCH();
+        return CESM_OK;
+    }
+    CESM_REQUIRE(lse != nullptr, "lse is required for F > 4");
     const long long total = (long long)B * F * HW * H;
     const int blocks = (int)((total + 127) / 128);
-    tattn_fwd_kernel<<<blocks, 128, 0, as_stream(stream)>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out,
-                                                            lse, B, F, HW, H, scale);
+    tattn_fwd_kernel<<<blocks, 128, 0, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out, lse, B, F, HW,
+                                             H, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -418,66 +451,35 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
                               const float* lse, const void* dout, void* dqkv, float* dbias, int B, int F, int HW, int H,
                               int dim_head, float scale, void* stream) {
     CESM_REQUIRE(dim_head == D, "temporal attention kernel needs dim_head == 32 (got %d)", dim_head);
+    CESM_REQUIRE(H >= 1 && H <= 8, "temporal attention kernel supports 1..8 heads (got %d)", H);
     cudaStream_t st = as_stream(stream);
     CESM_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * H * F * F, st));
+    if (F <= 4) {
+        const long long npix = (long long)B * HW, items = npix * H * 4;
+        long long want = (items + 255) / 256;
+        const int unit = H;  // blocks of 256 threads: a grid that is a multiple of H keeps (h, c) fixed per thread
+        long long cap = 148LL * 8;
+        if (want > cap) want = cap;
+        const int blocks = (int)(((want + unit - 1) / unit) * unit);
+#define TATTN_BWD(FF)                                                                                         \
+    tattn_small_bwd_kernel<FF><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn,                \
+                                                       (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias, \
+                                                       npix, HW, H, scale)
+        if (F == 1) TATTN_BWD(1);
+        else if (F == 2) TATTN_BWD(2);
+        else if (F == 3) TATTN_BWD(3);
+        else TATTN_BWD(4);
+#undef TATTN_BWD
+        CESM_CHECK_LAUNCH();
+        return CESM_OK;
+    }
+    CESM_REQUIRE(out != nullptr && lse != nullptr, "out and lse are required for F > 4");
     const long long total = (long long)B * F * HW * H;
     const int blocks = (int)((total + 127) / 128);
     const size_t sh = (H * F * F <= 2048) ? sizeof(float) * H * F * F : 0;
     tattn_bwd_kernel<<<blocks, 128, sh, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (const __nv_bfloat16*)out, lse,
                                               (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias, B, F, HW, H,
                                               scale);
-    CESM_CHECK_LAUNCH();
-    return CESM_OK;
-}
-
-static int la_chunk(int n) { return n >= 4096 ? 1024 : (n >= 512 ? 256 : 64); }
-
-// kstat: [NI][H*D][2] (max, sumexp); part: scratch [NI][nstrips<=64][H*D][2]; qk: [NI*n][2*H*D];
-// ctx: [NI][H][D][D] fp32; out: [NI*n][H*D]
-extern "C" int cesm_linattn_fwd(const void* qkv, float* part, float* kstat, void* qk, float* ctx, void* out, int NI,
-                                int n, int H, int dim_head, float scale, void* stream) {
-    CESM_REQUIRE(dim_head == D, "linear attention kernel needs dim_head == 32 (got %d)", dim_head);
-    cudaStream_t st = as_stream(stream);
-    const int HD = H * D;
-    const int nstrips = n >= 64 * 64 ? 64 : (n >= 256 ? 16 : 1);
-    la_kstats_partial_kernel<<<dim3(nstrips, NI), 256, 0, st>>>((const __nv_bfloat16*)qkv, part, n, HD, nstrips);
-    CESM_CHECK_LAUNCH();
-    la_kstats_combine_kernel<<<ceil_div(NI * HD, 256), 256, 0, st>>>(part, kstat, HD, nstrips, NI * HD);
-    CESM_CHECK_LAUNCH();
-    const long long rows = (long long)NI * n;
-    la_prep_kernel<<<(int)((rows * H + 127) / 128), 128, 0, st>>>((const __nv_bfloat16*)qkv, kstat, (__nv_bfloat16*)qk,
-                                                                  rows, n, H, scale);
-    CESM_CHECK_LAUNCH();
-    CESM_CHECK_CUDA(cudaMemsetAsync(ctx, 0, sizeof(float) * NI * H * D * D, st));
-    const int chunk = la_chunk(n);
-    dim3 grid(ceil_div(n, chunk), H, NI);
-    const __nv_bfloat16* qkp = (const __nv_bfloat16*)qk;
-    la_context_kernel<<<grid, 256, 0, st>>>(qkp + HD, 2 * HD, (const __nv_bfloat16*)qkv + 2 * HD, 3 * HD, ctx, n, H, chunk);
-    CESM_CHECK_LAUNCH();
-    la_apply_kernel<<<grid, 128, 0, st>>>(qkp, ctx, (__nv_bfloat16*)out, n, H, chunk);
-    CESM_CHECK_LAUNCH();
-    return CESM_OK;
-}
-
-// dctx, delta: scratch [NI][H][D][D], [NI][H][D]
-extern "C" int cesm_linattn_bwd(const void* qkv, const void* qk, const float* ctx, const void* dout, float* dctx,
-                                float* delta, void* dqkv, int NI, int n, int H, int dim_head, float scale,
-                                void* stream) {
-    CESM_REQUIRE(dim_head == D, "linear attention kernel needs dim_head == 32 (got %d)", dim_head);
-    cudaStream_t st = as_stream(stream);
-    const int HD = H * D;
-    CESM_CHECK_CUDA(cudaMemsetAsync(dctx, 0, sizeof(float) * NI * H * D * D, st));
-    const int chunk = la_chunk(n);
-    dim3 grid(ceil_div(n, chunk), H, NI);
-    // dctx[d][e] = sum_p (scale*softmax(q))[p][d] * dout[p][e]
-    la_context_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qk, 2 * HD, (const __nv_bfloat16*)dout, HD, dctx, n, H,
-                                            chunk);
-    CESM_CHECK_LAUNCH();
-    la_delta_kernel<<<ceil_div(NI * HD, 128), 128, 0, st>>>(ctx, dctx, delta, NI * HD);
-    CESM_CHECK_LAUNCH();
-    la_bwd_apply_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qk,
-                                              (const __nv_bfloat16*)dout, ctx, dctx, delta, (__nv_bfloat16*)dqkv, n, H,
-                                              chunk, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

@@ -1,0 +1,536 @@
+// Spatial linear attention core (video_net.py:338-344) for sm_100a, bf16 in / fp32 accumulate.
+//
+// Per image (one frame of one sample) and head, with n pixels and d = e = 32:
+//     qs = scale * softmax_d(q)         (over the 32 features of a pixel)
+//     kh = softmax_n(k)                 (over the n pixels, per feature)
+//     ctx[d][e] = sum_p kh[p][d] v[p][e]
+//     out[p][e] = sum_d ctx[d][e] qs[p][d]
+//
+// The op moves ~1 KB per pixel and does ~4 kFLOP per pixel per head: it is HBM-bound as long as
+// the two small contractions run on tensor cores, so they are warp-level mma.sync m16n8k16 tiles
+// (one warp per head; operands are exponentiated / normalised in registers on their way from
+// global memory to the fragments) and nothing but q, k, v, out ever touches HBM: the softmaxed
+// copies the reference materialises are recomputed where needed, forward and backward.
+//
+//   forward : colmax(k) -> context (exp(k-max) & v -> unnormalised ctx, Z) -> finalize (ctx /= Z)
+//             -> apply (softmax(q), ctx -> out)
+//   backward: context (qs & dout -> dctx) -> delta = rowsum(ctx * dctx) -> bwd_apply (dq, dk, dv)
+//
+// Workspace `ws` (fp32, per image): [HD] encoded column max | [HD] Z | [H][32][32] ctx.
+#include "api_common.h"
+#include "common.cuh"
+
+namespace cesm {
+
+static constexpr int LD = 32;        // head dim
+static constexpr int SPITCH = 40;    // bf16 elements per staged row (80 B: conflict-free ldmatrix)
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// order-preserving float <-> uint encoding, so that column maxima can use atomicMax on a zeroed buffer
+__device__ __forceinline__ uint32_t enc_ordered(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    return u;
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+struct LaWs {  // views into the per-image workspace
+    uint32_t* kmax;
+    float* z;
+    float* ctx;
+};
+__device__ __forceinline__ LaWs la_ws(float* ws, int ni, int HD, int H) {
+    float* base = ws + (size_t)ni * (2 * HD + (size_t)H * LD * LD);
+    return {reinterpret_cast<uint32_t*>(base), base + HD, base + 2 * HD};
+}
+
+// ------------------------------------------------------------------------------------------------
+// column max of k over the pixels of each image: thread = 8 channels (16 B), rows strided over the block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+la_colmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, int n, int H, int rows_per_block) {
+    const int HD = H * LD, cpr = HD / 8;
+    const int ni = blockIdx.y;
+    const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
+    const int p0 = blockIdx.x * rows_per_block, p1 = min(n, p0 + rows_per_block);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    if (rl < nrl) {
+        const __nv_bfloat16* base = qkv + ((size_t)ni * n) * (3 * HD) + HD + chunk * 8;
+        for (int p = p0 + rl; p < p1; p += nrl) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * 3 * HD)), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+        }
+    }
+    __shared__ float red[256][9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = m[i];
+    __syncthreads();
+    if ((int)threadIdx.x < HD) {
+        const int c = threadIdx.x, ch = c / 8, i = c % 8;
+        float v = -INFINITY;
+        for (int r = 0; r < nrl; ++r) v = fmaxf(v, red[r * cpr + ch][i]);
+        if (v > -INFINITY) atomicMax(la_ws(ws, ni, HD, H).kmax + c, enc_ordered(v));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context: acc[d][e] += sum_p A[p][d] * B[p][e] over a chunk of pixels; warp = head.
+//   MODE 0 (forward) : A = exp(k - colmax) (also accumulates Z[d] = sum_p A[p][d]),  B = v
+//   MODE 1 (backward): A = scale * softmax_d(q),                                     B = dout
+// Each 16-pixel step is staged through a warp-private smem tile and read back with
+// ldmatrix.trans, which yields the pixel-contracted (MN-major) fragments.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                  float* __restrict__ ws, float* __restrict__ acc_out /* MODE 1: dctx [NI][H][32][32] */, int n, int H,
+                  int chunk, float scale) {
+    extern __shared__ __align__(16) uint8_t la_smem[];
+    const int HD = H * LD, ld = 3 * HD;
+    const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, c = lane & 3;
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(la_smem) + (size_t)w * 2 * 16 * SPITCH;
+    __nv_bfloat16* sB = sA + 16 * SPITCH;
+    const LaWs W = la_ws(ws, ni, HD, H);
+
+    float cmax[8], zsum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        cmax[i] = (MODE == 0) ? dec_ordered(W.kmax[w * LD + c * 8 + i]) : 0.f;
+        zsum[i] = 0.f;
+    }
+    float acc[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[a][b][k] = 0.f;
+
+    const size_t img_row0 = (size_t)ni * n;
+    const __nv_bfloat16* a_base = qkv + img_row0 * ld + (MODE == 0 ? HD : 0) + w * LD + c * 8;
+    const __nv_bfloat16* b_base = (MODE == 0) ? qkv + img_row0 * ld + 2 * HD + w * LD + c * 8
+                                              : dout + img_row0 * HD + w * LD + c * 8;
+    const int b_ld = (MODE == 0) ? ld : HD;
+    const int p0 = blockIdx.x * chunk, p1 = min(n, p0 + chunk);
+
+    // ldmatrix lane addresses (fixed): A m-tile mt, B n-tile pair jp
+    const int mi = lane >> 3, rr = lane & 7;
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    uint32_t a_off[2], b_off[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) a_off[mt] = (((mi >> 1) * 8 + rr) * SPITCH + 16 * mt + (mi & 1) * 8) * 2;
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) b_off[jp] = (((mi & 1) * 8 + rr) * SPITCH + 8 * (jp * 2 + (mi >> 1))) * 2;
+
+    for (int p = p0; p < p1; p += 16) {
+        // ---- global -> registers (rows r and r+8 of this step) ----
+        uint4 ua[2], ub[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = p + r + 8 * h2;
+            if (row < p1) {
+                ua[h2] = __ldg(reinterpret_cast<const uint4*>(a_base + (size_t)row * ld));
+                ub[h2] = __ldg(reinterpret_cast<const uint4*>(b_base + (size_t)row * b_ld));
+            } else {
+                ua[h2] = make_uint4(0, 0, 0, 0);
+                ub[h2] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        // ---- transform A ----
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const bool valid = (p + r + 8 * h2) < p1;
+            float f[8];
+            unpack8(ua[h2], f);
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    f[i] = valid ? __expf(f[i] - cmax[i]) : 0.f;
+                    zsum[i] += f[i];
+                }
+            } else {
+                float m = f[0];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
+                m = quad_max(m);
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    f[i] = __expf(f[i] - m);
+                    s += f[i];
+                }
+                s = quad_sum(s);
+                const float inv = valid ? scale / s : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= inv;
+            }
+            *reinterpret_cast<uint4*>(sA + (r + 8 * h2) * SPITCH + c * 8) = pack8(f);
+            *reinterpret_cast<uint4*>(sB + (r + 8 * h2) * SPITCH + c * 8) = ub[h2];
+        }
+        __syncwarp();
+        uint32_t af[2][4], bf[2][4];
+        ldmatrix_x4_trans(af[0], sA_addr + a_off[0]);
+        ldmatrix_x4_trans(af[1], sA_addr + a_off[1]);
+        ldmatrix_x4_trans(bf[0], sB_addr + b_off[0]);
+        ldmatrix_x4_trans(bf[1], sB_addr + b_off[1]);
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_16816(acc[mt][j], af[mt], bf[j >> 1][(j & 1) * 2], bf[j >> 1][(j & 1) * 2 + 1]);
+    }
+
+    // ---- reduce into global (fp32 atomics; a few dozen blocks per image) ----
+    float* dst = (MODE == 0 ? W.ctx : acc_out + (size_t)ni * H * LD * LD) + (size_t)w * LD * LD;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d0 = 16 * mt + g, e0 = 8 * j + 2 * t;
+            atomicAdd(dst + d0 * LD + e0, acc[mt][j][0]);
+            atomicAdd(dst + d0 * LD + e0 + 1, acc[mt][j][1]);
+            atomicAdd(dst + (d0 + 8) * LD + e0, acc[mt][j][2]);
+            atomicAdd(dst + (d0 + 8) * LD + e0 + 1, acc[mt][j][3]);
+        }
+    if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float z = zsum[i];
+            z += __shfl_xor_sync(0xffffffffu, z, 4);
+            z += __shfl_xor_sync(0xffffffffu, z, 8);
+            z += __shfl_xor_sync(0xffffffffu, z, 16);
+            if (r == 0) atomicAdd(W.z + w * LD + c * 8 + i, z);
+        }
+    }
+}
+
+// ctx[d][e] /= Z[d]  (forward) -- one thread per element
+__global__ void la_finalize_kernel(float* __restrict__ ws, int H, int NI) {
+    const int HD = H * LD;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = H * LD * LD;
+    if (idx >= NI * per) return;
+    const int ni = idx / per, x = idx % per;
+    const LaWs W = la_ws(ws, ni, HD, H);
+    W.ctx[x] = W.ctx[x] / W.z[x / LD];  // x / LD == h*32 + d
+}
+
+// delta[ni][h*32+d] = sum_e ctx[d][e] * dctx[d][e]
+__global__ void la_delta_kernel(float* __restrict__ ws, const float* __restrict__ dctx, float* __restrict__ delta,
+                                int H, int NI) {
+    const int HD = H * LD;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // ni*HD + h*32 + d
+    if (idx >= NI * HD) return;
+    const int ni = idx / HD, hd = idx % HD;
+    const LaWs W = la_ws(ws, ni, HD, H);
+    const float* dc = dctx + ((size_t)ni * HD + hd) * LD;
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < LD; ++e) s = fmaf(W.ctx[hd * LD + e], dc[e], s);
+    delta[idx] = s;
+}
+
+// A fragment (16 rows x 32 k) of a row-major bf16 matrix straight from global memory:
+// v[ks][0..3] = a0..a3 of k-step ks; rows g / g+8, this lane's columns {2t,2t+1,2t+8,2t+9} + 16 ks.
+__device__ __forceinline__ void load_afrag(const __nv_bfloat16* row_g, const __nv_bfloat16* row_g8, bool vg, bool vg8,
+                                           int t, uint32_t (&v)[2][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const int c0 = 16 * ks + 2 * t;
+        v[ks][0] = vg ? __ldg(reinterpret_cast<const uint32_t*>(row_g + c0)) : 0u;
+        v[ks][1] = vg8 ? __ldg(reinterpret_cast<const uint32_t*>(row_g8 + c0)) : 0u;
+        v[ks][2] = vg ? __ldg(reinterpret_cast<const uint32_t*>(row_g + c0 + 8)) : 0u;
+        v[ks][3] = vg8 ? __ldg(reinterpret_cast<const uint32_t*>(row_g8 + c0 + 8)) : 0u;
+    }
+}
+// B fragments of a 32x32 fp32 matrix M (row-major) for C = A * Bm with Bm[k][n] = TRANS ? M[n][k] : M[k][n]
+template <bool TRANS>
+__device__ __forceinline__ void load_bfrag32(const float* __restrict__ M, int g, int t, uint32_t (&b)[2][4][2]) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k0 = 16 * ks + 2 * t, nn = 8 * j + g;
+            if (TRANS) {
+                b[ks][j][0] = pack_bf16x2(M[nn * LD + k0], M[nn * LD + k0 + 1]);
+                b[ks][j][1] = pack_bf16x2(M[nn * LD + k0 + 8], M[nn * LD + k0 + 9]);
+            } else {
+                b[ks][j][0] = pack_bf16x2(M[k0 * LD + nn], M[(k0 + 1) * LD + nn]);
+                b[ks][j][1] = pack_bf16x2(M[(k0 + 8) * LD + nn], M[(k0 + 9) * LD + nn]);
+            }
+        }
+}
+// This lane's 8 columns of a 32-wide row in fragment order: idx (ks, hi, lo) -> col 16ks + 8hi + 2t + lo
+__device__ __forceinline__ int frag_col(int t, int i) { return 16 * (i >> 2) + 8 * ((i >> 1) & 1) + 2 * t + (i & 1); }
+
+// softmax over the 32 columns of rows g and g+8 held as A fragments; returns probabilities (fp32)
+// in fragment order: p[row_half][i], i as in frag_col.
+__device__ __forceinline__ void frag_softmax(const uint32_t (&a)[2][4], float (&p)[2][8]) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const float2 lo = unpack_bf16x2(a[ks][hf]), hi = unpack_bf16x2(a[ks][hf + 2]);
+            p[hf][4 * ks + 0] = lo.x; p[hf][4 * ks + 1] = lo.y; p[hf][4 * ks + 2] = hi.x; p[hf][4 * ks + 3] = hi.y;
+        }
+        float m = p[hf][0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, p[hf][i]);
+        m = quad_max(m);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            p[hf][i] = __expf(p[hf][i] - m);
+            s += p[hf][i];
+        }
+        const float inv = 1.f / quad_sum(s);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[hf][i] *= inv;
+    }
+}
+// fp32 values in fragment order -> bf16 A fragments
+__device__ __forceinline__ void frag_pack(const float (&p)[2][8], uint32_t (&a)[2][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            a[ks][hf] = pack_bf16x2(p[hf][4 * ks + 0], p[hf][4 * ks + 1]);
+            a[ks][hf + 2] = pack_bf16x2(p[hf][4 * ks + 2], p[hf][4 * ks + 3]);
+        }
+}
+// C (16x32 as 4 n-tiles) = A (16x32) * B; c[j][0..3]
+__device__ __forceinline__ void frag_gemm(const uint32_t (&a)[2][4], const uint32_t (&b)[2][4][2], float (&c)[4][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) mma_16816(c[j], a[ks], b[ks][j][0], b[ks][j][1]);
+    }
+}
+// C fragments hold, for row half hf, columns 8j + 2t + {0,1}: the same column set as frag_col.
+// value of C for (hf, i) with i in fragment order
+__device__ __forceinline__ float c_at(const float (&c)[4][4], int hf, int i) {
+    const int j = 2 * (i >> 2) + ((i >> 1) & 1);  // col = 8j + 2t + lo  <->  16ks + 8hi + 2t + lo
+    return c[j][2 * hf + (i & 1)];
+}
+__device__ __forceinline__ void store_cfrag(__nv_bfloat16* row_g, __nv_bfloat16* row_g8, bool vg, bool vg8, int t,
+                                            const float (&c)[4][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (vg) *reinterpret_cast<uint32_t*>(row_g + 8 * j + 2 * t) = pack_bf16x2(c[j][0], c[j][1]);
+        if (vg8) *reinterpret_cast<uint32_t*>(row_g8 + 8 * j + 2 * t) = pack_bf16x2(c[j][2], c[j][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply (forward): out[p][e] = sum_d qs[p][d] ctx[d][e]; warp = head, 16 pixels per step
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int n,
+                int H, int chunk, float scale) {
+    const int HD = H * LD, ld = 3 * HD;
+    const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const LaWs W = la_ws(ws, ni, HD, H);
+    uint32_t bctx[2][4][2];
+    load_bfrag32<false>(W.ctx + (size_t)w * LD * LD, g, t, bctx);
+    const size_t row0 = (size_t)ni * n;
+    const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
+    for (int p = blockIdx.x * chunk; p < p1; p += 16) {
+        const bool vg = p + g < p1, vg8 = p + g + 8 < p1;
+        const __nv_bfloat16* qg = qkv + (row0 + p + g) * ld + w * LD;
+        uint32_t a[2][4];
+        load_afrag(qg, qg + (size_t)8 * ld, vg, vg8, t, a);
+        float pr[2][8];
+        frag_softmax(a, pr);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pr[hf][i] *= scale;
+        frag_pack(pr, a);
+        float c[4][4];
+        frag_gemm(a, bctx, c);
+        __nv_bfloat16* og = out + (row0 + p + g) * HD + w * LD;
+        store_cfrag(og, og + (size_t)8 * HD, vg, vg8, t, c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward apply: per pixel row
+//   dqh = dout ctx^T ; dq = sm (scale dqh - sum_j sm_j scale dqh_j)
+//   dkh = v dctx^T   ; dk = kh (dkh - delta) , kh = exp(k - max) / Z
+//   dv  = kh dctx
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                    float* __restrict__ ws, const float* __restrict__ dctx, const float* __restrict__ delta,
+                    __nv_bfloat16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
+    const int HD = H * LD, ld = 3 * HD;
+    const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const LaWs W = la_ws(ws, ni, HD, H);
+    const float* dcx = dctx + ((size_t)ni * H + w) * LD * LD;
+    uint32_t b_ctxT[2][4][2], b_dctxT[2][4][2], b_dctx[2][4][2];
+    load_bfrag32<true>(W.ctx + (size_t)w * LD * LD, g, t, b_ctxT);
+    load_bfrag32<true>(dcx, g, t, b_dctxT);
+    load_bfrag32<false>(dcx, g, t, b_dctx);
+    float kmx[8], kinvz[8], del[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int col = w * LD + frag_col(t, i);
+        kmx[i] = dec_ordered(W.kmax[col]);
+        kinvz[i] = 1.f / W.z[col];
+        del[i] = delta[(size_t)ni * HD + col];
+    }
+    const size_t row0 = (size_t)ni * n;
+    const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
+    for (int p = blockIdx.x * chunk; p < p1; p += 16) {
+        const bool vg = p + g < p1, vg8 = p + g + 8 < p1;
+        const size_t rg = row0 + p + g;
+        const __nv_bfloat16* xg = qkv + rg * ld + w * LD;
+        __nv_bfloat16* dg = dqkv + rg * ld + w * LD;
+        uint32_t a_do[2][4], a_x[2][4];
+        float c[4][4], pr[2][8], o[4][4];
+        load_afrag(dout + rg * HD + w * LD, dout + (rg + 8) * HD + w * LD, vg, vg8, t, a_do);
+        // ---- dq ----
+        load_afrag(xg, xg + (size_t)8 * ld, vg, vg8, t, a_x);
+        frag_softmax(a_x, pr);
+        frag_gemm(a_do, b_ctxT, c);  // dqh
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(pr[hf][i], c_at(c, hf, i), dot);
+            dot = quad_sum(dot);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = 2 * (i >> 2) + ((i >> 1) & 1);
+                o[j][2 * hf + (i & 1)] = pr[hf][i] * scale * (c_at(c, hf, i) - dot);
+            }
+        }
+        store_cfrag(dg, dg + (size_t)8 * ld, vg, vg8, t, o);
+        // ---- dk ----
+        uint32_t a_v[2][4];
+        load_afrag(xg + 2 * HD, xg + 2 * HD + (size_t)8 * ld, vg, vg8, t, a_v);
+        frag_gemm(a_v, b_dctxT, c);  // dkh
+        load_afrag(xg + HD, xg + HD + (size_t)8 * ld, vg, vg8, t, a_x);  // raw k
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const float2 lo = unpack_bf16x2(a_x[ks][hf]), hi = unpack_bf16x2(a_x[ks][hf + 2]);
+                const float kv[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = 4 * ks + q;
+                    pr[hf][i] = __expf(kv[q] - kmx[i]) * kinvz[i];  // kh
+                }
+            }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = 2 * (i >> 2) + ((i >> 1) & 1);
+                o[j][2 * hf + (i & 1)] = pr[hf][i] * (c_at(c, hf, i) - del[i]);
+            }
+        store_cfrag(dg + HD, dg + HD + (size_t)8 * ld, vg, vg8, t, o);
+        // ---- dv ----
+        frag_pack(pr, a_x);
+        frag_gemm(a_x, b_dctx, c);
+        store_cfrag(dg + 2 * HD, dg + 2 * HD + (size_t)8 * ld, vg, vg8, t, c);
+    }
+}
+
+}  // namespace cesm
+
+using namespace cesm;
+
+static int la_chunk(int n, int NI) {
+    // aim for >= ~4 blocks per SM-wave while keeping atomics per image modest
+    int chunk = 2048;
+    while (chunk > 64 && (long long)NI * ((n + chunk - 1) / chunk) < 296) chunk >>= 1;
+    return chunk;
+}
+
+extern "C" size_t cesm_linattn_ws_floats(int NI, int H) { return (size_t)NI * (2 * H * LD + (size_t)H * LD * LD); }
+
+extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, int n, int H, int dim_head, float scale,
+                                void* stream) {
+    CESM_REQUIRE(dim_head == LD, "linear attention kernel needs dim_head == 32 (got %d)", dim_head);
+    CESM_REQUIRE(H >= 1 && H <= 8, "linear attention kernel supports 1..8 heads (got %d)", H);
+    cudaStream_t st = as_stream(stream);
+    const int HD = H * LD;
+    CESM_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * cesm_linattn_ws_floats(NI, H), st));
+    const int chunk = la_chunk(n, NI);
+    dim3 grid(ceil_div(n, chunk), NI);
+    la_colmax_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, ws, n, H, chunk);
+    CESM_CHECK_LAUNCH();
+    const size_t sh = (size_t)H * 2 * 16 * SPITCH * sizeof(__nv_bfloat16);
+    la_context_kernel<0><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, nullptr, ws, nullptr, n, H, chunk, scale);
+    CESM_CHECK_LAUNCH();
+    la_finalize_kernel<<<ceil_div(NI * H * LD * LD, 256), 256, 0, st>>>(ws, H, NI);
+    CESM_CHECK_LAUNCH();
+    la_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk, scale);
+    CESM_CHECK_LAUNCH();
+    (void)HD;
+    return CESM_OK;
+}
+
+// scratch: fp32 [NI][H][32][32] (dctx) + [NI][H*32] (delta)
+extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, float* scratch, void* dqkv, int NI, int n,
+                                int H, int dim_head, float scale, void* stream) {
+    CESM_REQUIRE(dim_head == LD, "linear attention kernel needs dim_head == 32 (got %d)", dim_head);
+    CESM_REQUIRE(H >= 1 && H <= 8, "linear attention kernel supports 1..8 heads (got %d)", H);
+    cudaStream_t st = as_stream(stream);
+    float* dctx = scratch;
+    float* delta = scratch + (size_t)NI * H * LD * LD;
+    CESM_CHECK_CUDA(cudaMemsetAsync(dctx, 0, sizeof(float) * NI * H * LD * LD, st));
+    const int chunk = la_chunk(n, NI);
+    dim3 grid(ceil_div(n, chunk), NI);
+    const size_t sh = (size_t)H * 2 * 16 * SPITCH * sizeof(__nv_bfloat16);
+    la_context_kernel<1><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, n, H,
+                                                   chunk, scale);
+    CESM_CHECK_LAUNCH();
+    la_delta_kernel<<<ceil_div(NI * H * LD, 128), 128, 0, st>>>(ws, dctx, delta, H, NI);
+    CESM_CHECK_LAUNCH();
+    la_bwd_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
+                                                 (__nv_bfloat16*)dqkv, n, H, chunk, scale);
+    CESM_CHECK_LAUNCH();
+    return CESM_OK;
+}

@@ -31,6 +31,16 @@ def _req_cuda(*ts: Optional[torch.Tensor]) -> None:
             raise _lib.CesmError("cesm_emulator_b200 kernels need contiguous tensors")
 
 
+def _bytes_meta(*ts, kind=None):
+    """Profiler annotation: algorithmic bytes = the tensors a kernel must read or write once."""
+    if _lib.PROFILER is None:
+        return None
+    m = {"bytes": float(sum(t.numel() * t.element_size() for t in ts if t is not None))}
+    if kind:
+        m["kind"] = kind
+    return m
+
+
 TAPS_3x3 = [(dh, dw) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]
 TAPS_1x1 = [(0, 0)]
 
@@ -208,9 +218,10 @@ def tattn_fwd(qkv, bias, cs, sn, B: int, F: int, HW: int, H: int, D: int, scale:
     _req_cuda(qkv, bias, cs, sn)
     rows = B * F * HW
     out = torch.empty((rows, H * D), dtype=BF16, device=qkv.device)
-    lse = torch.empty((rows, H), dtype=torch.float32, device=qkv.device)
+    # F <= 4: the backward recomputes the softmax, so no log-sum-exp is kept
+    lse = torch.empty((rows, H), dtype=torch.float32, device=qkv.device) if F > 4 else None
     _lib.call("cesm_tattn_fwd", _ptr(qkv), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse), B, F, HW, H, D, scale,
-              _stream())
+              _stream(), _meta=_bytes_meta(qkv, out))
     return out, lse
 
 
@@ -219,32 +230,27 @@ def tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B: int, F: int, HW: int, H: int
     dqkv = torch.empty_like(qkv)
     dbias = torch.empty((H, F, F), dtype=torch.float32, device=qkv.device)
     _lib.call("cesm_tattn_bwd", _ptr(qkv), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse), _ptr(dout), _ptr(dqkv),
-              _ptr(dbias), B, F, HW, H, D, scale, _stream())
+              _ptr(dbias), B, F, HW, H, D, scale, _stream(), _meta=_bytes_meta(qkv, dout, dqkv))
     return dqkv, dbias
 
 
 def linattn_fwd(qkv, NI: int, n: int, H: int, D: int, scale: float):
+    """-> (out bf16 [NI*n, H*D], ws fp32 workspace kept for the backward)."""
     _req_cuda(qkv)
     dev = qkv.device
-    HD = H * D
-    part = torch.empty((NI, 64, HD, 2), dtype=torch.float32, device=dev)
-    kstat = torch.empty((NI, HD, 2), dtype=torch.float32, device=dev)
-    qk = torch.empty((NI * n, 2 * HD), dtype=BF16, device=dev)
-    ctx = torch.empty((NI, H, D, D), dtype=torch.float32, device=dev)
-    out = torch.empty((NI * n, HD), dtype=BF16, device=dev)
-    _lib.call("cesm_linattn_fwd", _ptr(qkv), _ptr(part), _ptr(kstat), _ptr(qk), _ptr(ctx), _ptr(out), NI, n, H, D, scale,
-              _stream())
-    return out, qk, ctx
+    ws = torch.empty(_lib.load().cesm_linattn_ws_floats(NI, H), dtype=torch.float32, device=dev)
+    out = torch.empty((NI * n, H * D), dtype=BF16, device=dev)
+    _lib.call("cesm_linattn_fwd", _ptr(qkv), _ptr(ws), _ptr(out), NI, n, H, D, scale, _stream(),
+              _meta=_bytes_meta(qkv, out))
+    return out, ws
 
 
-def linattn_bwd(qkv, qk, ctx, dout, NI: int, n: int, H: int, D: int, scale: float):
-    _req_cuda(qkv, qk, ctx, dout)
-    dev = qkv.device
-    dctx = torch.empty((NI, H, D, D), dtype=torch.float32, device=dev)
-    delta = torch.empty((NI, H, D), dtype=torch.float32, device=dev)
+def linattn_bwd(qkv, ws, dout, NI: int, n: int, H: int, D: int, scale: float):
+    _req_cuda(qkv, ws, dout)
+    scratch = torch.empty(NI * H * D * D + NI * H * D, dtype=torch.float32, device=qkv.device)
     dqkv = torch.empty_like(qkv)
-    _lib.call("cesm_linattn_bwd", _ptr(qkv), _ptr(qk), _ptr(ctx), _ptr(dout), _ptr(dctx), _ptr(delta), _ptr(dqkv), NI, n,
-              H, D, scale, _stream())
+    _lib.call("cesm_linattn_bwd", _ptr(qkv), _ptr(ws), _ptr(dout), _ptr(scratch), _ptr(dqkv), NI, n, H, D, scale,
+              _stream(), _meta=_bytes_meta(qkv, dout, dqkv))
     return dqkv
 
 

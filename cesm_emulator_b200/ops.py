@@ -31,6 +31,23 @@ def _phase(ph: int, pw: int):
     return taps, koff
 
 
+# Fused / capturable optimizers update parameters without bumping `Tensor._version`, so the
+# packed-operand caches are also keyed on a global epoch that every torch optimizer step advances.
+_WEIGHT_EPOCH = [0]
+
+
+def invalidate_weight_cache(*_args, **_kwargs) -> None:
+    """Call after modifying parameters by any means torch cannot see (raw pointer writes)."""
+    _WEIGHT_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(invalidate_weight_cache)
+except Exception:  # pragma: no cover - very old torch
+    pass
+
+
 class PackCache:
     """bf16 GEMM-operand copies of one layer's fp32 parameter, keyed by layout tag and re-made
     when the parameter changes (optimizer step bumps `_version`).  While a CUDA graph of a TRAINING
@@ -47,7 +64,7 @@ class PackCache:
         return weight.requires_grad and torch.is_grad_enabled() and torch.cuda.is_current_stream_capturing()
 
     def get(self, weight: torch.Tensor, tag, make, force: bool = False):
-        key = (weight.data_ptr(), weight._version)
+        key = (weight.data_ptr(), weight._version, _WEIGHT_EPOCH[0])
         if not force:
             hit = self._d.get(tag)
             if hit is not None and hit[0] == key:
@@ -257,14 +274,20 @@ class TemporalAttnCoreFn(torch.autograd.Function):
         qkv, pos_bias = qkv.contiguous(), pos_bias.contiguous().float()
         scale = D ** -0.5
         out, lse = K.tattn_fwd(qkv, pos_bias, cs, sn, B, F, HW, H, D, scale)
-        ctx.save_for_backward(qkv, pos_bias, cs, sn, out, lse)
+        if F <= 4:  # the small-window kernel recomputes the softmax in the backward
+            ctx.save_for_backward(qkv, pos_bias, cs, sn)
+        else:
+            ctx.save_for_backward(qkv, pos_bias, cs, sn, out, lse)
         ctx.dims = (B, F, HW, H, D, scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, pos_bias, cs, sn, out, lse = ctx.saved_tensors
         B, F, HW, H, D, scale = ctx.dims
+        if F <= 4:
+            (qkv, pos_bias, cs, sn), out, lse = ctx.saved_tensors, None, None
+        else:
+            qkv, pos_bias, cs, sn, out, lse = ctx.saved_tensors
         dqkv, dbias = K.tattn_bwd(qkv, pos_bias, cs, sn, out, lse, dout.contiguous(), B, F, HW, H, D, scale)
         return dqkv, dbias, None, None, None, None, None, None, None
 
@@ -294,16 +317,16 @@ class LinearAttnCoreFn(torch.autograd.Function):
     def forward(ctx, qkv, NI: int, n: int, H: int, D: int):
         qkv = qkv.contiguous()
         scale = D ** -0.5
-        out, qk, cx = K.linattn_fwd(qkv, NI, n, H, D, scale)
-        ctx.save_for_backward(qkv, qk, cx)
+        out, ws = K.linattn_fwd(qkv, NI, n, H, D, scale)
+        ctx.save_for_backward(qkv, ws)
         ctx.dims = (NI, n, H, D, scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, qk, cx = ctx.saved_tensors
+        qkv, ws = ctx.saved_tensors
         NI, n, H, D, scale = ctx.dims
-        return K.linattn_bwd(qkv, qk, cx, dout.contiguous(), NI, n, H, D, scale), None, None, None, None
+        return K.linattn_bwd(qkv, ws, dout.contiguous(), NI, n, H, D, scale), None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -150,7 +150,9 @@ int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, const void* d
  * q*scale -> RoPE(q), RoPE(k) -> q.k + rel-pos bias -> online softmax over frames -> .v
  *   qkv : bf16 [B*F*HW][3*H*32] (q | k | v), row = (b*F + f)*HW + pixel
  *   bias: fp32 [H][F][F];  cs, sn: fp32 [F][16] rotary cos / sin;  out: bf16 [B*F*HW][H*32]
- *   lse : fp32 [B*F*HW][H] log-sum-exp saved for the backward
+ *   lse : fp32 [B*F*HW][H] log-sum-exp saved for the backward.  For F <= 4 (the training window
+ *         K=3 and the one-frame sampling call) a register-resident kernel is used whose backward
+ *         recomputes the softmax from qkv: lse may then be NULL in fwd, and out / lse NULL in bwd.
  * ---------------------------------------------------------------------------------------------- */
 int cesm_tattn_fwd(const void* qkv, const float* bias, const float* cs, const float* sn, void* out, float* lse,
                    int B, int F, int HW, int H, int dim_head, float scale, void* stream);
@@ -159,17 +161,20 @@ int cesm_tattn_bwd(const void* qkv, const float* bias, const float* cs, const fl
                    int dim_head, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Spatial linear attention core, video_net.py:338-344, per image (frame) of n pixels:
- * softmax(q) over d, softmax(k) over n, ctx = k^T v, out = ctx^T q*scale.
- *   qkv: bf16 [NI*n][3*H*32];  part: fp32 scratch [NI][64][H*32][2];  kstat: fp32 [NI][H*32][2];
- *   qk : bf16 [NI*n][2*H*32] (scale*softmax(q) | softmax(k)), saved for the backward;
- *   ctx: fp32 [NI][H][32][32];  out: bf16 [NI*n][H*32]
- * bwd: dctx [NI][H][32][32] and delta [NI][H][32] are fp32 scratch; dqkv: bf16 [NI*n][3*H*32].
+ * Spatial linear attention core, video_net.py:338-344, per image (frame) of n pixels and head:
+ * qs = scale*softmax(q) over d, kh = softmax(k) over the n pixels, ctx = kh^T v, out = qs ctx.
+ * Both contractions run as warp-level bf16 tensor-core tiles; the softmaxed operands are
+ * recomputed from qkv where needed, so only q, k, v, out (and their gradients) touch HBM.
+ *   qkv: bf16 [NI*n][3*H*32];  out: bf16 [NI*n][H*32];  1 <= H <= 8
+ *   ws : fp32 [cesm_linattn_ws_floats(NI, H)], written by fwd and read by bwd; per image it
+ *        holds the column maxima of k (order-encoded), Z = sum_p exp(k - max) and ctx [H][32][32]
+ *   bwd: scratch fp32 [NI*H*32*32 + NI*H*32]; dqkv: bf16 [NI*n][3*H*32]
  * ---------------------------------------------------------------------------------------------- */
-int cesm_linattn_fwd(const void* qkv, float* part, float* kstat, void* qk, float* ctx, void* out, int NI, int n,
-                     int H, int dim_head, float scale, void* stream);
-int cesm_linattn_bwd(const void* qkv, const void* qk, const float* ctx, const void* dout, float* dctx, float* delta,
-                     void* dqkv, int NI, int n, int H, int dim_head, float scale, void* stream);
+size_t cesm_linattn_ws_floats(int NI, int H);
+int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, int n, int H, int dim_head, float scale,
+                     void* stream);
+int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, float* scratch, void* dqkv, int NI, int n, int H,
+                     int dim_head, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Network boundary convs.

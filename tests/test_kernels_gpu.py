@@ -213,15 +213,16 @@ def _linattn_ref(qkv, NI, n, H, D):
     return out.permute(0, 3, 1, 2).reshape(NI * n, H * D)
 
 
-@pytest.mark.parametrize("NI,n,H", [(2, 256, 8), (3, 1024, 8), (1, 4096, 8), (6, 64, 8), (2, 24 * 36, 8)])
+@pytest.mark.parametrize("NI,n,H", [(2, 256, 8), (3, 1024, 8), (1, 4096, 8), (6, 64, 8), (2, 24 * 36, 8), (2, 50, 8),
+                                     (1, 7 * 9, 4), (6, 96 * 144, 8)])
 def test_linear_attention_core(cuda, NI, n, H):
     from cesm_emulator_b200 import kernels as K
     torch.manual_seed(7)
     D = 32
     qkv = rnd((NI * n, 3 * H * D), cuda, 1.5)
     dout = rnd((NI * n, H * D), cuda)
-    out, qk, ctx = K.linattn_fwd(qkv, NI, n, H, D, D ** -0.5)
-    dqkv = K.linattn_bwd(qkv, qk, ctx, dout, NI, n, H, D, D ** -0.5)
+    out, ws = K.linattn_fwd(qkv, NI, n, H, D, D ** -0.5)
+    dqkv = K.linattn_bwd(qkv, ws, dout, NI, n, H, D, D ** -0.5)
     qr = qkv.float().requires_grad_(True)
     ref = _linattn_ref(qr, NI, n, H, D)
     assert err(out, ref) < 1.5e-2
