@@ -53,6 +53,17 @@ class WgradArgs(Structure):
     ]
 
 
+class PackDesc(Structure):
+    """Mirror of `cesm_pack_desc` (include/cesm_b200.h)."""
+
+    _fields_ = [
+        ("src", c_void_p), ("dst", c_void_p),
+        ("O", c_int32), ("T", c_int32), ("I", c_int32), ("pad_", c_int32),
+        ("so", ctypes.c_longlong), ("si", ctypes.c_longlong),
+        ("tap_off", c_int32 * CESM_MAX_TAPS),
+    ]
+
+
 class CesmError(RuntimeError):
     pass
 
@@ -86,11 +97,12 @@ _SIGNATURES: dict[str, list] = {
     "cesm_igemm": [POINTER(IgemmArgs), _P],
     "cesm_wgrad": [POINTER(WgradArgs), _P],
     "cesm_pack_weight": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _P],
+    "cesm_pack_weights_batched": [_P, _I, _P],
     "cesm_unpack_wgrad": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _I, _P],
     "cesm_colsum": [_P, _P, _L, _I, _P],
     "cesm_gn_stats": [_P, _P, _I, _L, _I, _I, _P],
     "cesm_gn_apply_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
-    "cesm_gn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
+    "cesm_gn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
     "cesm_ln_fwd": [_P, _P, _P, _L, _I, _F, _P],
     "cesm_ln_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "cesm_tattn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],

@@ -31,10 +31,11 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// fast-math forms (MUFU.EX2 + MUFU.RCP): the results are rounded to bf16 anyway
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // d/dx silu(x) = s + x*s*(1-s)
 __device__ __forceinline__ float dsilu_f(float x) {
-    float s = 1.f / (1.f + __expf(-x));
+    float s = __fdividef(1.f, 1.f + __expf(-x));
     return s * (1.f + x * (1.f - s));
 }
 

@@ -35,22 +35,36 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics: sums[b][g] = (sum x, sum x^2) over the group's channels and all pixels.
 // grid = (blocks_per_sample, B).  Requires (C/G) % 8 == 0 and 2048 % C == 0.
+// Each thread keeps UNR independent 16-byte loads in flight per trip (latency hiding: these
+// kernels are pure streams, so bytes in flight per SM is what sets the achieved bandwidth).
 // ------------------------------------------------------------------------------------------------
+static constexpr int UNR = 4;
+
 __global__ void __launch_bounds__(kNormThreads)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, long long P, int C, int G) {
     const int b = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;       // fixed channel vector of this thread
     const int pix_per_iter = kNormThreads / vec_per_pix;
-    const __nv_bfloat16* xb = x + (size_t)b * P * C;
+    const __nv_bfloat16* xb = x + (size_t)b * P * C + slot * 8;
+    const long long stride = (long long)gridDim.x * pix_per_iter;
     float s = 0.f, ss = 0.f;
-    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P;
-         p += (long long)gridDim.x * pix_per_iter) {
-        Vec8 v = load8(xb + p * C + slot * 8);
+    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
+        uint4 u[UNR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            s += v.v[i];
-            ss += v.v[i] * v.v[i];
+        for (int k = 0; k < UNR; ++k) {
+            const long long pk = p + k * stride;
+            u[k] = pk < P ? __ldg(reinterpret_cast<const uint4*>(xb + pk * C)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(w[i]);
+                s += f.x + f.y;
+                ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+            }
         }
     }
     __shared__ float sh[2][kNormThreads];
@@ -101,26 +115,45 @@ gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
         A[i] = ga;
         Bc[i] = be;
     }
-    const size_t base = (size_t)b * P * C;
-    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P;
-         p += (long long)gridDim.x * pix_per_iter) {
-        const size_t off = base + p * C + slot * 8;
-        Vec8 v = load8(x + off);
-        Vec8 o;
+    const size_t base = (size_t)b * P * C + slot * 8;
+    const long long stride = (long long)gridDim.x * pix_per_iter;
+    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
+        uint4 u[UNR], r[UNR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = silu_f(v.v[i] * A[i] + Bc[i]);
-        if (residual) {
-            Vec8 r = load8(residual + off);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o.v[i] += r.v[i];
+        for (int k = 0; k < UNR; ++k) {
+            const long long pk = p + k * stride;
+            if (pk < P) {
+                u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + pk * C));
+                if (residual) r[k] = __ldg(reinterpret_cast<const uint4*>(residual + base + pk * C));
+            }
         }
-        store8(out + off, o);
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const long long pk = p + k * stride;
+            if (pk >= P) break;
+            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+            const uint32_t rw[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(w[i]);
+                float o0 = silu_f(fmaf(f.x, A[2 * i], Bc[2 * i])), o1 = silu_f(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1]));
+                if (residual) {
+                    const float2 rr = unpack_bf16x2(rw[i]);
+                    o0 += rr.x;
+                    o1 += rr.y;
+                }
+                o[i] = pack_bf16x2(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(out + base + pk * C) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
-// Backward pass 1: per (b, c) sums over pixels of
-//   [0] dz, [1] dz*xhat, [2] du, [3] du*z    with z = xhat*gamma+beta, u = z*(sc+1)+sh, du = dout*silu'(u),
-//   dz = du*(sc+1).
+// Backward pass 1: per (b, c) sums over pixels of  [0] du, [1] du*xhat, [2] x
+//   with z = xhat*gamma+beta, u = z*(sc+1)+sh, du = dout*silu'(u).  Everything else the backward
+//   needs is algebra on these: dz = du*(sc+1), sum dz = (sc+1) T0, sum dz*xhat = (sc+1) T1,
+//   sum du*z = gamma T1 + beta T0.
 __global__ void __launch_bounds__(kNormThreads)
 gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ sums, const float* __restrict__ gamma,
@@ -135,49 +168,67 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     const float mean = sums[((size_t)b * G + g) * 2] / cnt;
     const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] / cnt - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
-    float ga[8], be[8], sc[8], sh[8];
+    float A[8], Bc[8];  // u = x*A + Bc
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = slot * 8 + i;
-        ga[i] = gamma[c];
-        be[i] = beta[c];
-        sc[i] = film ? film[(size_t)b * 2 * C + c] + 1.f : 1.f;
-        sh[i] = film ? film[(size_t)b * 2 * C + C + c] : 0.f;
+        float ga = gamma[c] * rstd, be = beta[c] - mean * rstd * gamma[c];
+        if (film) {
+            const float sc = film[(size_t)b * 2 * C + c] + 1.f, sh = film[(size_t)b * 2 * C + C + c];
+            ga *= sc;
+            be = be * sc + sh;
+        }
+        A[i] = ga;
+        Bc[i] = be;
     }
-    float acc[4][8];
+    float acc[3][8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-    const size_t base = (size_t)b * P * C;
-    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P;
-         p += (long long)gridDim.x * pix_per_iter) {
-        const size_t off = base + p * C + slot * 8;
-        Vec8 v = load8(x + off);
-        Vec8 d = load8(dout + off);
+    const size_t base = (size_t)b * P * C + slot * 8;
+    const long long stride = (long long)gridDim.x * pix_per_iter;
+    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
+        uint4 u[UNR], d[UNR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float xh = (v.v[i] - mean) * rstd;
-            const float z = xh * ga[i] + be[i];
-            const float u = z * sc[i] + sh[i];
-            const float du = d.v[i] * dsilu_f(u);
-            const float dz = du * sc[i];
-            acc[0][i] += dz;
-            acc[1][i] += dz * xh;
-            acc[2][i] += du;
-            acc[3][i] += du * z;
+        for (int k = 0; k < UNR; ++k) {
+            const long long pk = p + k * stride;
+            if (pk < P) {
+                u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + pk * C));
+                d[k] = __ldg(reinterpret_cast<const uint4*>(dout + base + pk * C));
+            } else {
+                u[k] = make_uint4(0, 0, 0, 0);
+                d[k] = make_uint4(0, 0, 0, 0);  // dout = 0 -> contributes nothing to T0/T1; x = 0 -> nothing to T2
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+            const uint32_t dw[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(w[i]), dd = unpack_bf16x2(dw[i]);
+                const float du0 = dd.x * dsilu_f(fmaf(f.x, A[2 * i], Bc[2 * i]));
+                const float du1 = dd.y * dsilu_f(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1]));
+                acc[0][2 * i] += du0;
+                acc[0][2 * i + 1] += du1;
+                acc[1][2 * i] = fmaf(du0, (f.x - mean) * rstd, acc[1][2 * i]);
+                acc[1][2 * i + 1] = fmaf(du1, (f.y - mean) * rstd, acc[1][2 * i + 1]);
+                acc[2][2 * i] += f.x;
+                acc[2][2 * i + 1] += f.y;
+            }
         }
     }
     // reduce threads that share a channel slot (stride vec_per_pix) through shared memory
     __shared__ float red[kNormThreads][9];
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 3; ++k) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[k][i];
         __syncthreads();
         for (int c = threadIdx.x; c < C; c += kNormThreads) {  // thread t sums channels t, t+256, ...
             float s = 0.f;
             for (int t = c >> 3; t < kNormThreads; t += vec_per_pix) s += red[t][c & 7];
-            atomicAdd(&csum[((size_t)b * C + c) * 4 + k], s);
+            atomicAdd(&csum[((size_t)b * C + c) * 3 + k], s);
         }
         __syncthreads();
     }
@@ -202,194 +253,245 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     const float rstd = rsqrtf(var + eps);
     float m1 = 0.f, m2 = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        m1 += gamma[c] * csum[((size_t)b * C + c) * 4 + 0];
-        m2 += gamma[c] * csum[((size_t)b * C + c) * 4 + 1];
+        const float sc = film ? film[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        m1 += gamma[c] * sc * csum[((size_t)b * C + c) * 3 + 0];
+        m2 += gamma[c] * sc * csum[((size_t)b * C + c) * 3 + 1];
     }
     m1 /= cnt;
     m2 /= cnt;
-    float ga[8], be[8], sc[8], sh[8];
+    // u = x*A + Bc ; dx = dout*silu'(u)*Gs - K0 - x*K1  with Gs = rstd*gamma*(sc+1), K1 = rstd^2*m2,
+    // K0 = rstd*m1 - mean*K1
+    float A[8], Bc[8], Gs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = slot * 8 + i;
-        ga[i] = gamma[c];
-        be[i] = beta[c];
-        sc[i] = film ? film[(size_t)b * 2 * C + c] + 1.f : 1.f;
-        sh[i] = film ? film[(size_t)b * 2 * C + C + c] : 0.f;
-    }
-    const size_t base = (size_t)b * P * C;
-    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P;
-         p += (long long)gridDim.x * pix_per_iter) {
-        const size_t off = base + p * C + slot * 8;
-        Vec8 v = load8(x + off);
-        Vec8 d = load8(dout + off);
-        Vec8 o;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float xh = (v.v[i] - mean) * rstd;
-            const float u = (xh * ga[i] + be[i]) * sc[i] + sh[i];
-            const float dz = d.v[i] * dsilu_f(u) * sc[i];
-            o.v[i] = rstd * (ga[i] * dz - m1 - xh * m2);
+        float ga = gamma[c] * rstd, be = beta[c] - mean * rstd * gamma[c];
+        float sc = 1.f;
+        if (film) {
+            sc = film[(size_t)b * 2 * C + c] + 1.f;
+            const float sh = film[(size_t)b * 2 * C + C + c];
+            ga *= sc;
+            be = be * sc + sh;
         }
-        store8(dx + off, o);
+        A[i] = ga;
+        Bc[i] = be;
+        Gs[i] = rstd * gamma[c] * sc;
+    }
+    const float K1 = rstd * rstd * m2, K0 = rstd * m1 - mean * K1;
+    const size_t base = (size_t)b * P * C + slot * 8;
+    const long long stride = (long long)gridDim.x * pix_per_iter;
+    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
+        uint4 u[UNR], d[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const long long pk = p + k * stride;
+            if (pk < P) {
+                u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + pk * C));
+                d[k] = __ldg(reinterpret_cast<const uint4*>(dout + base + pk * C));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const long long pk = p + k * stride;
+            if (pk >= P) break;
+            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+            const uint32_t dw[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(w[i]), dd = unpack_bf16x2(dw[i]);
+                const float o0 = dd.x * dsilu_f(fmaf(f.x, A[2 * i], Bc[2 * i])) * Gs[2 * i] - K0 - f.x * K1;
+                const float o1 = dd.y * dsilu_f(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1])) * Gs[2 * i + 1] - K0 - f.y * K1;
+                o[i] = pack_bf16x2(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(dx + base + pk * C) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
-// Parameter gradients from the per-(b,c) sums: dgamma[c] = sum_b S1, dbeta[c] = sum_b S0,
-// dfilm[b][c] = S3 (scale), dfilm[b][C+c] = S2 (shift).
-__global__ void gn_bwd_params_kernel(const float* __restrict__ csum, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, float* __restrict__ dfilm, int B, int C) {
+// Parameter gradients from the per-(b,c) sums T0 = sum du, T1 = sum du*xhat, T2 = sum x:
+//   dgamma[c] = sum_b (sc+1) T1,  dbeta[c] = sum_b (sc+1) T0,
+//   dfilm[b][c] (scale) = gamma T1 + beta T0,  dfilm[b][C+c] (shift) = T0,
+//   dcbias[c] = sum_b sum_p dx[b][p][c]  (the bias gradient of the convolution that produced x):
+//       sum_p dx = rstd*(gamma (sc+1) T0 - P m1) - rstd^2 m2 (T2 - P mean)
+__global__ void gn_bwd_params_kernel(const float* __restrict__ csum, const float* __restrict__ sums,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ film, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, float* __restrict__ dfilm,
+                                     float* __restrict__ dcbias, int B, long long P, int C, int G, float eps) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    float dg = 0.f, db = 0.f;
+    const int cpg = C / G, g = c / cpg;
+    const float cnt = (float)P * (float)cpg;
+    float dg = 0.f, db = 0.f, dcb = 0.f;
     for (int b = 0; b < B; ++b) {
-        const float* s = csum + ((size_t)b * C + c) * 4;
-        db += s[0];
-        dg += s[1];
+        const float* s = csum + ((size_t)b * C + c) * 3;
+        const float sc = film ? film[(size_t)b * 2 * C + c] + 1.f : 1.f;
+        db += sc * s[0];
+        dg += sc * s[1];
         if (dfilm) {
-            dfilm[(size_t)b * 2 * C + c] = s[3];
-            dfilm[(size_t)b * 2 * C + C + c] = s[2];
+            dfilm[(size_t)b * 2 * C + c] = gamma[c] * s[1] + beta[c] * s[0];
+            dfilm[(size_t)b * 2 * C + C + c] = s[0];
+        }
+        if (dcbias) {
+            const float mean = sums[((size_t)b * G + g) * 2] / cnt;
+            const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] / cnt - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + eps);
+            float m1 = 0.f, m2 = 0.f;
+            for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+                const float scc = film ? film[(size_t)b * 2 * C + cc] + 1.f : 1.f;
+                m1 += gamma[cc] * scc * csum[((size_t)b * C + cc) * 3 + 0];
+                m2 += gamma[cc] * scc * csum[((size_t)b * C + cc) * 3 + 1];
+            }
+            m1 /= cnt;
+            m2 /= cnt;
+            dcb += rstd * (gamma[c] * sc * s[0] - (float)P * m1) - rstd * rstd * m2 * (s[2] - (float)P * mean);
         }
     }
     dgamma[c] = dg;
     dbeta[c] = db;
+    if (dcbias) dcbias[c] = dcb;
 }
 
 // ------------------------------------------------------------------------------------------------
-// channel LayerNorm: one warp per pixel row of C channels (C <= 512, C % 64 == 0)
+// channel LayerNorm (gain only).  LPR lanes share one pixel row (LPR = min(32, C/8)), so a warp
+// normalises 32/LPR rows at once and no lane idles at C = 64 / 128; lanes own 8 channels per
+// 8*LPR-channel slab (NV slabs for C > 256).
 // ------------------------------------------------------------------------------------------------
-// Each lane owns channels {lane*8 .. lane*8+7} + 256*j for j < NV (NV = ceil(C/256)); lanes whose
-// vector starts beyond C are idle for that j.
-template <int NV>
+template <int LPR>
+__device__ __forceinline__ float sub_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int LPR, int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out,
               long long M, int C, float eps) {
-    const int lane = threadIdx.x & 31;
-    const long long row0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    for (long long row = row0; row < M; row += (long long)gridDim.x * 8) {
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sl = lane % LPR;
+    const long long rows_per_blk = 8 * RPW;
+    float gm[NV][8];
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gm[j][i] = gamma[j * 8 * LPR + sl * 8 + i];
+    const float invC = 1.f / C;
+    for (long long row0 = (long long)blockIdx.x * rows_per_blk; row0 < M; row0 += (long long)gridDim.x * rows_per_blk) {
+        const long long row = row0 + (threadIdx.x >> 5) * RPW + lane / LPR;
+        const bool valid = row < M;
+        const long long rr = valid ? row : 0;
         Vec8 v[NV];
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int c = j * 256 + lane * 8;
-            if (c < C) {
-                v[j] = load8(x + row * C + c);
+            v[j] = load8(x + rr * C + j * 8 * LPR + sl * 8);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s += v[j].v[i];
-            }
+            for (int i = 0; i < 8; ++i) s += v[j].v[i];
         }
-        const float mean = warp_sum(s) / C;
+        const float mean = sub_sum<LPR>(s) * invC;
         float q = 0.f;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c = j * 256 + lane * 8;
-            if (c < C) {
+        for (int j = 0; j < NV; ++j)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float d = v[j].v[i] - mean;
-                    q += d * d;
-                }
+            for (int i = 0; i < 8; ++i) {
+                const float d = v[j].v[i] - mean;
+                q = fmaf(d, d, q);
             }
-        }
-        const float rstd = rsqrtf(warp_sum(q) / C + eps);
+        const float rstd = rsqrtf(sub_sum<LPR>(q) * invC + eps);
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c = j * 256 + lane * 8;
-            if (c < C) {
+            for (int j = 0; j < NV; ++j) {
                 Vec8 o;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o.v[i] = (v[j].v[i] - mean) * rstd * gamma[c + i];
-                store8(out + row * C + c, o);
+                for (int i = 0; i < 8; ++i) o.v[i] = (v[j].v[i] - mean) * rstd * gm[j][i];
+                store8(out + row * C + j * 8 * LPR + sl * 8, o);
             }
         }
     }
 }
 
 // dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (+ dres), g = dy*gamma; dgamma[c] += sum_rows dy*xhat
-template <int NV>
+template <int LPR, int NV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, long long M, int C, float eps) {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    float dg[NV][8];
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sl = lane % LPR;
+    const long long rows_per_blk = 8 * RPW;
+    float gm[NV][8], dg[NV][8];
 #pragma unroll
     for (int j = 0; j < NV; ++j)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dg[j][i] = 0.f;
-    for (long long row = (long long)blockIdx.x * 8 + warp; row < M; row += (long long)gridDim.x * 8) {
-        Vec8 v[NV], d[NV];
+        for (int i = 0; i < 8; ++i) {
+            gm[j][i] = gamma[j * 8 * LPR + sl * 8 + i];
+            dg[j][i] = 0.f;
+        }
+    const float invC = 1.f / C;
+    for (long long row0 = (long long)blockIdx.x * rows_per_blk; row0 < M; row0 += (long long)gridDim.x * rows_per_blk) {
+        const long long row = row0 + (threadIdx.x >> 5) * RPW + lane / LPR;
+        const bool valid = row < M;
+        const long long rr = valid ? row : 0;
+        Vec8 v[NV], d[NV], r[NV];
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int c = j * 256 + lane * 8;
-            if (c < C) {
-                v[j] = load8(x + row * C + c);
-                d[j] = load8(dy + row * C + c);
+            const size_t off = rr * C + j * 8 * LPR + sl * 8;
+            v[j] = load8(x + off);
+            d[j] = load8(dy + off);
+            if (dres) r[j] = load8(dres + off);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s += v[j].v[i];
-            }
+            for (int i = 0; i < 8; ++i) s += v[j].v[i];
         }
-        const float mean = warp_sum(s) / C;
+        const float mean = sub_sum<LPR>(s) * invC;
         float q = 0.f;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c = j * 256 + lane * 8;
-            if (c < C) {
+        for (int j = 0; j < NV; ++j)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float t = v[j].v[i] - mean;
-                    q += t * t;
-                }
+            for (int i = 0; i < 8; ++i) {
+                const float t = v[j].v[i] - mean;
+                q = fmaf(t, t, q);
             }
-        }
-        const float rstd = rsqrtf(warp_sum(q) / C + eps);
+        const float rstd = rsqrtf(sub_sum<LPR>(q) * invC + eps);
         float sg = 0.f, sgx = 0.f;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c = j * 256 + lane * 8;
-            if (c < C) {
+        for (int j = 0; j < NV; ++j)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float xh = (v[j].v[i] - mean) * rstd;
-                    const float g = d[j].v[i] * gamma[c + i];
-                    dg[j][i] += d[j].v[i] * xh;
-                    sg += g;
-                    sgx += g * xh;
-                }
+            for (int i = 0; i < 8; ++i) {
+                const float xh = (v[j].v[i] - mean) * rstd;
+                const float g = d[j].v[i] * gm[j][i];
+                if (valid) dg[j][i] = fmaf(d[j].v[i], xh, dg[j][i]);
+                v[j].v[i] = xh;
+                sg += g;
+                sgx = fmaf(g, xh, sgx);
             }
-        }
-        const float mg = warp_sum(sg) / C, mgx = warp_sum(sgx) / C;
+        const float mg = sub_sum<LPR>(sg) * invC, mgx = sub_sum<LPR>(sgx) * invC;
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int c = j * 256 + lane * 8;
-            if (c < C) {
+            for (int j = 0; j < NV; ++j) {
                 Vec8 o;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float xh = (v[j].v[i] - mean) * rstd;
-                    o.v[i] = rstd * (d[j].v[i] * gamma[c + i] - mg - xh * mgx);
+                    o.v[i] = rstd * (d[j].v[i] * gm[j][i] - mg - v[j].v[i] * mgx);
+                    if (dres) o.v[i] += r[j].v[i];
                 }
-                if (dres) {
-                    Vec8 r = load8(dres + row * C + c);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o.v[i] += r.v[i];
-                }
-                store8(dx + row * C + c, o);
+                store8(dx + row * C + j * 8 * LPR + sl * 8, o);
             }
         }
     }
-    // block-level reduction of dgamma: 8 warps -> shared -> one atomic per channel per block
-    __shared__ float sh[8][NV * 256];
+    // block-level reduction of dgamma: threads with equal (lane % LPR) own the same channels
+    __shared__ float sh[256][NV * 8 + 1];
 #pragma unroll
     for (int j = 0; j < NV; ++j)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sh[warp][j * 256 + lane * 8 + i] = dg[j][i];
+        for (int i = 0; i < 8; ++i) sh[threadIdx.x][j * 8 + i] = dg[j][i];
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
+        const int j = c / (8 * LPR), l = (c >> 3) % LPR, i = c & 7;
         float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += sh[w][c];
+        for (int t = l; t < 256; t += LPR) s += sh[t][j * 8 + i];
         atomicAdd(&dgamma[c], s);
     }
 }
@@ -414,7 +516,7 @@ using namespace cesm;
 extern "C" int cesm_gn_stats(const void* x, float* sums, int B, long long P, int C, int G, void* stream) {
     GN_CHECK(C, G);
     CESM_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * B * G, as_stream(stream)));
-    const int per_block = kNormThreads / (C / 8) * 8;
+    const int per_block = kNormThreads / (C / 8) * UNR;
     dim3 grid(norm_grid(P, per_block), B);
     gn_stats_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, sums, P, C, G);
     CESM_CHECK_LAUNCH();
@@ -425,7 +527,7 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
                                  const float* film, const void* residual, void* out, int B, long long P, int C,
                                  int G, float eps, void* stream) {
     GN_CHECK(C, G);
-    const int per_block = kNormThreads / (C / 8) * 4;
+    const int per_block = kNormThreads / (C / 8) * UNR;
     dim3 grid(norm_grid(P, per_block), B);
     gn_apply_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)x, sums, gamma, beta, film, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, P, C, G,
@@ -435,13 +537,13 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
 }
 
 extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, const float* gamma, const float* beta,
-                           const float* film, float* csum /* [B][C][4] scratch */, void* dx, float* dgamma,
-                           float* dbeta, float* dfilm /* [B][2C] or NULL */, int B, long long P, int C, int G,
-                           float eps, void* stream) {
+                           const float* film, float* csum /* [B][C][3] scratch */, void* dx, float* dgamma,
+                           float* dbeta, float* dfilm /* [B][2C] or NULL */, float* dconv_bias /* [C] or NULL */,
+                           int B, long long P, int C, int G, float eps, void* stream) {
     GN_CHECK(C, G);
     cudaStream_t st = as_stream(stream);
-    CESM_CHECK_CUDA(cudaMemsetAsync(csum, 0, sizeof(float) * 4 * B * C, st));
-    const int per_block = kNormThreads / (C / 8) * 8;
+    CESM_CHECK_CUDA(cudaMemsetAsync(csum, 0, sizeof(float) * 3 * B * C, st));
+    const int per_block = kNormThreads / (C / 8) * UNR;
     dim3 grid(norm_grid(P, per_block), B);
     gn_bwd_reduce_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
@@ -449,36 +551,56 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     gn_bwd_apply_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
                                                        beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps);
     CESM_CHECK_LAUNCH();
-    gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, dgamma, dbeta, dfilm, B, C);
+    gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, sums, gamma, beta, film, dgamma, dbeta, dfilm,
+                                                           dconv_bias, B, P, C, G, eps);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
-#define LN_DISPATCH(KERNEL, ...)                                                  \
-    do {                                                                          \
-        const int nv = ceil_div(C, 256);                                          \
-        if (nv == 1) KERNEL<1><<<grid, 256, 0, st>>>(__VA_ARGS__);                \
-        else if (nv == 2) KERNEL<2><<<grid, 256, 0, st>>>(__VA_ARGS__);           \
-        else KERNEL<4><<<grid, 256, 0, st>>>(__VA_ARGS__);                        \
+template <int LPR, int NV>
+static void ln_launch_fwd(int grid, cudaStream_t st, const void* x, const float* gamma, void* out, long long M, int C,
+                          float eps) {
+    ln_fwd_kernel<LPR, NV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, (__nv_bfloat16*)out, M, C, eps);
+}
+template <int LPR, int NV>
+static void ln_launch_bwd(int grid, cudaStream_t st, const void* x, const float* gamma, const void* dy,
+                          const void* dres, void* dx, float* dgamma, long long M, int C, float eps) {
+    ln_bwd_kernel<LPR, NV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, (const __nv_bfloat16*)dy,
+                                                 (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, M, C, eps);
+}
+// C in {64, 128, 256, 512, 1024}: LPR = min(32, C/8), NV = C / (8*LPR)
+#define LN_DISPATCH(FN, ...)                                   \
+    do {                                                       \
+        switch (C) {                                           \
+            case 64: FN<8, 1>(__VA_ARGS__); break;             \
+            case 128: FN<16, 1>(__VA_ARGS__); break;           \
+            case 256: FN<32, 1>(__VA_ARGS__); break;           \
+            case 512: FN<32, 2>(__VA_ARGS__); break;           \
+            default: FN<32, 4>(__VA_ARGS__); break;            \
+        }                                                      \
     } while (0)
+#define LN_CHECK(C) \
+    CESM_REQUIRE((C) == 64 || (C) == 128 || (C) == 256 || (C) == 512 || (C) == 1024, \
+                 "LayerNorm supports C in {64,128,256,512,1024} (C=%d)", (C))
 
 extern "C" int cesm_ln_fwd(const void* x, const float* gamma, void* out, long long M, int C, float eps, void* stream) {
-    CESM_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "LayerNorm needs C %% 8 == 0 and C <= 1024 (C=%d)", C);
+    LN_CHECK(C);
     cudaStream_t st = as_stream(stream);
-    const int grid = norm_grid(M, 8 * 4);
-    LN_DISPATCH(ln_fwd_kernel, (const __nv_bfloat16*)x, gamma, (__nv_bfloat16*)out, M, C, eps);
+    const int lpr = C / 8 < 32 ? C / 8 : 32;
+    const int grid = norm_grid(M, 8 * (32 / lpr) * 2);
+    LN_DISPATCH(ln_launch_fwd, grid, st, x, gamma, out, M, C, eps);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
 extern "C" int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, const void* dres, void* dx,
                            float* dgamma, long long M, int C, float eps, void* stream) {
-    CESM_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1024, "LayerNorm needs C %% 8 == 0 and C <= 1024 (C=%d)", C);
+    LN_CHECK(C);
     cudaStream_t st = as_stream(stream);
     CESM_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st));
-    const int grid = norm_grid(M, 8 * 8);
-    LN_DISPATCH(ln_bwd_kernel, (const __nv_bfloat16*)x, gamma, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dres,
-                (__nv_bfloat16*)dx, dgamma, M, C, eps);
+    const int lpr = C / 8 < 32 ? C / 8 : 32;
+    const int grid = norm_grid(M, 8 * (32 / lpr) * 4);
+    LN_DISPATCH(ln_launch_bwd, grid, st, x, gamma, dy, dres, dx, dgamma, M, C, eps);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

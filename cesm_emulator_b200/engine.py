@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import kernels as K
+from . import ops
 
 
 def _ready_order(named_params):
@@ -58,7 +59,7 @@ class GradBuckets:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             b = len(self.bounds) - 1
-            self._bucket_of[id(p)] = b
+            self._bucket_of[p.data_ptr()] = b
             if len(self._pending_init) <= b:
                 self._pending_init.append(0)
             self._pending_init[b] += 1
@@ -73,13 +74,23 @@ class GradBuckets:
         if self.world > 1:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._owned = {p.data_ptr() for p in self.params}
+        ops.set_grad_sink(self)  # weight gradients are accumulated straight into the flat buffer
+
+    # grad-sink protocol (ops._wgrad_to_param)
+    def owns(self, p) -> bool:
+        return p.data_ptr() in self._owned
+
+    def ready(self, p) -> None:
+        if self.world > 1:
+            self._on_grad(p)
 
     def begin_step(self):
         self.flat.zero_()
         self._pending = list(self._pending_init)
 
     def _on_grad(self, p):
-        b = self._bucket_of[id(p)]
+        b = self._bucket_of[p.data_ptr()]
         self._pending[b] -= 1
         if self._pending[b] == 0:
             cur = torch.cuda.current_stream()
@@ -129,6 +140,8 @@ class TrainEngine:
 
     # the captured region ----------------------------------------------------------------------
     def _step_body(self):
+        ops.set_grad_sink(self.buckets)
+        ops.prepack_all()  # one kernel refreshes every bf16 operand copy of the (just updated) weights
         self.buckets.begin_step()
         loss = self.diffusion.loss(self.x0, self.cond)
         (loss / self.world if self.world > 1 else loss).backward()

@@ -166,7 +166,7 @@ def gn_stats(x: torch.Tensor, B: int, G: int) -> torch.Tensor:
     C = x.shape[-1]
     P = x.numel() // (B * C)
     sums = torch.empty((B, G, 2), dtype=torch.float32, device=x.device)
-    _lib.call("cesm_gn_stats", _ptr(x), _ptr(sums), B, P, C, G, _stream())
+    _lib.call("cesm_gn_stats", _ptr(x), _ptr(sums), B, P, C, G, _stream(), _meta=_bytes_meta(x))
     return sums
 
 
@@ -176,22 +176,29 @@ def gn_apply_fwd(x, sums, gamma, beta, film, residual, B: int, G: int, eps: floa
     P = x.numel() // (B * C)
     out = torch.empty_like(x)
     _lib.call("cesm_gn_apply_fwd", _ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(film), _ptr(residual), _ptr(out),
-              B, P, C, G, eps, _stream())
+              B, P, C, G, eps, _stream(), _meta=_bytes_meta(x, residual, out))
     return out
 
 
-def gn_bwd(x, dout, sums, gamma, beta, film, B: int, G: int, eps: float):
+def gn_bwd(x, dout, sums, gamma, beta, film, B: int, G: int, eps: float, conv_bias_grad: bool = False):
+    """-> (dx, dgamma, dbeta, dfilm or None[, dconv_bias]).  `dconv_bias` is sum_pixels dx per
+    channel, i.e. the bias gradient of the convolution that produced x, obtained from the same
+    per-channel sums (no extra pass over dx)."""
     _req_cuda(x, dout, sums, gamma, beta, film)
     C = x.shape[-1]
     P = x.numel() // (B * C)
     dev = x.device
-    csum = torch.empty((B, C, 4), dtype=torch.float32, device=dev)
+    csum = torch.empty((B, C, 3), dtype=torch.float32, device=dev)
     dx = torch.empty_like(x)
     dgamma = torch.empty(C, dtype=torch.float32, device=dev)
     dbeta = torch.empty(C, dtype=torch.float32, device=dev)
     dfilm = torch.empty((B, 2 * C), dtype=torch.float32, device=dev) if film is not None else None
+    dcb = torch.empty(C, dtype=torch.float32, device=dev) if conv_bias_grad else None
     _lib.call("cesm_gn_bwd", _ptr(x), _ptr(dout), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(film), _ptr(csum), _ptr(dx),
-              _ptr(dgamma), _ptr(dbeta), _ptr(dfilm), B, P, C, G, eps, _stream())
+              _ptr(dgamma), _ptr(dbeta), _ptr(dfilm), _ptr(dcb), B, P, C, G, eps, _stream(),
+              _meta=_bytes_meta(x, dout, x, dout, dx))
+    if conv_bias_grad:
+        return dx, dgamma, dbeta, dfilm, dcb
     return dx, dgamma, dbeta, dfilm
 
 
@@ -199,7 +206,8 @@ def ln_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
     _req_cuda(x, gamma)
     C = x.shape[-1]
     out = torch.empty_like(x)
-    _lib.call("cesm_ln_fwd", _ptr(x), _ptr(gamma), _ptr(out), x.numel() // C, C, eps, _stream())
+    _lib.call("cesm_ln_fwd", _ptr(x), _ptr(gamma), _ptr(out), x.numel() // C, C, eps, _stream(),
+              _meta=_bytes_meta(x, out))
     return out
 
 
@@ -209,7 +217,7 @@ def ln_bwd(x, gamma, dy, dres, eps: float):
     dx = torch.empty_like(x)
     dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
     _lib.call("cesm_ln_bwd", _ptr(x), _ptr(gamma), _ptr(dy), _ptr(dres), _ptr(dx), _ptr(dgamma), x.numel() // C, C, eps,
-              _stream())
+              _stream(), _meta=_bytes_meta(x, dy, dres, dx))
     return dx, dgamma
 
 

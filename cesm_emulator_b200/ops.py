@@ -1,15 +1,26 @@
-"""torch.autograd.Function wrappers: one per fused CUDA op, forward and backward both in the C ABI.
+"""torch.autograd.Function wrappers: forward and backward both run in the C ABI kernels.
 
 Internal activation layout is channels-last bf16 `[N, H, W, C]` with N = batch*frames (the
 reference's NCDHW tensors, permuted once at the network boundary).  Parameters stay fp32 in the
-reference's layouts; bf16 GEMM operands are re-packed from them on the fly.
+reference's layouts; the bf16 GEMM operand copies (forward layout and data-gradient layout) live in
+a registry (`PackCache`) and are refreshed by ONE batched kernel per optimizer step.
+
+Two granularities are offered:
+  * block level (`ResnetBlockFn`, `TemporalAttnBlockFn`, `SpatialAttnBlockFn`): one autograd node
+    per reference block (video_net.py ResnetBlock / Residual(PreNorm(attention))), with a
+    hand-ordered backward in which residual-gradient adds live in GEMM / LayerNorm epilogues and
+    conv-bias gradients come out of the GroupNorm backward's per-channel sums.  `UNetModel3D` uses these.
+  * op level (`ConvFn`, `GroupNormSiLUFn`, `LayerNormFn`, ... ): the same kernels one at a time,
+    used by the reference-style stand-alone module calls (Block(x), LayerNorm(x), ...).
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+import weakref
+from typing import Optional, Tuple
 
 import torch
 
+from . import _lib
 from . import kernels as K
 
 BF16 = torch.bfloat16
@@ -31,8 +42,11 @@ def _phase(ph: int, pw: int):
     return taps, koff
 
 
-# Fused / capturable optimizers update parameters without bumping `Tensor._version`, so the
-# packed-operand caches are also keyed on a global epoch that every torch optimizer step advances.
+# ------------------------------------------------------------------------------------------------
+# packed bf16 operand copies of the fp32 parameters
+# ------------------------------------------------------------------------------------------------
+# Fused / capturable optimizers update parameters without bumping `Tensor._version`, so validity is
+# also keyed on a global epoch that every torch optimizer step advances.
 _WEIGHT_EPOCH = [0]
 
 
@@ -48,37 +62,148 @@ except Exception:  # pragma: no cover - very old torch
     pass
 
 
+class _PackEntry:
+    __slots__ = ("wref", "src_off", "O", "T", "I", "so", "si", "taps", "out", "key", "serial")
+
+
+_ENTRIES: list = []          # every packed copy ever requested (weak refs to the parameters)
+_PLAN = {"n": -1, "ptrs": None, "descs": None}
+_PREPACK_SERIAL = [0]        # bumped by prepack_all(); entries packed in the current step carry it
+
+
+def _key(weight: torch.Tensor):
+    return (weight.data_ptr(), weight._version, _WEIGHT_EPOCH[0])
+
+
 class PackCache:
-    """bf16 GEMM-operand copies of one layer's fp32 parameter, keyed by layout tag and re-made
-    when the parameter changes (optimizer step bumps `_version`).  While a CUDA graph of a TRAINING
-    step is being captured a trainable parameter is always re-packed, so that the pack kernel is
-    part of the graph and replays see the current weights; a no-grad (sampling) capture uses the
-    cached copy, which stays valid as long as the weights are not modified."""
+    """Per-layer view of the packed-operand registry: `get(weight, tag, spec)` returns the bf16 copy
+    `dst[o][t][i] = weight.flatten()[src_off + o*so + i*si + taps[t]]`, re-packing it (in place, so
+    the address is stable for CUDA graphs) when the parameter changed.  While a training step is
+    being captured, a copy that was not refreshed by `prepack_all()` in this step is always
+    re-packed so that the pack is part of the graph."""
 
     def __init__(self):
         self._d = {}
 
-    @staticmethod
-    def must_repack(weight: torch.Tensor) -> bool:
-        """True in the forward of a training step that is being graph-captured."""
-        return weight.requires_grad and torch.is_grad_enabled() and torch.cuda.is_current_stream_capturing()
-
-    def get(self, weight: torch.Tensor, tag, make, force: bool = False):
-        key = (weight.data_ptr(), weight._version, _WEIGHT_EPOCH[0])
-        if not force:
-            hit = self._d.get(tag)
-            if hit is not None and hit[0] == key:
-                return hit[1]
-        val = make()
-        self._d[tag] = (key, val)
-        return val
+    def get(self, weight: torch.Tensor, tag, spec, train: bool = False) -> torch.Tensor:
+        """`train`: the caller is the forward of a step that will be back-propagated (inside an
+        autograd.Function grad mode is always off, so the caller passes any(ctx.needs_input_grad))."""
+        ent = self._d.get(tag)
+        if ent is None or ent.wref() is not weight:
+            ent = _PackEntry()
+            ent.wref = weakref.ref(weight)
+            ent.src_off, ent.O, ent.T, ent.I, ent.so, ent.si, ent.taps = spec
+            ent.out = torch.empty((ent.O, ent.T * ent.I), dtype=BF16, device=weight.device)
+            ent.key, ent.serial = None, -1
+            self._d[tag] = ent
+            _ENTRIES.append(ent)
+        key = _key(weight)
+        force = (train and weight.is_cuda and torch.cuda.is_current_stream_capturing()
+                 and ent.serial != _PREPACK_SERIAL[0])
+        if force or ent.key != key:
+            src = weight.detach().reshape(-1)
+            if ent.src_off:
+                src = src[ent.src_off:]
+            K.pack_weight(src, ent.O, ent.T, ent.I, ent.so, ent.si, ent.taps, out=ent.out)
+            ent.key, ent.serial = key, _PREPACK_SERIAL[0]
+        return ent.out
 
     def __deepcopy__(self, memo):
         return PackCache()
 
 
+def prepack_all() -> int:
+    """Refresh every registered packed copy with one kernel launch (the training engine calls this
+    at the top of each step, after the optimizer changed the weights).  Returns the entry count."""
+    live = [e for e in _ENTRIES if e.wref() is not None]
+    if len(live) != len(_ENTRIES):
+        _ENTRIES[:] = live
+    if not live:
+        return 0
+    ptrs = tuple((e.wref().data_ptr(), e.out.data_ptr()) for e in live)
+    if _PLAN["n"] != len(live) or _PLAN["ptrs"] != ptrs:
+        arr = (_lib.PackDesc * len(live))()
+        for d, e in zip(arr, live):
+            d.src = e.wref().data_ptr() + 4 * e.src_off
+            d.dst = e.out.data_ptr()
+            d.O, d.T, d.I, d.so, d.si = e.O, e.T, e.I, e.so, e.si
+            for i, o in enumerate(e.taps):
+                d.tap_off[i] = int(o)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        _PLAN.update(n=len(live), ptrs=ptrs, descs=host.to(live[0].out.device))
+    _PREPACK_SERIAL[0] += 1
+    _lib.call("cesm_pack_weights_batched", _PLAN["descs"].data_ptr(), len(live), K._stream())
+    for e in live:
+        e.key, e.serial = _key(e.wref()), _PREPACK_SERIAL[0]
+    return len(live)
+
+
 # ------------------------------------------------------------------------------------------------
-# convolutions / linears on the tcgen05 implicit GEMM
+# gradient delivery
+# ------------------------------------------------------------------------------------------------
+# The training engine pre-allocates every parameter gradient as a view into one flat buffer and
+# registers itself here; weight gradients are then accumulated straight into those views by the
+# un-packing kernel (no temporary, no autograd add) and the sink is told the parameter is ready.
+_GRAD_SINK = [None]
+
+
+def set_grad_sink(sink) -> None:
+    _GRAD_SINK[0] = sink
+
+
+def _direct(weight: torch.Tensor) -> bool:
+    sink = _GRAD_SINK[0]
+    return sink is not None and weight.grad is not None and sink.owns(weight)
+
+
+def _wgrad_to_param(weight, g, O, T, I, so, si, taps, last: bool = True, into: Optional[torch.Tensor] = None):
+    """g: fp32 [O, T, I] from cesm_wgrad -> gradient in `weight`'s own layout.  Returns None when it
+    was accumulated directly into weight.grad (engine mode), else a tensor (`into` if given)."""
+    if _direct(weight):
+        K.unpack_wgrad(g, weight.grad.view(-1), O, T, I, so, si, taps, accumulate=True)
+        if last:
+            _GRAD_SINK[0].ready(weight)
+        return None
+    dwt = torch.empty_like(weight) if into is None else into
+    K.unpack_wgrad(g, dwt.view(-1), O, T, I, so, si, taps)
+    return dwt
+
+
+# ------------------------------------------------------------------------------------------------
+# conv helpers shared by the op-level and block-level functions
+# ------------------------------------------------------------------------------------------------
+def _sq_taps(ks: int):
+    r = ks // 2
+    return [(kh - r, kw - r) for kh in range(ks) for kw in range(ks)]
+
+
+def _conv_fwd_weight(cache: PackCache, weight, cout: int, ctot: int, ks: int, train: bool):
+    kk = ks * ks
+    return cache.get(weight, "fwd", (0, cout, kk, ctot, ctot * kk, kk, list(range(kk))), train)
+
+
+def _conv_dgrad_weights(cache: PackCache, weight, cout: int, c0: int, c1: int, ks: int, train: bool):
+    """Data-gradient operands [ci][t][co] = W[co, ci, t] for each concatenated source (only made
+    for a step that will be back-propagated)."""
+    if not train:
+        return None, None
+    kk, ctot = ks * ks, c0 + c1
+    w0 = cache.get(weight, "dgrad0", (0, c0, kk, cout, kk, ctot * kk, list(range(kk))), train)
+    w1 = (cache.get(weight, "dgrad1", (c0 * kk, c1, kk, cout, kk, ctot * kk, list(range(kk))), train)
+          if c1 else None)
+    return w0, w1
+
+
+def _conv_wgrad(weight, x0, x1, dy, ks: int):
+    cout = weight.shape[0]
+    ctot = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
+    kk = ks * ks
+    g = K.wgrad(x0, dy, x1=x1, taps=_sq_taps(ks))  # [cout, kk, ctot]
+    return _wgrad_to_param(weight, g, cout, kk, ctot, ctot * kk, kk, list(range(kk)))
+
+
+# ------------------------------------------------------------------------------------------------
+# op-level: convolutions / linears on the tcgen05 implicit GEMM
 # ------------------------------------------------------------------------------------------------
 class ConvFn(torch.autograd.Function):
     """Stride-1 conv with a square k x k kernel (k in {1, 3}) or a linear layer, over one or two
@@ -94,43 +219,27 @@ class ConvFn(torch.autograd.Function):
         cout = weight.shape[0]
         c0 = x0.shape[-1]
         c1 = 0 if x1 is None else x1.shape[-1]
-        kk = ksize * ksize
-        assert weight.numel() == cout * (c0 + c1) * kk, (weight.shape, c0, c1, ksize)
-        r = ksize // 2
-        taps = [(kh - r, kw - r) for kh in range(ksize) for kw in range(ksize)]
-        ctx.force = PackCache.must_repack(weight)
-        wt = cache.get(weight, "fwd",
-                       lambda: K.pack_weight(weight, cout, kk, c0 + c1, (c0 + c1) * kk, kk, list(range(kk))), ctx.force)
-        y = K.igemm(x0, wt, a1=x1, taps=taps, bias=bias, residual=residual)
+        assert weight.numel() == cout * (c0 + c1) * ksize * ksize, (weight.shape, c0, c1, ksize)
+        train = any(ctx.needs_input_grad)
+        wt = _conv_fwd_weight(cache, weight, cout, c0 + c1, ksize, train)
+        ctx.wd = _conv_dgrad_weights(cache, weight, cout, c0, c1, ksize, train)
+        y = K.igemm(x0, wt, a1=x1, taps=_sq_taps(ksize), bias=bias, residual=residual)
         ctx.save_for_backward(x0, x1, weight)
         ctx.ksize, ctx.has_bias, ctx.has_res = ksize, bias is not None, residual is not None
-        ctx.taps, ctx.cache = taps, cache
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x0, x1, weight = ctx.saved_tensors
         dy = dy.contiguous()
-        cout = weight.shape[0]
-        c0 = x0.shape[-1]
-        c1 = 0 if x1 is None else x1.shape[-1]
-        ctot, kk = c0 + c1, ctx.ksize * ctx.ksize
-        ntaps = [(-dh, -dw) for dh, dw in ctx.taps]
+        ntaps = [(-dh, -dw) for dh, dw in _sq_taps(ctx.ksize)]
         dx0 = dx1 = dwt = db = None
-        wflat = weight.reshape(-1)
         if ctx.needs_input_grad[0]:
-            wd = ctx.cache.get(weight, "dgrad0",
-                               lambda: K.pack_weight(wflat, c0, kk, cout, kk, ctot * kk, list(range(kk))), ctx.force)
-            dx0 = K.igemm(dy, wd, taps=ntaps)
+            dx0 = K.igemm(dy, ctx.wd[0], taps=ntaps)
         if x1 is not None and ctx.needs_input_grad[1]:
-            wd = ctx.cache.get(weight, "dgrad1",
-                               lambda: K.pack_weight(wflat[c0 * kk:], c1, kk, cout, kk, ctot * kk, list(range(kk))),
-                               ctx.force)
-            dx1 = K.igemm(dy, wd, taps=ntaps)
+            dx1 = K.igemm(dy, ctx.wd[1], taps=ntaps)
         if ctx.needs_input_grad[2]:
-            g = K.wgrad(x0, dy, x1=x1, taps=ctx.taps)  # [cout, kk, ctot]
-            dwt = torch.empty_like(weight)
-            K.unpack_wgrad(g, dwt, cout, kk, ctot, ctot * kk, kk, list(range(kk)))
+            dwt = _conv_wgrad(weight, x0, x1, dy, ctx.ksize)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = K.colsum(dy)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
@@ -146,11 +255,13 @@ class DownsampleFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, cache: PackCache):
         x = x.contiguous()
         c = x.shape[-1]
-        ctx.force = PackCache.must_repack(weight)
-        wt = cache.get(weight, "fwd", lambda: K.pack_weight(weight, c, 16, c, c * 16, 16, list(range(16))), ctx.force)
+        train = any(ctx.needs_input_grad)
+        wt = cache.get(weight, "fwd", (0, c, 16, c, c * 16, 16, list(range(16))), train)
+        # data gradient: four sub-pixel phases, [ci][t][co] = W[co, ci, kh_t, kw_t]
+        ctx.wd = {(ph, pw): cache.get(weight, ("dgrad", ph, pw), (0, c, 4, c, 16, c * 16, _phase(ph, pw)[1]), train)
+                  for ph in (0, 1) for pw in (0, 1)} if train else None
         y = K.igemm(x, wt, taps=DownsampleFn.TAPS, stride=2, bias=bias)
         ctx.save_for_backward(x, weight)
-        ctx.cache = cache
         return y
 
     @staticmethod
@@ -161,17 +272,11 @@ class DownsampleFn(torch.autograd.Function):
         dx = dwt = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            for ph in (0, 1):
-                for pw in (0, 1):
-                    taps, koff = _phase(ph, pw)
-                    # [ci][t][co] = W[co, ci, kh_t, kw_t]
-                    wd = ctx.cache.get(weight, ("dgrad", ph, pw),
-                                       lambda: K.pack_weight(weight, c, 4, c, 16, c * 16, koff), ctx.force)
-                    K.igemm(dy, wd, taps=taps, out=dx, out_hw=(h // 2, w // 2), out_place=(2, 2, ph, pw))
+            for (ph, pw), wd in ctx.wd.items():
+                K.igemm(dy, wd, taps=_phase(ph, pw)[0], out=dx, out_hw=(h // 2, w // 2), out_place=(2, 2, ph, pw))
         if ctx.needs_input_grad[1]:
             g = K.wgrad(x, dy, taps=DownsampleFn.TAPS, stride=2)
-            dwt = torch.empty_like(weight)
-            K.unpack_wgrad(g, dwt, c, 16, c, c * 16, 16, list(range(16)))
+            dwt = _wgrad_to_param(weight, g, c, 16, c, c * 16, 16, list(range(16)))
         if ctx.needs_input_grad[2]:
             db = K.colsum(dy)
         return dx, dwt, db, None
@@ -185,16 +290,16 @@ class UpsampleFn(torch.autograd.Function):
         x = x.contiguous()
         n, h, w, c = x.shape
         out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
-        ctx.force = PackCache.must_repack(weight)
+        # [ci][t][co] = W[ci, co, kh, kw] for the data gradient (a stride-2 conv of dy)
+        train = any(ctx.needs_input_grad)
+        ctx.wd = cache.get(weight, "dgrad", (0, c, 16, c, c * 16, 16, list(range(16))), train) if train else None
         for ph in (0, 1):
             for pw in (0, 1):
                 taps, koff = _phase(ph, pw)
                 # [co][t][ci] = W[ci, co, kh_t, kw_t]
-                wt = cache.get(weight, ("fwd", ph, pw), lambda: K.pack_weight(weight, c, 4, c, 16, c * 16, koff),
-                               ctx.force)
+                wt = cache.get(weight, ("fwd", ph, pw), (0, c, 4, c, 16, c * 16, koff), train)
                 K.igemm(x, wt, taps=taps, out=out, out_hw=(h, w), out_place=(2, 2, ph, pw), bias=bias)
         ctx.save_for_backward(x, weight)
-        ctx.cache = cache
         return out
 
     @staticmethod
@@ -204,24 +309,20 @@ class UpsampleFn(torch.autograd.Function):
         n, h, w, c = x.shape
         dx = dwt = db = None
         if ctx.needs_input_grad[0]:
-            # [ci][t][co] = W[ci, co, kh, kw]
-            wd = ctx.cache.get(weight, "dgrad", lambda: K.pack_weight(weight, c, 16, c, c * 16, 16, list(range(16))),
-                               ctx.force)
-            dx = K.igemm(dy, wd, taps=DownsampleFn.TAPS, stride=2)
+            dx = K.igemm(dy, ctx.wd, taps=DownsampleFn.TAPS, stride=2)
         if ctx.needs_input_grad[1]:
-            dwt = torch.empty_like(weight)
-            for ph in (0, 1):
-                for pw in (0, 1):
-                    taps, koff = _phase(ph, pw)
-                    g = K.wgrad(x, dy, taps=taps, grid_hw=(h, w), dy_place=(2, 2, ph, pw))  # [co, 4, ci]
-                    K.unpack_wgrad(g, dwt, c, 4, c, 16, c * 16, koff)
+            into = None if _direct(weight) else torch.empty_like(weight)
+            for n_ph, (ph, pw) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
+                taps, koff = _phase(ph, pw)
+                g = K.wgrad(x, dy, taps=taps, grid_hw=(h, w), dy_place=(2, 2, ph, pw))  # [co, 4, ci]
+                dwt = _wgrad_to_param(weight, g, c, 4, c, 16, c * 16, koff, last=(n_ph == 3), into=into)
         if ctx.needs_input_grad[2]:
             db = K.colsum(dy)
         return dx, dwt, db, None
 
 
 # ------------------------------------------------------------------------------------------------
-# normalisation
+# op-level: normalisation
 # ------------------------------------------------------------------------------------------------
 class GroupNormSiLUFn(torch.autograd.Function):
     """GroupNorm -> optional FiLM (x*(scale+1)+shift) -> SiLU -> optional residual add
@@ -264,7 +365,7 @@ class LayerNormFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
-# attention cores
+# op-level: attention cores
 # ------------------------------------------------------------------------------------------------
 class TemporalAttnCoreFn(torch.autograd.Function):
     """q*scale, RoPE, q.k + bias, softmax over frames, .v (video_net.py:413-453).  qkv: [B*F*HW, 3*H*D]."""
@@ -327,6 +428,169 @@ class LinearAttnCoreFn(torch.autograd.Function):
         qkv, ws = ctx.saved_tensors
         NI, n, H, D, scale = ctx.dims
         return K.linattn_bwd(qkv, ws, dout.contiguous(), NI, n, H, D, scale), None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# block level
+# ------------------------------------------------------------------------------------------------
+class BlockMeta:
+    """Static configuration + pack caches of one block (kept on the nn.Module)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def __deepcopy__(self, memo):
+        return BlockMeta(**{k: (PackCache() if isinstance(v, PackCache) else v) for k, v in self.__dict__.items()})
+
+
+class ResnetBlockFn(torch.autograd.Function):
+    """video_net.py:254-265 as one node:  out = Block2(Block1(cat(x, x1); film)) + res(cat(x, x1)),
+    Block = conv(1,3,3) + bias -> GroupNorm -> FiLM -> SiLU, res = 1x1x1 conv or identity.
+
+    args: x, x1 (or None), film fp32 [B, 2C] (or None), w1, b1, g1w, g1b, w2, b2, g2w, g2b,
+          wres, bres (or None, None), B, meta(G, eps, c1, c2, cres: PackCache)."""
+
+    @staticmethod
+    def forward(ctx, x, x1, film, w1, b1, g1w, g1b, w2, b2, g2w, g2b, wres, bres, B, meta):
+        x, x1, film = x.contiguous(), _c(x1), _c(film)
+        G, eps = meta.G, meta.eps
+        c0 = x.shape[-1]
+        cx1 = 0 if x1 is None else x1.shape[-1]
+        cout = w1.shape[0]
+        train = any(ctx.needs_input_grad)
+        if wres is None:
+            res = x
+        else:
+            res = K.igemm(x, _conv_fwd_weight(meta.cres, wres, cout, c0 + cx1, 1, train), a1=x1, bias=bres)
+        y1 = K.igemm(x, _conv_fwd_weight(meta.c1, w1, cout, c0 + cx1, 3, train), a1=x1, taps=K.TAPS_3x3, bias=b1)
+        sums1 = K.gn_stats(y1, B, G)
+        h1 = K.gn_apply_fwd(y1, sums1, g1w, g1b, film, None, B, G, eps)
+        y2 = K.igemm(h1, _conv_fwd_weight(meta.c2, w2, cout, cout, 3, train), taps=K.TAPS_3x3, bias=b2)
+        sums2 = K.gn_stats(y2, B, G)
+        out = K.gn_apply_fwd(y2, sums2, g2w, g2b, None, res, B, G, eps)
+        ctx.wd1 = _conv_dgrad_weights(meta.c1, w1, cout, c0, cx1, 3, train)
+        ctx.wd2 = _conv_dgrad_weights(meta.c2, w2, cout, cout, 0, 3, train)
+        ctx.wdres = None if wres is None else _conv_dgrad_weights(meta.cres, wres, cout, c0, cx1, 1, train)
+        ctx.save_for_backward(x, x1, film, y1, sums1, h1, y2, sums2, w1, g1w, g1b, w2, g2w, g2b, wres)
+        ctx.cfg = (B, G, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, x1, film, y1, sums1, h1, y2, sums2, w1, g1w, g1b, w2, g2w, g2b, wres = ctx.saved_tensors
+        B, G, eps = ctx.cfg
+        dout = dout.contiguous()
+        ntaps = [(-dh, -dw) for dh, dw in K.TAPS_3x3]
+        # ---- block 2 ----
+        dy2, dg2w, dg2b, _, db2 = K.gn_bwd(y2, dout, sums2, g2w, g2b, None, B, G, eps, conv_bias_grad=True)
+        dw2 = _conv_wgrad(w2, h1, None, dy2, 3)
+        dh1 = K.igemm(dy2, ctx.wd2[0], taps=ntaps)
+        # ---- block 1 ----
+        dy1, dg1w, dg1b, dfilm, db1 = K.gn_bwd(y1, dh1, sums1, g1w, g1b, film, B, G, eps, conv_bias_grad=True)
+        dw1 = _conv_wgrad(w1, x, x1, dy1, 3)
+        # ---- inputs: conv-1 data gradient with the residual-branch gradient added in its epilogue ----
+        dx = dx1 = dwres = dbres = None
+        if wres is None:
+            if ctx.needs_input_grad[0]:
+                dx = K.igemm(dy1, ctx.wd1[0], taps=ntaps, residual=dout)
+        else:
+            if ctx.needs_input_grad[0]:
+                r0 = K.igemm(dout, ctx.wdres[0])
+                dx = K.igemm(dy1, ctx.wd1[0], taps=ntaps, residual=r0)
+            if x1 is not None and ctx.needs_input_grad[1]:
+                r1 = K.igemm(dout, ctx.wdres[1])
+                dx1 = K.igemm(dy1, ctx.wd1[1], taps=ntaps, residual=r1)
+            dwres = _conv_wgrad(wres, x, x1, dout, 1)
+            dbres = K.colsum(dout)
+        return dx, dx1, dfilm, dw1, db1, dg1w, dg1b, dw2, db2, dg2w, dg2b, dwres, dbres, None, None
+
+
+class TemporalAttnBlockFn(torch.autograd.Function):
+    """Residual(PreNorm(EinopsToAndFrom(Attention))) (video_net.py:69-98, 357-454) as one node:
+    y = to_out(attn(to_qkv(LN(x)))) + x.
+    args: x, gamma [1,C,1,1,1], wqkv, wout, pos_bias, cs, sn, B, F, meta(heads, dim_head, eps, cq, co)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, wqkv, wout, pos_bias, cs, sn, B, F, meta):
+        x = x.contiguous()
+        NI, H_, W_, C = x.shape
+        heads, D, eps = meta.heads, meta.dim_head, meta.eps
+        hidden = heads * D
+        g = gamma.reshape(-1)
+        pos_bias = pos_bias.contiguous().float()
+        train = any(ctx.needs_input_grad)
+        xn = K.ln_fwd(x, g, eps)
+        qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
+        o, lse = K.tattn_fwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
+        y = K.igemm(o.view(NI, H_, W_, hidden), _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), residual=x)
+        ctx.wdq = _conv_dgrad_weights(meta.cq, wqkv, 3 * hidden, C, 0, 1, train)[0]
+        ctx.wdo = _conv_dgrad_weights(meta.co, wout, C, hidden, 0, 1, train)[0]
+        if F <= 4:
+            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout)
+        else:
+            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, lse)
+        ctx.cfg, ctx.gshape = (B, F, heads, D, eps), gamma.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout = saved[:10]
+        lse = saved[10] if len(saved) > 10 else None
+        B, F, heads, D, eps = ctx.cfg
+        hidden = heads * D
+        NI, H_, W_, C = x.shape
+        dy = dy.contiguous()
+        do = K.igemm(dy, ctx.wdo)
+        dwout = _conv_wgrad(wout, o.view(NI, H_, W_, hidden), None, dy, 1)
+        dqkv, dbias = K.tattn_bwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, o if F > 4 else None, lse,
+                                  do.view(-1, hidden), B, F, H_ * W_, heads, D, D ** -0.5)
+        dqkv4 = dqkv.view(NI, H_, W_, 3 * hidden)
+        dxn = K.igemm(dqkv4, ctx.wdq)
+        dwqkv = _conv_wgrad(wqkv, xn, None, dqkv4, 1)
+        dx, dg = K.ln_bwd(x, g, dxn, dy, eps)  # + dy: the residual branch, added in the LN-backward epilogue
+        return dx, dg.view(ctx.gshape), dwqkv, dwout, dbias, None, None, None, None, None
+
+
+class SpatialAttnBlockFn(torch.autograd.Function):
+    """Residual(PreNorm(SpatialLinearAttention)) (video_net.py:313-347) as one node.
+    args: x, gamma, wqkv [3*hidden, C, 1, 1], wout [C, hidden, 1, 1], bout [C], meta."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, wqkv, wout, bout, meta):
+        x = x.contiguous()
+        NI, H_, W_, C = x.shape
+        heads, D, eps = meta.heads, meta.dim_head, meta.eps
+        hidden = heads * D
+        g = gamma.reshape(-1)
+        train = any(ctx.needs_input_grad)
+        xn = K.ln_fwd(x, g, eps)
+        qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
+        o, ws = K.linattn_fwd(qkv.view(-1, 3 * hidden), NI, H_ * W_, heads, D, D ** -0.5)
+        y = K.igemm(o.view(NI, H_, W_, hidden), _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), bias=bout,
+                    residual=x)
+        ctx.wdq = _conv_dgrad_weights(meta.cq, wqkv, 3 * hidden, C, 0, 1, train)[0]
+        ctx.wdo = _conv_dgrad_weights(meta.co, wout, C, hidden, 0, 1, train)[0]
+        ctx.save_for_backward(x, g, xn, qkv, o, ws, wqkv, wout)
+        ctx.cfg, ctx.gshape = (heads, D, eps), gamma.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, xn, qkv, o, ws, wqkv, wout = ctx.saved_tensors
+        heads, D, eps = ctx.cfg
+        hidden = heads * D
+        NI, H_, W_, C = x.shape
+        dy = dy.contiguous()
+        do = K.igemm(dy, ctx.wdo)
+        dwout = _conv_wgrad(wout, o.view(NI, H_, W_, hidden), None, dy, 1)
+        dbout = K.colsum(dy)
+        dqkv = K.linattn_bwd(qkv.view(-1, 3 * hidden), ws, do.view(-1, hidden), NI, H_ * W_, heads, D, D ** -0.5)
+        dqkv4 = dqkv.view(NI, H_, W_, 3 * hidden)
+        dxn = K.igemm(dqkv4, ctx.wdq)
+        dwqkv = _conv_wgrad(wqkv, xn, None, dqkv4, 1)
+        dx, dg = K.ln_bwd(x, g, dxn, dy, eps)
+        return dx, dg.view(ctx.gshape), dwqkv, dwout, dbout, None
 
 
 # ------------------------------------------------------------------------------------------------

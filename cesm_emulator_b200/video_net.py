@@ -120,11 +120,44 @@ class Residual(nn.Module):
         self.fn = fn
 
     def forward_cl(self, x, B, F, **kwargs):
+        fused = _fused_attention_block(self, x, B, F, **kwargs)
+        if fused is not None:
+            return fused
         return self.fn.forward_cl(x, B, F, residual=x, **kwargs)
 
     def forward(self, x, *args, **kwargs):
         xc, B, F = ops.to_cl(x)
         return ops.from_cl(self.forward_cl(xc, B, F, **kwargs), B, F).to(x.dtype)
+
+
+def _fused_attention_block(res: "Residual", x, B, F, pos_bias=None, focus_present_mask=None):
+    """Residual(PreNorm(SpatialLinearAttention)) and Residual(PreNorm(EinopsToAndFrom(Attention)))
+    with the default all-False focus mask run as ONE autograd node (ops.*AttnBlockFn); anything
+    else returns None and takes the generic op-by-op path."""
+    pre = res.fn
+    if not isinstance(pre, PreNorm):
+        return None
+    inner = pre.fn
+    if isinstance(inner, SpatialLinearAttention):
+        meta = inner.__dict__.get("_bmeta")
+        if meta is None:
+            meta = inner.__dict__["_bmeta"] = ops.BlockMeta(heads=inner.heads, dim_head=inner.dim_head,
+                                                            eps=pre.norm.eps, cq=ops.PackCache(), co=ops.PackCache())
+        return ops.SpatialAttnBlockFn.apply(x, pre.norm.gamma, inner.to_qkv.weight, inner.to_out.weight,
+                                            inner.to_out.bias, meta)
+    if (isinstance(inner, EinopsToAndFrom) and inner.to_einops == "b (h w) f c" and isinstance(inner.fn, Attention)
+            and focus_present_mask is None and exists(inner.fn.rotary_emb)):
+        att = inner.fn
+        meta = att.__dict__.get("_bmeta")
+        if meta is None:
+            meta = att.__dict__["_bmeta"] = ops.BlockMeta(heads=att.heads, dim_head=att.dim_head, eps=pre.norm.eps,
+                                                          cq=ops.PackCache(), co=ops.PackCache())
+        cs, sn = att.rotary_emb.tables(F)
+        if pos_bias is None:
+            pos_bias = torch.zeros((att.heads, F, F), dtype=torch.float32, device=x.device)
+        return ops.TemporalAttnBlockFn.apply(x, pre.norm.gamma, att.to_qkv.weight, att.to_out.weight, pos_bias, cs, sn,
+                                             B, F, meta)
+    return None
 
 
 class LayerNorm(nn.Module):
@@ -205,21 +238,25 @@ class ResnetBlock(nn.Module):
         self.block1 = Block(dim, dim_out, groups=groups)
         self.block2 = Block(dim_out, dim_out, groups=groups)
         self.res_conv = nn.Conv3d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
-        self._cache = ops.PackCache()
+        self._meta = ops.BlockMeta(G=groups, eps=self.block1.norm.eps, c1=ops.PackCache(), c2=ops.PackCache(),
+                                   cres=ops.PackCache())
 
     def forward_cl(self, x, B, F, time_emb=None, x1=None):
-        """x1: optional second channels-last source, concatenated after x (U-Net skip)."""
+        """x1: optional second channels-last source, concatenated after x (U-Net skip).
+        The whole block is one autograd node (ops.ResnetBlockFn)."""
         film = None
         if exists(self.mlp):
             assert exists(time_emb), "time emb must be passed in"
             film = ops.SmallLinearFn.apply(time_emb, self.mlp[1].weight, self.mlp[1].bias, True)
         if isinstance(self.res_conv, nn.Identity):
             assert x1 is None
-            res = x
+            wres = bres = None
         else:
-            res = ops.ConvFn.apply(x, x1, self.res_conv.weight, self.res_conv.bias, None, 1, self._cache)
-        h = self.block1.forward_cl(x, B, F, film=film, x1=x1)
-        return self.block2.forward_cl(h, B, F, residual=res)
+            wres, bres = self.res_conv.weight, self.res_conv.bias
+        b1, b2 = self.block1, self.block2
+        return ops.ResnetBlockFn.apply(x, x1, film, b1.proj.weight, b1.proj.bias, b1.norm.weight, b1.norm.bias,
+                                       b2.proj.weight, b2.proj.bias, b2.norm.weight, b2.norm.bias, wres, bres, B,
+                                       self._meta)
 
     def forward(self, x, time_emb=None):
         xc, B, F = ops.to_cl(x)

@@ -119,6 +119,16 @@ int cesm_wgrad(const cesm_wgrad_args* args, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 int cesm_pack_weight(const float* src, void* dst, int O, int T, int I, long long so, long long si,
                      const int32_t* tap_off, void* stream);
+/* One launch re-packs many parameters: `descs_device` is an array of n descriptors in DEVICE memory
+ * (the training engine refreshes every bf16 operand copy with it once per optimizer step). */
+typedef struct cesm_pack_desc {
+    const float* src;
+    void* dst;
+    int32_t O, T, I, pad_;
+    long long so, si;
+    int32_t tap_off[CESM_MAX_TAPS];
+} cesm_pack_desc;
+int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* stream);
 int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int I, long long so, long long si,
                       const int32_t* tap_off, int accumulate, void* stream);
 /* out[c] = sum over rows of bf16 x[M][C] (bias gradients). */
@@ -130,16 +140,19 @@ int cesm_colsum(const void* x, float* out, long long M, int C, void* stream);
  *   sums  : fp32 [B][G][2]  (sum, sum of squares), written by cesm_gn_stats
  *   film  : fp32 [B][2C] = (scale | shift) from the time-embedding MLP, or NULL
  *   out   = silu(((x-mean)*rstd*gamma+beta)*(scale+1)+shift) (+ residual)
- * cesm_gn_bwd returns dx (bf16), dgamma/dbeta [C], dfilm [B][2C] (if film); csum is fp32 scratch [B][C][4].
+ * cesm_gn_bwd returns dx (bf16), dgamma/dbeta [C], dfilm [B][2C] (if film) and, if dconv_bias is not
+ * NULL, dconv_bias[c] = sum over samples and pixels of dx -- the bias gradient of the convolution
+ * that produced x (video_net.py:215), from the same per-channel sums.  csum is fp32 scratch [B][C][3].
  * ---------------------------------------------------------------------------------------------- */
 int cesm_gn_stats(const void* x, float* sums, int B, long long P, int C, int G, void* stream);
 int cesm_gn_apply_fwd(const void* x, const float* sums, const float* gamma, const float* beta, const float* film,
                       const void* residual, void* out, int B, long long P, int C, int G, float eps, void* stream);
 int cesm_gn_bwd(const void* x, const void* dout, const float* sums, const float* gamma, const float* beta,
-                const float* film, float* csum, void* dx, float* dgamma, float* dbeta, float* dfilm, int B,
-                long long P, int C, int G, float eps, void* stream);
+                const float* film, float* csum, void* dx, float* dgamma, float* dbeta, float* dfilm,
+                float* dconv_bias, int B, long long P, int C, int G, float eps, void* stream);
 
-/* Channel LayerNorm with gain only, video_net.py:78-87.  x, out, dy, dres, dx: bf16 [M][C].
+/* Channel LayerNorm with gain only, video_net.py:78-87.  x, out, dy, dres, dx: bf16 [M][C],
+ * C in {64, 128, 256, 512, 1024}.
  * bwd: dx = LN'(dy) (+ dres if not NULL); dgamma fp32 [C] is overwritten. */
 int cesm_ln_fwd(const void* x, const float* gamma, void* out, long long M, int C, float eps, void* stream);
 int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, const void* dres, void* dx, float* dgamma,

@@ -129,7 +129,7 @@ def test_groupnorm_fwd_bwd(cuda, B, P, C, film, res):
     dout = rnd((B, P, C), cuda)
     sums = K.gn_stats(x, B, G)
     out = K.gn_apply_fwd(x, sums, gamma, beta, fl, r, B, G, 1e-5)
-    dx, dg, db, dfl = K.gn_bwd(x, dout, sums, gamma, beta, fl, B, G, 1e-5)
+    dx, dg, db, dfl, dcb = K.gn_bwd(x, dout, sums, gamma, beta, fl, B, G, 1e-5, conv_bias_grad=True)
 
     xr = x.float().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
@@ -145,6 +145,8 @@ def test_groupnorm_fwd_bwd(cuda, B, P, C, film, res):
     assert err(dg, grads[1]) < 2e-3 and err(db, grads[2]) < 2e-3
     if film:
         assert err(dfl, grads[3]) < 2e-3
+    # bias gradient of the producing conv = sum over samples and pixels of dx (here of the exact dx)
+    assert err(dcb, grads[0].sum(dim=(0, 1))) < 5e-3
 
 
 @pytest.mark.parametrize("M,C", [(1000, 64), (513, 128), (300, 256), (77, 512)])
