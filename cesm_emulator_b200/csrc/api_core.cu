@@ -1,5 +1,7 @@
 // C-ABI core: error reporting, TMA descriptor cache, and the cesm_igemm entry point
 // (tile-shape selection + tensor-map construction for igemm.cu).
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -151,6 +153,234 @@ extern "C" const char* cesm_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* cesm_version(void) { return "cesm_b200 0.1 sm_100a"; }
 extern "C" long long cesm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// ------------------------------------------------------------------------------------------------
+// second-generation persistent kernel: tile / shared-memory plan
+// ------------------------------------------------------------------------------------------------
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            n = 148;
+    }
+    return n;
+}
+
+// tuning / bisection knobs (read once): CESM_IGEMM_V1=1 routes everything to the first-generation
+// kernel, CESM_IGEMM_NO_HALO=1 disables the halo-reuse mode, CESM_IGEMM_NO_BRES=1 streams weights.
+static int env_flag(const char* name) {
+    const char* v = getenv(name);
+    return (v && v[0] && v[0] != '0') ? 1 : 0;
+}
+static int knob_v1() { static int v = env_flag("CESM_IGEMM_V1"); return v; }
+static int knob_no_halo() { static int v = env_flag("CESM_IGEMM_NO_HALO"); return v; }
+static int knob_no_bres() { static int v = env_flag("CESM_IGEMM_NO_BRES"); return v; }
+static int knob_dbg() {
+    static int v = [] { const char* e = getenv("CESM_IGEMM_DBG"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+static bool is_3x3_unit_taps(const cesm_igemm_args* a) {
+    if (a->num_taps != 9 || a->stride != 1) return false;
+    bool seen[9] = {false};
+    for (int t = 0; t < 9; ++t) {
+        const int dh = a->tap_dh[t], dw = a->tap_dw[t];
+        if (dh < -1 || dh > 1 || dw < -1 || dw > 1) return false;
+        seen[(dh + 1) * 3 + dw + 1] = true;
+    }
+    for (bool b : seen)
+        if (!b) return false;
+    return true;
+}
+
+static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
+    Igemm2Params p{};
+    p.c0 = a->c0;
+    p.c1 = a->c1;
+    p.num_taps = a->num_taps;
+    const int ctot = a->c0 + a->c1;
+    p.num_kb = a->num_taps * (ctot / 64);
+    p.n = a->n;
+    p.oh = a->oh;
+    p.ow = a->ow;
+    p.cout = a->cout;
+    const int block_n = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
+    p.n_tiles = a->cout / block_n;
+
+    // ---- HALO candidates: padded row width pw in {16, 32, 64, 128}, bw = pw - 2, bh = 128 / pw ----
+    bool halo = false;
+    if (is_3x3_unit_taps(a) && !knob_no_halo()) {
+        double best = 0.0;
+        int best_pw = 0;
+        for (int pw = 16; pw <= 128; pw <<= 1) {
+            const int bw = pw - 2, bh = 128 / pw;
+            const double tiles = (double)ceil_div(a->ow, bw) * ceil_div(a->oh, bh);
+            const double useful = ((double)a->ow * a->oh) / (tiles * 128.0);
+            // prefer taller tiles (less halo re-fetch) when the useful fraction is close
+            const double score = useful * (1.0 - 0.08 * 2.0 / (bh + 2));
+            if (score > best) {
+                best = score;
+                best_pw = pw;
+            }
+        }
+        if (best_pw && best >= 0.55) {
+            halo = true;
+            p.bw = best_pw - 2;
+            p.bh = 128 / best_pw;
+            p.bn = 1;
+        }
+    }
+    if (!halo) choose_tile(a->n, a->oh, a->ow, &p.bw, &p.bh, &p.bn);
+    p.tiles_w = ceil_div(a->ow, p.bw);
+    p.tiles_h = ceil_div(a->oh, p.bh);
+    p.m_tiles = p.tiles_w * p.tiles_h * ceil_div(a->n, p.bn);
+
+    // ---- GroupNorm statistics: every tile must lie within one sample ----
+    p.gn_sums = a->gn_sums;
+    if (a->gn_sums) {
+        CESM_REQUIRE(a->gn_groups > 0 && a->gn_frames > 0 && a->cout % a->gn_groups == 0 && a->n % a->gn_frames == 0,
+                     "bad GroupNorm statistics arguments (groups=%d frames=%d)", a->gn_groups, a->gn_frames);
+        p.gn_groups = a->gn_groups;
+        p.gn_cpg = a->cout / a->gn_groups;
+        p.gn_frames = a->gn_frames;
+        CESM_REQUIRE(a->gn_groups <= 32, "fused GroupNorm statistics support at most 32 groups (got %d)", a->gn_groups);
+        CESM_REQUIRE(p.gn_cpg % 8 == 0 && (p.gn_cpg >= 64 ? p.gn_cpg % 64 == 0 : 64 % p.gn_cpg == 0),
+                     "fused GroupNorm statistics need 8 | cout/groups and cout/groups | 64 or 64 | cout/groups (got %d)",
+                     p.gn_cpg);
+        if (p.bn > 1 && a->gn_frames % p.bn != 0) {  // re-tile with one image per tile
+            p.bn = 1;
+            p.m_tiles = p.tiles_w * p.tiles_h * a->n;
+        }
+        CESM_CHECK_CUDA(cudaMemsetAsync(a->gn_sums, 0, sizeof(float) * 2 * (a->n / a->gn_frames) * a->gn_groups, st));
+    }
+
+    // ---- shared-memory plan ----
+    const int pw = halo ? p.bw + 2 : p.bw;
+    if (halo) {
+        const int rows_box = pw * (p.bh + 2), rows_need = 2 * pw + 2 + 128;
+        const int rows = rows_box > rows_need ? rows_box : rows_need;
+        p.a_stage_bytes = (uint32_t)((rows * 128 + 1023) / 1024 * 1024);
+        p.a_box_bytes = (uint32_t)rows_box * 128u;
+    } else {
+        p.a_stage_bytes = 16384;
+        p.a_box_bytes = 128u * p.bw * p.bh * p.bn;
+    }
+    const long long budget = (long long)kIgemm2MaxSmem - 1024 /*align*/ - 1024 /*barriers*/ - 2 * 16384 /*out staging*/;
+    const long long b_total = (long long)a->cout * p.num_kb * 128;
+    const long long b_blk = (long long)block_n * 128;
+    const int a_min = 2;
+    if (b_total + a_min * (long long)p.a_stage_bytes <= budget && !knob_no_bres()) {
+        p.b_resident = 1;
+        p.b_stages = 1;
+        long long as = (budget - b_total) / p.a_stage_bytes;
+        const int a_cap = halo ? 4 : 8;
+        p.a_stages = (int)(as > a_cap ? a_cap : as);
+    } else {
+        p.b_resident = 0;
+        p.a_stages = halo ? 2 : 4;
+        long long bs = (budget - (long long)p.a_stages * p.a_stage_bytes) / b_blk;
+        if (bs > 16) bs = 16;
+        if (bs < 2) {  // very wide tiles: trade activation stages for weight stages
+            p.a_stages = 2;
+            bs = (budget - (long long)p.a_stages * p.a_stage_bytes) / b_blk;
+        }
+        CESM_REQUIRE(bs >= 2, "igemm2: no shared-memory plan for cout=%d K=%d", a->cout, p.num_kb * 64);
+        p.b_stages = (int)bs;
+    }
+    const long long b_bytes = p.b_resident ? b_total : (long long)p.b_stages * b_blk;
+    const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)b_bytes + 2 * 16384 + 1024;
+    CESM_REQUIRE(smem <= kIgemm2MaxSmem, "igemm2: shared-memory plan of %zu B exceeds the limit", smem);
+
+    p.out_h = a->out_h;
+    p.out_w = a->out_w;
+    p.o_sh = a->o_sh;
+    p.o_sw = a->o_sw;
+    p.o_h0 = a->o_h0;
+    p.o_w0 = a->o_w0;
+    p.bias = a->bias;
+    p.residual = a->residual;
+    p.ldr = a->ldr;
+    p.dbg = knob_dbg();
+
+    // ---- tensor maps ----
+    Igemm2Maps maps;
+    int n_amaps = 0;
+    const uint32_t abox[4] = {64u, (uint32_t)(halo ? pw : p.bw), (uint32_t)(halo ? p.bh + 2 : p.bh), (uint32_t)p.bn};
+    if (a->stride == 1) {
+        const void* src[2] = {a->a0, a->a1};
+        const int cs[2] = {a->c0, a->c1};
+        for (int s = 0; s < 2; ++s) {
+            if (!src[s]) continue;
+            const uint64_t dims[4] = {(uint64_t)cs[s], (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+            const uint64_t str[3] = {(uint64_t)cs[s] * 2, (uint64_t)a->w * cs[s] * 2, (uint64_t)a->h * a->w * cs[s] * 2};
+            int rc = get_tensor_map_bf16(&maps.a[s], src[s], 4, dims, str, abox);
+            if (rc) return rc;
+            n_amaps = s + 1;
+        }
+        for (int t = 0; t < a->num_taps; ++t) {
+            p.tap_map[t] = 0;
+            p.tap_dh[t] = a->tap_dh[t];
+            p.tap_dw[t] = a->tap_dw[t];
+        }
+    } else {
+        const int c = a->c0;
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw2 = 0; pw2 < 2; ++pw2) {
+                const char* base = static_cast<const char*>(a->a0) + (size_t)(ph * a->w + pw2) * c * 2;
+                const uint64_t dims[4] = {(uint64_t)c, (uint64_t)a->w / 2, (uint64_t)a->h / 2, (uint64_t)a->n};
+                const uint64_t str[3] = {(uint64_t)c * 4, (uint64_t)a->w * c * 4, (uint64_t)a->h * a->w * c * 2};
+                int rc = get_tensor_map_bf16(&maps.a[ph * 2 + pw2], base, 4, dims, str, abox);
+                if (rc) return rc;
+            }
+        n_amaps = 4;
+        for (int t = 0; t < a->num_taps; ++t) {
+            const int ph = a->tap_dh[t] & 1, pw2 = a->tap_dw[t] & 1;
+            p.tap_map[t] = ph * 2 + pw2;
+            p.tap_dh[t] = (a->tap_dh[t] - ph) / 2;
+            p.tap_dw[t] = (a->tap_dw[t] - pw2) / 2;
+        }
+    }
+    for (int i = n_amaps; i < 4; ++i) maps.a[i] = maps.a[0];
+    {
+        const int ktot = p.num_kb * 64;
+        const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->cout};
+        const uint64_t str[1] = {(uint64_t)ktot * 2};
+        const uint32_t bbox[2] = {64u, (uint32_t)block_n};
+        int rc = get_tensor_map_bf16(&maps.b, a->wt, 2, dims, str, bbox);
+        if (rc) return rc;
+    }
+    {
+        // output as a (possibly strided) [cout, ow, oh, n] tensor: pixel (n, oh, ow) lives at row
+        // (n*out_h + oh*o_sh + o_h0)*out_w + ow*o_sw + o_w0 of a [*, ldo] matrix
+        const char* base = static_cast<const char*>(a->out) + ((size_t)a->o_h0 * a->out_w + a->o_w0) * a->ldo * 2;
+        const uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)a->ow, (uint64_t)a->oh, (uint64_t)a->n};
+        const uint64_t str[3] = {(uint64_t)a->o_sw * a->ldo * 2, (uint64_t)a->o_sh * a->out_w * a->ldo * 2,
+                                 (uint64_t)a->out_h * a->out_w * a->ldo * 2};
+        // warp-private epilogue: each warp's 32 accumulator rows are one box
+        if (halo)
+            p.epi_warp = (pw == 32);
+        else
+            p.epi_warp = (p.bw % 32 == 0);
+        if (knob_dbg() & 8) p.epi_warp = 0;
+        uint32_t obox[4] = {64u, (uint32_t)p.bw, (uint32_t)(halo ? 1 : p.bh), (uint32_t)(halo ? 1 : p.bn)};
+        if (p.epi_warp && !halo) {
+            obox[1] = 32u;
+            obox[2] = 1u;
+            obox[3] = 1u;
+        }
+        int rc = get_tensor_map_bf16(&maps.out, base, 4, dims, str, obox);
+        if (rc) return rc;
+    }
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    note_launch();
+    CESM_CHECK_CUDA(igemm2_launch(maps, p, block_n, halo, grid, smem, st));
+    return CESM_OK;
+}
+
 extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
     CESM_REQUIRE(a != nullptr, "args is NULL");
     CESM_REQUIRE(a->c0 > 0 && a->c0 % 64 == 0 && a->c1 >= 0 && a->c1 % 64 == 0,
@@ -163,6 +393,9 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
     CESM_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0 && a->oh > 0 && a->ow > 0, "empty geometry");
     CESM_REQUIRE((a->c1 == 0) == (a->a1 == nullptr), "a1 / c1 mismatch");
     CESM_REQUIRE(a->ldo % 8 == 0 && (a->residual == nullptr || a->ldr % 8 == 0), "row pitches must be multiples of 8");
+    if (!a->out_fp32 && !(knob_v1() && a->gn_sums == nullptr))
+        return igemm2_run(a, as_stream(stream));  // persistent kernel (igemm2.cu)
+    CESM_REQUIRE(a->gn_sums == nullptr, "fused GroupNorm statistics need bf16 output");
 
     IgemmParams p{};
     p.c0 = a->c0;

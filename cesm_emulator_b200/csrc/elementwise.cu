@@ -317,16 +317,28 @@ __global__ void small_linear_wgrad_kernel(const float* __restrict__ x, const flo
     if (k == 0 && db) db[n] = sb;
 }
 // dx[b][k] = act'(x[b][k]) * sum_n dy[b][n] W[n][k]
-__global__ void small_linear_dgrad_kernel(const float* __restrict__ x, const float* __restrict__ W,
-                                          const float* __restrict__ dy, float* __restrict__ dx, int B, int K, int N,
-                                          int act) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)B * K) return;
-    const int k = idx % K, b = idx / K;
+// block = (32 k-lanes x 8 n-groups); grid = (ceil(K/32), B): rows of W are read coalesced along k,
+// the 8 warps split n and combine through shared memory.
+__global__ void __launch_bounds__(256)
+small_linear_dgrad_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ dy,
+                          float* __restrict__ dx, int B, int K, int N, int act) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + lane, b = blockIdx.y;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(dy[(size_t)b * N + n], W[(size_t)n * K + k], s);
-    if (act) s *= dsilu_f(x[idx]);
-    dx[idx] = s;
+    if (k < K) {
+#pragma unroll 4
+        for (int n = w; n < N; n += 8) s = fmaf(__ldg(dy + (size_t)b * N + n), __ldg(W + (size_t)n * K + k), s);
+    }
+    __shared__ float red[8][33];
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && k < K) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][lane];
+        if (act) t *= dsilu_f(x[(size_t)b * K + k]);
+        dx[(size_t)b * K + k] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -496,7 +508,7 @@ extern "C" int cesm_small_linear_bwd(const float* x, const float* W, const float
     small_linear_wgrad_kernel<<<nblk((long long)N * K, 256), 256, 0, st>>>(x, dy, dW, db, B, K, N, act_silu_in);
     CESM_CHECK_LAUNCH();
     if (dx) {
-        small_linear_dgrad_kernel<<<nblk((long long)B * K, 256), 256, 0, st>>>(x, W, dy, dx, B, K, N, act_silu_in);
+        small_linear_dgrad_kernel<<<dim3(ceil_div(K, 32), B), 256, 0, st>>>(x, W, dy, dx, B, K, N, act_silu_in);
         CESM_CHECK_LAUNCH();
     }
     return CESM_OK;

@@ -42,6 +42,42 @@ struct WgradParams {
     float* dw;              // fp32 [cout][num_taps][c0+c1], accumulated with red.add
 };
 
+// ---- second-generation persistent kernel (igemm2.cu) ------------------------------------------
+static constexpr size_t kIgemm2MaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+struct Igemm2Maps {
+    CUtensorMap a[4];
+    CUtensorMap b;
+    CUtensorMap out;
+};
+
+struct Igemm2Params {
+    int32_t c0, c1;
+    int32_t num_taps, num_kb;          // num_kb = num_taps * (c0 + c1) / 64
+    int32_t tap_map[16];
+    int32_t tap_dh[16];
+    int32_t tap_dw[16];
+    int32_t n, oh, ow;                 // output pixel space
+    int32_t bw, bh, bn;                // useful pixels of a tile (HALO: accumulator rows are (bw+2) wide)
+    int32_t tiles_w, tiles_h, m_tiles, n_tiles;
+    int32_t cout;
+    // shared-memory plan
+    int32_t a_stages, b_stages, b_resident;
+    uint32_t a_stage_bytes, a_box_bytes;
+    // epilogue
+    int32_t out_h, out_w, o_sh, o_sw, o_h0, o_w0;   // residual addressing (same pixel map as the output)
+    const float* bias;
+    const void* residual;
+    int32_t ldr;
+    float* gn_sums;                    // [B][gn_groups][2] (sum, sum of squares) or null
+    int32_t gn_groups, gn_cpg, gn_frames;
+    int32_t epi_warp;                  // 1: every epilogue warp stores its own 32-row slab (see igemm2.cu)
+    int32_t dbg;                       // CESM_IGEMM_DBG bisection bits (0 in production)
+};
+
+cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, int grid, size_t smem,
+                          cudaStream_t stream);
+
 cudaError_t wgrad_launch(const CUtensorMap* xmaps, int n_xmaps, const CUtensorMap& ymap, const WgradParams& p,
                          int block_n, int ksplit, cudaStream_t stream);
 

@@ -1,0 +1,485 @@
+// Persistent tcgen05 / TMEM / TMA implicit GEMM for sm_100a (second generation of igemm.cu).
+//
+//     out[pixel, co] = sum_{tap, ci} A[pixel + tap, ci] * Wt[co, tap, ci]   (+ bias) (+ residual)
+//
+// What bounds these contractions on B200 is not the tensor pipe but the L2 -> shared-memory feed:
+// a 128 x 64 tile needs 24 KB of operands per 128 MMA cycles when every tap re-fetches its pixels
+// and its weights (~190 B/clk/SM against ~42 B/clk/SM of L2 bandwidth per SM).  This kernel removes
+// that traffic instead of hiding it:
+//
+//   * HALO mode (3x3, stride 1): the (bw+2) x (bh+2) pixel halo of a tile is fetched ONCE per 64
+//     input channels; the nine taps are nine row-shifted views of it (UMMA descriptors whose start
+//     address is advanced by whole 128-byte rows -- exact on B200, tools/probe_umma_desc.cu).  The
+//     accumulator rows live on the padded (bw+2)-wide grid; the two pad columns are dropped by
+//     the epilogue.  A traffic: 9 x -> ~1.6 x.
+//   * resident weights: when cout x K fits, the whole weight matrix is loaded once per CTA and
+//     stays in shared memory across the persistent tile loop; otherwise it is streamed through its
+//     own mbarrier ring, decoupled from the activation ring.
+//   * persistent CTAs (one per SM) with two TMEM accumulator stages: the epilogue of tile i overlaps
+//     the MMAs of tile i+1.
+//   * the epilogue goes TMEM -> registers -> swizzled shared memory -> TMA store (full 128-byte
+//     lines), fusing bias, residual add and -- for the convs that feed a GroupNorm -- the per-sample
+//     per-group sum / sum-of-squares of the bf16-rounded outputs (video_net.py:216).
+//
+// Warp roles (224 threads): 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer
+// (+ TMEM allocation), 3..6 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+#include "common.cuh"
+#include "igemm.h"
+
+namespace cesm {
+
+static constexpr int kTileM = 128;
+static constexpr int kKBlk = 64;
+static constexpr int kStageRowBytes = 128;                       // 64 bf16
+static constexpr int kOutStageBytes = kTileM * kStageRowBytes;   // one 64-column output chunk
+
+__device__ __forceinline__ void tma_store_4d(const void* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BLOCK_N, bool HALO>
+__global__ void __launch_bounds__(224, 1)
+igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + p.a_stages * p.a_stage_bytes;
+    const uint32_t b_blk_bytes = BLOCK_N * kStageRowBytes;
+    const uint32_t b_bytes = p.b_resident ? (uint32_t)p.n_tiles * p.num_kb * b_blk_bytes : p.b_stages * b_blk_bytes;
+    const uint32_t o_base = b_base + b_bytes;                 // 2 output staging buffers
+    const uint32_t bar_base = o_base + 2 * kOutStageBytes;
+    // barrier map
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };
+    auto b_full = [&](int s) { return bar_base + 8u * (16 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8u * (32 + s); };
+    auto t_full = [&](int s) { return bar_base + 8u * (48 + s); };
+    auto t_empty = [&](int s) { return bar_base + 8u * (50 + s); };
+    const uint32_t b_all_bar = bar_base + 8u * 52;
+    const uint32_t tmem_ptr_addr = bar_base + 8u * 53;
+    const uint32_t gn_base = bar_base + 8u * 56;  // 64 floats: per-CTA GroupNorm (sum, sumsq) accumulators
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int cblk0 = p.c0 >> 6;
+    const int cblk = (p.c0 + p.c1) >> 6;
+    const int a_loads = HALO ? cblk : p.num_kb;    // activation loads per tile
+    const int taps_per_a = HALO ? 9 : 1;
+    const int pw = HALO ? p.bw + 2 : p.bw;         // accumulator rows per tile row
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.b);
+        tma_prefetch_desc(&maps.out);
+        for (int s = 0; s < p.a_stages; ++s) {
+            mbar_init(a_full(s), 1);
+            mbar_init(a_empty(s), 1);
+        }
+        for (int s = 0; s < p.b_stages; ++s) {
+            mbar_init(b_full(s), 1);
+            mbar_init(b_empty(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(t_full(s), 1);
+            mbar_init(t_empty(s), 4);
+        }
+        mbar_init(b_all_bar, 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 64) reinterpret_cast<float*>(smem_gen + (gn_base - smem_base))[threadIdx.x] = 0.f;
+    if (warp == 2) tmem_alloc(tmem_ptr_addr, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    auto tile_coords = [&](int tile, int& n_tile, int& n0, int& oh0, int& ow0) {
+        n_tile = tile / p.m_tiles;          // n-major: concurrently running CTAs share the weight tile
+        int t = tile - n_tile * p.m_tiles;
+        const int tw = t % p.tiles_w;
+        t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tn = t / p.tiles_h;
+        ow0 = tw * p.bw;
+        oh0 = th * p.bh;
+        n0 = tn * p.bn;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ===== activation producer =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int n_tile, n0, oh0, ow0;
+            tile_coords(tile, n_tile, n0, oh0, ow0);
+            for (int ai = 0; ai < a_loads; ++ai) {
+                mbar_wait(a_empty(stage), phase ^ 1u, 11);
+                const uint32_t dst = a_base + stage * p.a_stage_bytes;
+                mbar_arrive_expect_tx(a_full(stage), p.a_box_bytes);
+                if (HALO) {
+                    int midx = 0, c = ai << 6;
+                    if (ai >= cblk0) {
+                        midx = 1;
+                        c = (ai - cblk0) << 6;
+                    }
+                    tma_load_4d(dst, &maps.a[midx], a_full(stage), c, ow0 - 1, oh0 - 1, n0);
+                } else {
+                    const int tap = ai / cblk;
+                    const int cb = ai - tap * cblk;
+                    int midx = p.tap_map[tap], c = cb << 6;
+                    if (cb >= cblk0) {
+                        midx += 1;
+                        c = (cb - cblk0) << 6;
+                    }
+                    tma_load_4d(dst, &maps.a[midx], a_full(stage), c, ow0 + p.tap_dw[tap], oh0 + p.tap_dh[tap], n0);
+                }
+                if (++stage == p.a_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== weight producer =====
+        if (p.b_resident) {
+            const uint32_t total_bytes = (uint32_t)p.n_tiles * p.num_kb * b_blk_bytes;
+            mbar_arrive_expect_tx(b_all_bar, total_bytes);
+            for (int nt = 0; nt < p.n_tiles; ++nt)
+                for (int kb = 0; kb < p.num_kb; ++kb)
+                    tma_load_2d(b_base + (nt * p.num_kb + kb) * b_blk_bytes, &maps.b, b_all_bar, kb * kKBlk,
+                                nt * BLOCK_N);
+        } else {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile / p.m_tiles;
+                for (int ai = 0; ai < a_loads; ++ai)
+                    for (int ti = 0; ti < taps_per_a; ++ti) {
+                        const int kb = HALO ? ti * cblk + ai : ai;
+                        mbar_wait(b_empty(stage), phase ^ 1u, 12);
+                        mbar_arrive_expect_tx(b_full(stage), b_blk_bytes);
+                        tma_load_2d(b_base + stage * b_blk_bytes, &maps.b, b_full(stage), kb * kKBlk, n_tile * BLOCK_N);
+                        if (++stage == p.b_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+            }
+        }
+    } else if (warp == 2 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+        int a_stage = 0, b_stage = 0, acc = 0;
+        uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+        if (p.b_resident) mbar_wait(b_all_bar, 0, 13);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile / p.m_tiles;
+            mbar_wait(t_empty(acc), acc_phase ^ 1u, 14);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int ai = 0; ai < a_loads; ++ai) {
+                mbar_wait(a_full(a_stage), a_phase, 15);
+                tc_fence_after();
+                const uint32_t sa0 = a_base + a_stage * p.a_stage_bytes;
+                for (int ti = 0; ti < taps_per_a; ++ti) {
+                    const int kb = HALO ? ti * cblk + ai : ai;
+                    uint32_t sb;
+                    if (p.b_resident) {
+                        sb = b_base + (n_tile * p.num_kb + kb) * b_blk_bytes;
+                    } else {
+                        mbar_wait(b_full(b_stage), b_phase, 16);
+                        tc_fence_after();
+                        sb = b_base + b_stage * b_blk_bytes;
+                    }
+                    // HALO: tap (dh, dw) is the view of the halo tile that starts (1+dh)*pw + (1+dw) rows in
+                    const uint32_t sa =
+                        HALO ? sa0 + ((1 + p.tap_dh[ti]) * pw + (1 + p.tap_dw[ti])) * kStageRowBytes : sa0;
+                    if (!(p.dbg & 4)) {
+#pragma unroll
+                        for (int k = 0; k < kKBlk / 16; ++k) {
+                            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
+                            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
+                            umma_bf16(d_tmem, da, db, idesc, (ai | ti | k) != 0);
+                        }
+                    }
+                    if (!p.b_resident) {
+                        umma_commit(b_empty(b_stage));
+                        if (++b_stage == p.b_stages) {
+                            b_stage = 0;
+                            b_phase ^= 1u;
+                        }
+                    }
+                }
+                umma_commit(a_empty(a_stage));
+                if (++a_stage == p.a_stages) {
+                    a_stage = 0;
+                    a_phase ^= 1u;
+                }
+            }
+            umma_commit(t_full(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 3) {
+        // ===== epilogue =====
+        // Two staging schemes.  "warp-private" (p.epi_warp): the 32 accumulator rows of a warp are one
+        // storable box (a 32-pixel run of an image row, or -- HALO with 32-wide padded rows -- one tile
+        // row), so every warp stages, fences and TMA-stores its own 4 KB slab with no block-level
+        // barrier.  Otherwise the four warps fill one 16 KB buffer and one thread stores the tile box.
+        const int q = warp & 3;            // TMEM lane quadrant this warp may read
+        const int r = q * 32 + lane;       // accumulator row
+        const bool blk_issuer = (warp == 3 && lane == 0);
+        const bool warp_mode = p.epi_warp != 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t chunk_ctr = 0;
+        int cur_b = -1;
+        auto gn_flush = [&](int b) {
+            epi_bar_sync();
+            if (warp == 3 && lane < 2 * p.gn_groups && b >= 0) {
+                float* acc_s = reinterpret_cast<float*>(smem_gen + (gn_base - smem_base));
+                atomicAdd(p.gn_sums + (size_t)b * p.gn_groups * 2 + lane, acc_s[lane]);
+                if (32 + lane < 2 * p.gn_groups) {
+                    atomicAdd(p.gn_sums + (size_t)b * p.gn_groups * 2 + 32 + lane, acc_s[32 + lane]);
+                    acc_s[32 + lane] = 0.f;
+                }
+                acc_s[lane] = 0.f;
+            }
+            epi_bar_sync();
+        };
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int n_tile, n0, oh0, ow0;
+            tile_coords(tile, n_tile, n0, oh0, ow0);
+            // row -> pixel
+            const int rw = r % pw;
+            const int rh = (r / pw) % p.bh;
+            const int rn = r / (pw * p.bh);
+            const int n = n0 + rn, oh = oh0 + rh, ow = ow0 + rw;
+            const bool valid = (rw < p.bw) && (rn < p.bn) && (n < p.n) && (oh < p.oh) && (ow < p.ow);
+            const long long pix = (static_cast<long long>(n) * p.out_h + (oh * p.o_sh + p.o_h0)) * p.out_w +
+                                  (ow * p.o_sw + p.o_w0);
+            if (p.gn_sums) {
+                const int b = n0 / p.gn_frames;  // the tile lies within one sample (host guarantees)
+                if (b != cur_b) {
+                    if (cur_b >= 0) gn_flush(cur_b);
+                    cur_b = b;
+                }
+            }
+            mbar_wait(t_full(acc), acc_phase, 17);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int cc = 0; cc < ((p.dbg & 2) ? 0 : BLOCK_N); cc += 64, ++chunk_ctr) {
+                const uint32_t obuf = o_base + (chunk_ctr & 1u) * kOutStageBytes;
+                // both TMEM loads in flight before anything else
+                uint32_t v0[32], v1[32];
+                if (!(p.dbg & 16)) {
+                    tmem_ld_32x32(taddr + cc, v0);
+                    tmem_ld_32x32(taddr + cc + 32, v1);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v0[i] = v1[i] = i + lane;
+                }
+                // the store that last read this staging buffer must have drained
+                if (warp_mode) {
+                    if (lane == 0 && !(p.dbg & 512)) tma_store_wait_read<1>();
+                    __syncwarp();
+                } else {
+                    if (blk_issuer) tma_store_wait_read<1>();
+                    epi_bar_sync();
+                }
+                if (!(p.dbg & 256)) tmem_ld_wait();
+                const int col = n_tile * BLOCK_N + cc;
+                float sv[16];  // [0..7] per 8-column octet sums of this row, [8..15] sums of squares
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(h2 ? v1[i] : v0[i]);
+                    if (p.bias && !(p.dbg & 128)) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + col + 32 * h2);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = __ldg(bp + j);
+                            f[4 * j] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+                        }
+                    }
+                    if (p.residual && valid) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(
+                            reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + col + 32 * h2);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = __ldg(rp + j);
+                            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
+                                         d = unpack_bf16x2(u.w);
+                            f[j * 8 + 0] += a.x; f[j * 8 + 1] += a.y; f[j * 8 + 2] += b.x; f[j * 8 + 3] += b.y;
+                            f[j * 8 + 4] += c2.x; f[j * 8 + 5] += c2.y; f[j * 8 + 6] += d.x; f[j * 8 + 7] += d.y;
+                        }
+                    }
+                    // pack to bf16, write the 4 swizzled 16-byte units of this half row
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                        u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                        u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        const int unit = h2 * 4 + j;
+                        const uint32_t addr = obuf + r * kStageRowBytes + ((unit ^ (r & 7)) << 4);
+                        if (!(p.dbg & 32) || u.x == 0x7fc07fc1u)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y),
+                                         "r"(u.z), "r"(u.w)
+                                         : "memory");
+                        if (p.gn_sums) {
+                            // statistics of what the consumer will read: the bf16-rounded values
+                            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
+                                         d = unpack_bf16x2(u.w);
+                            const float s = ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
+                            const float qq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c2.x, c2.x,
+                                             fmaf(c2.y, c2.y, fmaf(d.x, d.x, d.y * d.y)))))));
+                            sv[unit] = valid ? s : 0.f;
+                            sv[8 + unit] = valid ? qq : 0.f;
+                        }
+                    }
+                }
+                if (p.gn_sums) {
+                    // 16 values x 32 rows -> 16 totals with a halving butterfly (16 shuffles): after the
+                    // step for lane bit b a lane keeps the half of its values selected by that bit.
+                    {
+                        const bool up = lane & 16;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[i] : sv[i + 8], 16);
+                            sv[i] = (up ? sv[i + 8] : sv[i]) + recv;
+                        }
+                    }
+                    {
+                        const bool up = lane & 8;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[i] : sv[i + 4], 8);
+                            sv[i] = (up ? sv[i + 4] : sv[i]) + recv;
+                        }
+                    }
+                    {
+                        const bool up = lane & 4;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[i] : sv[i + 2], 4);
+                            sv[i] = (up ? sv[i + 2] : sv[i]) + recv;
+                        }
+                    }
+                    {
+                        const bool up = lane & 2;
+                        const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[0] : sv[1], 2);
+                        sv[0] = (up ? sv[1] : sv[0]) + recv;
+                    }
+                    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                    if ((lane & 1) == 0) {
+                        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                                        ((lane >> 1) & 1);
+                        const int g = (col + 8 * (idx & 7)) / p.gn_cpg;
+                        float* acc_s = reinterpret_cast<float*>(smem_gen + (gn_base - smem_base));
+                        atomicAdd(acc_s + 2 * g + (idx >> 3), sv[0]);
+                    }
+                }
+                if (!(p.dbg & 64)) fence_proxy_async();
+                if (warp_mode) {
+                    __syncwarp();
+                    if (lane == 0 && !(p.dbg & 1)) {
+                        const uint32_t slab = obuf + q * 32 * kStageRowBytes;
+                        if (HALO) {  // 32-wide padded rows: warp q holds tile row q
+                            if (q < p.bh && oh0 + q < p.oh) tma_store_4d(&maps.out, slab, col, ow0, oh0 + q, n0);
+                        } else {     // 32 consecutive pixels of one image row
+                            const int r0 = q * 32;
+                            const int sw = r0 % p.bw, sh = (r0 / p.bw) % p.bh, sn = r0 / (p.bw * p.bh);
+                            if (sn < p.bn) tma_store_4d(&maps.out, slab, col, ow0 + sw, oh0 + sh, n0 + sn);
+                        }
+                        tma_store_commit();
+                    }
+                } else {
+                    epi_bar_sync();
+                    if (blk_issuer && !(p.dbg & 1)) {
+                        if (HALO) {
+                            // one store per tile row: the bw useful pixels of each padded accumulator row
+                            for (int h = 0; h < p.bh; ++h)
+                                if (oh0 + h < p.oh)
+                                    tma_store_4d(&maps.out, obuf + h * pw * kStageRowBytes, col, ow0, oh0 + h, n0);
+                        } else {
+                            tma_store_4d(&maps.out, obuf, col, ow0, oh0, n0);
+                        }
+                        tma_store_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+        if (p.gn_sums) gn_flush(cur_b);
+        if (lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool HALO>
+static cudaError_t launch_igemm2(const Igemm2Maps& maps, const Igemm2Params& p, int grid, size_t smem,
+                                 cudaStream_t stream) {
+    static size_t configured = 0;  // benign race: attribute set is idempotent and monotone
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BLOCK_N, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kIgemm2MaxSmem);
+        if (e != cudaSuccess) return e;
+        configured = kIgemm2MaxSmem;
+    }
+    igemm2_kernel<BLOCK_N, HALO><<<grid, 224, smem, stream>>>(maps, p);
+    return cudaGetLastError();
+}
+
+cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, int grid, size_t smem,
+                          cudaStream_t stream) {
+    if (halo) {
+        switch (block_n) {
+            case 64: return launch_igemm2<64, true>(maps, p, grid, smem, stream);
+            case 128: return launch_igemm2<128, true>(maps, p, grid, smem, stream);
+            case 256: return launch_igemm2<256, true>(maps, p, grid, smem, stream);
+        }
+    } else {
+        switch (block_n) {
+            case 64: return launch_igemm2<64, false>(maps, p, grid, smem, stream);
+            case 128: return launch_igemm2<128, false>(maps, p, grid, smem, stream);
+            case 256: return launch_igemm2<256, false>(maps, p, grid, smem, stream);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace cesm

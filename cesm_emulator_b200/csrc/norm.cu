@@ -67,23 +67,16 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, l
             }
         }
     }
-    __shared__ float sh[2][kNormThreads];
-    sh[0][threadIdx.x] = s;
-    sh[1][threadIdx.x] = ss;
+    // block reduction per group: shared-memory atomics (a few-way conflict per warp), then one
+    // global atomic per (block, group, moment)
+    __shared__ float sh[2 * 256];
+    for (int i = threadIdx.x; i < 2 * G; i += kNormThreads) sh[i] = 0.f;
     __syncthreads();
-    // one thread per group gathers every slot that maps to it
-    if (threadIdx.x < G) {
-        const int cpg8 = (C / G) >> 3;  // channel vectors per group
-        float a = 0.f, q = 0.f;
-        for (int t = 0; t < kNormThreads; ++t) {
-            if ((t % vec_per_pix) / cpg8 == (int)threadIdx.x) {
-                a += sh[0][t];
-                q += sh[1][t];
-            }
-        }
-        atomicAdd(&sums[((size_t)b * G + threadIdx.x) * 2 + 0], a);
-        atomicAdd(&sums[((size_t)b * G + threadIdx.x) * 2 + 1], q);
-    }
+    const int g = slot / ((C / G) >> 3);
+    atomicAdd(&sh[2 * g], s);
+    atomicAdd(&sh[2 * g + 1], ss);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += kNormThreads) atomicAdd(&sums[(size_t)b * G * 2 + i], sh[i]);
 }
 
 // out = silu(((x-mean)*rstd*gamma + beta) * (scale+1) + shift) (+ residual)
@@ -496,9 +489,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
     }
 }
 
-static int norm_grid(long long work_items, int per_block) {
+// Streaming kernels want every SM busy for the whole launch: a grid of ~4 resident blocks per SM in
+// total (over all `batches` of grid.y), each thread looping many trips, instead of one trip per block
+// (whose latency would be the whole kernel) -- no wave quantisation, no tail.
+static int norm_grid(long long work_items, int per_block, int batches = 1) {
     long long blocks = (work_items + per_block - 1) / per_block;
-    const long long cap = 148 * 8;
+    long long cap = (148 * 4) / (batches < 1 ? 1 : batches);
+    if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
@@ -517,7 +514,7 @@ extern "C" int cesm_gn_stats(const void* x, float* sums, int B, long long P, int
     GN_CHECK(C, G);
     CESM_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * B * G, as_stream(stream)));
     const int per_block = kNormThreads / (C / 8) * UNR;
-    dim3 grid(norm_grid(P, per_block), B);
+    dim3 grid(norm_grid(P, per_block, B), B);
     gn_stats_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, sums, P, C, G);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
@@ -528,7 +525,7 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
                                  int G, float eps, void* stream) {
     GN_CHECK(C, G);
     const int per_block = kNormThreads / (C / 8) * UNR;
-    dim3 grid(norm_grid(P, per_block), B);
+    dim3 grid(norm_grid(P, per_block, B), B);
     gn_apply_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)x, sums, gamma, beta, film, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, P, C, G,
         eps);
@@ -544,7 +541,7 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     cudaStream_t st = as_stream(stream);
     CESM_CHECK_CUDA(cudaMemsetAsync(csum, 0, sizeof(float) * 3 * B * C, st));
     const int per_block = kNormThreads / (C / 8) * UNR;
-    dim3 grid(norm_grid(P, per_block), B);
+    dim3 grid(norm_grid(P, per_block, B), B);
     gn_bwd_reduce_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
     CESM_CHECK_LAUNCH();

@@ -50,7 +50,7 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
           out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None,
           out_place: Tuple[int, int, int, int] = (1, 1, 0, 0),
           bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-          out_dtype: torch.dtype = BF16) -> torch.Tensor:
+          out_dtype: torch.dtype = BF16, gn_sums: Optional[torch.Tensor] = None, gn_frames: int = 1):
     """out[n,oh,ow,:] = sum_t A[n, oh*stride+dh_t, ow*stride+dw_t, :] @ wt[:, t, :]^T (+bias)(+residual).
 
     a0/a1: bf16 [N,H,W,C]; wt: bf16 [cout, len(taps)*(C0+C1)].  `out_hw` is the iterated output
@@ -82,6 +82,10 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
     args.bias = _ptr(bias)
     args.residual = _ptr(residual)
     args.ldr = 0 if residual is None else residual.shape[-1]
+    if gn_sums is not None:
+        # fused GroupNorm statistics: gn_sums fp32 [n / gn_frames, groups, 2] (zeroed by the call)
+        assert gn_sums.dtype == torch.float32 and gn_sums.dim() == 3 and gn_sums.shape[0] * gn_frames == n
+        args.gn_sums, args.gn_groups, args.gn_frames = _ptr(gn_sums), gn_sums.shape[1], gn_frames
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == cout
     if residual is not None:

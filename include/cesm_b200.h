@@ -80,6 +80,12 @@ typedef struct cesm_igemm_args {
     const float* bias;    /* fp32 [cout] or NULL */
     const void* residual; /* bf16, addressed like out with pitch ldr, or NULL */
     int32_t ldr;
+    /* Optional fused GroupNorm statistics (video_net.py:216): if gn_sums != NULL it is zeroed and then
+     * receives, per sample b = image / gn_frames and group g of cout / gn_groups channels,
+     * (sum, sum of squares) of the bf16-rounded outputs: fp32 [n / gn_frames][gn_groups][2]. */
+    float* gn_sums;
+    int32_t gn_groups;
+    int32_t gn_frames;
 } cesm_igemm_args;
 
 int cesm_igemm(const cesm_igemm_args* args, void* stream);

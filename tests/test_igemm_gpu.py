@@ -100,3 +100,46 @@ def test_upsample_convT4x4s2(cuda, n, h, w, c):
             K.igemm(x, wg, taps=taps, out=out, out_hw=(h, w), out_place=(2, 2, ph, pw), bias=bias)
     ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
     assert _err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,frames", [(6, 64, 64, 64, 64, 3), (6, 48, 72, 128, 128, 3), (4, 16, 24, 64, 256, 2),
+                                                    (2, 192, 288, 64, 64, 1), (6, 8, 8, 128, 128, 3)])
+def test_conv3x3_fused_groupnorm_stats_and_flipped_taps(cuda, n, h, w, cin, cout, frames):
+    """Persistent kernel extras: (a) the per-sample per-group (sum, sum of squares) of the bf16
+    outputs from the epilogue equal those of the stored tensor; (b) the data-gradient form
+    (negated taps, residual added in the epilogue) matches conv_transpose."""
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(7)
+    G = 8
+    x = _rand((n, h, w, cin), cuda)
+    wt = _rand((cout, cin, 3, 3), cuda, 0.05)
+    bias = torch.randn(cout, device=cuda)
+    wg = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    sums = torch.full((n // frames, G, 2), 123.0, device=cuda)
+    out = K.igemm(x, wg, taps=K.TAPS_3x3, bias=bias, gn_sums=sums, gn_frames=frames)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert _err(out, ref) < 1e-2
+    o = out.float().view(n // frames, frames * h * w, G, cout // G)
+    want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+    assert _err(sums, want) < 1e-4
+    assert _err(sums, K.gn_stats(out, n // frames, G)) < 1e-4
+    # data gradient: dx = conv_transpose(dy, W) + r  ==  conv with negated taps and [ci][t][co] weights
+    dy = _rand((n, h, w, cout), cuda)
+    r = _rand((n, h, w, cin), cuda)
+    wd = wt.permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous()
+    dx = K.igemm(dy, wd, taps=[(-a, -b) for a, b in K.TAPS_3x3], residual=r)
+    ref_dx = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1) + r.float()
+    assert _err(dx, ref_dx) < 1e-2
+
+
+@pytest.mark.parametrize("m,k,n", [(331776, 64, 768), (82944, 256, 128), (20736, 256, 256), (1000, 1024, 64)])
+def test_gemm_large_and_streamed_weights(cuda, m, k, n):
+    """Projection shapes of the baseline model at full grid: resident (98 KB) and streamed weights."""
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(8)
+    a = _rand((1, 1, m, k), cuda)
+    w = _rand((n, k), cuda, 0.1)
+    out = K.igemm(a, w)
+    idx = torch.randint(0, m, (4096,), device=cuda)
+    ref = a.float().view(m, k)[idx] @ w.float().t()
+    assert _err(out.view(m, n)[idx], ref) < 1e-2
