@@ -364,7 +364,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
             p.epi_warp = (pw == 32);
         else
             p.epi_warp = (p.bw % 32 == 0);
-        if (knob_dbg() & 8) p.epi_warp = 0;
+        if (knob_dbg() & 8) p.epi_warp = 0;  // bisection: force the block-staged epilogue
         uint32_t obox[4] = {64u, (uint32_t)p.bw, (uint32_t)(halo ? 1 : p.bh), (uint32_t)(halo ? 1 : p.bn)};
         if (p.epi_warp && !halo) {
             obox[1] = 32u;

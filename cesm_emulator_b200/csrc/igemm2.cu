@@ -21,8 +21,9 @@
 //     lines), fusing bias, residual add and -- for the convs that feed a GroupNorm -- the per-sample
 //     per-group sum / sum-of-squares of the bf16-rounded outputs (video_net.py:216).
 //
-// Warp roles (224 threads): 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer
-// (+ TMEM allocation), 3..6 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Warp roles (352 threads): 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer
+// (+ TMEM allocation), 3..10 = epilogue: two groups of four warps (warp w reads TMEM lanes
+// 32*(w%4)..+31), the groups alternating over the 64-column chunks of a tile.
 #include "common.cuh"
 #include "igemm.h"
 
@@ -32,6 +33,7 @@ static constexpr int kTileM = 128;
 static constexpr int kKBlk = 64;
 static constexpr int kStageRowBytes = 128;                       // 64 bf16
 static constexpr int kOutStageBytes = kTileM * kStageRowBytes;   // one 64-column output chunk
+static constexpr int kIgemm2Threads = 352;
 
 __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -45,10 +47,33 @@ __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier of one epilogue group (4 warps): ids 1 and 2
+__device__ __forceinline__ void epi_bar_sync(int group) {
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+// 32 lanes x 64 consecutive fp32 columns in one instruction
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+          "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+          "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+          "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+          "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
 
-template <int BLOCK_N, bool HALO>
-__global__ void __launch_bounds__(224, 1)
+template <int BLOCK_N, bool HALO, bool GN>
+__global__ void __launch_bounds__(kIgemm2Threads, 1)
 igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -97,7 +122,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(t_full(s), 1);
-            mbar_init(t_empty(s), 4);
+            mbar_init(t_empty(s), 8);
         }
         mbar_init(b_all_bar, 1);
         fence_barrier_init();
@@ -210,13 +235,11 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                     // HALO: tap (dh, dw) is the view of the halo tile that starts (1+dh)*pw + (1+dw) rows in
                     const uint32_t sa =
                         HALO ? sa0 + ((1 + p.tap_dh[ti]) * pw + (1 + p.tap_dw[ti])) * kStageRowBytes : sa0;
-                    if (!(p.dbg & 4)) {
 #pragma unroll
-                        for (int k = 0; k < kKBlk / 16; ++k) {
-                            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
-                            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
-                            umma_bf16(d_tmem, da, db, idesc, (ai | ti | k) != 0);
-                        }
+                    for (int k = 0; k < kKBlk / 16; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
+                        const uint64_t db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
+                        umma_bf16(d_tmem, da, db, idesc, (ai | ti | k) != 0);
                     }
                     if (!p.b_resident) {
                         umma_commit(b_empty(b_stage));
@@ -239,44 +262,49 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             }
         }
     } else if (warp >= 3) {
-        // ===== epilogue =====
-        // Two staging schemes.  "warp-private" (p.epi_warp): the 32 accumulator rows of a warp are one
-        // storable box (a 32-pixel run of an image row, or -- HALO with 32-wide padded rows -- one tile
-        // row), so every warp stages, fences and TMA-stores its own 4 KB slab with no block-level
-        // barrier.  Otherwise the four warps fill one 16 KB buffer and one thread stores the tile box.
-        const int q = warp & 3;            // TMEM lane quadrant this warp may read
-        const int r = q * 32 + lane;       // accumulator row
-        const bool blk_issuer = (warp == 3 && lane == 0);
+        // ===== epilogue: two groups of four warps; group g takes the 64-column chunks with index % 2 == g =====
+        // Staging: "warp-private" (p.epi_warp) when the 32 accumulator rows of a warp are one storable
+        // box (a 32-pixel run of an image row, or -- HALO with 32-wide padded rows -- one tile row): the
+        // warp stages, fences and TMA-stores its own 4 KB slab with no block-level barrier.  Otherwise the
+        // four warps of a group fill the group's 16 KB buffer and one thread stores the tile box.
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int group = (warp - 3) >> 2;      // 0 or 1
+        const int r = q * 32 + lane;            // accumulator row
+        const bool grp_issuer = (lane == 0) && (warp == 3 || warp == 7);
         const bool warp_mode = p.epi_warp != 0;
+        const uint32_t obuf = o_base + group * kOutStageBytes;
+        const uint32_t my_row = obuf + r * kStageRowBytes;
+        const uint32_t sw7 = (r & 7);
+        float* gn_acc = reinterpret_cast<float*>(smem_gen + (gn_base - smem_base));
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint32_t chunk_ctr = 0;
         int cur_b = -1;
         auto gn_flush = [&](int b) {
-            epi_bar_sync();
-            if (warp == 3 && lane < 2 * p.gn_groups && b >= 0) {
-                float* acc_s = reinterpret_cast<float*>(smem_gen + (gn_base - smem_base));
-                atomicAdd(p.gn_sums + (size_t)b * p.gn_groups * 2 + lane, acc_s[lane]);
-                if (32 + lane < 2 * p.gn_groups) {
-                    atomicAdd(p.gn_sums + (size_t)b * p.gn_groups * 2 + 32 + lane, acc_s[32 + lane]);
-                    acc_s[32 + lane] = 0.f;
+            epi_bar_sync_all();
+            if (warp == 3 && b >= 0) {
+                for (int i = lane; i < 2 * p.gn_groups; i += 32) {
+                    atomicAdd(p.gn_sums + (size_t)b * p.gn_groups * 2 + i, gn_acc[i]);
+                    gn_acc[i] = 0.f;
                 }
-                acc_s[lane] = 0.f;
             }
-            epi_bar_sync();
+            epi_bar_sync_all();
         };
+        // per-tile constants of the row -> pixel map
+        const int rw = r % pw;
+        const int rh = (r / pw) % p.bh;
+        const int rn = r / (pw * p.bh);
+        // warp-private store box origin (relative to the tile)
+        const int r0 = q * 32;
+        const int st_w = HALO ? 0 : r0 % p.bw, st_h = HALO ? q : (r0 / p.bw) % p.bh, st_n = HALO ? 0 : r0 / (p.bw * p.bh);
+        const bool st_ok = HALO ? (q < p.bh) : (st_n < p.bn);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int n_tile, n0, oh0, ow0;
             tile_coords(tile, n_tile, n0, oh0, ow0);
-            // row -> pixel
-            const int rw = r % pw;
-            const int rh = (r / pw) % p.bh;
-            const int rn = r / (pw * p.bh);
             const int n = n0 + rn, oh = oh0 + rh, ow = ow0 + rw;
             const bool valid = (rw < p.bw) && (rn < p.bn) && (n < p.n) && (oh < p.oh) && (ow < p.ow);
             const long long pix = (static_cast<long long>(n) * p.out_h + (oh * p.o_sh + p.o_h0)) * p.out_w +
                                   (ow * p.o_sw + p.o_w0);
-            if (p.gn_sums) {
+            if (GN) {
                 const int b = n0 / p.gn_frames;  // the tile lies within one sample (host guarantees)
                 if (b != cur_b) {
                     if (cur_b >= 0) gn_flush(cur_b);
@@ -287,80 +315,62 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int cc = 0; cc < ((p.dbg & 2) ? 0 : BLOCK_N); cc += 64, ++chunk_ctr) {
-                const uint32_t obuf = o_base + (chunk_ctr & 1u) * kOutStageBytes;
-                // both TMEM loads in flight before anything else
-                uint32_t v0[32], v1[32];
-                if (!(p.dbg & 16)) {
-                    tmem_ld_32x32(taddr + cc, v0);
-                    tmem_ld_32x32(taddr + cc + 32, v1);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v0[i] = v1[i] = i + lane;
-                }
-                // the store that last read this staging buffer must have drained
+            for (int cc = group * 64; cc < BLOCK_N; cc += 128) {
+                uint32_t v[64];
+                tmem_ld_32x64(taddr + cc, v);
+                // the store that last read this group's staging buffer must have drained
                 if (warp_mode) {
-                    if (lane == 0 && !(p.dbg & 512)) tma_store_wait_read<1>();
+                    if (lane == 0) tma_store_wait_read<0>();
                     __syncwarp();
                 } else {
-                    if (blk_issuer) tma_store_wait_read<1>();
-                    epi_bar_sync();
+                    if (grp_issuer) tma_store_wait_read<0>();
+                    epi_bar_sync(group);
                 }
-                if (!(p.dbg & 256)) tmem_ld_wait();
                 const int col = n_tile * BLOCK_N + cc;
-                float sv[16];  // [0..7] per 8-column octet sums of this row, [8..15] sums of squares
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+                const bool has_res = p.residual != nullptr;
+                const uint4* rp = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + (valid ? pix : 0) * p.ldr + col);
+                tmem_ld_wait();
+                float sv[16];  // GN: [0..7] per 8-column octet sums of this row, [8..15] sums of squares
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    float f[32];
+                for (int j = 0; j < 8; ++j) {  // 8 columns = one 16-byte unit
+                    float f[8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(h2 ? v1[i] : v0[i]);
-                    if (p.bias && !(p.dbg & 128)) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + col + 32 * h2);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = __ldg(bp + j);
-                            f[4 * j] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
-                        }
+                    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]);
+                    if (p.bias) {
+                        const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
+                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                     }
-                    if (p.residual && valid) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(
-                            reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + col + 32 * h2);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 u = __ldg(rp + j);
-                            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
-                                         d = unpack_bf16x2(u.w);
-                            f[j * 8 + 0] += a.x; f[j * 8 + 1] += a.y; f[j * 8 + 2] += b.x; f[j * 8 + 3] += b.y;
-                            f[j * 8 + 4] += c2.x; f[j * 8 + 5] += c2.y; f[j * 8 + 6] += d.x; f[j * 8 + 7] += d.y;
-                        }
+                    if (has_res && valid) {
+                        const uint4 rr = __ldg(rp + j);
+                        const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y),
+                                     c2 = unpack_bf16x2(rr.z), d = unpack_bf16x2(rr.w);
+                        f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
+                        f[4] += c2.x; f[5] += c2.y; f[6] += d.x; f[7] += d.y;
                     }
-                    // pack to bf16, write the 4 swizzled 16-byte units of this half row
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                        u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                        u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                        u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                        const int unit = h2 * 4 + j;
-                        const uint32_t addr = obuf + r * kStageRowBytes + ((unit ^ (r & 7)) << 4);
-                        if (!(p.dbg & 32) || u.x == 0x7fc07fc1u)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y),
-                                         "r"(u.z), "r"(u.w)
-                                         : "memory");
-                        if (p.gn_sums) {
-                            // statistics of what the consumer will read: the bf16-rounded values
-                            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
-                                         d = unpack_bf16x2(u.w);
-                            const float s = ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
-                            const float qq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c2.x, c2.x,
-                                             fmaf(c2.y, c2.y, fmaf(d.x, d.x, d.y * d.y)))))));
-                            sv[unit] = valid ? s : 0.f;
-                            sv[8 + unit] = valid ? qq : 0.f;
-                        }
+                    uint4 u;
+                    u.x = pack_bf16x2(f[0], f[1]);
+                    u.y = pack_bf16x2(f[2], f[3]);
+                    u.z = pack_bf16x2(f[4], f[5]);
+                    u.w = pack_bf16x2(f[6], f[7]);
+                    const uint32_t addr = my_row + ((j ^ sw7) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z),
+                                 "r"(u.w)
+                                 : "memory");
+                    if (GN) {
+                        // statistics of what the consumer will read: the bf16-rounded values
+                        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
+                                     d = unpack_bf16x2(u.w);
+                        const float s = ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
+                        const float qq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c2.x, c2.x,
+                                         fmaf(c2.y, c2.y, fmaf(d.x, d.x, d.y * d.y)))))));
+                        sv[j] = valid ? s : 0.f;
+                        sv[8 + j] = valid ? qq : 0.f;
                     }
                 }
-                if (p.gn_sums) {
+                if (GN) {
                     // 16 values x 32 rows -> 16 totals with a halving butterfly (16 shuffles): after the
                     // step for lane bit b a lane keeps the half of its values selected by that bit.
                     {
@@ -397,27 +407,21 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                         const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
                                         ((lane >> 1) & 1);
                         const int g = (col + 8 * (idx & 7)) / p.gn_cpg;
-                        float* acc_s = reinterpret_cast<float*>(smem_gen + (gn_base - smem_base));
-                        atomicAdd(acc_s + 2 * g + (idx >> 3), sv[0]);
+                        atomicAdd(gn_acc + 2 * g + (idx >> 3), sv[0]);
                     }
                 }
-                if (!(p.dbg & 64)) fence_proxy_async();
+                fence_proxy_async();
                 if (warp_mode) {
                     __syncwarp();
-                    if (lane == 0 && !(p.dbg & 1)) {
+                    if (lane == 0) {
                         const uint32_t slab = obuf + q * 32 * kStageRowBytes;
-                        if (HALO) {  // 32-wide padded rows: warp q holds tile row q
-                            if (q < p.bh && oh0 + q < p.oh) tma_store_4d(&maps.out, slab, col, ow0, oh0 + q, n0);
-                        } else {     // 32 consecutive pixels of one image row
-                            const int r0 = q * 32;
-                            const int sw = r0 % p.bw, sh = (r0 / p.bw) % p.bh, sn = r0 / (p.bw * p.bh);
-                            if (sn < p.bn) tma_store_4d(&maps.out, slab, col, ow0 + sw, oh0 + sh, n0 + sn);
-                        }
+                        if (st_ok && (!HALO || oh0 + st_h < p.oh))
+                            tma_store_4d(&maps.out, slab, col, ow0 + st_w, oh0 + st_h, n0 + st_n);
                         tma_store_commit();
                     }
                 } else {
-                    epi_bar_sync();
-                    if (blk_issuer && !(p.dbg & 1)) {
+                    epi_bar_sync(group);
+                    if (grp_issuer) {
                         if (HALO) {
                             // one store per tile row: the bw useful pixels of each padded accumulator row
                             for (int h = 0; h < p.bh; ++h)
@@ -438,7 +442,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                 acc_phase ^= 1u;
             }
         }
-        if (p.gn_sums) gn_flush(cur_b);
+        if (GN) gn_flush(cur_b);
         if (lane == 0) tma_store_wait_all();
     }
 
@@ -450,34 +454,36 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO>
+template <int BLOCK_N, bool HALO, bool GN>
 static cudaError_t launch_igemm2(const Igemm2Maps& maps, const Igemm2Params& p, int grid, size_t smem,
                                  cudaStream_t stream) {
-    static size_t configured = 0;  // benign race: attribute set is idempotent and monotone
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BLOCK_N, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kIgemm2MaxSmem);
+    static bool configured = false;  // benign race: attribute set is idempotent
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BLOCK_N, HALO, GN>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIgemm2MaxSmem);
         if (e != cudaSuccess) return e;
-        configured = kIgemm2MaxSmem;
+        configured = true;
     }
-    igemm2_kernel<BLOCK_N, HALO><<<grid, 224, smem, stream>>>(maps, p);
+    igemm2_kernel<BLOCK_N, HALO, GN><<<grid, kIgemm2Threads, smem, stream>>>(maps, p);
     return cudaGetLastError();
+}
+
+template <int BLOCK_N>
+static cudaError_t launch_igemm2_n(const Igemm2Maps& maps, const Igemm2Params& p, bool halo, int grid, size_t smem,
+                                   cudaStream_t stream) {
+    const bool gn = p.gn_sums != nullptr;
+    if (halo) return gn ? launch_igemm2<BLOCK_N, true, true>(maps, p, grid, smem, stream)
+                        : launch_igemm2<BLOCK_N, true, false>(maps, p, grid, smem, stream);
+    return gn ? launch_igemm2<BLOCK_N, false, true>(maps, p, grid, smem, stream)
+              : launch_igemm2<BLOCK_N, false, false>(maps, p, grid, smem, stream);
 }
 
 cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, int grid, size_t smem,
                           cudaStream_t stream) {
-    if (halo) {
-        switch (block_n) {
-            case 64: return launch_igemm2<64, true>(maps, p, grid, smem, stream);
-            case 128: return launch_igemm2<128, true>(maps, p, grid, smem, stream);
-            case 256: return launch_igemm2<256, true>(maps, p, grid, smem, stream);
-        }
-    } else {
-        switch (block_n) {
-            case 64: return launch_igemm2<64, false>(maps, p, grid, smem, stream);
-            case 128: return launch_igemm2<128, false>(maps, p, grid, smem, stream);
-            case 256: return launch_igemm2<256, false>(maps, p, grid, smem, stream);
-        }
+    switch (block_n) {
+        case 64: return launch_igemm2_n<64>(maps, p, halo, grid, smem, stream);
+        case 128: return launch_igemm2_n<128>(maps, p, halo, grid, smem, stream);
+        case 256: return launch_igemm2_n<256>(maps, p, halo, grid, smem, stream);
     }
     return cudaErrorInvalidValue;
 }
