@@ -69,7 +69,8 @@ class GradBuckets:
         self.bounds.append(total)
         self.n_buckets = len(self.bounds) - 1
         self._pending = list(self._pending_init)
-        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.on_cuda = dev.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and self.on_cuda) else None
         self._hooks = []
         if self.world > 1:
             for p in self.params:
@@ -93,13 +94,17 @@ class GradBuckets:
         b = self._bucket_of[p.data_ptr()]
         self._pending[b] -= 1
         if self._pending[b] == 0:
+            bucket = self.flat[self.bounds[b]:self.bounds[b + 1]]
+            if not self.on_cuda:  # host tensors (gloo): used by the CPU tests of the bucket logic
+                dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.pg)
+                return
             cur = torch.cuda.current_stream()
             self.comm_stream.wait_stream(cur)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(self.flat[self.bounds[b]:self.bounds[b + 1]], op=dist.ReduceOp.SUM, group=self.pg)
+                dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.pg)
 
     def finish_step(self):
-        if self.world > 1:
+        if self.world > 1 and self.on_cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def clip_(self, max_norm: float) -> torch.Tensor:
