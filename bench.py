@@ -294,6 +294,8 @@ def run_b200(args, H, W, arch_kw):
     step_tf = (gflop_sample * B / (ms_res / args.steps)) if gflop_sample else None  # GFLOP/ms == TFLOP/s
     if not args.no_kernel_pass:
         # every rank runs the step (it contains the all-reduce); rank 0 reports
+        for h in eng.buckets._hooks:
+            h.remove()
         prof_eng = TrainEngine(diff, (B, 1, H, W), (B, 1, Kf, H, W), use_graph=False)
         prof_eng.x0.copy_(eng.x0)
         prof_eng.cond.copy_(eng.cond)
@@ -352,8 +354,14 @@ def run_b200(args, H, W, arch_kw):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down: the captured graphs hold NCCL kernels, and destroying the communicator under them
+        # can block; everything is measured and printed, so synchronise, meet at a barrier and leave.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
