@@ -51,6 +51,8 @@ class WgradArgs(Structure):
         ("y_h", c_int32), ("y_w", c_int32),
         ("y_sh", c_int32), ("y_sw", c_int32), ("y_h0", c_int32), ("y_w0", c_int32),
         ("dw", c_void_p),
+        ("dw_so", ctypes.c_longlong), ("dw_si", ctypes.c_longlong),
+        ("dw_tap_off", c_int32 * CESM_MAX_TAPS),
     ]
 
 
@@ -99,6 +101,7 @@ _SIGNATURES: dict[str, list] = {
     "cesm_wgrad": [POINTER(WgradArgs), _P],
     "cesm_pack_weight": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _P],
     "cesm_pack_weights_batched": [_P, _I, _P],
+    "cesm_unpack_wgrads_batched": [_P, _I, _P],
     "cesm_unpack_wgrad": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _I, _P],
     "cesm_colsum": [_P, _P, _L, _I, _P],
     "cesm_gn_stats": [_P, _P, _I, _L, _I, _I, _P],

@@ -562,7 +562,16 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
         if (rc) return rc;
     }
     const int ctot = a->c0 + a->c1;
-    CESM_CHECK_CUDA(cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * a->num_taps * ctot, st));
+    if (a->dw_so != 0) {  // accumulate straight into the caller's layout
+        p.so = a->dw_so;
+        p.si = a->dw_si;
+        for (int t = 0; t < a->num_taps; ++t) p.tap_off[t] = a->dw_tap_off[t];
+    } else {
+        p.so = (long long)a->num_taps * ctot;
+        p.si = 1;
+        for (int t = 0; t < a->num_taps; ++t) p.tap_off[t] = t * ctot;
+        CESM_CHECK_CUDA(cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * a->num_taps * ctot, st));
+    }
     const int block_n = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
     const int units = a->num_taps * (ctot / 64);
     const int base_ctas = ((units + 1) / 2) * (a->cout / block_n);

@@ -39,6 +39,24 @@ pack_weights_batched_kernel(const cesm_pack_desc* __restrict__ descs) {
         dst[idx] = __float2bfloat16(src[o * d.so + i * d.si + d.tap_off[t]]);
     }
 }
+// Batched inverse: dst[o*so + i*si + off[t]] += src[o][t][i], then src[o][t][i] = 0 (the fp32 scratch
+// the weight-gradient kernels accumulate into is ready for the next step without a memset).
+__global__ void __launch_bounds__(256)
+unpack_wgrads_batched_kernel(const cesm_pack_desc* __restrict__ descs) {
+    const cesm_pack_desc d = descs[blockIdx.y];
+    const long long total = (long long)d.O * d.T * d.I;
+    float* __restrict__ src = const_cast<float*>(d.src);
+    float* __restrict__ dst = reinterpret_cast<float*>(d.dst);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = idx % d.I;
+        const int t = (idx / d.I) % d.T;
+        const int o = idx / ((long long)d.I * d.T);
+        float* q = dst + o * d.so + i * d.si + d.tap_off[t];
+        *q += src[idx];
+        src[idx] = 0.f;
+    }
+}
 // dst[o*so + i*si + off[t]] (+)= src[o][t][i]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int T, int I,
                                     long long so, long long si, TapOffsets taps, int accumulate) {
@@ -146,14 +164,22 @@ __global__ void __launch_bounds__(256)
 input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
                         const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db, int NI,
                         int F, int H, int W) {
-    constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS, Q = 256 / COUT;
+    // thread = 4 output channels x TPT taps: 4*TPT FMAs per (4 + TPT) shared-memory reads per pixel
+    constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS, CG = COUT / 4, Q = 256 / CG;
     constexpr int TPT = (NT + Q - 1) / Q;  // taps per thread
     __shared__ float sin_[2][PW][PW + 1];
-    __shared__ __nv_bfloat16 sdy[T * T][COUT + 8];
-    const int co = threadIdx.x % COUT, q = threadIdx.x / COUT;
-    float acc[TPT], accb = 0.f;
+    __shared__ __align__(16) __nv_bfloat16 sdy[T * T][COUT + 8];
+    const int cg = threadIdx.x % CG, q = threadIdx.x / CG;
+    float acc[TPT][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
+    int toff[TPT];  // offset of tap (ci, kh, kw) inside sin_ relative to [0][ty][tx]
 #pragma unroll
-    for (int i = 0; i < TPT; ++i) acc[i] = 0.f;
+    for (int i = 0; i < TPT; ++i) {
+        acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        const int tap = q + i * Q;
+        const int ci = tap / (KS * KS), kh = (tap / KS) % KS, kw = tap % KS;
+        toff[i] = tap < NT ? (ci * PW + kh) * (PW + 1) + kw : 0;
+    }
+    const float* sflat = &sin_[0][0][0];
     const int tiles_w = (W + T - 1) / T, tiles_h = (H + T - 1) / T;
     const int ntiles = tiles_w * tiles_h * NI;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -177,26 +203,36 @@ input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__
             *reinterpret_cast<uint4*>(&sdy[px][v8 * 8]) = u;
         }
         __syncthreads();
+#pragma unroll 2
         for (int px = 0; px < T * T; ++px) {
-            const float g = __bfloat162float(sdy[px][co]);
-            const int ty = px / T, tx = px % T;
-            if (q == 0) accb += g;
+            const uint2 gu = *reinterpret_cast<const uint2*>(&sdy[px][cg * 4]);
+            const float2 g01 = unpack_bf16x2(gu.x), g23 = unpack_bf16x2(gu.y);
+            const int poff = (px / T) * (PW + 1) + (px % T);
+            if (q == 0) {
+                accb[0] += g01.x; accb[1] += g01.y; accb[2] += g23.x; accb[3] += g23.y;
+            }
 #pragma unroll
             for (int i = 0; i < TPT; ++i) {
-                const int tap = q + i * Q;
-                if (tap < NT) {
-                    const int ci = tap / (KS * KS), kh = (tap / KS) % KS, kw = tap % KS;
-                    acc[i] = fmaf(g, sin_[ci][ty + kh][tx + kw], acc[i]);
-                }
+                const float xv = sflat[poff + toff[i]];
+                acc[i][0] = fmaf(g01.x, xv, acc[i][0]);
+                acc[i][1] = fmaf(g01.y, xv, acc[i][1]);
+                acc[i][2] = fmaf(g23.x, xv, acc[i][2]);
+                acc[i][3] = fmaf(g23.y, xv, acc[i][3]);
             }
         }
     }
 #pragma unroll
     for (int i = 0; i < TPT; ++i) {
         const int tap = q + i * Q;
-        if (tap < NT) atomicAdd(&dw[co * NT + tap], acc[i]);
+        if (tap < NT) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(&dw[(cg * 4 + c) * NT + tap], acc[i][c]);
+        }
     }
-    if (q == 0) atomicAdd(&db[co], accb);
+    if (q == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(&db[cg * 4 + c], accb[c]);
+    }
 }
 
 // eps[b][h][w] = bias + sum_c a[(b*F + mid)][h][w][c] * w[c]   ; 8 lanes per pixel (C == 64)
@@ -415,6 +451,14 @@ extern "C" int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int
     CESM_REQUIRE(n >= 0 && descs_device != nullptr, "bad descriptor table");
     if (n == 0) return CESM_OK;
     pack_weights_batched_kernel<<<dim3(16, n), 256, 0, as_stream(stream)>>>(descs_device);
+    CESM_CHECK_LAUNCH();
+    return CESM_OK;
+}
+
+extern "C" int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream) {
+    CESM_REQUIRE(n >= 0 && descs_device != nullptr, "bad descriptor table");
+    if (n == 0) return CESM_OK;
+    unpack_wgrads_batched_kernel<<<dim3(16, n), 256, 0, as_stream(stream)>>>(descs_device);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

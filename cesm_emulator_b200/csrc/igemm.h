@@ -39,7 +39,9 @@ struct WgradParams {
     int32_t bw, bh, bn;     // 64-pixel K tile box (bw*bh*bn == 64)
     uint32_t box_bytes;     // bytes of one 64-channel x 64-pixel TMA box
     int32_t cout;
-    float* dw;              // fp32 [cout][num_taps][c0+c1], accumulated with red.add
+    float* dw;              // fp32, accumulated with red.add at dw[co*so + ci*si + tap_off[tap]]
+    long long so, si;
+    int32_t tap_off[16];
 };
 
 // ---- second-generation persistent kernel (igemm2.cu) ------------------------------------------

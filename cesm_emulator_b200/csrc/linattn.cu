@@ -361,7 +361,7 @@ __device__ __forceinline__ void store_cfrag(__nv_bfloat16* row_g, __nv_bfloat16*
 // ------------------------------------------------------------------------------------------------
 // apply (forward): out[p][e] = sum_d qs[p][d] ctx[d][e]; warp = head, 16 pixels per step
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int n,
                 int H, int chunk, float scale) {
     const int HD = H * LD, ld = 3 * HD;
@@ -397,7 +397,7 @@ la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, _
 //   dkh = v dctx^T   ; dk = kh (dkh - delta) , kh = exp(k - max) / Z
 //   dv  = kh dctx
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     float* __restrict__ ws, const float* __restrict__ dctx, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
@@ -482,9 +482,10 @@ la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 using namespace cesm;
 
 static int la_chunk(int n, int NI) {
-    // aim for >= ~4 blocks per SM-wave while keeping atomics per image modest
+    // many more blocks than SMs (>= ~8 per SM) so that the tail wave is a small fraction, while a
+    // block still amortises its per-head fragment preloads and atomics over >= 128 pixels
     int chunk = 2048;
-    while (chunk > 64 && (long long)NI * ((n + chunk - 1) / chunk) < 296) chunk >>= 1;
+    while (chunk > 128 && (long long)NI * ((n + chunk - 1) / chunk) < 148 * 8) chunk >>= 1;
     return chunk;
 }
 

@@ -149,9 +149,8 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         const bool valid = u < units;
         const int tap = valid ? u / cblk : 0;
         const int ci = valid ? ((u - tap * cblk) << 6) + (r & 63) : 0;
-        const int ctot = p.c0 + p.c1;
-        float* base = p.dw + (size_t)tap * ctot + ci;
-        const size_t co_stride = (size_t)p.num_taps * ctot;
+        float* base = p.dw + (size_t)p.tap_off[tap] + (size_t)ci * p.si;
+        const size_t co_stride = (size_t)p.so;
         mbar_wait(tmem_full_bar, 0, 23);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);

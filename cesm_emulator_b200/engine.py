@@ -76,11 +76,46 @@ class GradBuckets:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self._owned = {p.data_ptr() for p in self.params}
+        # packed fp32 scratch of the multi-tap weight gradients: (param ptr, tap key) -> (tensor, spec)
+        self._scratch = {}
+        self._unpack_plan = {}   # bucket -> (entry count, device descriptor table)
         ops.set_grad_sink(self)  # weight gradients are accumulated straight into the flat buffer
 
     # grad-sink protocol (ops._wgrad_to_param)
     def owns(self, p) -> bool:
         return p.data_ptr() in self._owned
+
+    def scratch(self, p, key, spec) -> torch.Tensor:
+        """Persistent zeroed fp32 [O, T, I] buffer the tcgen05 weight-gradient kernel accumulates into;
+        `unpack_bucket` adds it into p.grad (layout `spec`) and re-zeroes it."""
+        k = (p.data_ptr(), key)
+        ent = self._scratch.get(k)
+        if ent is None:
+            O, T, I = spec[0], spec[1], spec[2]
+            ent = (torch.zeros((O, T, I), dtype=torch.float32, device=p.device), spec, p,
+                   self._bucket_of[p.data_ptr()])
+            self._scratch[k] = ent
+            self._unpack_plan.clear()
+        return ent[0]
+
+    def unpack_bucket(self, b: Optional[int]) -> None:
+        """One kernel adds every packed scratch of bucket `b` (all buckets if None) into the flat gradient."""
+        from . import _lib
+        ents = [e for e in self._scratch.values() if b is None or e[3] == b]
+        if not ents:
+            return
+        plan = self._unpack_plan.get(b)
+        if plan is None or plan[0] != len(ents):
+            arr = (_lib.PackDesc * len(ents))()
+            for d, (buf, spec, p, _) in zip(arr, ents):
+                d.src, d.dst = buf.data_ptr(), p.grad.data_ptr()
+                d.O, d.T, d.I, d.so, d.si = spec[0], spec[1], spec[2], spec[3], spec[4]
+                for i, o in enumerate(spec[5]):
+                    d.tap_off[i] = int(o)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            plan = (len(ents), host.to(self.flat.device))
+            self._unpack_plan[b] = plan
+        _lib.call("cesm_unpack_wgrads_batched", plan[1].data_ptr(), plan[0], K._stream())
 
     def ready(self, p) -> None:
         if self.world > 1:
@@ -94,6 +129,7 @@ class GradBuckets:
         b = self._bucket_of[p.data_ptr()]
         self._pending[b] -= 1
         if self._pending[b] == 0:
+            self.unpack_bucket(b)
             bucket = self.flat[self.bounds[b]:self.bounds[b + 1]]
             if not self.on_cuda:  # host tensors (gloo): used by the CPU tests of the bucket logic
                 dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.pg)
@@ -104,6 +140,8 @@ class GradBuckets:
                 dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.pg)
 
     def finish_step(self):
+        if self.world == 1:
+            self.unpack_bucket(None)
         if self.world > 1 and self.on_cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 

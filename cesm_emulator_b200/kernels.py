@@ -102,16 +102,27 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
 
 def wgrad(x0: torch.Tensor, dy: torch.Tensor, *, taps: Sequence[Tuple[int, int]] = TAPS_1x1,
           x1: Optional[torch.Tensor] = None, stride: int = 1, grid_hw: Optional[Tuple[int, int]] = None,
-          dy_place: Tuple[int, int, int, int] = (1, 1, 0, 0)) -> torch.Tensor:
-    """dw[co, t, ci] = sum_pixels dy[n,oh,ow,co] * X[n, oh*stride+dh_t, ow*stride+dw_t, ci]  -> fp32 [cout, T, C0+C1]."""
+          dy_place: Tuple[int, int, int, int] = (1, 1, 0, 0), into: Optional[torch.Tensor] = None,
+          layout: Optional[Tuple[int, int, Sequence[int]]] = None) -> torch.Tensor:
+    """dw[co, t, ci] = sum_pixels dy[n,oh,ow,co] * X[n, oh*stride+dh_t, ow*stride+dw_t, ci]  -> fp32 [cout, T, C0+C1].
+
+    With `into` (an fp32 tensor) and `layout` = (so, si, tap_off) the result is instead ACCUMULATED
+    at into.flatten()[co*so + ci*si + tap_off[t]] (e.g. straight into a parameter's .grad)."""
     _req_cuda(x0, x1, dy)
     assert x0.dtype == BF16 and dy.dtype == BF16 and x0.dim() == 4 and dy.dim() == 4
     n, h, w, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
     cout = dy.shape[-1]
     oh, ow = grid_hw if grid_hw is not None else (h // stride, w // stride)
-    dw_ = torch.empty((cout, len(taps), c0 + c1), dtype=torch.float32, device=x0.device)
     a = _lib.WgradArgs()
+    if into is not None:
+        assert layout is not None and into.dtype == torch.float32 and into.is_contiguous()
+        dw_ = into
+        a.dw_so, a.dw_si = int(layout[0]), int(layout[1])
+        for i, o in enumerate(layout[2]):
+            a.dw_tap_off[i] = int(o)
+    else:
+        dw_ = torch.empty((cout, len(taps), c0 + c1), dtype=torch.float32, device=x0.device)
     a.x0, a.x1, a.c0, a.c1 = _ptr(x0), _ptr(x1), c0, c1
     a.n, a.h, a.w, a.stride = n, h, w, stride
     a.num_taps = len(taps)

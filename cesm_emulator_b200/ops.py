@@ -156,16 +156,25 @@ def _direct(weight: torch.Tensor) -> bool:
     return sink is not None and weight.grad is not None and sink.owns(weight)
 
 
-def _wgrad_to_param(weight, g, O, T, I, so, si, taps, last: bool = True, into: Optional[torch.Tensor] = None):
-    """g: fp32 [O, T, I] from cesm_wgrad -> gradient in `weight`'s own layout.  Returns None when it
-    was accumulated directly into weight.grad (engine mode), else a tensor (`into` if given)."""
+def _wgrad_into_param(weight, x0, x1, dy, taps, so, si, tap_off, last: bool = True,
+                      into: Optional[torch.Tensor] = None, **kw):
+    """Weight gradient accumulated by the tcgen05 kernel's epilogue directly in `weight`'s own layout:
+    into weight.grad (engine mode; returns None and notifies the sink) or into a zeroed tensor."""
+    T = len(taps)
     if _direct(weight):
-        K.unpack_wgrad(g, weight.grad.view(-1), O, T, I, so, si, taps, accumulate=True)
+        sink = _GRAD_SINK[0]
+        if T == 1:  # same layout as the kernel's packed output: coalesced atomics straight into .grad
+            K.wgrad(x0, dy, x1=x1, taps=taps, into=weight.grad, layout=(so, si, tap_off), **kw)
+        else:       # accumulate into a persistent packed scratch; the sink un-packs a whole bucket at once
+            cout = dy.shape[-1]
+            ctot = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
+            scratch = sink.scratch(weight, tuple(tap_off), (cout, T, ctot, so, si, list(tap_off)))
+            K.wgrad(x0, dy, x1=x1, taps=taps, into=scratch, layout=(T * ctot, 1, [t * ctot for t in range(T)]), **kw)
         if last:
-            _GRAD_SINK[0].ready(weight)
+            sink.ready(weight)
         return None
-    dwt = torch.empty_like(weight) if into is None else into
-    K.unpack_wgrad(g, dwt.view(-1), O, T, I, so, si, taps)
+    dwt = torch.zeros_like(weight) if into is None else into
+    K.wgrad(x0, dy, x1=x1, taps=taps, into=dwt, layout=(so, si, tap_off), **kw)
     return dwt
 
 
@@ -198,8 +207,7 @@ def _conv_wgrad(weight, x0, x1, dy, ks: int):
     cout = weight.shape[0]
     ctot = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
     kk = ks * ks
-    g = K.wgrad(x0, dy, x1=x1, taps=_sq_taps(ks))  # [cout, kk, ctot]
-    return _wgrad_to_param(weight, g, cout, kk, ctot, ctot * kk, kk, list(range(kk)))
+    return _wgrad_into_param(weight, x0, x1, dy, _sq_taps(ks), ctot * kk, kk, list(range(kk)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -275,8 +283,7 @@ class DownsampleFn(torch.autograd.Function):
             for (ph, pw), wd in ctx.wd.items():
                 K.igemm(dy, wd, taps=_phase(ph, pw)[0], out=dx, out_hw=(h // 2, w // 2), out_place=(2, 2, ph, pw))
         if ctx.needs_input_grad[1]:
-            g = K.wgrad(x, dy, taps=DownsampleFn.TAPS, stride=2)
-            dwt = _wgrad_to_param(weight, g, c, 16, c, c * 16, 16, list(range(16)))
+            dwt = _wgrad_into_param(weight, x, None, dy, DownsampleFn.TAPS, c * 16, 16, list(range(16)), stride=2)
         if ctx.needs_input_grad[2]:
             db = K.colsum(dy)
         return dx, dwt, db, None
@@ -311,11 +318,12 @@ class UpsampleFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.igemm(dy, ctx.wd, taps=DownsampleFn.TAPS, stride=2)
         if ctx.needs_input_grad[1]:
-            into = None if _direct(weight) else torch.empty_like(weight)
+            into = None if _direct(weight) else torch.zeros_like(weight)
             for n_ph, (ph, pw) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
                 taps, koff = _phase(ph, pw)
-                g = K.wgrad(x, dy, taps=taps, grid_hw=(h, w), dy_place=(2, 2, ph, pw))  # [co, 4, ci]
-                dwt = _wgrad_to_param(weight, g, c, 4, c, 16, c * 16, koff, last=(n_ph == 3), into=into)
+                # ConvTranspose weight is [ci, co, kh, kw]: co stride 16, ci stride c*16
+                dwt = _wgrad_into_param(weight, x, None, dy, taps, 16, c * 16, koff, last=(n_ph == 3), into=into,
+                                        grid_hw=(h, w), dy_place=(2, 2, ph, pw))
         if ctx.needs_input_grad[2]:
             db = K.colsum(dy)
         return dx, dwt, db, None

@@ -95,7 +95,8 @@ int cesm_igemm(const cesm_igemm_args* args, void* stream);
  *     dw[co, t, ci] = sum_{n, oh, ow}  dy[n, oh, ow, co] * X[n, oh*stride + tap_dh[t], ow*stride + tap_dw[t], ci]
  * X = concat(x0, x1) as in cesm_igemm.  dy pixel (n, oh, ow) is row
  * ((n*y_h + oh*y_sh + y_h0)*y_w + ow*y_sw + y_w0) of a bf16 [*, cout] matrix (sub-pixel phases of
- * a transposed conv).  dw is fp32 [cout, num_taps, c0+c1] and is overwritten.
+ * a transposed conv).  dw is fp32 [cout, num_taps, c0+c1] and is overwritten (see dw_so for the
+ * accumulate-in-place form).
  *
  * Replaces the weight-gradient halves of cuDNN/cuBLAS backward for the call sites listed above.
  */
@@ -113,6 +114,12 @@ typedef struct cesm_wgrad_args {
     int32_t oh, ow;
     int32_t y_h, y_w, y_sh, y_sw, y_h0, y_w0;
     float* dw;
+    /* Optional destination layout: if dw_so != 0 the result is ACCUMULATED (fp32 atomics, dw is not
+     * cleared) at dw[co*dw_so + ci*dw_si + dw_tap_off[t]] -- e.g. straight into a PyTorch conv-weight
+     * gradient [cout][cin][kh][kw] (dw_so = cin*kh*kw, dw_si = kh*kw, dw_tap_off[t] = t).  With
+     * dw_so == 0, dw is the packed fp32 [cout][num_taps][c0+c1] and is overwritten. */
+    long long dw_so, dw_si;
+    int32_t dw_tap_off[CESM_MAX_TAPS];
 } cesm_wgrad_args;
 
 int cesm_wgrad(const cesm_wgrad_args* args, void* stream);
@@ -135,6 +142,9 @@ typedef struct cesm_pack_desc {
     int32_t tap_off[CESM_MAX_TAPS];
 } cesm_pack_desc;
 int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* stream);
+/* Batched inverse for gradients: for each descriptor, dst (fp32, the parameter-gradient layout)
+ * += src[o][t][i] (fp32 packed scratch written by cesm_wgrad) and the scratch is zeroed. */
+int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream);
 int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int I, long long so, long long si,
                       const int32_t* tap_off, int accumulate, void* stream);
 /* out[c] = sum over rows of bf16 x[M][C] (bias gradients). */
