@@ -205,13 +205,16 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                 const float du1 = dd.y * dsilu_f(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1]));
                 acc[0][2 * i] += du0;
                 acc[0][2 * i + 1] += du1;
-                acc[1][2 * i] = fmaf(du0, (f.x - mean) * rstd, acc[1][2 * i]);
-                acc[1][2 * i + 1] = fmaf(du1, (f.y - mean) * rstd, acc[1][2 * i + 1]);
+                acc[1][2 * i] = fmaf(du0, f.x, acc[1][2 * i]);      // sum du*x; xhat folded in below
+                acc[1][2 * i + 1] = fmaf(du1, f.y, acc[1][2 * i + 1]);
                 acc[2][2 * i] += f.x;
                 acc[2][2 * i + 1] += f.y;
             }
         }
     }
+    // sum du*xhat = rstd * (sum du*x - mean * sum du)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[1][i] = rstd * (acc[1][i] - mean * acc[0][i]);
     // reduce threads that share a channel slot (stride vec_per_pix) through shared memory
     __shared__ float red[kNormThreads][9];
     for (int k = 0; k < 3; ++k) {
@@ -492,13 +495,22 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 // Streaming kernels want every SM busy for the whole launch: a grid of ~4 resident blocks per SM in
 // total (over all `batches` of grid.y), each thread looping many trips, instead of one trip per block
 // (whose latency would be the whole kernel) -- no wave quantisation, no tail.
-static int norm_grid(long long work_items, int per_block, int batches = 1) {
+// `resident` = blocks of this kernel that fit on the whole GPU at once (SMs x occupancy): the grid is
+// exactly one resident wave, so there is no partially filled second wave.
+static int norm_grid(long long work_items, int per_block, int batches = 1, int resident = 148 * 4) {
     long long blocks = (work_items + per_block - 1) / per_block;
-    long long cap = (148 * 4) / (batches < 1 ? 1 : batches);
+    long long cap = resident / (batches < 1 ? 1 : batches);
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
+}
+template <typename Kern>
+static int resident_blocks(Kern kern, int threads) {
+    int per_sm = 0, dev = 0, sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * per_sm;
 }
 
 }  // namespace cesm
@@ -514,7 +526,8 @@ extern "C" int cesm_gn_stats(const void* x, float* sums, int B, long long P, int
     GN_CHECK(C, G);
     CESM_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * B * G, as_stream(stream)));
     const int per_block = kNormThreads / (C / 8) * UNR;
-    dim3 grid(norm_grid(P, per_block, B), B);
+    static const int res = resident_blocks(gn_stats_kernel, kNormThreads);
+    dim3 grid(norm_grid(P, per_block, B, res), B);
     gn_stats_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, sums, P, C, G);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
@@ -525,7 +538,8 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
                                  int G, float eps, void* stream) {
     GN_CHECK(C, G);
     const int per_block = kNormThreads / (C / 8) * UNR;
-    dim3 grid(norm_grid(P, per_block, B), B);
+    static const int res = resident_blocks(gn_apply_fwd_kernel, kNormThreads);
+    dim3 grid(norm_grid(P, per_block, B, res), B);
     gn_apply_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)x, sums, gamma, beta, film, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, P, C, G,
         eps);
@@ -541,11 +555,14 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     cudaStream_t st = as_stream(stream);
     CESM_CHECK_CUDA(cudaMemsetAsync(csum, 0, sizeof(float) * 3 * B * C, st));
     const int per_block = kNormThreads / (C / 8) * UNR;
-    dim3 grid(norm_grid(P, per_block, B), B);
+    static const int res_r = resident_blocks(gn_bwd_reduce_kernel, kNormThreads);
+    static const int res_a = resident_blocks(gn_bwd_apply_kernel, kNormThreads);
+    dim3 grid(norm_grid(P, per_block, B, res_r), B);
+    dim3 grid_a(norm_grid(P, per_block, B, res_a), B);
     gn_bwd_reduce_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
     CESM_CHECK_LAUNCH();
-    gn_bwd_apply_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
+    gn_bwd_apply_kernel<<<grid_a, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
                                                        beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps);
     CESM_CHECK_LAUNCH();
     gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, sums, gamma, beta, film, dgamma, dbeta, dfilm,
@@ -555,13 +572,17 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
 }
 
 template <int LPR, int NV>
-static void ln_launch_fwd(int grid, cudaStream_t st, const void* x, const float* gamma, void* out, long long M, int C,
-                          float eps) {
+static void ln_launch_fwd(int /*grid*/, cudaStream_t st, const void* x, const float* gamma, void* out, long long M,
+                          int C, float eps) {
+    static const int res = resident_blocks(ln_fwd_kernel<LPR, NV>, 256);
+    const int grid = norm_grid(M, 8 * (32 / LPR), 1, res);
     ln_fwd_kernel<LPR, NV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, (__nv_bfloat16*)out, M, C, eps);
 }
 template <int LPR, int NV>
-static void ln_launch_bwd(int grid, cudaStream_t st, const void* x, const float* gamma, const void* dy,
+static void ln_launch_bwd(int /*grid*/, cudaStream_t st, const void* x, const float* gamma, const void* dy,
                           const void* dres, void* dx, float* dgamma, long long M, int C, float eps) {
+    static const int res = resident_blocks(ln_bwd_kernel<LPR, NV>, 256);
+    const int grid = norm_grid(M, 8 * (32 / LPR), 1, res);
     ln_bwd_kernel<LPR, NV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, (const __nv_bfloat16*)dy,
                                                  (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, M, C, eps);
 }
