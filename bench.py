@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=2, help="per-GPU batch (config/baseline train.batch_size = 2)")
     ap.add_argument("--hw", default="192x288", help="grid (lat x lon); 192x288 = full CESM2 f09 grid")
     ap.add_argument("--frames", type=int, default=3, help="dataset.K condition frames")
+    ap.add_argument("--workload", default="train", choices=["train", "sample"],
+                    help="train: the headline training step; sample: reverse-diffusion steps of ensemble generation")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
@@ -364,12 +366,66 @@ def run_b200(args, H, W, arch_kw):
         os._exit(0)
 
 
+def run_sample(args, H, W, arch_kw):
+    """Secondary metric (BASELINE.json: "ensemble-gen fields/s"): reverse-diffusion steps for a batch of
+    independent fields (inference.py:217-232 -> model.py:186-194), one CUDA-graph replay per step.
+    A step = one UNet call (F = 1) + fused p_sample update; fields/s = batch / (T * step time), T = 1000."""
+    import torch
+    from cesm_emulator_b200.engine import SampleEngine
+    from cesm_emulator_b200.model import Diffusion, UNet
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch if args.batch != 2 else 16  # inference.py:180 default batch_size 16
+    torch.manual_seed(0)
+    diff = Diffusion(UNet(**arch_kw), timesteps=1000).to(dev)
+    diff.eval()
+    for p_ in diff.parameters():
+        p_.requires_grad_(False)
+    eng = SampleEngine(diff, (B, 1, H, W), use_graph=not args.no_graph)
+    eng.cond.normal_()
+    eng.x.normal_()
+    eng.t.fill_(999)
+    for _ in range(3 + args.warmup):
+        eng.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if rank == 0:
+        gflop = 178.5 * (H * W) / (192 * 288) if args.arch == "baseline" else None  # SURVEY 8(d): per UNet call per field
+        peaks = load_peaks()
+        tf = gflop * B / ms if gflop else None
+        print(json.dumps({
+            "metric": "ensemble-gen fields/s (1000-step DDPM chain)", "value": B * world / (1000 * ms * 1e-3),
+            "unit": "fields/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"config/{args.arch} sampling: {args.steps} timed reverse steps of a {B}-field batch, "
+                                   f"{H}x{W}, F=1; value extrapolated to the full 1000-step chain",
+                       "fields_per_batch": B, "grid": [H, W], "cuda_graph": not args.no_graph},
+            "gpu_launches": eng.launches_per_step * args.steps, "launches_per_step": eng.launches_per_step,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["bf16_tflops_sustained"] if tf else None, "traffic": None,
+                         "note": "whole reverse step: algorithmic 178.5 GFLOP per field per UNet call"},
+        }), flush=True)
+
+
 def main():
     args = parse_args()
     H, W = (int(v) for v in args.hw.lower().split("x"))
     arch_kw = BASELINE_KW if args.arch == "baseline" else MORE_BLOCKS_KW
     if args.impl == "reference":
         run_reference(args, H, W, arch_kw)
+    elif args.workload == "sample":
+        run_sample(args, H, W, arch_kw)
     else:
         run_b200(args, H, W, arch_kw)
 

@@ -31,11 +31,24 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// fast-math forms (MUFU.EX2 + MUFU.RCP): the results are rounded to bf16 anyway
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// sigmoid through one MUFU op: sigma(x) = 0.5 * tanh(x / 2) + 0.5 (tanh.approx.f32, ~2^-11 relative
+// error; every consumer rounds to bf16 afterwards).  The exp + rcp form costs two MUFU ops, and the
+// GroupNorm kernels are MUFU/ALU-limited before they are HBM-limited.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_fast(x); }
 // d/dx silu(x) = s + x*s*(1-s)
 __device__ __forceinline__ float dsilu_f(float x) {
-    float s = __fdividef(1.f, 1.f + __expf(-x));
+    const float s = sigmoid_fast(x);
+    return s * (1.f + x * (1.f - s));
+}
+// full-precision variants for the fp32 paths (time-embedding MLP)
+__device__ __forceinline__ float silu_precise(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float dsilu_precise(float x) {
+    const float s = __fdividef(1.f, 1.f + __expf(-x));
     return s * (1.f + x * (1.f - s));
 }
 

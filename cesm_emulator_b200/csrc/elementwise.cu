@@ -328,7 +328,7 @@ small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W
         float s = 0.f;
         for (int k = lane; k < K; k += 32) {
             float v = x[(size_t)b * K + k];
-            if (act) v = silu_f(v);
+            if (act) v = silu_precise(v);
             s = fmaf(v, W[(size_t)n * K + k], s);
         }
         s = warp_sum(s);
@@ -344,7 +344,7 @@ __global__ void small_linear_wgrad_kernel(const float* __restrict__ x, const flo
     float s = 0.f, sb = 0.f;
     for (int b = 0; b < B; ++b) {
         float v = x[(size_t)b * K + k];
-        if (act) v = silu_f(v);
+        if (act) v = silu_precise(v);
         const float g = dy[(size_t)b * N + n];
         s = fmaf(g, v, s);
         sb += g;
@@ -372,7 +372,7 @@ small_linear_dgrad_kernel(const float* __restrict__ x, const float* __restrict__
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][lane];
-        if (act) t *= dsilu_f(x[(size_t)b * K + k]);
+        if (act) t *= dsilu_precise(x[(size_t)b * K + k]);
         dx[(size_t)b * K + k] = t;
     }
 }

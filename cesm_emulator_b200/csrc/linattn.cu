@@ -157,20 +157,25 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
 #pragma unroll
     for (int jp = 0; jp < 2; ++jp) b_off[jp] = (((mi & 1) * 8 + rr) * SPITCH + 8 * (jp * 2 + (mi >> 1))) * 2;
 
-    for (int p = p0; p < p1; p += 16) {
-        // ---- global -> registers (rows r and r+8 of this step) ----
-        uint4 ua[2], ub[2];
+    uint4 na[2], nb[2];
+    auto issue_loads = [&](int pp) {
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = p + r + 8 * h2;
+            const int row = pp + r + 8 * h2;
             if (row < p1) {
-                ua[h2] = __ldg(reinterpret_cast<const uint4*>(a_base + (size_t)row * ld));
-                ub[h2] = __ldg(reinterpret_cast<const uint4*>(b_base + (size_t)row * b_ld));
+                na[h2] = __ldg(reinterpret_cast<const uint4*>(a_base + (size_t)row * ld));
+                nb[h2] = __ldg(reinterpret_cast<const uint4*>(b_base + (size_t)row * b_ld));
             } else {
-                ua[h2] = make_uint4(0, 0, 0, 0);
-                ub[h2] = make_uint4(0, 0, 0, 0);
+                na[h2] = make_uint4(0, 0, 0, 0);
+                nb[h2] = make_uint4(0, 0, 0, 0);
             }
         }
+    };
+    if (p0 < p1) issue_loads(p0);
+    for (int p = p0; p < p1; p += 16) {
+        // ---- this step's rows (loaded one step ahead); next step's loads are issued right away ----
+        uint4 ua[2] = {na[0], na[1]}, ub[2] = {nb[0], nb[1]};
+        if (p + 16 < p1) issue_loads(p + 16);
         // ---- transform A ----
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -266,19 +271,6 @@ __global__ void la_delta_kernel(float* __restrict__ ws, const float* __restrict_
     delta[idx] = s;
 }
 
-// A fragment (16 rows x 32 k) of a row-major bf16 matrix straight from global memory:
-// v[ks][0..3] = a0..a3 of k-step ks; rows g / g+8, this lane's columns {2t,2t+1,2t+8,2t+9} + 16 ks.
-__device__ __forceinline__ void load_afrag(const __nv_bfloat16* row_g, const __nv_bfloat16* row_g8, bool vg, bool vg8,
-                                           int t, uint32_t (&v)[2][4]) {
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-        const int c0 = 16 * ks + 2 * t;
-        v[ks][0] = vg ? __ldg(reinterpret_cast<const uint32_t*>(row_g + c0)) : 0u;
-        v[ks][1] = vg8 ? __ldg(reinterpret_cast<const uint32_t*>(row_g8 + c0)) : 0u;
-        v[ks][2] = vg ? __ldg(reinterpret_cast<const uint32_t*>(row_g + c0 + 8)) : 0u;
-        v[ks][3] = vg8 ? __ldg(reinterpret_cast<const uint32_t*>(row_g8 + c0 + 8)) : 0u;
-    }
-}
 // B fragments of a 32x32 fp32 matrix M (row-major) for C = A * Bm with Bm[k][n] = TRANS ? M[n][k] : M[k][n]
 template <bool TRANS>
 __device__ __forceinline__ void load_bfrag32(const float* __restrict__ M, int g, int t, uint32_t (&b)[2][4][2]) {
@@ -296,45 +288,26 @@ __device__ __forceinline__ void load_bfrag32(const float* __restrict__ M, int g,
             }
         }
 }
-// This lane's 8 columns of a 32-wide row in fragment order: idx (ks, hi, lo) -> col 16ks + 8hi + 2t + lo
-__device__ __forceinline__ int frag_col(int t, int i) { return 16 * (i >> 2) + 8 * ((i >> 1) & 1) + 2 * t + (i & 1); }
-
-// softmax over the 32 columns of rows g and g+8 held as A fragments; returns probabilities (fp32)
-// in fragment order: p[row_half][i], i as in frag_col.
-__device__ __forceinline__ void frag_softmax(const uint32_t (&a)[2][4], float (&p)[2][8]) {
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const float2 lo = unpack_bf16x2(a[ks][hf]), hi = unpack_bf16x2(a[ks][hf + 2]);
-            p[hf][4 * ks + 0] = lo.x; p[hf][4 * ks + 1] = lo.y; p[hf][4 * ks + 2] = hi.x; p[hf][4 * ks + 3] = hi.y;
-        }
-        float m = p[hf][0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) m = fmaxf(m, p[hf][i]);
-        m = quad_max(m);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            p[hf][i] = __expf(p[hf][i] - m);
-            s += p[hf][i];
-        }
-        const float inv = 1.f / quad_sum(s);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) p[hf][i] *= inv;
-    }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
 }
-// fp32 values in fragment order -> bf16 A fragments
-__device__ __forceinline__ void frag_pack(const float (&p)[2][8], uint32_t (&a)[2][4]) {
+// The apply kernels move data in the "row layout": lane = (r = lane >> 2, c = lane & 3) owns the 8
+// channels c*8.. of pixel rows r and r + 8 of a 16-pixel step, i.e. one 16-byte global access per row --
+// every global load/store is a full 128-bit transaction on 64 contiguous bytes per pixel and head.
+// Tensor-core fragments are produced from / returned to that layout through a warp-private
+// shared-memory tile (bf16 [16][SPITCH] for A operands via ldmatrix, fp32 [16][CPITCH] for results).
+static constexpr int CPITCH = 34;  // floats per result row (8-byte aligned float2 slots)
+
+// A fragments (16 x 32, two k-steps) of a staged bf16 tile
+__device__ __forceinline__ void lds_afrag(uint32_t tile_addr, int lane, uint32_t (&a)[2][4]) {
+    const int mi = lane >> 3, rr = lane & 7;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            a[ks][hf] = pack_bf16x2(p[hf][4 * ks + 0], p[hf][4 * ks + 1]);
-            a[ks][hf + 2] = pack_bf16x2(p[hf][4 * ks + 2], p[hf][4 * ks + 3]);
-        }
+        ldmatrix_x4(a[ks], tile_addr + (((mi & 1) * 8 + rr) * SPITCH + 16 * ks + (mi >> 1) * 8) * 2);
 }
-// C (16x32 as 4 n-tiles) = A (16x32) * B; c[j][0..3]
+// C (16x32 as 4 n-tiles) = A (16x32) * B
 __device__ __forceinline__ void frag_gemm(const uint32_t (&a)[2][4], const uint32_t (&b)[2][4][2], float (&c)[4][4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -343,19 +316,40 @@ __device__ __forceinline__ void frag_gemm(const uint32_t (&a)[2][4], const uint3
         for (int ks = 0; ks < 2; ++ks) mma_16816(c[j], a[ks], b[ks][j][0], b[ks][j][1]);
     }
 }
-// C fragments hold, for row half hf, columns 8j + 2t + {0,1}: the same column set as frag_col.
-// value of C for (hf, i) with i in fragment order
-__device__ __forceinline__ float c_at(const float (&c)[4][4], int hf, int i) {
-    const int j = 2 * (i >> 2) + ((i >> 1) & 1);  // col = 8j + 2t + lo  <->  16ks + 8hi + 2t + lo
-    return c[j][2 * hf + (i & 1)];
-}
-__device__ __forceinline__ void store_cfrag(__nv_bfloat16* row_g, __nv_bfloat16* row_g8, bool vg, bool vg8, int t,
-                                            const float (&c)[4][4]) {
+// result fragments -> fp32 tile -> this lane's 8 columns of rows r and r+8
+__device__ __forceinline__ void c_to_rows(float* sC, int lane, const float (&c)[4][4], float (&o)[2][8]) {
+    const int g = lane >> 2, t = lane & 3;
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        if (vg) *reinterpret_cast<uint32_t*>(row_g + 8 * j + 2 * t) = pack_bf16x2(c[j][0], c[j][1]);
-        if (vg8) *reinterpret_cast<uint32_t*>(row_g8 + 8 * j + 2 * t) = pack_bf16x2(c[j][2], c[j][3]);
+        *reinterpret_cast<float2*>(sC + g * CPITCH + 8 * j + 2 * t) = make_float2(c[j][0], c[j][1]);
+        *reinterpret_cast<float2*>(sC + (g + 8) * CPITCH + 8 * j + 2 * t) = make_float2(c[j][2], c[j][3]);
     }
+    __syncwarp();
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 v = *reinterpret_cast<const float2*>(sC + (g + 8 * h2) * CPITCH + t * 8 + 2 * k);
+            o[h2][2 * k] = v.x;
+            o[h2][2 * k + 1] = v.y;
+        }
+}
+// softmax over the 32 channels of a row held by a quad (8 per lane)
+__device__ __forceinline__ void row_softmax(float (&f)[8]) {
+    float m = f[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
+    m = quad_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        f[i] = __expf(f[i] - m);
+        s += f[i];
+    }
+    const float inv = 1.f / quad_sum(s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= inv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,30 +358,55 @@ __device__ __forceinline__ void store_cfrag(__nv_bfloat16* row_g, __nv_bfloat16*
 __global__ void __launch_bounds__(256, 3)
 la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int n,
                 int H, int chunk, float scale) {
+    extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
+    const int r = lane >> 2, c = lane & 3;
+    constexpr int kWarpBytes = 16 * SPITCH * 2 + 16 * CPITCH * 4;
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(la_smem + (size_t)w * kWarpBytes);
+    float* sC = reinterpret_cast<float*>(la_smem + (size_t)w * kWarpBytes + 16 * SPITCH * 2);
+    const uint32_t sA_addr = smem_u32(sA);
     const LaWs W = la_ws(ws, ni, HD, H);
     uint32_t bctx[2][4][2];
-    load_bfrag32<false>(W.ctx + (size_t)w * LD * LD, g, t, bctx);
+    load_bfrag32<false>(W.ctx + (size_t)w * LD * LD, lane >> 2, lane & 3, bctx);
     const size_t row0 = (size_t)ni * n;
     const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
-    for (int p = blockIdx.x * chunk; p < p1; p += 16) {
-        const bool vg = p + g < p1, vg8 = p + g + 8 < p1;
-        const __nv_bfloat16* qg = qkv + (row0 + p + g) * ld + w * LD;
+    uint4 nq[2];
+    auto issue_loads = [&](int pp) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = pp + r + 8 * h2;
+            nq[h2] = __ldg(reinterpret_cast<const uint4*>(qkv + (row0 + (row < p1 ? row : p1 - 1)) * ld + w * LD + c * 8));
+        }
+    };
+    const int pstart = blockIdx.x * chunk;
+    if (pstart < p1) issue_loads(pstart);
+    for (int p = pstart; p < p1; p += 16) {
+        uint4 cq[2] = {nq[0], nq[1]};
+        if (p + 16 < p1) issue_loads(p + 16);  // next step's loads fly during this step's math
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = p + r + 8 * h2;
+            const bool valid = row < p1;  // no divergent branch around the quad shuffles of row_softmax
+            float f[8];
+            unpack8(cq[h2], f);
+            row_softmax(f);
+            const float sc = valid ? scale : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] *= sc;
+            *reinterpret_cast<uint4*>(sA + (r + 8 * h2) * SPITCH + c * 8) = pack8(f);
+        }
+        __syncwarp();
         uint32_t a[2][4];
-        load_afrag(qg, qg + (size_t)8 * ld, vg, vg8, t, a);
-        float pr[2][8];
-        frag_softmax(a, pr);
+        lds_afrag(sA_addr, lane, a);
+        float cfr[4][4], o[2][8];
+        frag_gemm(a, bctx, cfr);
+        c_to_rows(sC, lane, cfr, o);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pr[hf][i] *= scale;
-        frag_pack(pr, a);
-        float c[4][4];
-        frag_gemm(a, bctx, c);
-        __nv_bfloat16* og = out + (row0 + p + g) * HD + w * LD;
-        store_cfrag(og, og + (size_t)8 * HD, vg, vg8, t, c);
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = p + r + 8 * h2;
+            if (row < p1) *reinterpret_cast<uint4*>(out + (row0 + row) * HD + w * LD + c * 8) = pack8(o[h2]);
+        }
     }
 }
 
@@ -401,79 +420,113 @@ __global__ void __launch_bounds__(256, 2)
 la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     float* __restrict__ ws, const float* __restrict__ dctx, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
+    extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
+    const int r = lane >> 2, c = lane & 3;
+    constexpr int kTile = 16 * SPITCH * 2;
+    constexpr int kWarpBytes = 3 * kTile + 16 * CPITCH * 4;
+    uint8_t* base = la_smem + (size_t)w * kWarpBytes;
+    __nv_bfloat16* sD = reinterpret_cast<__nv_bfloat16*>(base);           // dout
+    __nv_bfloat16* sV = reinterpret_cast<__nv_bfloat16*>(base + kTile);   // v
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(base + 2 * kTile);  // kh
+    float* sC = reinterpret_cast<float*>(base + 3 * kTile);
+    const uint32_t sD_addr = smem_u32(sD), sV_addr = smem_u32(sV), sK_addr = smem_u32(sK);
     const LaWs W = la_ws(ws, ni, HD, H);
     const float* dcx = dctx + ((size_t)ni * H + w) * LD * LD;
     uint32_t b_ctxT[2][4][2], b_dctxT[2][4][2], b_dctx[2][4][2];
-    load_bfrag32<true>(W.ctx + (size_t)w * LD * LD, g, t, b_ctxT);
-    load_bfrag32<true>(dcx, g, t, b_dctxT);
-    load_bfrag32<false>(dcx, g, t, b_dctx);
+    load_bfrag32<true>(W.ctx + (size_t)w * LD * LD, lane >> 2, lane & 3, b_ctxT);
+    load_bfrag32<true>(dcx, lane >> 2, lane & 3, b_dctxT);
+    load_bfrag32<false>(dcx, lane >> 2, lane & 3, b_dctx);
     float kmx[8], kinvz[8], del[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int col = w * LD + frag_col(t, i);
+        const int col = w * LD + c * 8 + i;
         kmx[i] = dec_ordered(W.kmax[col]);
         kinvz[i] = 1.f / W.z[col];
         del[i] = delta[(size_t)ni * HD + col];
     }
     const size_t row0 = (size_t)ni * n;
     const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
-    for (int p = blockIdx.x * chunk; p < p1; p += 16) {
-        const bool vg = p + g < p1, vg8 = p + g + 8 < p1;
-        const size_t rg = row0 + p + g;
-        const __nv_bfloat16* xg = qkv + rg * ld + w * LD;
-        __nv_bfloat16* dg = dqkv + rg * ld + w * LD;
-        uint32_t a_do[2][4], a_x[2][4];
-        float c[4][4], pr[2][8], o[4][4];
-        load_afrag(dout + rg * HD + w * LD, dout + (rg + 8) * HD + w * LD, vg, vg8, t, a_do);
-        // ---- dq ----
-        load_afrag(xg, xg + (size_t)8 * ld, vg, vg8, t, a_x);
-        frag_softmax(a_x, pr);
-        frag_gemm(a_do, b_ctxT, c);  // dqh
+    // software pipeline: the 8 x 16-byte loads of step i+1 are issued before the tensor-core work of
+    // step i, so that a warp always has a step's worth of bytes in flight
+    uint4 nd[2], nq[2], nk[2], nv[2];
+    auto issue_loads = [&](int pp) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = pp + r + 8 * h2;
+            const size_t rg = row0 + (row < p1 ? row : p1 - 1);
+            const __nv_bfloat16* xg = qkv + rg * ld + w * LD + c * 8;
+            nd[h2] = __ldg(reinterpret_cast<const uint4*>(dout + rg * HD + w * LD + c * 8));
+            nq[h2] = __ldg(reinterpret_cast<const uint4*>(xg));
+            nk[h2] = __ldg(reinterpret_cast<const uint4*>(xg + HD));
+            nv[h2] = __ldg(reinterpret_cast<const uint4*>(xg + 2 * HD));
+        }
+    };
+    const int pstart = blockIdx.x * chunk;
+    if (pstart < p1) issue_loads(pstart);
+    for (int p = pstart; p < p1; p += 16) {
+        float sm[2][8], kh[2][8];
+        __syncwarp();
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = p + r + 8 * h2;
+            const bool valid = row < p1;
+            uint4 ud = nd[h2], uv = nv[h2];
+            const uint4 uq = nq[h2], uk = nk[h2];
+            if (!valid) {
+                ud = make_uint4(0, 0, 0, 0);
+                uv = make_uint4(0, 0, 0, 0);
+            }
+            unpack8(uq, sm[h2]);
+            row_softmax(sm[h2]);
+            float kv[8];
+            unpack8(uk, kv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) kh[h2][i] = valid ? __expf(kv[i] - kmx[i]) * kinvz[i] : 0.f;
+            *reinterpret_cast<uint4*>(sD + (r + 8 * h2) * SPITCH + c * 8) = ud;
+            *reinterpret_cast<uint4*>(sV + (r + 8 * h2) * SPITCH + c * 8) = uv;
+            *reinterpret_cast<uint4*>(sK + (r + 8 * h2) * SPITCH + c * 8) = pack8(kh[h2]);
+        }
+        if (p + 16 < p1) issue_loads(p + 16);
+        __syncwarp();
+        uint32_t a[2][4];
+        float cfr[4][4], o[2][8];
+        // ---- dq ----
+        lds_afrag(sD_addr, lane, a);
+        frag_gemm(a, b_ctxT, cfr);  // dqh
+        c_to_rows(sC, lane, cfr, o);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
             float dot = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dot = fmaf(pr[hf][i], c_at(c, hf, i), dot);
+            for (int i = 0; i < 8; ++i) dot = fmaf(sm[h2][i], o[h2][i], dot);
             dot = quad_sum(dot);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = 2 * (i >> 2) + ((i >> 1) & 1);
-                o[j][2 * hf + (i & 1)] = pr[hf][i] * scale * (c_at(c, hf, i) - dot);
-            }
+            for (int i = 0; i < 8; ++i) o[h2][i] = sm[h2][i] * scale * (o[h2][i] - dot);
+            const int row = p + r + 8 * h2;
+            if (row < p1) *reinterpret_cast<uint4*>(dqkv + (row0 + row) * ld + w * LD + c * 8) = pack8(o[h2]);
         }
-        store_cfrag(dg, dg + (size_t)8 * ld, vg, vg8, t, o);
         // ---- dk ----
-        uint32_t a_v[2][4];
-        load_afrag(xg + 2 * HD, xg + 2 * HD + (size_t)8 * ld, vg, vg8, t, a_v);
-        frag_gemm(a_v, b_dctxT, c);  // dkh
-        load_afrag(xg + HD, xg + HD + (size_t)8 * ld, vg, vg8, t, a_x);  // raw k
+        lds_afrag(sV_addr, lane, a);
+        frag_gemm(a, b_dctxT, cfr);  // dkh
+        c_to_rows(sC, lane, cfr, o);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf)
+        for (int h2 = 0; h2 < 2; ++h2) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const float2 lo = unpack_bf16x2(a_x[ks][hf]), hi = unpack_bf16x2(a_x[ks][hf + 2]);
-                const float kv[4] = {lo.x, lo.y, hi.x, hi.y};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = 4 * ks + q;
-                    pr[hf][i] = __expf(kv[q] - kmx[i]) * kinvz[i];  // kh
-                }
-            }
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = 2 * (i >> 2) + ((i >> 1) & 1);
-                o[j][2 * hf + (i & 1)] = pr[hf][i] * (c_at(c, hf, i) - del[i]);
-            }
-        store_cfrag(dg + HD, dg + HD + (size_t)8 * ld, vg, vg8, t, o);
+            for (int i = 0; i < 8; ++i) o[h2][i] = kh[h2][i] * (o[h2][i] - del[i]);
+            const int row = p + r + 8 * h2;
+            if (row < p1) *reinterpret_cast<uint4*>(dqkv + (row0 + row) * ld + HD + w * LD + c * 8) = pack8(o[h2]);
+        }
         // ---- dv ----
-        frag_pack(pr, a_x);
-        frag_gemm(a_x, b_dctx, c);
-        store_cfrag(dg + 2 * HD, dg + 2 * HD + (size_t)8 * ld, vg, vg8, t, c);
+        lds_afrag(sK_addr, lane, a);
+        frag_gemm(a, b_dctx, cfr);
+        c_to_rows(sC, lane, cfr, o);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int row = p + r + 8 * h2;
+            if (row < p1) *reinterpret_cast<uint4*>(dqkv + (row0 + row) * ld + 2 * HD + w * LD + c * 8) = pack8(o[h2]);
+        }
     }
 }
 
@@ -507,7 +560,9 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, i
     CESM_CHECK_LAUNCH();
     la_finalize_kernel<<<ceil_div(NI * H * LD * LD, 256), 256, 0, st>>>(ws, H, NI);
     CESM_CHECK_LAUNCH();
-    la_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk, scale);
+    const size_t sh_apply = (size_t)H * (16 * SPITCH * 2 + 16 * CPITCH * 4);
+    la_apply_kernel<<<grid, 32 * H, sh_apply, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
+                                                    scale);
     CESM_CHECK_LAUNCH();
     (void)HD;
     return CESM_OK;
@@ -530,7 +585,13 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
     CESM_CHECK_LAUNCH();
     la_delta_kernel<<<ceil_div(NI * H * LD, 128), 128, 0, st>>>(ws, dctx, delta, H, NI);
     CESM_CHECK_LAUNCH();
-    la_bwd_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
+    const size_t sh_bwd = (size_t)H * (3 * 16 * SPITCH * 2 + 16 * CPITCH * 4);
+    static bool bwd_cfg = false;
+    if (!bwd_cfg) {
+        CESM_CHECK_CUDA(cudaFuncSetAttribute(la_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        bwd_cfg = true;
+    }
+    la_bwd_apply_kernel<<<grid, 32 * H, sh_bwd, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
                                                  (__nv_bfloat16*)dqkv, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;

@@ -128,3 +128,34 @@ def test_reference_style_module_calls(cuda, baseline):
         ref = O.unet3d_forward({"net." + k: v for k, v in sd.items()}, cfg, x[:, :1].cpu(), torch.tensor([3, 900]),
                                x[:, 1:2].cpu())
         assert full.shape == ref.shape and rel_err(full, ref) < 2e-2
+
+
+def _parity_case(cuda, unet_kw, B, K, H, W, med_bar, worst_bar):
+    from cesm_emulator_b200 import ops
+    from cesm_emulator_b200.model import Diffusion, UNet
+    ops.set_grad_sink(None)
+    torch.manual_seed(0)
+    diff = Diffusion(UNet(**unet_kw), timesteps=1000).to(cuda)
+    diff.train()
+    x0, cond, t, noise = make_inputs(B, K, H, W, seed=8, device=cuda)
+    eps, loss, grads = module_loss_and_grads(diff, x0, cond, t, noise)
+    ref_eps, ref_loss, ref_grads = oracle_loss_and_grads(diff.model, unet_kw, x0, cond, t, noise)
+    assert rel_err(eps, ref_eps) < FWD_TOL
+    assert abs(loss.item() - ref_loss.item()) < 1e-2 * abs(ref_loss.item())
+    assert set(grads) == set(ref_grads)
+    vals = np.array([rel_err(grads[k], ref_grads[k]) for k in grads])
+    assert np.median(vals) < med_bar and vals.max() < worst_bar, (np.median(vals), vals.max())
+
+
+def test_more_blocks_architecture_against_oracle(cuda):
+    """config/more_blocks: ch_mults [1,2,4,8] -> a fourth level with 512 channels (and the level-0
+    temporal attention going through `temporal_op`, video_net.py:701)."""
+    kw = dict(in_channels=2, out_channels=1, base_ch=64, ch_mults=(1, 2, 4, 8), num_res_blocks=6, time_dim=124,
+              groups=8, dropout=0.0, use_checkpoint=True)
+    _parity_case(cuda, kw, B=2, K=3, H=64, W=64, med_bar=1.5e-2, worst_bar=9e-2)
+
+
+def test_long_window_temporal_attention_against_oracle(cuda):
+    """BASELINE.json configs[4]: a longer condition window (K = 12 frames > 4 selects the streaming
+    online-softmax temporal-attention kernels and the log-bucketed part of the relative-position table)."""
+    _parity_case(cuda, BASELINE_KW, B=1, K=12, H=16, W=16, med_bar=2e-2, worst_bar=9e-2)
