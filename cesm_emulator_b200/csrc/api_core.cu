@@ -178,6 +178,12 @@ static int env_flag(const char* name) {
 static int knob_v1() { static int v = env_flag("CESM_IGEMM_V1"); return v; }
 static int knob_no_halo() { static int v = env_flag("CESM_IGEMM_NO_HALO"); return v; }
 static int knob_no_bres() { static int v = env_flag("CESM_IGEMM_NO_BRES"); return v; }
+static int knob_int(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+static int knob_pw() { static int v = knob_int("CESM_IGEMM_PW"); return v; }            // force halo row width
+static int knob_astages() { static int v = knob_int("CESM_IGEMM_ASTAGES"); return v; }  // force A stages
 static int knob_dbg() {
     static int v = [] { const char* e = getenv("CESM_IGEMM_DBG"); return e ? atoi(e) : 0; }();
     return v;
@@ -216,6 +222,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
         double best = 0.0;
         int best_pw = 0;
         for (int pw = 16; pw <= 128; pw <<= 1) {
+            if (knob_pw() && pw != knob_pw()) continue;
             const int bw = pw - 2, bh = 128 / pw;
             const double tiles = (double)ceil_div(a->ow, bw) * ceil_div(a->oh, bh);
             const double useful = ((double)a->ow * a->oh) / (tiles * 128.0);
@@ -290,6 +297,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
         CESM_REQUIRE(bs >= 2, "igemm2: no shared-memory plan for cout=%d K=%d", a->cout, p.num_kb * 64);
         p.b_stages = (int)bs;
     }
+    if (knob_astages() > 0 && knob_astages() <= p.a_stages) p.a_stages = knob_astages();
     const long long b_bytes = p.b_resident ? b_total : (long long)p.b_stages * b_blk;
     const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)b_bytes + 2 * 16384 + 1024;
     CESM_REQUIRE(smem <= kIgemm2MaxSmem, "igemm2: shared-memory plan of %zu B exceeds the limit", smem);

@@ -24,6 +24,7 @@
 // Warp roles (352 threads): 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer
 // (+ TMEM allocation), 3..10 = epilogue: two groups of four warps (warp w reads TMEM lanes
 // 32*(w%4)..+31), the groups alternating over the 64-column chunks of a tile.
+
 #include "common.cuh"
 #include "igemm.h"
 
@@ -94,7 +95,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
     auto t_empty = [&](int s) { return bar_base + 8u * (50 + s); };
     const uint32_t b_all_bar = bar_base + 8u * 52;
     const uint32_t tmem_ptr_addr = bar_base + 8u * 53;
-    const uint32_t gn_base = bar_base + 8u * 56;  // 64 floats: per-CTA GroupNorm (sum, sumsq) accumulators
+    const uint32_t gn_base = bar_base + 8u * 56;  // 2 x 64 floats: per-epilogue-group GroupNorm (sum, sumsq) accumulators
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
 
     const int warp = threadIdx.x >> 5;
@@ -122,12 +123,12 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(t_full(s), 1);
-            mbar_init(t_empty(s), 8);
+            mbar_init(t_empty(s), BLOCK_N == 64 ? 4 : 8);
         }
         mbar_init(b_all_bar, 1);
         fence_barrier_init();
     }
-    if (threadIdx.x < 64) reinterpret_cast<float*>(smem_gen + (gn_base - smem_base))[threadIdx.x] = 0.f;
+    if (threadIdx.x < 128) reinterpret_cast<float*>(smem_gen + (gn_base - smem_base))[threadIdx.x] = 0.f;
     if (warp == 2) tmem_alloc(tmem_ptr_addr, kTmemCols);
     tc_fence_before();
     __syncthreads();
@@ -156,6 +157,14 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             for (int ai = 0; ai < a_loads; ++ai) {
                 mbar_wait(a_empty(stage), phase ^ 1u, 11);
                 const uint32_t dst = a_base + stage * p.a_stage_bytes;
+                if (p.dbg & 32) {  // bisection: no activation traffic at all
+                    mbar_arrive(a_full(stage));
+                    if (++stage == p.a_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                    continue;
+                }
                 mbar_arrive_expect_tx(a_full(stage), p.a_box_bytes);
                 if (HALO) {
                     int midx = 0, c = ai << 6;
@@ -207,55 +216,90 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                     }
             }
         }
-    } else if (warp == 2 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 2) {
+        // ===== MMA issuer (the whole warp walks the loops; one elected lane issues) =====
+        const bool leader = elect_one();
+        // One thread issues every MMA, so its instruction stream is on the critical path: a 128x64x16 MMA
+        // occupies the tensor pipe for only 32 clocks.  Descriptors are therefore not rebuilt per MMA: the
+        // constant upper word is hoisted, the 14-bit start-address field is advanced by adds (+2 per
+        // 16-element K step = 32 B, + 8 per 128-byte row for the halo tap views).
         constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+        const uint64_t desc_hi = make_smem_desc_sw128(0, 0, 1024);   // start-address field = 0
         int a_stage = 0, b_stage = 0, acc = 0;
         uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+        uint32_t tap_rows8[9];  // HALO: ((1+dh)*pw + (1+dw)) * 8 = row offset of the tap view in 16-byte units
+#pragma unroll
+        for (int ti = 0; ti < 9; ++ti) tap_rows8[ti] = HALO ? ((1 + p.tap_dh[ti]) * pw + (1 + p.tap_dw[ti])) * 8 : 0;
+        const uint32_t b_blk16 = b_blk_bytes >> 4;
         if (p.b_resident) mbar_wait(b_all_bar, 0, 13);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_tile = tile / p.m_tiles;
-            mbar_wait(t_empty(acc), acc_phase ^ 1u, 14);
+            if (!(p.dbg & 16)) mbar_wait(t_empty(acc), acc_phase ^ 1u, 14);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            const uint32_t b_tile16 = (b_base >> 4) + n_tile * p.num_kb * b_blk16;  // resident weights of this n tile
+            uint32_t accum = 0;
             for (int ai = 0; ai < a_loads; ++ai) {
                 mbar_wait(a_full(a_stage), a_phase, 15);
                 tc_fence_after();
-                const uint32_t sa0 = a_base + a_stage * p.a_stage_bytes;
-                for (int ti = 0; ti < taps_per_a; ++ti) {
-                    const int kb = HALO ? ti * cblk + ai : ai;
-                    uint32_t sb;
+                const uint32_t sa16 = (a_base + a_stage * p.a_stage_bytes) >> 4;
+                auto issue_tap = [&](uint32_t a16, uint32_t b16) {
+                    if (!(p.dbg & 4)) {  // bisection knob: CESM_IGEMM_DBG=4 issues no MMAs
+#pragma unroll
+                        for (int k = 0; k < kKBlk / 16; ++k) {
+                            if (leader)
+                                umma_bf16(d_tmem, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k),
+                                          idesc, accum);
+                            accum = 1;
+                        }
+                    }
+                };
+                if (HALO) {
+#pragma unroll
+                    for (int ti = 0; ti < 9; ++ti) {
+                        const int kb = ti * cblk + ai;
+                        uint32_t b16;
+                        if (p.b_resident) {
+                            b16 = b_tile16 + kb * b_blk16;
+                        } else {
+                            mbar_wait(b_full(b_stage), b_phase, 16);
+                            tc_fence_after();
+                            b16 = (b_base >> 4) + b_stage * b_blk16;
+                        }
+                        issue_tap(sa16 + tap_rows8[ti], b16);
+                        if (!p.b_resident) {
+                            if (leader) umma_commit(b_empty(b_stage));
+                            if (++b_stage == p.b_stages) {
+                                b_stage = 0;
+                                b_phase ^= 1u;
+                            }
+                        }
+                    }
+                } else {
+                    uint32_t b16;
                     if (p.b_resident) {
-                        sb = b_base + (n_tile * p.num_kb + kb) * b_blk_bytes;
+                        b16 = b_tile16 + ai * b_blk16;
                     } else {
                         mbar_wait(b_full(b_stage), b_phase, 16);
                         tc_fence_after();
-                        sb = b_base + b_stage * b_blk_bytes;
+                        b16 = (b_base >> 4) + b_stage * b_blk16;
                     }
-                    // HALO: tap (dh, dw) is the view of the halo tile that starts (1+dh)*pw + (1+dw) rows in
-                    const uint32_t sa =
-                        HALO ? sa0 + ((1 + p.tap_dh[ti]) * pw + (1 + p.tap_dw[ti])) * kStageRowBytes : sa0;
-#pragma unroll
-                    for (int k = 0; k < kKBlk / 16; ++k) {
-                        const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
-                        const uint64_t db = make_smem_desc_sw128(sb + k * 32, 0, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (ai | ti | k) != 0);
-                    }
+                    issue_tap(sa16, b16);
                     if (!p.b_resident) {
-                        umma_commit(b_empty(b_stage));
+                        if (leader) umma_commit(b_empty(b_stage));
                         if (++b_stage == p.b_stages) {
                             b_stage = 0;
                             b_phase ^= 1u;
                         }
                     }
                 }
-                umma_commit(a_empty(a_stage));
+                if (leader) umma_commit(a_empty(a_stage));
                 if (++a_stage == p.a_stages) {
                     a_stage = 0;
                     a_phase ^= 1u;
                 }
             }
-            umma_commit(t_full(acc));
+            if (leader && !(p.dbg & 16)) umma_commit(t_full(acc));
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;
@@ -275,19 +319,19 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         const uint32_t obuf = o_base + group * kOutStageBytes;
         const uint32_t my_row = obuf + r * kStageRowBytes;
         const uint32_t sw7 = (r & 7);
-        float* gn_acc = reinterpret_cast<float*>(smem_gen + (gn_base - smem_base));
+        float* gn_acc = reinterpret_cast<float*>(smem_gen + (gn_base - smem_base)) + 64 * group;  // per group
         int acc = 0;
         uint32_t acc_phase = 0;
         int cur_b = -1;
-        auto gn_flush = [&](int b) {
-            epi_bar_sync_all();
-            if (warp == 3 && b >= 0) {
+        auto gn_flush = [&](int b) {  // per group: no cross-group synchronisation
+            epi_bar_sync(group);
+            if (q == 3 && b >= 0) {   // warps 3 and 7: the first warp of each group
                 for (int i = lane; i < 2 * p.gn_groups; i += 32) {
                     atomicAdd(p.gn_sums + (size_t)b * p.gn_groups * 2 + i, gn_acc[i]);
                     gn_acc[i] = 0.f;
                 }
             }
-            epi_bar_sync_all();
+            epi_bar_sync(group);
         };
         // per-tile constants of the row -> pixel map
         const int rw = r % pw;
@@ -297,7 +341,15 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         const int r0 = q * 32;
         const int st_w = HALO ? 0 : r0 % p.bw, st_h = HALO ? q : (r0 / p.bw) % p.bh, st_n = HALO ? 0 : r0 / (p.bw * p.bh);
         const bool st_ok = HALO ? (q < p.bh) : (st_n < p.bn);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tile_it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+            if (BLOCK_N == 64) {
+                // one 64-column chunk per tile: the groups alternate over tiles instead (stage == group),
+                // so each has two tile periods for its TMEM read-out, statistics and store
+                if ((tile_it & 1) != group) continue;
+                acc = group;
+                acc_phase = (tile_it >> 1) & 1;  // k-th use of this stage
+            }
             int n_tile, n0, oh0, ow0;
             tile_coords(tile, n_tile, n0, oh0, ow0);
             const int n = n0 + rn, oh = oh0 + rh, ow = ow0 + rw;
@@ -311,11 +363,11 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                     cur_b = b;
                 }
             }
-            mbar_wait(t_full(acc), acc_phase, 17);
+            if (!(p.dbg & 16)) mbar_wait(t_full(acc), acc_phase, 17);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int cc = group * 64; cc < BLOCK_N; cc += 128) {
+            for (int cc = (BLOCK_N == 64 ? 0 : group * 64); cc < ((p.dbg & 2) ? 0 : BLOCK_N); cc += 128) {  // dbg 2: no epilogue
                 uint32_t v[64];
                 tmem_ld_32x64(taddr + cc, v);
                 // the store that last read this group's staging buffer must have drained
@@ -436,8 +488,8 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty(acc));
-            if (++acc == 2) {
+            if (lane == 0 && !(p.dbg & 16)) mbar_arrive(t_empty(acc));
+            if (BLOCK_N != 64 && ++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;
             }
