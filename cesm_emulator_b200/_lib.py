@@ -103,12 +103,12 @@ _SIGNATURES: dict[str, list] = {
     "cesm_pack_weights_batched": [_P, _I, _P],
     "cesm_unpack_wgrads_batched": [_P, _I, _P],
     "cesm_unpack_wgrad": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _I, _P],
-    "cesm_colsum": [_P, _P, _L, _I, _P],
+    "cesm_colsum": [_P, _P, _L, _I, _I, _P],
     "cesm_gn_stats": [_P, _P, _I, _L, _I, _I, _P],
     "cesm_gn_apply_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
-    "cesm_gn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
+    "cesm_gn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _P],
     "cesm_ln_fwd": [_P, _P, _P, _L, _I, _F, _P],
-    "cesm_ln_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "cesm_ln_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
     "cesm_tattn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "cesm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "cesm_linattn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
@@ -119,7 +119,7 @@ _SIGNATURES: dict[str, list] = {
     "cesm_out_conv_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _P],
     "cesm_sinusoidal": [_P, _P, _I, _I, _P],
     "cesm_small_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "cesm_small_linear_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "cesm_small_linear_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cesm_q_sample": [_P, _P, _P, _P, _P, _P, _I, _L, _P],
     "cesm_mse_fwd": [_P, _P, _P, _P, _L, _P],
     "cesm_scale_by_scalar": [_P, _P, _F, _P, _L, _P],

@@ -337,7 +337,8 @@ small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W
 }
 // dW[n][k] = sum_b dy[b][n] act(x[b][k]) ; db[n] = sum_b dy[b][n]
 __global__ void small_linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                          float* __restrict__ dW, float* __restrict__ db, int B, int K, int N, int act) {
+                                          float* __restrict__ dW, float* __restrict__ db, int B, int K, int N, int act,
+                                          int accumulate) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * K) return;
     const int k = idx % K, n = idx / K;
@@ -349,8 +350,8 @@ __global__ void small_linear_wgrad_kernel(const float* __restrict__ x, const flo
         s = fmaf(g, v, s);
         sb += g;
     }
-    dW[idx] = s;
-    if (k == 0 && db) db[n] = sb;
+    dW[idx] = accumulate ? dW[idx] + s : s;
+    if (k == 0 && db) db[n] = accumulate ? db[n] + sb : sb;
 }
 // dx[b][k] = act'(x[b][k]) * sum_n dy[b][n] W[n][k]
 // block = (32 k-lanes x 8 n-groups); grid = (ceil(K/32), B): rows of W are read coalesced along k,
@@ -474,10 +475,10 @@ extern "C" int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int
     return CESM_OK;
 }
 
-extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, void* stream) {
+extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, int accumulate, void* stream) {
     CESM_REQUIRE(C % 8 == 0 && C <= 2048 && 2048 % C == 0, "colsum needs C dividing 2048 (C=%d)", C);
     cudaStream_t st = as_stream(stream);
-    CESM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+    if (!accumulate) CESM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
     long long blocks = (M + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
@@ -547,9 +548,10 @@ extern "C" int cesm_small_linear_fwd(const float* x, const float* W, const float
 }
 
 extern "C" int cesm_small_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
-                                     int B, int K, int N, int act_silu_in, void* stream) {
+                                     int B, int K, int N, int act_silu_in, int accumulate, void* stream) {
     cudaStream_t st = as_stream(stream);
-    small_linear_wgrad_kernel<<<nblk((long long)N * K, 256), 256, 0, st>>>(x, dy, dW, db, B, K, N, act_silu_in);
+    small_linear_wgrad_kernel<<<nblk((long long)N * K, 256), 256, 0, st>>>(x, dy, dW, db, B, K, N, act_silu_in,
+                                                                           accumulate);
     CESM_CHECK_LAUNCH();
     if (dx) {
         small_linear_dgrad_kernel<<<dim3(ceil_div(K, 32), B), 256, 0, st>>>(x, W, dy, dx, B, K, N, act_silu_in);

@@ -314,7 +314,8 @@ __global__ void gn_bwd_params_kernel(const float* __restrict__ csum, const float
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const float* __restrict__ film, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, float* __restrict__ dfilm,
-                                     float* __restrict__ dcbias, int B, long long P, int C, int G, float eps) {
+                                     float* __restrict__ dcbias, int B, long long P, int C, int G, float eps,
+                                     int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int cpg = C / G, g = c / cpg;
@@ -344,9 +345,15 @@ __global__ void gn_bwd_params_kernel(const float* __restrict__ csum, const float
             dcb += rstd * (gamma[c] * sc * s[0] - (float)P * m1) - rstd * rstd * m2 * (s[2] - (float)P * mean);
         }
     }
-    dgamma[c] = dg;
-    dbeta[c] = db;
-    if (dcbias) dcbias[c] = dcb;
+    if (accumulate) {
+        dgamma[c] += dg;
+        dbeta[c] += db;
+        if (dcbias) dcbias[c] += dcb;
+    } else {
+        dgamma[c] = dg;
+        dbeta[c] = db;
+        if (dcbias) dcbias[c] = dcb;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -550,7 +557,7 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
 extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, const float* gamma, const float* beta,
                            const float* film, float* csum /* [B][C][3] scratch */, void* dx, float* dgamma,
                            float* dbeta, float* dfilm /* [B][2C] or NULL */, float* dconv_bias /* [C] or NULL */,
-                           int B, long long P, int C, int G, float eps, void* stream) {
+                           int B, long long P, int C, int G, float eps, int accumulate_params, void* stream) {
     GN_CHECK(C, G);
     cudaStream_t st = as_stream(stream);
     CESM_CHECK_CUDA(cudaMemsetAsync(csum, 0, sizeof(float) * 3 * B * C, st));
@@ -566,7 +573,7 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
                                                        beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps);
     CESM_CHECK_LAUNCH();
     gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, sums, gamma, beta, film, dgamma, dbeta, dfilm,
-                                                           dconv_bias, B, P, C, G, eps);
+                                                           dconv_bias, B, P, C, G, eps, accumulate_params);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -612,10 +619,10 @@ extern "C" int cesm_ln_fwd(const void* x, const float* gamma, void* out, long lo
 }
 
 extern "C" int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, const void* dres, void* dx,
-                           float* dgamma, long long M, int C, float eps, void* stream) {
+                           float* dgamma, long long M, int C, float eps, int accumulate, void* stream) {
     LN_CHECK(C);
     cudaStream_t st = as_stream(stream);
-    CESM_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st));
+    if (!accumulate) CESM_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st));
     const int lpr = C / 8 < 32 ? C / 8 : 32;
     const int grid = norm_grid(M, 8 * (32 / lpr) * 4);
     LN_DISPATCH(ln_launch_bwd, grid, st, x, gamma, dy, dres, dx, dgamma, M, C, eps);

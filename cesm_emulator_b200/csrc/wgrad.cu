@@ -117,25 +117,29 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                 phase ^= 1u;
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp walks the loop (warp-uniform operands), one elected lane issues;
+        // the constant descriptor word is hoisted and only the start-address field advances =====
         constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+        const bool leader = elect_one();
+        const uint64_t desc_hi = make_smem_desc_sw128(0, kPix * 128, 1024);
         int stage = 0;
-        uint32_t phase = 0;
+        uint32_t phase = 0, accum = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(full_bar(stage), phase, 22);
             tc_fence_after();
-            const uint32_t sa = smem_base + stage * S::kStageBytes;
-            const uint32_t sb = sa + S::kABytes;
+            const uint32_t sa16 = (smem_base + stage * S::kStageBytes) >> 4;
+            const uint32_t sb16 = sa16 + (S::kABytes >> 4);
 #pragma unroll
             for (int k = 0; k < kPix / 16; ++k) {
                 // 16 pixels = two 8-row groups = 2048 B further along K
-                const uint64_t da = make_smem_desc_sw128(sa + k * 2048, kPix * 128, 1024);
-                const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kPix * 128, 1024);
-                umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+                if (leader)
+                    umma_bf16(tmem_base, desc_hi | (uint64_t)(sa16 + k * 128), desc_hi | (uint64_t)(sb16 + k * 128), idesc,
+                              accum);
+                accum = 1;
             }
-            umma_commit(empty_bar(stage));
-            if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+            if (leader) umma_commit(empty_bar(stage));
+            if (leader && kb == num_kb - 1) umma_commit(tmem_full_bar);
             if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;

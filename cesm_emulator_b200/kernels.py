@@ -167,11 +167,12 @@ def unpack_wgrad(src: torch.Tensor, dst: torch.Tensor, O: int, T: int, I: int, s
     return dst
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
-    _req_cuda(x)
+def colsum(x: torch.Tensor, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Column sums of bf16 x[..., C]; with `into` (fp32 [C]) the sums are ADDED to it."""
+    _req_cuda(x, into)
     C = x.shape[-1]
-    out = torch.empty(C, dtype=torch.float32, device=x.device)
-    _lib.call("cesm_colsum", _ptr(x), _ptr(out), x.numel() // C, C, _stream())
+    out = torch.empty(C, dtype=torch.float32, device=x.device) if into is None else into
+    _lib.call("cesm_colsum", _ptr(x), _ptr(out), x.numel() // C, C, int(into is not None), _stream())
     return out
 
 
@@ -195,7 +196,8 @@ def gn_apply_fwd(x, sums, gamma, beta, film, residual, B: int, G: int, eps: floa
     return out
 
 
-def gn_bwd(x, dout, sums, gamma, beta, film, B: int, G: int, eps: float, conv_bias_grad: bool = False):
+def gn_bwd(x, dout, sums, gamma, beta, film, B: int, G: int, eps: float, conv_bias_grad: bool = False,
+           into=None):
     """-> (dx, dgamma, dbeta, dfilm or None[, dconv_bias]).  `dconv_bias` is sum_pixels dx per
     channel, i.e. the bias gradient of the convolution that produced x, obtained from the same
     per-channel sums (no extra pass over dx)."""
@@ -205,12 +207,15 @@ def gn_bwd(x, dout, sums, gamma, beta, film, B: int, G: int, eps: float, conv_bi
     dev = x.device
     csum = torch.empty((B, C, 3), dtype=torch.float32, device=dev)
     dx = torch.empty_like(x)
-    dgamma = torch.empty(C, dtype=torch.float32, device=dev)
-    dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+    if into is not None:  # (dgamma, dbeta, dconv_bias) buffers to ACCUMULATE into (parameter .grad views)
+        dgamma, dbeta, dcb = into
+    else:
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        dcb = torch.empty(C, dtype=torch.float32, device=dev) if conv_bias_grad else None
     dfilm = torch.empty((B, 2 * C), dtype=torch.float32, device=dev) if film is not None else None
-    dcb = torch.empty(C, dtype=torch.float32, device=dev) if conv_bias_grad else None
     _lib.call("cesm_gn_bwd", _ptr(x), _ptr(dout), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(film), _ptr(csum), _ptr(dx),
-              _ptr(dgamma), _ptr(dbeta), _ptr(dfilm), _ptr(dcb), B, P, C, G, eps, _stream(),
+              _ptr(dgamma), _ptr(dbeta), _ptr(dfilm), _ptr(dcb), B, P, C, G, eps, int(into is not None), _stream(),
               _meta=_bytes_meta(x, dout, x, dout, dx))
     if conv_bias_grad:
         return dx, dgamma, dbeta, dfilm, dcb
@@ -226,13 +231,14 @@ def ln_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float) -> torch.Tensor:
     return out
 
 
-def ln_bwd(x, gamma, dy, dres, eps: float):
-    _req_cuda(x, gamma, dy, dres)
+def ln_bwd(x, gamma, dy, dres, eps: float, into: Optional[torch.Tensor] = None):
+    """`into`: fp32 [C] buffer the gain gradient is ADDED to (else a fresh tensor is returned)."""
+    _req_cuda(x, gamma, dy, dres, into)
     C = x.shape[-1]
     dx = torch.empty_like(x)
-    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if into is None else into
     _lib.call("cesm_ln_bwd", _ptr(x), _ptr(gamma), _ptr(dy), _ptr(dres), _ptr(dx), _ptr(dgamma), x.numel() // C, C, eps,
-              _stream(), _meta=_bytes_meta(x, dy, dres, dx))
+              int(into is not None), _stream(), _meta=_bytes_meta(x, dy, dres, dx))
     return dx, dgamma
 
 
@@ -336,15 +342,19 @@ def small_linear_fwd(x, W, bias, act_silu_in: bool):
     return y
 
 
-def small_linear_bwd(x, W, dy, act_silu_in: bool, need_dx: bool):
+def small_linear_bwd(x, W, dy, act_silu_in: bool, need_dx: bool, into=None):
+    """`into`: (dW, db) buffers to ACCUMULATE into (parameter .grad views)."""
     _req_cuda(x, W, dy)
     B, K = x.shape
     N = W.shape[0]
-    dW = torch.empty_like(W)
-    db = torch.empty(N, dtype=torch.float32, device=x.device)
+    if into is not None:
+        dW, db = into
+    else:
+        dW = torch.empty_like(W)
+        db = torch.empty(N, dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x) if need_dx else None
     _lib.call("cesm_small_linear_bwd", _ptr(x), _ptr(W), _ptr(dy), _ptr(dx), _ptr(dW), _ptr(db), B, K, N,
-              int(act_silu_in), _stream())
+              int(act_silu_in), int(into is not None), _stream())
     return dx, dW, db
 
 

@@ -156,6 +156,15 @@ def _direct(weight: torch.Tensor) -> bool:
     return sink is not None and weight.grad is not None and sink.owns(weight)
 
 
+def _direct_all(*params) -> bool:
+    return all(p is not None and _direct(p) for p in params)
+
+
+def _ready(*params) -> None:
+    for p in params:
+        _GRAD_SINK[0].ready(p)
+
+
 def _wgrad_into_param(weight, x0, x1, dy, taps, so, si, tap_off, last: bool = True,
                       into: Optional[torch.Tensor] = None, **kw):
     """Weight gradient accumulated by the tcgen05 kernel's epilogue directly in `weight`'s own layout:
@@ -483,22 +492,35 @@ class ResnetBlockFn(torch.autograd.Function):
         ctx.wd1 = _conv_dgrad_weights(meta.c1, w1, cout, c0, cx1, 3, train)
         ctx.wd2 = _conv_dgrad_weights(meta.c2, w2, cout, cout, 0, 3, train)
         ctx.wdres = None if wres is None else _conv_dgrad_weights(meta.cres, wres, cout, c0, cx1, 1, train)
-        ctx.save_for_backward(x, x1, film, y1, sums1, h1, y2, sums2, w1, g1w, g1b, w2, g2w, g2b, wres)
+        ctx.save_for_backward(x, x1, film, y1, sums1, h1, y2, sums2, w1, g1w, g1b, w2, g2w, g2b, wres, b1, b2, bres)
         ctx.cfg = (B, G, eps)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, x1, film, y1, sums1, h1, y2, sums2, w1, g1w, g1b, w2, g2w, g2b, wres = ctx.saved_tensors
+        x, x1, film, y1, sums1, h1, y2, sums2, w1, g1w, g1b, w2, g2w, g2b, wres, b1, b2, bres = ctx.saved_tensors
         B, G, eps = ctx.cfg
         dout = dout.contiguous()
         ntaps = [(-dh, -dw) for dh, dw in K.TAPS_3x3]
+        # GroupNorm / conv-bias gradients go straight into the parameters' .grad in engine mode
         # ---- block 2 ----
-        dy2, dg2w, dg2b, _, db2 = K.gn_bwd(y2, dout, sums2, g2w, g2b, None, B, G, eps, conv_bias_grad=True)
+        if _direct_all(g2w, g2b, b2):
+            dy2, _, _, _, _ = K.gn_bwd(y2, dout, sums2, g2w, g2b, None, B, G, eps, conv_bias_grad=True,
+                                       into=(g2w.grad, g2b.grad, b2.grad))
+            _ready(g2w, g2b, b2)
+            dg2w = dg2b = db2 = None
+        else:
+            dy2, dg2w, dg2b, _, db2 = K.gn_bwd(y2, dout, sums2, g2w, g2b, None, B, G, eps, conv_bias_grad=True)
         dw2 = _conv_wgrad(w2, h1, None, dy2, 3)
         dh1 = K.igemm(dy2, ctx.wd2[0], taps=ntaps)
         # ---- block 1 ----
-        dy1, dg1w, dg1b, dfilm, db1 = K.gn_bwd(y1, dh1, sums1, g1w, g1b, film, B, G, eps, conv_bias_grad=True)
+        if _direct_all(g1w, g1b, b1):
+            dy1, _, _, dfilm, _ = K.gn_bwd(y1, dh1, sums1, g1w, g1b, film, B, G, eps, conv_bias_grad=True,
+                                           into=(g1w.grad, g1b.grad, b1.grad))
+            _ready(g1w, g1b, b1)
+            dg1w = dg1b = db1 = None
+        else:
+            dy1, dg1w, dg1b, dfilm, db1 = K.gn_bwd(y1, dh1, sums1, g1w, g1b, film, B, G, eps, conv_bias_grad=True)
         dw1 = _conv_wgrad(w1, x, x1, dy1, 3)
         # ---- inputs: conv-1 data gradient with the residual-branch gradient added in its epilogue ----
         dx = dx1 = dwres = dbres = None
@@ -513,7 +535,11 @@ class ResnetBlockFn(torch.autograd.Function):
                 r1 = K.igemm(dout, ctx.wdres[1])
                 dx1 = K.igemm(dy1, ctx.wd1[1], taps=ntaps, residual=r1)
             dwres = _conv_wgrad(wres, x, x1, dout, 1)
-            dbres = K.colsum(dout)
+            if _direct_all(bres):
+                K.colsum(dout, into=bres.grad)
+                _ready(bres)
+            else:
+                dbres = K.colsum(dout)
         return dx, dx1, dfilm, dw1, db1, dg1w, dg1b, dw2, db2, dg2w, dg2b, dwres, dbres, None, None
 
 
@@ -538,17 +564,17 @@ class TemporalAttnBlockFn(torch.autograd.Function):
         ctx.wdq = _conv_dgrad_weights(meta.cq, wqkv, 3 * hidden, C, 0, 1, train)[0]
         ctx.wdo = _conv_dgrad_weights(meta.co, wout, C, hidden, 0, 1, train)[0]
         if F <= 4:
-            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout)
+            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, gamma)
         else:
-            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, lse)
+            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, gamma, lse)
         ctx.cfg, ctx.gshape = (B, F, heads, D, eps), gamma.shape
         return y
 
     @staticmethod
     def backward(ctx, dy):
         saved = ctx.saved_tensors
-        x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout = saved[:10]
-        lse = saved[10] if len(saved) > 10 else None
+        x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, gamma = saved[:11]
+        lse = saved[11] if len(saved) > 11 else None
         B, F, heads, D, eps = ctx.cfg
         hidden = heads * D
         NI, H_, W_, C = x.shape
@@ -560,8 +586,15 @@ class TemporalAttnBlockFn(torch.autograd.Function):
         dqkv4 = dqkv.view(NI, H_, W_, 3 * hidden)
         dxn = K.igemm(dqkv4, ctx.wdq)
         dwqkv = _conv_wgrad(wqkv, xn, None, dqkv4, 1)
-        dx, dg = K.ln_bwd(x, g, dxn, dy, eps)  # + dy: the residual branch, added in the LN-backward epilogue
-        return dx, dg.view(ctx.gshape), dwqkv, dwout, dbias, None, None, None, None, None
+        # + dy: the residual branch, added in the LN-backward epilogue
+        if _direct_all(gamma):
+            dx, _ = K.ln_bwd(x, g, dxn, dy, eps, into=gamma.grad.view(-1))
+            _ready(gamma)
+            dgamma = None
+        else:
+            dx, dg = K.ln_bwd(x, g, dxn, dy, eps)
+            dgamma = dg.view(ctx.gshape)
+        return dx, dgamma, dwqkv, dwout, dbias, None, None, None, None, None
 
 
 class SpatialAttnBlockFn(torch.autograd.Function):
@@ -583,26 +616,37 @@ class SpatialAttnBlockFn(torch.autograd.Function):
                     residual=x)
         ctx.wdq = _conv_dgrad_weights(meta.cq, wqkv, 3 * hidden, C, 0, 1, train)[0]
         ctx.wdo = _conv_dgrad_weights(meta.co, wout, C, hidden, 0, 1, train)[0]
-        ctx.save_for_backward(x, g, xn, qkv, o, ws, wqkv, wout)
+        ctx.save_for_backward(x, g, xn, qkv, o, ws, wqkv, wout, gamma, bout)
         ctx.cfg, ctx.gshape = (heads, D, eps), gamma.shape
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, g, xn, qkv, o, ws, wqkv, wout = ctx.saved_tensors
+        x, g, xn, qkv, o, ws, wqkv, wout, gamma, bout = ctx.saved_tensors
         heads, D, eps = ctx.cfg
         hidden = heads * D
         NI, H_, W_, C = x.shape
         dy = dy.contiguous()
         do = K.igemm(dy, ctx.wdo)
         dwout = _conv_wgrad(wout, o.view(NI, H_, W_, hidden), None, dy, 1)
-        dbout = K.colsum(dy)
+        if _direct_all(bout):
+            K.colsum(dy, into=bout.grad)
+            _ready(bout)
+            dbout = None
+        else:
+            dbout = K.colsum(dy)
         dqkv = K.linattn_bwd(qkv.view(-1, 3 * hidden), ws, do.view(-1, hidden), NI, H_ * W_, heads, D, D ** -0.5)
         dqkv4 = dqkv.view(NI, H_, W_, 3 * hidden)
         dxn = K.igemm(dqkv4, ctx.wdq)
         dwqkv = _conv_wgrad(wqkv, xn, None, dqkv4, 1)
-        dx, dg = K.ln_bwd(x, g, dxn, dy, eps)
-        return dx, dg.view(ctx.gshape), dwqkv, dwout, dbout, None
+        if _direct_all(gamma):
+            dx, _ = K.ln_bwd(x, g, dxn, dy, eps, into=gamma.grad.view(-1))
+            _ready(gamma)
+            dgamma = None
+        else:
+            dx, dg = K.ln_bwd(x, g, dxn, dy, eps)
+            dgamma = dg.view(ctx.gshape)
+        return dx, dgamma, dwqkv, dwout, dbout, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -657,13 +701,18 @@ class SmallLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act_in: bool):
         x = x.contiguous()
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x, weight, bias)
         ctx.act_in = act_in
         return K.small_linear_fwd(x, weight, bias, act_in)
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, bias = ctx.saved_tensors
+        if _direct_all(weight, bias):
+            dx, _, _ = K.small_linear_bwd(x, weight, dy.contiguous(), ctx.act_in, ctx.needs_input_grad[0],
+                                          into=(weight.grad, bias.grad))
+            _ready(weight, bias)
+            return dx, None, None, None
         dx, dW, db = K.small_linear_bwd(x, weight, dy.contiguous(), ctx.act_in, ctx.needs_input_grad[0])
         return dx, dW, db, None
 

@@ -147,8 +147,10 @@ int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* s
 int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream);
 int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int I, long long so, long long si,
                       const int32_t* tap_off, int accumulate, void* stream);
-/* out[c] = sum over rows of bf16 x[M][C] (bias gradients). */
-int cesm_colsum(const void* x, float* out, long long M, int C, void* stream);
+/* out[c] (+)= sum over rows of bf16 x[M][C] (bias gradients).  `accumulate` != 0 here and in the other
+ * backward entry points adds into the parameter-gradient outputs instead of overwriting them, which
+ * lets the caller pass the parameter's .grad buffer directly. */
+int cesm_colsum(const void* x, float* out, long long M, int C, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm + FiLM + SiLU (+ residual), video_net.py:216-227 and :265.   x: bf16 [B][P][C],
@@ -165,14 +167,14 @@ int cesm_gn_apply_fwd(const void* x, const float* sums, const float* gamma, cons
                       const void* residual, void* out, int B, long long P, int C, int G, float eps, void* stream);
 int cesm_gn_bwd(const void* x, const void* dout, const float* sums, const float* gamma, const float* beta,
                 const float* film, float* csum, void* dx, float* dgamma, float* dbeta, float* dfilm,
-                float* dconv_bias, int B, long long P, int C, int G, float eps, void* stream);
+                float* dconv_bias, int B, long long P, int C, int G, float eps, int accumulate_params, void* stream);
 
 /* Channel LayerNorm with gain only, video_net.py:78-87.  x, out, dy, dres, dx: bf16 [M][C],
  * C in {64, 128, 256, 512, 1024}.
  * bwd: dx = LN'(dy) (+ dres if not NULL); dgamma fp32 [C] is overwritten. */
 int cesm_ln_fwd(const void* x, const float* gamma, void* out, long long M, int C, float eps, void* stream);
 int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, const void* dres, void* dx, float* dgamma,
-                long long M, int C, float eps, void* stream);
+                long long M, int C, float eps, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Temporal attention core, video_net.py:413-453 + rotary_embedding.py:29-48, fused:
@@ -231,7 +233,7 @@ int cesm_sinusoidal(const long long* t, float* out, int B, int dim, void* stream
 int cesm_small_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
                           int act_silu_in, void* stream);
 int cesm_small_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db, int B,
-                          int K, int N, int act_silu_in, void* stream);
+                          int K, int N, int act_silu_in, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DDPM elementwise steps (model.py:168-208); t is an int64 device vector, schedule buffers fp32 [T].
