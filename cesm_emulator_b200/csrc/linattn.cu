@@ -64,6 +64,19 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
+// cp.async (LDGSTS) ring: every global byte of these kernels goes global -> shared without passing
+// through registers, several 16-pixel steps ahead of its use, so a warp keeps (stages-1) steps of
+// loads in flight whatever its register budget.  Buffers are warp-private: only __syncwarp is needed.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+static constexpr int kTileBytes = 16 * SPITCH * 2;  // one staged 16-pixel x 32-channel bf16 tile
+
 struct LaWs {  // views into the per-image workspace
     uint32_t* kmax;
     float* z;
@@ -114,6 +127,7 @@ la_colmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, 
 // Each 16-pixel step is staged through a warp-private smem tile and read back with
 // ldmatrix.trans, which yields the pixel-contracted (MN-major) fragments.
 // ------------------------------------------------------------------------------------------------
+static constexpr int CTX_STAGES = 4;
 template <int MODE>
 __global__ void __launch_bounds__(256)
 la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
@@ -123,8 +137,10 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
-    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(la_smem) + (size_t)w * 2 * 16 * SPITCH;
-    __nv_bfloat16* sB = sA + 16 * SPITCH;
+    // per warp: [CTX_STAGES][2] raw tiles (A source, B) filled by cp.async + one transformed A tile
+    uint8_t* wbase = la_smem + (size_t)w * (2 * CTX_STAGES + 1) * kTileBytes;
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(wbase + 2 * CTX_STAGES * kTileBytes);
+    const uint32_t ring_addr = smem_u32(wbase);
     const LaWs W = la_ws(ws, ni, HD, H);
 
     float cmax[8], zsum[8];
@@ -150,32 +166,45 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
 
     // ldmatrix lane addresses (fixed): A m-tile mt, B n-tile pair jp
     const int mi = lane >> 3, rr = lane & 7;
-    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    const uint32_t sA_addr = smem_u32(sA);
     uint32_t a_off[2], b_off[2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) a_off[mt] = (((mi >> 1) * 8 + rr) * SPITCH + 16 * mt + (mi & 1) * 8) * 2;
 #pragma unroll
     for (int jp = 0; jp < 2; ++jp) b_off[jp] = (((mi & 1) * 8 + rr) * SPITCH + 8 * (jp * 2 + (mi >> 1))) * 2;
 
-    uint4 na[2], nb[2];
-    auto issue_loads = [&](int pp) {
+    auto issue_loads = [&](int step) {  // rows beyond the chunk are clamped (finite data) and masked later
+        const int pp = p0 + 16 * step;
+        const uint32_t st = ring_addr + (step % CTX_STAGES) * 2 * kTileBytes;
+        if (pp < p1) {
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = pp + r + 8 * h2;
-            if (row < p1) {
-                na[h2] = __ldg(reinterpret_cast<const uint4*>(a_base + (size_t)row * ld));
-                nb[h2] = __ldg(reinterpret_cast<const uint4*>(b_base + (size_t)row * b_ld));
-            } else {
-                na[h2] = make_uint4(0, 0, 0, 0);
-                nb[h2] = make_uint4(0, 0, 0, 0);
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int row = min(pp + r + 8 * h2, p1 - 1);
+                const uint32_t off = ((r + 8 * h2) * SPITCH + c * 8) * 2;
+                cp_async16(st + off, a_base + (size_t)row * ld);
+                cp_async16(st + kTileBytes + off, b_base + (size_t)row * b_ld);
             }
         }
+        cp_async_commit();
     };
-    if (p0 < p1) issue_loads(p0);
-    for (int p = p0; p < p1; p += 16) {
-        // ---- this step's rows (loaded one step ahead); next step's loads are issued right away ----
-        uint4 ua[2] = {na[0], na[1]}, ub[2] = {nb[0], nb[1]};
-        if (p + 16 < p1) issue_loads(p + 16);
+    const int nsteps = (p1 - p0 + 15) / 16;
+#pragma unroll
+    for (int s0 = 0; s0 < CTX_STAGES - 1; ++s0) issue_loads(s0);
+    for (int step = 0; step < nsteps; ++step) {
+        const int p = p0 + 16 * step;
+        issue_loads(step + CTX_STAGES - 1);      // refills the stage consumed in the previous iteration
+        cp_async_wait<CTX_STAGES - 1>();         // this step's tiles have landed
+        __syncwarp();
+        const uint32_t st = ring_addr + (step % CTX_STAGES) * 2 * kTileBytes;
+        const uint32_t sB_addr = st + kTileBytes;
+        uint4 ua[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const uint32_t off = ((r + 8 * h2) * SPITCH + c * 8) * 2;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(ua[h2].x), "=r"(ua[h2].y), "=r"(ua[h2].z), "=r"(ua[h2].w)
+                         : "r"(st + off));
+        }
         // ---- transform A ----
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -205,7 +234,6 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
                 for (int i = 0; i < 8; ++i) f[i] *= inv;
             }
             *reinterpret_cast<uint4*>(sA + (r + 8 * h2) * SPITCH + c * 8) = pack8(f);
-            *reinterpret_cast<uint4*>(sB + (r + 8 * h2) * SPITCH + c * 8) = ub[h2];
         }
         __syncwarp();
         uint32_t af[2][4], bf[2][4];
@@ -271,43 +299,41 @@ __global__ void la_delta_kernel(float* __restrict__ ws, const float* __restrict_
     delta[idx] = s;
 }
 
-// B fragments of a 32x32 fp32 matrix M (row-major) for C = A * Bm with Bm[k][n] = TRANS ? M[n][k] : M[k][n]
+// ------------------------------------------------------------------------------------------------
+// The apply kernels keep everything in registers.  Lane (g = lane >> 2, t = lane & 3) owns the 8
+// channels 8t..8t+7 (one 16-byte global access) of pixel rows g and g+8 of a 16-pixel step.  With the
+// channel permutation  phi(8j + 2t + b) = 8t + 2j + b  (logical mma column -> physical channel) that
+// row layout IS the mma.m16n8k16 C-fragment layout (n-tile j <-> 32-bit word j of the lane's uint4)
+// and, k-step ks taking words 2ks and 2ks+1, also the A-fragment layout.  Only the small 32x32
+// B operands (ctx, dctx) need the permutation, applied once per block when their fragments are read
+// from global memory; the contraction index order is irrelevant to a sum.  So: 16-byte loads ->
+// softmax / exp in registers -> mma -> 16-byte stores, no shared memory, no warp syncs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int phi32(int L) { return ((L >> 1) & 3) * 8 + (L >> 3) * 2 + (L & 1); }
+
+// B fragments of a 32x32 fp32 matrix M (row-major) for C = A * Bm, Bm[k][n] = TRANS ? M[n][k] : M[k][n],
+// with both k and n taken through phi32
 template <bool TRANS>
 __device__ __forceinline__ void load_bfrag32(const float* __restrict__ M, int g, int t, uint32_t (&b)[2][4][2]) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int k0 = 16 * ks + 2 * t, nn = 8 * j + g;
-            if (TRANS) {
-                b[ks][j][0] = pack_bf16x2(M[nn * LD + k0], M[nn * LD + k0 + 1]);
-                b[ks][j][1] = pack_bf16x2(M[nn * LD + k0 + 8], M[nn * LD + k0 + 9]);
-            } else {
-                b[ks][j][0] = pack_bf16x2(M[k0 * LD + nn], M[(k0 + 1) * LD + nn]);
-                b[ks][j][1] = pack_bf16x2(M[(k0 + 8) * LD + nn], M[(k0 + 9) * LD + nn]);
+            const int nn = phi32(8 * j + g);
+#pragma unroll
+            for (int hi = 0; hi < 2; ++hi) {
+                const int k0 = phi32(16 * ks + 8 * hi + 2 * t), k1 = k0 + 1;  // phi keeps (even, odd) pairs adjacent
+                b[ks][j][hi] = TRANS ? pack_bf16x2(M[nn * LD + k0], M[nn * LD + k1])
+                                     : pack_bf16x2(M[k0 * LD + nn], M[k1 * LD + nn]);
             }
         }
 }
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(addr));
+// A fragments of a 16 x 32 tile whose rows g / g+8 this lane holds as packed bf16 (lo / hi)
+__device__ __forceinline__ void rows_to_afrag(const uint4& lo, const uint4& hi, uint32_t (&a)[2][4]) {
+    a[0][0] = lo.x; a[0][1] = hi.x; a[0][2] = lo.y; a[0][3] = hi.y;
+    a[1][0] = lo.z; a[1][1] = hi.z; a[1][2] = lo.w; a[1][3] = hi.w;
 }
-// The apply kernels move data in the "row layout": lane = (r = lane >> 2, c = lane & 3) owns the 8
-// channels c*8.. of pixel rows r and r + 8 of a 16-pixel step, i.e. one 16-byte global access per row --
-// every global load/store is a full 128-bit transaction on 64 contiguous bytes per pixel and head.
-// Tensor-core fragments are produced from / returned to that layout through a warp-private
-// shared-memory tile (bf16 [16][SPITCH] for A operands via ldmatrix, fp32 [16][CPITCH] for results).
-static constexpr int CPITCH = 34;  // floats per result row (8-byte aligned float2 slots)
-
-// A fragments (16 x 32, two k-steps) of a staged bf16 tile
-__device__ __forceinline__ void lds_afrag(uint32_t tile_addr, int lane, uint32_t (&a)[2][4]) {
-    const int mi = lane >> 3, rr = lane & 7;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-        ldmatrix_x4(a[ks], tile_addr + (((mi & 1) * 8 + rr) * SPITCH + 16 * ks + (mi >> 1) * 8) * 2);
-}
-// C (16x32 as 4 n-tiles) = A (16x32) * B
+// C (16x32 as 4 n-tiles) = A (16x32) * B; c[j][0..1] = row g, words j; c[j][2..3] = row g+8
 __device__ __forceinline__ void frag_gemm(const uint32_t (&a)[2][4], const uint32_t (&b)[2][4][2], float (&c)[4][4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -316,24 +342,12 @@ __device__ __forceinline__ void frag_gemm(const uint32_t (&a)[2][4], const uint3
         for (int ks = 0; ks < 2; ++ks) mma_16816(c[j], a[ks], b[ks][j][0], b[ks][j][1]);
     }
 }
-// result fragments -> fp32 tile -> this lane's 8 columns of rows r and r+8
-__device__ __forceinline__ void c_to_rows(float* sC, int lane, const float (&c)[4][4], float (&o)[2][8]) {
-    const int g = lane >> 2, t = lane & 3;
-    __syncwarp();
+__device__ __forceinline__ void c_to_rows(const float (&c)[4][4], float (&o)[2][8]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        *reinterpret_cast<float2*>(sC + g * CPITCH + 8 * j + 2 * t) = make_float2(c[j][0], c[j][1]);
-        *reinterpret_cast<float2*>(sC + (g + 8) * CPITCH + 8 * j + 2 * t) = make_float2(c[j][2], c[j][3]);
+        o[0][2 * j] = c[j][0]; o[0][2 * j + 1] = c[j][1];
+        o[1][2 * j] = c[j][2]; o[1][2 * j + 1] = c[j][3];
     }
-    __syncwarp();
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 v = *reinterpret_cast<const float2*>(sC + (g + 8 * h2) * CPITCH + t * 8 + 2 * k);
-            o[h2][2 * k] = v.x;
-            o[h2][2 * k + 1] = v.y;
-        }
 }
 // softmax over the 32 channels of a row held by a quad (8 per lane)
 __device__ __forceinline__ void row_softmax(float (&f)[8]) {
@@ -351,61 +365,71 @@ __device__ __forceinline__ void row_softmax(float (&f)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] *= inv;
 }
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {  // read-once data: do not pollute L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------------
-// apply (forward): out[p][e] = sum_d qs[p][d] ctx[d][e]; warp = head, 16 pixels per step
+// apply (forward): out[p][e] = sum_d qs[p][d] ctx[d][e]; warp = head; APPLY_MT 16-pixel tiles per
+// step, the next step's loads issued before this step's math
 // ------------------------------------------------------------------------------------------------
+static constexpr int APPLY_MT = 2;
 __global__ void __launch_bounds__(256, 3)
 la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int n,
                 int H, int chunk, float scale) {
-    extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
-    constexpr int kWarpBytes = 16 * SPITCH * 2 + 16 * CPITCH * 4;
-    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(la_smem + (size_t)w * kWarpBytes);
-    float* sC = reinterpret_cast<float*>(la_smem + (size_t)w * kWarpBytes + 16 * SPITCH * 2);
-    const uint32_t sA_addr = smem_u32(sA);
     const LaWs W = la_ws(ws, ni, HD, H);
     uint32_t bctx[2][4][2];
-    load_bfrag32<false>(W.ctx + (size_t)w * LD * LD, lane >> 2, lane & 3, bctx);
+    load_bfrag32<false>(W.ctx + (size_t)w * LD * LD, r, c, bctx);
     const size_t row0 = (size_t)ni * n;
     const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
-    uint4 nq[2];
+    const __nv_bfloat16* qbase = qkv + row0 * ld + w * LD + c * 8;
+    __nv_bfloat16* obase = out + row0 * HD + w * LD + c * 8;
+    uint4 nq[APPLY_MT][2];
     auto issue_loads = [&](int pp) {
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = pp + r + 8 * h2;
-            nq[h2] = __ldg(reinterpret_cast<const uint4*>(qkv + (row0 + (row < p1 ? row : p1 - 1)) * ld + w * LD + c * 8));
-        }
+        for (int mt = 0; mt < APPLY_MT; ++mt)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int row = min(pp + 16 * mt + r + 8 * h2, p1 - 1);
+                nq[mt][h2] = ldg_stream16(qbase + (size_t)row * ld);
+            }
     };
     const int pstart = blockIdx.x * chunk;
     if (pstart < p1) issue_loads(pstart);
-    for (int p = pstart; p < p1; p += 16) {
-        uint4 cq[2] = {nq[0], nq[1]};
-        if (p + 16 < p1) issue_loads(p + 16);  // next step's loads fly during this step's math
+    for (int p = pstart; p < p1; p += 16 * APPLY_MT) {
+        uint4 cq[APPLY_MT][2];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = p + r + 8 * h2;
-            const bool valid = row < p1;  // no divergent branch around the quad shuffles of row_softmax
-            float f[8];
-            unpack8(cq[h2], f);
-            row_softmax(f);
-            const float sc = valid ? scale : 0.f;
+        for (int mt = 0; mt < APPLY_MT; ++mt) { cq[mt][0] = nq[mt][0]; cq[mt][1] = nq[mt][1]; }
+        if (p + 16 * APPLY_MT < p1) issue_loads(p + 16 * APPLY_MT);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] *= sc;
-            *reinterpret_cast<uint4*>(sA + (r + 8 * h2) * SPITCH + c * 8) = pack8(f);
-        }
-        __syncwarp();
-        uint32_t a[2][4];
-        lds_afrag(sA_addr, lane, a);
-        float cfr[4][4], o[2][8];
-        frag_gemm(a, bctx, cfr);
-        c_to_rows(sC, lane, cfr, o);
+        for (int mt = 0; mt < APPLY_MT; ++mt) {
+            uint4 pk[2];
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = p + r + 8 * h2;
-            if (row < p1) *reinterpret_cast<uint4*>(out + (row0 + row) * HD + w * LD + c * 8) = pack8(o[h2]);
+            for (int h2 = 0; h2 < 2; ++h2) {
+                float f[8];
+                unpack8(cq[mt][h2], f);
+                row_softmax(f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= scale;
+                pk[h2] = pack8(f);
+            }
+            uint32_t a[2][4];
+            rows_to_afrag(pk[0], pk[1], a);
+            float cfr[4][4], o[2][8];
+            frag_gemm(a, bctx, cfr);
+            c_to_rows(cfr, o);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int row = p + 16 * mt + r + 8 * h2;
+                if (row < p1) *reinterpret_cast<uint4*>(obase + (size_t)row * HD) = pack8(o[h2]);
+            }
         }
     }
 }
@@ -420,82 +444,66 @@ __global__ void __launch_bounds__(256, 2)
 la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     float* __restrict__ ws, const float* __restrict__ dctx, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
-    extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
-    constexpr int kTile = 16 * SPITCH * 2;
-    constexpr int kWarpBytes = 3 * kTile + 16 * CPITCH * 4;
-    uint8_t* base = la_smem + (size_t)w * kWarpBytes;
-    __nv_bfloat16* sD = reinterpret_cast<__nv_bfloat16*>(base);           // dout
-    __nv_bfloat16* sV = reinterpret_cast<__nv_bfloat16*>(base + kTile);   // v
-    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(base + 2 * kTile);  // kh
-    float* sC = reinterpret_cast<float*>(base + 3 * kTile);
-    const uint32_t sD_addr = smem_u32(sD), sV_addr = smem_u32(sV), sK_addr = smem_u32(sK);
     const LaWs W = la_ws(ws, ni, HD, H);
     const float* dcx = dctx + ((size_t)ni * H + w) * LD * LD;
     uint32_t b_ctxT[2][4][2], b_dctxT[2][4][2], b_dctx[2][4][2];
-    load_bfrag32<true>(W.ctx + (size_t)w * LD * LD, lane >> 2, lane & 3, b_ctxT);
-    load_bfrag32<true>(dcx, lane >> 2, lane & 3, b_dctxT);
-    load_bfrag32<false>(dcx, lane >> 2, lane & 3, b_dctx);
-    float kmx[8], kinvz[8], del[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int col = w * LD + c * 8 + i;
-        kmx[i] = dec_ordered(W.kmax[col]);
-        kinvz[i] = 1.f / W.z[col];
-        del[i] = delta[(size_t)ni * HD + col];
+    load_bfrag32<true>(W.ctx + (size_t)w * LD * LD, r, c, b_ctxT);
+    load_bfrag32<true>(dcx, r, c, b_dctxT);
+    load_bfrag32<false>(dcx, r, c, b_dctx);
+    // per-channel constants live in shared memory (read back as two float4 per use: registers are
+    // what bounds this kernel's occupancy).  kh = exp(k - max) / Z = exp(k - (max + log Z))
+    __shared__ __align__(16) float s_kml[8 * LD], s_del[8 * LD];
+    {
+        const int col = threadIdx.x;  // blockDim.x == HD
+        s_kml[col] = dec_ordered(W.kmax[col]) + __logf(W.z[col]);
+        s_del[col] = delta[(size_t)ni * HD + col];
     }
+    __syncthreads();
+    const float* kml = s_kml + w * LD + c * 8;
+    const float* del = s_del + w * LD + c * 8;
     const size_t row0 = (size_t)ni * n;
     const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
+    const __nv_bfloat16* xbase = qkv + row0 * ld + w * LD + c * 8;
+    const __nv_bfloat16* dbase = dout + row0 * HD + w * LD + c * 8;
+    __nv_bfloat16* gbase = dqkv + row0 * ld + w * LD + c * 8;
     // software pipeline: the 8 x 16-byte loads of step i+1 are issued before the tensor-core work of
     // step i, so that a warp always has a step's worth of bytes in flight
     uint4 nd[2], nq[2], nk[2], nv[2];
     auto issue_loads = [&](int pp) {
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = pp + r + 8 * h2;
-            const size_t rg = row0 + (row < p1 ? row : p1 - 1);
-            const __nv_bfloat16* xg = qkv + rg * ld + w * LD + c * 8;
-            nd[h2] = __ldg(reinterpret_cast<const uint4*>(dout + rg * HD + w * LD + c * 8));
-            nq[h2] = __ldg(reinterpret_cast<const uint4*>(xg));
-            nk[h2] = __ldg(reinterpret_cast<const uint4*>(xg + HD));
-            nv[h2] = __ldg(reinterpret_cast<const uint4*>(xg + 2 * HD));
+            const int row = min(pp + r + 8 * h2, p1 - 1);
+            const __nv_bfloat16* xg = xbase + (size_t)row * ld;
+            nd[h2] = ldg_stream16(dbase + (size_t)row * HD);
+            nq[h2] = ldg_stream16(xg);
+            nk[h2] = ldg_stream16(xg + HD);
+            nv[h2] = ldg_stream16(xg + 2 * HD);
         }
     };
     const int pstart = blockIdx.x * chunk;
     if (pstart < p1) issue_loads(pstart);
     for (int p = pstart; p < p1; p += 16) {
-        float sm[2][8], kh[2][8];
-        __syncwarp();
+        float sm[2][8];
+        uint4 ud[2], uv[2], uk[2];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = p + r + 8 * h2;
-            const bool valid = row < p1;
-            uint4 ud = nd[h2], uv = nv[h2];
-            const uint4 uq = nq[h2], uk = nk[h2];
-            if (!valid) {
-                ud = make_uint4(0, 0, 0, 0);
-                uv = make_uint4(0, 0, 0, 0);
-            }
-            unpack8(uq, sm[h2]);
-            row_softmax(sm[h2]);
-            float kv[8];
-            unpack8(uk, kv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) kh[h2][i] = valid ? __expf(kv[i] - kmx[i]) * kinvz[i] : 0.f;
-            *reinterpret_cast<uint4*>(sD + (r + 8 * h2) * SPITCH + c * 8) = ud;
-            *reinterpret_cast<uint4*>(sV + (r + 8 * h2) * SPITCH + c * 8) = uv;
-            *reinterpret_cast<uint4*>(sK + (r + 8 * h2) * SPITCH + c * 8) = pack8(kh[h2]);
+            ud[h2] = nd[h2];
+            uv[h2] = nv[h2];
+            uk[h2] = nk[h2];
+            unpack8(nq[h2], sm[h2]);
         }
         if (p + 16 < p1) issue_loads(p + 16);
-        __syncwarp();
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) row_softmax(sm[h2]);
         uint32_t a[2][4];
         float cfr[4][4], o[2][8];
         // ---- dq ----
-        lds_afrag(sD_addr, lane, a);
+        rows_to_afrag(ud[0], ud[1], a);
         frag_gemm(a, b_ctxT, cfr);  // dqh
-        c_to_rows(sC, lane, cfr, o);
+        c_to_rows(cfr, o);
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
             float dot = 0.f;
@@ -505,27 +513,38 @@ la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[h2][i] = sm[h2][i] * scale * (o[h2][i] - dot);
             const int row = p + r + 8 * h2;
-            if (row < p1) *reinterpret_cast<uint4*>(dqkv + (row0 + row) * ld + w * LD + c * 8) = pack8(o[h2]);
+            if (row < p1) *reinterpret_cast<uint4*>(gbase + (size_t)row * ld) = pack8(o[h2]);
         }
         // ---- dk ----
-        lds_afrag(sV_addr, lane, a);
+        rows_to_afrag(uv[0], uv[1], a);
         frag_gemm(a, b_dctxT, cfr);  // dkh
-        c_to_rows(sC, lane, cfr, o);
+        c_to_rows(cfr, o);
+        uint4 ukh[2];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
+            float kh[8], km[8], dl[8];
+            unpack8(uk[h2], kh);
+            *reinterpret_cast<float4*>(km) = *reinterpret_cast<const float4*>(kml);
+            *reinterpret_cast<float4*>(km + 4) = *reinterpret_cast<const float4*>(kml + 4);
+            *reinterpret_cast<float4*>(dl) = *reinterpret_cast<const float4*>(del);
+            *reinterpret_cast<float4*>(dl + 4) = *reinterpret_cast<const float4*>(del + 4);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[h2][i] = kh[h2][i] * (o[h2][i] - del[i]);
+            for (int i = 0; i < 8; ++i) {
+                kh[i] = __expf(kh[i] - km[i]);
+                o[h2][i] = kh[i] * (o[h2][i] - dl[i]);
+            }
+            ukh[h2] = pack8(kh);
             const int row = p + r + 8 * h2;
-            if (row < p1) *reinterpret_cast<uint4*>(dqkv + (row0 + row) * ld + HD + w * LD + c * 8) = pack8(o[h2]);
+            if (row < p1) *reinterpret_cast<uint4*>(gbase + (size_t)row * ld + HD) = pack8(o[h2]);
         }
         // ---- dv ----
-        lds_afrag(sK_addr, lane, a);
+        rows_to_afrag(ukh[0], ukh[1], a);
         frag_gemm(a, b_dctx, cfr);
-        c_to_rows(sC, lane, cfr, o);
+        c_to_rows(cfr, o);
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
             const int row = p + r + 8 * h2;
-            if (row < p1) *reinterpret_cast<uint4*>(dqkv + (row0 + row) * ld + 2 * HD + w * LD + c * 8) = pack8(o[h2]);
+            if (row < p1) *reinterpret_cast<uint4*>(gbase + (size_t)row * ld + 2 * HD) = pack8(o[h2]);
         }
     }
 }
@@ -542,6 +561,17 @@ static int la_chunk(int n, int NI) {
     return chunk;
 }
 
+static size_t la_context_smem(int H) {
+    // per warp (= head): CTX_STAGES x {A source, B} cp.async tiles + one transformed A tile
+    static bool cfg = false;
+    if (!cfg) {
+        cudaFuncSetAttribute(la_context_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * CTX_STAGES + 1) * kTileBytes);
+        cudaFuncSetAttribute(la_context_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * CTX_STAGES + 1) * kTileBytes);
+        cfg = true;
+    }
+    return (size_t)H * (2 * CTX_STAGES + 1) * kTileBytes;
+}
+
 extern "C" size_t cesm_linattn_ws_floats(int NI, int H) { return (size_t)NI * (2 * H * LD + (size_t)H * LD * LD); }
 
 extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, int n, int H, int dim_head, float scale,
@@ -555,13 +585,12 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, i
     dim3 grid(ceil_div(n, chunk), NI);
     la_colmax_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, ws, n, H, chunk);
     CESM_CHECK_LAUNCH();
-    const size_t sh = (size_t)H * 2 * 16 * SPITCH * sizeof(__nv_bfloat16);
+    const size_t sh = la_context_smem(H);
     la_context_kernel<0><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, nullptr, ws, nullptr, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     la_finalize_kernel<<<ceil_div(NI * H * LD * LD, 256), 256, 0, st>>>(ws, H, NI);
     CESM_CHECK_LAUNCH();
-    const size_t sh_apply = (size_t)H * (16 * SPITCH * 2 + 16 * CPITCH * 4);
-    la_apply_kernel<<<grid, 32 * H, sh_apply, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
+    la_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
                                                     scale);
     CESM_CHECK_LAUNCH();
     (void)HD;
@@ -579,19 +608,13 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
     CESM_CHECK_CUDA(cudaMemsetAsync(dctx, 0, sizeof(float) * NI * H * LD * LD, st));
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
-    const size_t sh = (size_t)H * 2 * 16 * SPITCH * sizeof(__nv_bfloat16);
+    const size_t sh = la_context_smem(H);
     la_context_kernel<1><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, n, H,
                                                    chunk, scale);
     CESM_CHECK_LAUNCH();
     la_delta_kernel<<<ceil_div(NI * H * LD, 128), 128, 0, st>>>(ws, dctx, delta, H, NI);
     CESM_CHECK_LAUNCH();
-    const size_t sh_bwd = (size_t)H * (3 * 16 * SPITCH * 2 + 16 * CPITCH * 4);
-    static bool bwd_cfg = false;
-    if (!bwd_cfg) {
-        CESM_CHECK_CUDA(cudaFuncSetAttribute(la_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        bwd_cfg = true;
-    }
-    la_bwd_apply_kernel<<<grid, 32 * H, sh_bwd, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
+    la_bwd_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
                                                  (__nv_bfloat16*)dqkv, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
