@@ -12,6 +12,7 @@
 //
 // Replaces the weight-gradient halves of cuDNN/cuBLAS backward for video_net.py:215, :246, :62,
 // :66, :322-323, :380-381.
+#include <cstdlib>
 #include "common.cuh"
 #include "igemm.h"
 
@@ -198,7 +199,9 @@ cudaError_t wgrad_launch(const CUtensorMap* xmaps, int n_xmaps, const CUtensorMa
     switch (block_n) {
         case 64: return launch_wgrad<64, 4>(maps, p, grid, stream);
         case 128: return launch_wgrad<128, 3>(maps, p, grid, stream);
-        case 256: return launch_wgrad<256, 2>(maps, p, grid, stream);
+        // 256 columns: one CTA per SM with a 4-deep 48 KB ring beats two CTAs with 2 stages each
+        // (64->768 projection gradient at 192x288: 104 -> 87 us, 6.3 TB/s; tools/bench_wgrad.py)
+        case 256: return launch_wgrad<256, 4>(maps, p, grid, stream);
         default: return cudaErrorInvalidValue;
     }
 }
