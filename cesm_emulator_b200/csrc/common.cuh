@@ -45,6 +45,13 @@ __device__ __forceinline__ float dsilu_f(float x) {
     const float s = sigmoid_fast(x);
     return s * (1.f + x * (1.f - s));
 }
+// The same derivative from h = x/2 with two fewer ops: t = tanh(h), s = (1+t)/2, s(1-s) = (1-t^2)/4, so
+//   silu'(x) = 0.5 * (1 + R),  R = t + h (1 - t^2)          (callers fold the 0.5 * (1 + .) into their own FMAs)
+__device__ __forceinline__ float dsilu_R_from_half(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, fmaf(-t, t, 1.f), t);
+}
 // full-precision variants for the fp32 paths (time-embedding MLP)
 __device__ __forceinline__ float silu_precise(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float dsilu_precise(float x) {
@@ -56,9 +63,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// one ALU op per element (shift / mask) instead of the PRMT + shift pair the intrinsic compiles to
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-    return __bfloat1622float2(v);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -39,6 +39,14 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
 // kernels are pure streams, so bytes in flight per SM is what sets the achieved bandwidth).
 // ------------------------------------------------------------------------------------------------
 static constexpr int UNR = 4;
+static constexpr int PF = 2;   // vectors per tensor per software-pipeline stage in the backward kernels
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once stream: keep it out of L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
 
 __global__ void __launch_bounds__(kNormThreads)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, long long P, int C, int G) {
@@ -147,7 +155,7 @@ gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 //   with z = xhat*gamma+beta, u = z*(sc+1)+sh, du = dout*silu'(u).  Everything else the backward
 //   needs is algebra on these: dz = du*(sc+1), sum dz = (sc+1) T0, sum dz*xhat = (sc+1) T1,
 //   sum du*z = gamma T1 + beta T0.
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 3)
 gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ sums, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ film, float* __restrict__ csum,
@@ -171,8 +179,8 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
             ga *= sc;
             be = be * sc + sh;
         }
-        A[i] = ga;
-        Bc[i] = be;
+        A[i] = 0.5f * ga;  // u / 2 (see dsilu_R_from_half)
+        Bc[i] = 0.5f * be;
     }
     float acc[3][8];
 #pragma unroll
@@ -181,28 +189,42 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
     const size_t base = (size_t)b * P * C + slot * 8;
     const long long stride = (long long)gridDim.x * pix_per_iter;
-    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
-        uint4 u[UNR], d[UNR];
+    // software pipeline: the PF loads of trip i+1 are in flight while trip i is being reduced
+    uint4 nu[PF], nd[PF];
+    auto issue = [&](long long p) {
 #pragma unroll
-        for (int k = 0; k < UNR; ++k) {
+        for (int k = 0; k < PF; ++k) {
             const long long pk = p + k * stride;
             if (pk < P) {
-                u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + pk * C));
-                d[k] = __ldg(reinterpret_cast<const uint4*>(dout + base + pk * C));
+                nu[k] = ld_stream16(x + base + pk * C);
+                nd[k] = ld_stream16(dout + base + pk * C);
             } else {
-                u[k] = make_uint4(0, 0, 0, 0);
-                d[k] = make_uint4(0, 0, 0, 0);  // dout = 0 -> contributes nothing to T0/T1; x = 0 -> nothing to T2
+                nu[k] = make_uint4(0, 0, 0, 0);
+                nd[k] = make_uint4(0, 0, 0, 0);  // dout = 0 -> contributes nothing to T0/T1; x = 0 -> nothing to T2
             }
         }
+    };
+    long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix;
+    if (p < P) issue(p);
+    for (; p < P; p += PF * stride) {
+        uint4 u[PF], d[PF];
 #pragma unroll
-        for (int k = 0; k < UNR; ++k) {
+        for (int k = 0; k < PF; ++k) {
+            u[k] = nu[k];
+            d[k] = nd[k];
+        }
+        if (p + PF * stride < P) issue(p + PF * stride);
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
             const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
             const uint32_t dw[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 f = unpack_bf16x2(w[i]), dd = unpack_bf16x2(dw[i]);
-                const float du0 = dd.x * dsilu_f(fmaf(f.x, A[2 * i], Bc[2 * i]));
-                const float du1 = dd.y * dsilu_f(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1]));
+                // A, Bc hold u/2 coefficients; du = dout * silu'(u) = (dout/2) (1 + R)
+                const float e0 = 0.5f * dd.x, e1 = 0.5f * dd.y;
+                const float du0 = fmaf(e0, dsilu_R_from_half(fmaf(f.x, A[2 * i], Bc[2 * i])), e0);
+                const float du1 = fmaf(e1, dsilu_R_from_half(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1])), e1);
                 acc[0][2 * i] += du0;
                 acc[0][2 * i + 1] += du1;
                 acc[1][2 * i] = fmaf(du0, f.x, acc[1][2 * i]);      // sum du*x; xhat folded in below
@@ -231,7 +253,7 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 }
 
 // Backward pass 2: dx = rstd * (gamma*dz - m1 - xhat*m2), m1/m2 = group means of gamma*dz and gamma*dz*xhat.
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 3)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dout,
                     const float* __restrict__ sums, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ film,
@@ -269,25 +291,36 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
             ga *= sc;
             be = be * sc + sh;
         }
-        A[i] = ga;
-        Bc[i] = be;
-        Gs[i] = rstd * gamma[c] * sc;
+        A[i] = 0.5f * ga;  // u / 2 (see dsilu_R_from_half)
+        Bc[i] = 0.5f * be;
+        Gs[i] = 0.5f * rstd * gamma[c] * sc;
     }
     const float K1 = rstd * rstd * m2, K0 = rstd * m1 - mean * K1;
     const size_t base = (size_t)b * P * C + slot * 8;
     const long long stride = (long long)gridDim.x * pix_per_iter;
-    for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
-        uint4 u[UNR], d[UNR];
+    uint4 nu[PF], nd[PF];
+    auto issue = [&](long long p) {
 #pragma unroll
-        for (int k = 0; k < UNR; ++k) {
+        for (int k = 0; k < PF; ++k) {
             const long long pk = p + k * stride;
             if (pk < P) {
-                u[k] = __ldg(reinterpret_cast<const uint4*>(x + base + pk * C));
-                d[k] = __ldg(reinterpret_cast<const uint4*>(dout + base + pk * C));
+                nu[k] = ld_stream16(x + base + pk * C);
+                nd[k] = ld_stream16(dout + base + pk * C);
             }
         }
+    };
+    long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix;
+    if (p < P) issue(p);
+    for (; p < P; p += PF * stride) {
+        uint4 u[PF], d[PF];
 #pragma unroll
-        for (int k = 0; k < UNR; ++k) {
+        for (int k = 0; k < PF; ++k) {
+            u[k] = nu[k];
+            d[k] = nd[k];
+        }
+        if (p + PF * stride < P) issue(p + PF * stride);
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
             const long long pk = p + k * stride;
             if (pk >= P) break;
             const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
@@ -296,8 +329,10 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 f = unpack_bf16x2(w[i]), dd = unpack_bf16x2(dw[i]);
-                const float o0 = dd.x * dsilu_f(fmaf(f.x, A[2 * i], Bc[2 * i])) * Gs[2 * i] - K0 - f.x * K1;
-                const float o1 = dd.y * dsilu_f(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1])) * Gs[2 * i + 1] - K0 - f.y * K1;
+                // dout silu'(u) Gs = e (1 + R) with e = dout * Gs / 2 (Gs already halved)
+                const float e0 = dd.x * Gs[2 * i], e1 = dd.y * Gs[2 * i + 1];
+                const float o0 = fmaf(e0, dsilu_R_from_half(fmaf(f.x, A[2 * i], Bc[2 * i])), e0) + fmaf(-K1, f.x, -K0);
+                const float o1 = fmaf(e1, dsilu_R_from_half(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1])), e1) + fmaf(-K1, f.y, -K0);
                 o[i] = pack_bf16x2(o0, o1);
             }
             *reinterpret_cast<uint4*>(dx + base + pk * C) = make_uint4(o[0], o[1], o[2], o[3]);
