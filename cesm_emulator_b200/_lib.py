@@ -89,6 +89,7 @@ def load() -> ctypes.CDLL:
     lib.cesm_launch_count.restype = ctypes.c_longlong
     lib.cesm_linattn_ws_floats.restype = ctypes.c_size_t
     lib.cesm_linattn_ws_floats.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.cesm_adamw_partials.restype = ctypes.c_int
     _declare(lib)
     _lib = lib
     return lib
@@ -103,6 +104,7 @@ _SIGNATURES: dict[str, list] = {
     "cesm_pack_weights_batched": [_P, _I, _P],
     "cesm_unpack_wgrads_batched": [_P, _I, _P],
     "cesm_unpack_wgrad": [_P, _P, _I, _I, _I, _L, _L, POINTER(c_int32), _I, _P],
+    "cesm_adamw_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _F, _P],
     "cesm_colsum": [_P, _P, _L, _I, _I, _P],
     "cesm_gn_stats": [_P, _P, _I, _L, _I, _I, _P],
     "cesm_gn_apply_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
@@ -135,7 +137,8 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 
 def exported_symbols() -> list[str]:
-    return ["cesm_last_error", "cesm_version", "cesm_launch_count", "cesm_linattn_ws_floats", *sorted(_SIGNATURES)]
+    return ["cesm_last_error", "cesm_version", "cesm_launch_count", "cesm_linattn_ws_floats", "cesm_adamw_partials",
+            *sorted(_SIGNATURES)]
 
 
 def launch_count() -> int:

@@ -24,39 +24,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16*
     const int o = idx / ((long long)I * T);
     dst[idx] = __float2bfloat16(src[o * so + i * si + taps.off[t]]);
 }
-// Batched form: blockIdx.y selects a descriptor (in device memory), blockIdx.x strides over its elements.
-__global__ void __launch_bounds__(256)
-pack_weights_batched_kernel(const cesm_pack_desc* __restrict__ descs) {
-    const cesm_pack_desc d = descs[blockIdx.y];
-    const long long total = (long long)d.O * d.T * d.I;
-    const float* __restrict__ src = d.src;
-    __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(d.dst);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int i = idx % d.I;
-        const int t = (idx / d.I) % d.T;
-        const int o = idx / ((long long)d.I * d.T);
-        dst[idx] = __float2bfloat16(src[o * d.so + i * d.si + d.tap_off[t]]);
-    }
-}
-// Batched inverse: dst[o*so + i*si + off[t]] += src[o][t][i], then src[o][t][i] = 0 (the fp32 scratch
-// the weight-gradient kernels accumulate into is ready for the next step without a memset).
-__global__ void __launch_bounds__(256)
-unpack_wgrads_batched_kernel(const cesm_pack_desc* __restrict__ descs) {
-    const cesm_pack_desc d = descs[blockIdx.y];
-    const long long total = (long long)d.O * d.T * d.I;
-    float* __restrict__ src = const_cast<float*>(d.src);
-    float* __restrict__ dst = reinterpret_cast<float*>(d.dst);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int i = idx % d.I;
-        const int t = (idx / d.I) % d.T;
-        const int o = idx / ((long long)d.I * d.T);
-        float* q = dst + o * d.so + i * d.si + d.tap_off[t];
-        *q += src[idx];
-        src[idx] = 0.f;
-    }
-}
 // dst[o*so + i*si + off[t]] (+)= src[o][t][i]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int T, int I,
                                     long long so, long long si, TapOffsets taps, int accumulate) {
@@ -444,22 +411,6 @@ extern "C" int cesm_pack_weight(const float* src, void* dst, int O, int T, int I
     for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
     const long long total = (long long)O * T * I;
     pack_weight_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, O, T, I, so, si, taps);
-    CESM_CHECK_LAUNCH();
-    return CESM_OK;
-}
-
-extern "C" int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* stream) {
-    CESM_REQUIRE(n >= 0 && descs_device != nullptr, "bad descriptor table");
-    if (n == 0) return CESM_OK;
-    pack_weights_batched_kernel<<<dim3(16, n), 256, 0, as_stream(stream)>>>(descs_device);
-    CESM_CHECK_LAUNCH();
-    return CESM_OK;
-}
-
-extern "C" int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream) {
-    CESM_REQUIRE(n >= 0 && descs_device != nullptr, "bad descriptor table");
-    if (n == 0) return CESM_OK;
-    unpack_wgrads_batched_kernel<<<dim3(16, n), 256, 0, as_stream(stream)>>>(descs_device);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

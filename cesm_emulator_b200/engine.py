@@ -47,7 +47,10 @@ class GradBuckets:
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
         order = _ready_order(module.named_parameters())
         self.params = [p for _, p in order]
-        total = sum(p.numel() for p in self.params)
+        # every tensor starts on a 64-byte boundary of the flat buffers (kernels read parameters with
+        # 16-byte vector loads); the padding stays zero in the gradient, parameter and moment buffers
+        pad = lambda n: (n + 15) // 16 * 16
+        total = sum(pad(p.numel()) for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
@@ -63,7 +66,7 @@ class GradBuckets:
             if len(self._pending_init) <= b:
                 self._pending_init.append(0)
             self._pending_init[b] += 1
-            off += n
+            off += pad(n)
             if off - self.bounds[-1] >= per_bucket and off < total:
                 self.bounds.append(off)
         self.bounds.append(total)
@@ -145,12 +148,71 @@ class GradBuckets:
         if self.world > 1 and self.on_cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
+    def flatten_params_(self) -> torch.Tensor:
+        """Re-home every parameter into one flat fp32 buffer laid out like `flat` (same offsets), so the
+        optimizer step is one elementwise kernel over four flat arrays.  `p.data` become views: state
+        dicts, `load_state_dict` (in-place copies) and the modules themselves see no difference."""
+        assert not self._scratch, "flatten the parameters before the first step"
+        flat_p = torch.zeros_like(self.flat)
+        off = 0
+        bucket_of = {}
+        for p in self.params:
+            n = p.numel()
+            view = flat_p[off:off + n].view_as(p)
+            view.copy_(p.data)
+            b = self._bucket_of[p.data_ptr()]
+            p.data = view
+            bucket_of[p.data_ptr()] = b  # the sink protocol is keyed on the (new) storage address
+            off += (n + 15) // 16 * 16
+        self._bucket_of = bucket_of
+        self._owned = set(bucket_of)
+        return flat_p
+
     def clip_(self, max_norm: float) -> torch.Tensor:
         """Global-norm clip of every gradient (train.py:865) on the flat buffer: two kernels, no sync."""
         total = torch.linalg.vector_norm(self.flat)
         coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
         self.flat.mul_(coef)
         return total
+
+
+class FusedAdamW:
+    """torch.optim.AdamW semantics (train.py:1078-1083) + clip_grad_norm_ (train.py:865) as two launches of
+    the library's own kernel over flat buffers (`cesm_adamw_step`).  The step counter lives on the device so
+    that a replayed CUDA graph advances the bias correction.  Drop-in for what the engine and train.py use
+    of an optimizer: `step()`, `state_dict()`, `load_state_dict()`, `param_groups[0]["lr"]`."""
+
+    def __init__(self, buckets: "GradBuckets", lr, betas, weight_decay, eps, max_grad_norm):
+        from . import _lib
+        self.g = buckets.flat
+        self.p = buckets.flatten_params_()
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.state = torch.zeros(2, dtype=torch.float32, device=self.p.device)  # [step, last grad norm]
+        self.partials = torch.zeros(_lib.load().cesm_adamw_partials(), dtype=torch.float32, device=self.p.device)
+        self.param_groups = [dict(lr=lr, betas=tuple(betas), weight_decay=weight_decay, eps=eps)]
+        self.max_grad_norm = max_grad_norm
+
+    @property
+    def grad_norm(self) -> torch.Tensor:
+        return self.state[1]
+
+    def step(self) -> None:
+        hp = self.param_groups[0]
+        K.adamw_step(self.p, self.g, self.m, self.v, self.partials, self.state, hp["lr"], hp["betas"][0],
+                     hp["betas"][1], hp["eps"], hp["weight_decay"], self.max_grad_norm)
+        ops.invalidate_weight_cache()  # the bf16 operand copies are stale now
+
+    def state_dict(self) -> dict:
+        return {"step": self.state[:1].clone(), "exp_avg": self.m.clone(), "exp_avg_sq": self.v.clone(),
+                "param_groups": [dict(g) for g in self.param_groups]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.state[:1].copy_(sd["step"])
+        self.m.copy_(sd["exp_avg"])
+        self.v.copy_(sd["exp_avg_sq"])
+        for g, src in zip(self.param_groups, sd.get("param_groups", [])):
+            g.update(src)
 
 
 class TrainEngine:
@@ -169,9 +231,11 @@ class TrainEngine:
                 dist.broadcast(t.data, src=0, group=process_group)  # what DDP's constructor does
         self.buckets = GradBuckets(diffusion, n_buckets=n_buckets, process_group=process_group)
         self.max_grad_norm = max_grad_norm
-        # AdamW as train.py:1078-1083; capturable so that the step lives inside the graph
-        self.opt = torch.optim.AdamW(self.buckets.params, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps,
-                                     capturable=True, fused=True)
+        # AdamW as train.py:1078-1083 with the clip of train.py:865 folded in; the step lives inside the graph
+        if self.buckets.on_cuda:
+            self.opt = FusedAdamW(self.buckets, lr, betas, weight_decay, eps, max_grad_norm)
+        else:  # host tensors: only the gloo tests of the bucket logic come through here
+            self.opt = torch.optim.AdamW(self.buckets.params, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps)
         self.x0 = torch.zeros(batch_shape, dtype=torch.float32, device=dev)
         self.cond = torch.zeros(cond_shape, dtype=torch.float32, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
@@ -189,9 +253,13 @@ class TrainEngine:
         loss = self.diffusion.loss(self.x0, self.cond)
         (loss / self.world if self.world > 1 else loss).backward()
         self.buckets.finish_step()
-        if self.max_grad_norm is not None:
-            self.grad_norm.copy_(self.buckets.clip_(self.max_grad_norm))
-        self.opt.step()
+        if isinstance(self.opt, FusedAdamW):
+            self.opt.step()
+            self.grad_norm.copy_(self.opt.grad_norm)
+        else:
+            if self.max_grad_norm is not None:
+                self.grad_norm.copy_(self.buckets.clip_(self.max_grad_norm))
+            self.opt.step()
         self.loss.copy_(loss.detach())
 
     def _run(self):

@@ -167,6 +167,21 @@ def unpack_wgrad(src: torch.Tensor, dst: torch.Tensor, O: int, T: int, I: int, s
     return dst
 
 
+def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, partials: torch.Tensor,
+               state: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
+               max_norm: Optional[float]) -> None:
+    """Global-norm clip + AdamW over flat fp32 buffers (see cesm_adamw_step in include/cesm_b200.h)."""
+    _req_cuda(p, g, m, v, partials, state)
+    for t in (p, g, m, v, partials, state):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert p.numel() == g.numel() == m.numel() == v.numel() and state.numel() >= 2
+    assert partials.numel() >= _lib.load().cesm_adamw_partials()
+    _lib.call("cesm_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(partials), _ptr(state),
+              float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+              float(max_norm) if max_norm is not None else 0.0, _stream(),
+              _meta={"bytes": 28.0 * p.numel()})
+
+
 def colsum(x: torch.Tensor, into: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Column sums of bf16 x[..., C]; with `into` (fp32 [C]) the sums are ADDED to it."""
     _req_cuda(x, into)

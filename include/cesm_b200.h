@@ -145,6 +145,16 @@ int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* s
 /* Batched inverse for gradients: for each descriptor, dst (fp32, the parameter-gradient layout)
  * += src[o][t][i] (fp32 packed scratch written by cesm_wgrad) and the scratch is zeroed. */
 int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream);
+/* Optimizer step of train.py:864-867 + 1078-1083 on FLAT fp32 buffers (every parameter, its gradient and
+ * both AdamW moments are views into four contiguous arrays of n floats, 16-byte aligned): global-norm
+ * clip (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (|g| + 1e-6)); max_norm <= 0 disables it)
+ * folded into torch.optim.AdamW's update.  `partials`: fp32 scratch of cesm_adamw_partials() floats.
+ * `state`: fp32[2] in device memory -- [0] step count, incremented by the call (so that a CUDA-graph
+ * replay advances the bias correction), [1] <- pre-clip gradient norm.  Two launches, no host sync. */
+int cesm_adamw_partials(void);
+int cesm_adamw_step(float* p, const float* g, float* m, float* v, long long n, float* partials, float* state,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                    void* stream);
 int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int I, long long so, long long si,
                       const int32_t* tap_off, int accumulate, void* stream);
 /* out[c] (+)= sum over rows of bf16 x[M][C] (bias gradients).  `accumulate` != 0 here and in the other

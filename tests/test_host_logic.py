@@ -67,7 +67,8 @@ def _bucket_worker(rank, world, port, q):
         (net(x).pow(2).mean() / world).backward()   # mean over ranks == sum of (loss / world)
         buckets.finish_step()
         norm = buckets.clip_(1e9)
-        q.put((rank, buckets.flat.clone(), x, float(norm)))
+        # the flat buffer pads every tensor to a 64-byte boundary: compare the per-parameter views
+        q.put((rank, torch.cat([p.grad.reshape(-1) for p in buckets.params]), x, float(norm)))
     finally:
         dist.destroy_process_group()
 

@@ -315,3 +315,85 @@ def test_ddpm_elementwise(cuda):
     assert err(got, ref) < 1e-6
     assert err(got[0], mean[0]) < 1e-6  # t == 0 adds no noise (model.py:178-179): posterior_variance[0] == 0
     assert buf["posterior_variance"][0].item() == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer-step kernels: tiled batched re-layouts and the fused clip + AdamW
+# ------------------------------------------------------------------------------------------------
+def _descs(entries, cuda):
+    from cesm_emulator_b200 import _lib
+    arr = (_lib.PackDesc * len(entries))()
+    for d, (src, dst, O, T, I, so, si, taps) in zip(arr, entries):
+        d.src, d.dst, d.O, d.T, d.I, d.so, d.si = src, dst, O, T, I, so, si
+        for i, o in enumerate(taps):
+            d.tap_off[i] = int(o)
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(cuda)
+
+
+def test_batched_relayouts_match_single(cuda):
+    """Every descriptor family the model registers (ops.py): forward [co][t][ci], data-gradient
+    [ci][t][co] incl. the concat split, 1x1, 4x4 down-sampling and the 4-of-16-tap sub-pixel phases,
+    ragged channel counts; pack is bit-exact, un-pack adds exactly and zeroes its scratch."""
+    from cesm_emulator_b200 import _lib, kernels as K
+    torch.manual_seed(5)
+    cases = []  # (weight shape [A][B][T'], O, T, I, so, si, taps, src_off)
+    for co, ci, kk in ((128, 64, 9), (64, 192, 9), (96, 40, 9), (768, 64, 1), (64, 256, 1), (64, 64, 16)):
+        cases.append(((co, ci, kk), co, kk, ci, ci * kk, kk, list(range(kk)), 0))          # forward
+        cases.append(((co, ci, kk), ci, kk, co, kk, ci * kk, list(range(kk)), 0))          # data gradient
+    cases.append(((64, 128, 9), 64, 9, 64, 9, 128 * 9, list(range(9)), 64 * 9))            # concat split, 2nd half
+    for ph in ([0, 2, 8, 10], [5, 7, 13, 15]):
+        cases.append(((64, 64, 16), 64, 4, 64, 16, 64 * 16, ph, 0))                        # sub-pixel phase
+    ws, outs, ents = [], [], []
+    for shape, O, T, I, so, si, taps, off in cases:
+        w = torch.randn(*shape, device=cuda)
+        out = torch.empty(O, T * I, device=cuda, dtype=BF)
+        ws.append(w); outs.append(out)
+        ents.append((w.data_ptr() + 4 * off, out.data_ptr(), O, T, I, so, si, taps))
+    tab = _descs(ents, cuda)
+    _lib.call("cesm_pack_weights_batched", tab.data_ptr(), len(ents), K._stream())
+    for (shape, O, T, I, so, si, taps, off), w, out in zip(cases, ws, outs):
+        ref = K.pack_weight(w.reshape(-1)[off:], O, T, I, so, si, taps)
+        assert torch.equal(out, ref), (shape, O, T, I)
+    # un-pack: dst += scratch, scratch = 0
+    grads, scr, ents = [], [], []
+    shared = torch.randn(64, 64, 16, device=cuda)  # both sub-pixel phases add into ONE parameter gradient
+    for shape, O, T, I, so, si, taps, off in cases:
+        g = shared if T == 4 else torch.randn(*shape, device=cuda)
+        s_ = torch.randn(O, T, I, device=cuda)
+        grads.append(g); scr.append(s_)
+        ents.append((s_.data_ptr(), g.data_ptr() + 4 * off, O, T, I, so, si, taps))
+    want, shared_ref = [], shared.clone()
+    for (shape, O, T, I, so, si, taps, off), g, s_ in zip(cases, grads, scr):
+        r = shared_ref if T == 4 else g.clone()
+        K.unpack_wgrad(s_, r.reshape(-1)[off:], O, T, I, so, si, taps, accumulate=True)
+        want.append(r)
+    tab = _descs(ents, cuda)
+    _lib.call("cesm_unpack_wgrads_batched", tab.data_ptr(), len(ents), K._stream())
+    for g, r, s_ in zip(grads, want, scr):
+        assert torch.equal(g, r)
+        assert not s_.any()
+
+
+@pytest.mark.parametrize("n,max_norm", [(10_001, 1.0), (4096, None), (1_234_567, 0.05)])
+def test_fused_adamw_matches_torch(cuda, n, max_norm):
+    from cesm_emulator_b200 import _lib, kernels as K
+    torch.manual_seed(1)
+    hp = dict(lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-8)
+    p0 = torch.randn(n, device=cuda)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], **hp)
+    p, m, v = p0.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    state = torch.zeros(2, device=cuda)
+    partials = torch.zeros(_lib.load().cesm_adamw_partials(), device=cuda)
+    for step in range(4):
+        g = torch.randn(n, device=cuda) * (0.5 + step)
+        ref.grad = g.clone()
+        norm = torch.linalg.vector_norm(g)
+        if max_norm is not None:
+            torch.nn.utils.clip_grad_norm_([ref], max_norm)
+        opt.step()
+        K.adamw_step(p, g, m, v, partials, state, hp["lr"], *hp["betas"], hp["eps"], hp["weight_decay"], max_norm)
+        assert state[0].item() == step + 1
+        assert abs(state[1].item() - norm.item()) < 1e-4 * norm.item()
+        assert (p - ref.data).abs().max().item() < 2e-6, step
+    assert err(m, opt.state[ref]["exp_avg"]) < 1e-4 and err(v, opt.state[ref]["exp_avg_sq"]) < 1e-4
