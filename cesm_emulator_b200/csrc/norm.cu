@@ -258,7 +258,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
                     const float* __restrict__ sums, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ film,
                     const float* __restrict__ csum, __nv_bfloat16* __restrict__ dx, long long P, int C, int G,
-                    float eps) {
+                    float eps, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dfilm,
+                    float* __restrict__ dcbias) {
     const int b = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;
@@ -296,6 +297,25 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
         Gs[i] = 0.5f * rstd * gamma[c] * sc;
     }
     const float K1 = rstd * rstd * m2, K0 = rstd * m1 - mean * K1;
+    // parameter gradients (the formulas of gn_bwd_params_kernel) ACCUMULATED by the first block of each
+    // sample: saves a launch per GroupNorm when the caller hands in the parameters' .grad buffers
+    if (dgamma != nullptr && blockIdx.x == 0 && (int)threadIdx.x < vec_per_pix) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = slot * 8 + i;
+            const float* s3 = csum + ((size_t)b * C + c) * 3;
+            const float sc = film ? film[(size_t)b * 2 * C + c] + 1.f : 1.f;
+            atomicAdd(dbeta + c, sc * s3[0]);
+            atomicAdd(dgamma + c, sc * s3[1]);
+            if (dfilm) {
+                dfilm[(size_t)b * 2 * C + c] = gamma[c] * s3[1] + beta[c] * s3[0];
+                dfilm[(size_t)b * 2 * C + C + c] = s3[0];
+            }
+            if (dcbias)
+                atomicAdd(dcbias + c, rstd * (gamma[c] * sc * s3[0] - (float)P * m1) -
+                                          rstd * rstd * m2 * (s3[2] - (float)P * mean));
+        }
+    }
     const size_t base = (size_t)b * P * C + slot * 8;
     const long long stride = (long long)gridDim.x * pix_per_iter;
     uint4 nu[PF], nd[PF];
@@ -604,12 +624,16 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     gn_bwd_reduce_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
     CESM_CHECK_LAUNCH();
+    const bool fused = accumulate_params != 0;  // accumulate mode: the apply kernel adds the parameter gradients
     gn_bwd_apply_kernel<<<grid_a, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
-                                                       beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps);
+                                                       beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps,
+                                                       fused ? dgamma : nullptr, dbeta, dfilm, dconv_bias);
     CESM_CHECK_LAUNCH();
-    gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, sums, gamma, beta, film, dgamma, dbeta, dfilm,
-                                                           dconv_bias, B, P, C, G, eps, accumulate_params);
-    CESM_CHECK_LAUNCH();
+    if (!fused) {
+        gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, sums, gamma, beta, film, dgamma, dbeta, dfilm,
+                                                               dconv_bias, B, P, C, G, eps, 0);
+        CESM_CHECK_LAUNCH();
+    }
     return CESM_OK;
 }
 

@@ -147,6 +147,16 @@ def test_groupnorm_fwd_bwd(cuda, B, P, C, film, res):
         assert err(dfl, grads[3]) < 2e-3
     # bias gradient of the producing conv = sum over samples and pixels of dx (here of the exact dx)
     assert err(dcb, grads[0].sum(dim=(0, 1))) < 5e-3
+    # accumulate mode (the engine hands in the parameters' .grad views): the apply kernel adds the
+    # parameter gradients itself, on top of what is already there
+    base = [torch.randn(C, device=cuda) for _ in range(3)]
+    into = [t.clone() for t in base]
+    dx2, _, _, dfl2, _ = K.gn_bwd(x, dout, sums, gamma, beta, fl, B, G, 1e-5, conv_bias_grad=True, into=tuple(into))
+    assert err(dx2, dx) < 2e-3  # the per-channel sums are fp32 atomics: run-to-run rounding differs
+    for got, b0, want in zip(into, base, (dg, db, dcb)):
+        assert err(got - b0, want) < 1e-4
+    if film:
+        assert err(dfl2, dfl) < 1e-4
 
 
 @pytest.mark.parametrize("M,C", [(1000, 64), (513, 128), (300, 256), (77, 512)])
