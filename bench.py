@@ -313,10 +313,17 @@ def run_b200(args, H, W, arch_kw):
         total_ms = sum(v["ms"] for v in table.values())
         peak = peaks["bf16_tflops_sustained"]
         ach = ig_fl / (ig_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv fwd + dgrad + projections)",
+        traffic = None  # DRAM bytes per launch of the same kernels, from the committed ncu pass of this workload
+        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_traffic_final.json")
+        if args.arch == "baseline" and (B, Kf, H, W) == (2, 3, 192, 288) and os.path.exists(tj):
+            tk = [v for k, v in json.load(open(tj)).items() if "igemm2_kernel" in k]
+            traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in tk) / max(1, sum(v["launches"] for v in tk))
+        roofline = {"bound": "tensor", "kernel": "igemm2_kernel (tcgen05 implicit GEMM: conv fwd + dgrad + projections)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                    "launches_per_step": ig_calls, "share_of_kernel_time": ig_ms / total_ms, "traffic": None,
+                    "launches_per_step": ig_calls, "share_of_kernel_time": ig_ms / total_ms, "traffic": traffic,
+                    "traffic_source": "profiles/r01_step_traffic_final.txt (ncu dram__bytes_read+write, mean per launch)",
+                    "algorithmic_bytes_per_launch": sum(v["bytes"] for v in ig) / max(1, ig_calls),
                     "step_achieved": step_tf, "step_frac": (step_tf / peak) if step_tf else None}
         lines = [f"{'kernel':40s} {'calls':>6s} {'ms':>9s} {'share':>7s} {'TFLOP/s':>9s} {'GB/s':>9s}"]
         for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):

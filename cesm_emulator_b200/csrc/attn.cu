@@ -245,66 +245,120 @@ __device__ __forceinline__ void rope8_t(float (&f)[8], const float (&c4)[4], con
     }
 }
 
+// Both small-window kernels are persistent and feed themselves through a thread-private cp.async
+// ring in shared memory: the 16-byte pieces of item i+2 are already in flight (global -> shared,
+// no registers involved) while item i is being computed, so a thread keeps 2 items' worth of bytes
+// outstanding regardless of its register budget.  A thread only ever reads back what it copied
+// itself, so cp.async.wait_group is the only synchronisation.
+static constexpr int TS_STAGES = 3;
+__device__ __forceinline__ void ts_cp16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ts_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ts_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(TS_STAGES - 1) : "memory"); }
+__device__ __forceinline__ void lds8(uint32_t addr, float (&f)[8]) {
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+extern __shared__ __align__(16) uint8_t ts_smem[];
+
 template <int F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 tattn_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
                        const float* __restrict__ cs, const float* __restrict__ sn, __nv_bfloat16* __restrict__ out,
                        float* __restrict__ lse, long long npix /* B*HW */, int HW, int H, float scale) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = idx & 3;
-    const int h = (idx >> 2) % H;
-    long long pix = idx / (4 * H);
-    const bool valid = pix < npix;  // no early return: the quad shuffles below use the full-warp mask
-    if (!valid) pix = 0;
-    const long long b = pix / HW, hw = pix % HW;
+    constexpr int NV = 3 * F;  // 16-byte vectors per item: (q, k, v) x F frames
+    const int c = threadIdx.x & 3;
     const int HD = H * D, ld = 3 * HD;
-    float cf[F][4], sf[F][4];
+    const long long items = npix * H * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;  // multiple of 4*H: (h, c) fixed per thread
+    const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = (idx0 >> 2) % H;
+    float cf[F][4], sf[F][4], bs[F][F];
 #pragma unroll
-    for (int f = 0; f < F; ++f)
+    for (int f = 0; f < F; ++f) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             cf[f][m] = __ldg(cs + f * (D / 2) + c * 4 + m);
             sf[f][m] = __ldg(sn + f * (D / 2) + c * 4 + m);
         }
-    float q[F][8], k[F][8], v[F][8];
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-        const __nv_bfloat16* row = qkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
-        ld8(row, q[f]);
-        ld8(row + HD, k[f]);
-        ld8(row + 2 * HD, v[f]);
-        rope8(q[f], cf[f], sf[f], scale);
-        rope8(k[f], cf[f], sf[f], 1.f);
+        for (int j = 0; j < F; ++j) bs[f][j] = __ldg(bias + (h * F + f) * F + j);
     }
+    // ring: [stage][vector][thread] of 16 bytes
+    const uint32_t ring = smem_u32(ts_smem) + threadIdx.x * 16u;
+    constexpr uint32_t kVec = 256 * 16, kStage = NV * kVec;
+    auto issue = [&](long long idx, int stage) {
+        if (idx < items) {
+            const long long pix = idx / (4 * H);
+            const long long b = pix / HW, hw = pix % HW;
+            const uint32_t st = ring + stage * kStage;
 #pragma unroll
-    for (int i = 0; i < F; ++i) {
-        float s[F], m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < F; ++j) {
-            s[j] = qsum(dot8(q[i], k[j])) + __ldg(bias + (h * F + i) * F + j);
-            m = fmaxf(m, s[j]);
+            for (int f = 0; f < F; ++f) {
+                const __nv_bfloat16* row = qkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
+                ts_cp16(st + (3 * f + 0) * kVec, row);
+                ts_cp16(st + (3 * f + 1) * kVec, row + HD);
+                ts_cp16(st + (3 * f + 2) * kVec, row + 2 * HD);
+            }
         }
-        float l = 0.f;
+        ts_commit();
+    };
 #pragma unroll
-        for (int j = 0; j < F; ++j) {
-            s[j] = __expf(s[j] - m);
-            l += s[j];
+    for (int s0 = 0; s0 < TS_STAGES - 1; ++s0) issue(idx0 + s0 * stride, s0);
+    int stage = 0;
+    for (long long idx = idx0; idx - threadIdx.x + (threadIdx.x & ~31) < items; idx += stride) {
+        {
+            int ns = stage + TS_STAGES - 1;
+            if (ns >= TS_STAGES) ns -= TS_STAGES;
+            issue(idx + (TS_STAGES - 1) * stride, ns);
         }
-        const float inv = 1.f / l;
-        float o[8];
+        ts_wait();
+        const bool valid = idx < items;  // warp-uniform trip count: the quad shuffles use the full mask
+        const long long pix = valid ? idx / (4 * H) : 0;
+        const long long b = pix / HW, hw = pix % HW;
+        const uint32_t st = ring + stage * kStage;
+        float q[F][8], k[F][8], v[F][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = 0.f;
-#pragma unroll
-        for (int j = 0; j < F; ++j) {
-            const float p = s[j] * inv;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = fmaf(p, v[j][e], o[e]);
+        for (int f = 0; f < F; ++f) {
+            lds8(st + (3 * f + 0) * kVec, q[f]);
+            lds8(st + (3 * f + 1) * kVec, k[f]);
+            lds8(st + (3 * f + 2) * kVec, v[f]);
+            rope8(q[f], cf[f], sf[f], scale);
+            rope8(k[f], cf[f], sf[f], 1.f);
         }
-        const long long row_i = (b * F + i) * HW + hw;
-        if (valid) {
-            st8(out + row_i * HD + h * D + c * 8, o);
-            if (c == 0 && lse) lse[row_i * H + h] = m + __logf(l);
+#pragma unroll
+        for (int i = 0; i < F; ++i) {
+            float s[F], m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                s[j] = qsum(dot8(q[i], k[j])) + bs[i][j];
+                m = fmaxf(m, s[j]);
+            }
+            float l = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                s[j] = __expf(s[j] - m);
+                l += s[j];
+            }
+            const float inv = 1.f / l;
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                const float p = s[j] * inv;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(p, v[j][e], o[e]);
+            }
+            const long long row_i = (b * F + i) * HW + hw;
+            if (valid) {
+                st8(out + row_i * HD + h * D + c * 8, o);
+                if (c == 0 && lse) lse[row_i * H + h] = m + __logf(l);
+            }
         }
+        if (++stage == TS_STAGES) stage = 0;
     }
 }
 
@@ -338,20 +392,49 @@ tattn_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
     const long long stride = (long long)gridDim.x * blockDim.x;  // multiple of 4*H: (h, c) fixed per thread
     const long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int h = (idx0 >> 2) % H;
+    constexpr int NV = 4 * F;  // (q, k, v, dout) x F frames
+    const uint32_t ring = smem_u32(ts_smem) + threadIdx.x * 16u;
+    constexpr uint32_t kVec = 128 * 16, kStage = NV * kVec;
+    auto issue = [&](long long idx, int stage) {
+        if (idx < items) {
+            const long long pix = idx / (4 * H);
+            const long long b = pix / HW, hw = pix % HW;
+            const uint32_t st = ring + stage * kStage;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const long long r = (b * F + f) * HW + hw;
+                const __nv_bfloat16* row = qkv + r * ld + h * D + c * 8;
+                ts_cp16(st + (4 * f + 0) * kVec, row);
+                ts_cp16(st + (4 * f + 1) * kVec, row + HD);
+                ts_cp16(st + (4 * f + 2) * kVec, row + 2 * HD);
+                ts_cp16(st + (4 * f + 3) * kVec, dout + r * HD + h * D + c * 8);
+            }
+        }
+        ts_commit();
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < TS_STAGES - 1; ++s0) issue(idx0 + s0 * stride, s0);
+    int stage = 0;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < items; base += stride) {
         const long long idx = base + threadIdx.x;
+        {
+            int ns = stage + TS_STAGES - 1;
+            if (ns >= TS_STAGES) ns -= TS_STAGES;
+            issue(idx + (TS_STAGES - 1) * stride, ns);
+        }
+        ts_wait();
         const bool valid = idx < items;  // warp-uniform trip count: shuffles use the full mask
         const long long pix = valid ? idx / (4 * H) : 0;
         const long long b = pix / HW, hw = pix % HW;
+        const uint32_t st = ring + stage * kStage;
+        if (++stage == TS_STAGES) stage = 0;
         float q[F][8], k[F][8], v[F][8], go[F][8];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-            const long long r = (b * F + f) * HW + hw;
-            const __nv_bfloat16* row = qkv + r * ld + h * D + c * 8;
-            ld8(row, q[f]);
-            ld8(row + HD, k[f]);
-            ld8(row + 2 * HD, v[f]);
-            ld8(dout + r * HD + h * D + c * 8, go[f]);
+            lds8(st + (4 * f + 0) * kVec, q[f]);
+            lds8(st + (4 * f + 1) * kVec, k[f]);
+            lds8(st + (4 * f + 2) * kVec, v[f]);
+            lds8(st + (4 * f + 3) * kVec, go[f]);
             rope8(q[f], cf[f], sf[f], scale);
             rope8(k[f], cf[f], sf[f], 1.f);
         }
@@ -428,14 +511,27 @@ extern "C" int cesm_tattn_fwd(const void* qkv, const float* bias, const float* c
     cudaStream_t st = as_stream(stream);
     if (F <= 4) {
         const long long npix = (long long)B * HW, items = npix * H * 4;
-        const int blocks = (int)((items + 255) / 256);
-#define TATTN_FWD(FF)                                                                                              \
-    tattn_small_fwd_kernel<FF><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out, \
-                                                       lse, npix, HW, H, scale)
-        if (F == 1) TATTN_FWD(1);
-        else if (F == 2) TATTN_FWD(2);
-        else if (F == 3) TATTN_FWD(3);
-        else TATTN_FWD(4);
+        long long want = (items + 255) / 256;
+        if (want > 148 * 2) want = 148 * 2;  // persistent: one resident wave (two 110 KB rings per SM at F = 3)
+        const int blocks = (int)want;
+#define TATTN_FWD(FF)                                                                                               \
+    {                                                                                                               \
+        constexpr int kSm = TS_STAGES * 3 * FF * 256 * 16;                                                          \
+        static bool cfg = false;                                                                                    \
+        if (!cfg) {                                                                                                 \
+            CESM_CHECK_CUDA(cudaFuncSetAttribute(tattn_small_fwd_kernel<FF>,                                        \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                \
+            cfg = true;                                                                                             \
+        }                                                                                                           \
+        tattn_small_fwd_kernel<FF><<<blocks, 256, kSm, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn,               \
+                                                             (__nv_bfloat16*)out, lse, npix, HW, H, scale);         \
+    }
+        switch (F) {
+            case 1: TATTN_FWD(1) break;
+            case 2: TATTN_FWD(2) break;
+            case 3: TATTN_FWD(3) break;
+            default: TATTN_FWD(4) break;
+        }
 #undef TATTN_FWD
         CESM_CHECK_LAUNCH();
         return CESM_OK;
@@ -463,14 +559,25 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
         long long cap = 148LL * 3 * 4;
         if (want > cap) want = cap;
         const int blocks = (int)(((want + unit - 1) / unit) * unit);
-#define TATTN_BWD(FF)                                                                                         \
-    tattn_small_bwd_kernel<FF><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn,                \
-                                                       (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias, \
-                                                       npix, HW, H, scale)
-        if (F == 1) TATTN_BWD(1);
-        else if (F == 2) TATTN_BWD(2);
-        else if (F == 3) TATTN_BWD(3);
-        else TATTN_BWD(4);
+#define TATTN_BWD(FF)                                                                                          \
+    {                                                                                                          \
+        constexpr int kSm = TS_STAGES * 4 * FF * 128 * 16;                                                     \
+        static bool cfg = false;                                                                               \
+        if (!cfg) {                                                                                            \
+            CESM_CHECK_CUDA(cudaFuncSetAttribute(tattn_small_bwd_kernel<FF>,                                   \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));           \
+            cfg = true;                                                                                        \
+        }                                                                                                      \
+        tattn_small_bwd_kernel<FF><<<blocks, 128, kSm, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn,          \
+                                                             (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, \
+                                                             dbias, npix, HW, H, scale);                       \
+    }
+        switch (F) {
+            case 1: TATTN_BWD(1) break;
+            case 2: TATTN_BWD(2) break;
+            case 3: TATTN_BWD(3) break;
+            default: TATTN_BWD(4) break;
+        }
 #undef TATTN_BWD
         CESM_CHECK_LAUNCH();
         return CESM_OK;
