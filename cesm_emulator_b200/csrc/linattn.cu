@@ -378,9 +378,16 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {  // read-once dat
 // step, the next step's loads issued before this step's math
 // ------------------------------------------------------------------------------------------------
 static constexpr int APPLY_MT = 2;
+static constexpr int RING_STAGES = 3;
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+    return u;
+}
 __global__ void __launch_bounds__(256, 3)
 la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int n,
                 int H, int chunk, float scale) {
+    extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
@@ -391,23 +398,39 @@ la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, _
     const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
     const __nv_bfloat16* qbase = qkv + row0 * ld + w * LD + c * 8;
     __nv_bfloat16* obase = out + row0 * HD + w * LD + c * 8;
-    uint4 nq[APPLY_MT][2];
-    auto issue_loads = [&](int pp) {
+    // thread-private cp.async ring: [stage][vector][thread] x 16 B; the loads of step i+2 are in flight
+    // while step i is computed, and a lane only reads back what it copied itself (no barriers)
+    const uint32_t ring = smem_u32(la_smem) + threadIdx.x * 16u;
+    constexpr uint32_t kVec = 256 * 16, kStage = APPLY_MT * 2 * kVec;
+    auto issue_loads = [&](int pp, int stage) {
+        if (pp < p1) {
+#pragma unroll
+            for (int mt = 0; mt < APPLY_MT; ++mt)
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int row = min(pp + 16 * mt + r + 8 * h2, p1 - 1);
+                    cp_async16(ring + stage * kStage + (mt * 2 + h2) * kVec, qbase + (size_t)row * ld);
+                }
+        }
+        cp_async_commit();
+    };
+    const int pstart = blockIdx.x * chunk;
+#pragma unroll
+    for (int s0 = 0; s0 < RING_STAGES - 1; ++s0) issue_loads(pstart + s0 * 16 * APPLY_MT, s0);
+    int stage = 0;
+    for (int p = pstart; p < p1; p += 16 * APPLY_MT) {
+        {
+            int ns = stage + RING_STAGES - 1;
+            if (ns >= RING_STAGES) ns -= RING_STAGES;
+            issue_loads(p + (RING_STAGES - 1) * 16 * APPLY_MT, ns);
+        }
+        cp_async_wait<RING_STAGES - 1>();
+        uint4 cq[APPLY_MT][2];
 #pragma unroll
         for (int mt = 0; mt < APPLY_MT; ++mt)
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                const int row = min(pp + 16 * mt + r + 8 * h2, p1 - 1);
-                nq[mt][h2] = ldg_stream16(qbase + (size_t)row * ld);
-            }
-    };
-    const int pstart = blockIdx.x * chunk;
-    if (pstart < p1) issue_loads(pstart);
-    for (int p = pstart; p < p1; p += 16 * APPLY_MT) {
-        uint4 cq[APPLY_MT][2];
-#pragma unroll
-        for (int mt = 0; mt < APPLY_MT; ++mt) { cq[mt][0] = nq[mt][0]; cq[mt][1] = nq[mt][1]; }
-        if (p + 16 * APPLY_MT < p1) issue_loads(p + 16 * APPLY_MT);
+            for (int h2 = 0; h2 < 2; ++h2) cq[mt][h2] = lds16(ring + stage * kStage + (mt * 2 + h2) * kVec);
+        if (++stage == RING_STAGES) stage = 0;
 #pragma unroll
         for (int mt = 0; mt < APPLY_MT; ++mt) {
             uint4 pk[2];
@@ -444,6 +467,7 @@ __global__ void __launch_bounds__(256, 2)
 la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     float* __restrict__ ws, const float* __restrict__ dctx, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
+    extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
@@ -469,33 +493,46 @@ la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     const __nv_bfloat16* xbase = qkv + row0 * ld + w * LD + c * 8;
     const __nv_bfloat16* dbase = dout + row0 * HD + w * LD + c * 8;
     __nv_bfloat16* gbase = dqkv + row0 * ld + w * LD + c * 8;
-    // software pipeline: the 8 x 16-byte loads of step i+1 are issued before the tensor-core work of
-    // step i, so that a warp always has a step's worth of bytes in flight
-    uint4 nd[2], nq[2], nk[2], nv[2];
-    auto issue_loads = [&](int pp) {
+    // thread-private cp.async ring (see la_apply_kernel): 8 x 16 B per lane and step, two steps ahead
+    const uint32_t ring = smem_u32(la_smem) + threadIdx.x * 16u;
+    constexpr uint32_t kVec = 256 * 16, kStage = 8 * kVec;
+    auto issue_loads = [&](int pp, int stage) {
+        if (pp < p1) {
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const int row = min(pp + r + 8 * h2, p1 - 1);
-            const __nv_bfloat16* xg = xbase + (size_t)row * ld;
-            nd[h2] = ldg_stream16(dbase + (size_t)row * HD);
-            nq[h2] = ldg_stream16(xg);
-            nk[h2] = ldg_stream16(xg + HD);
-            nv[h2] = ldg_stream16(xg + 2 * HD);
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int row = min(pp + r + 8 * h2, p1 - 1);
+                const __nv_bfloat16* xg = xbase + (size_t)row * ld;
+                const uint32_t st = ring + stage * kStage + h2 * 4 * kVec;
+                cp_async16(st, dbase + (size_t)row * HD);
+                cp_async16(st + kVec, xg);
+                cp_async16(st + 2 * kVec, xg + HD);
+                cp_async16(st + 3 * kVec, xg + 2 * HD);
+            }
         }
+        cp_async_commit();
     };
     const int pstart = blockIdx.x * chunk;
-    if (pstart < p1) issue_loads(pstart);
+#pragma unroll
+    for (int s0 = 0; s0 < RING_STAGES - 1; ++s0) issue_loads(pstart + s0 * 16, s0);
+    int stage = 0;
     for (int p = pstart; p < p1; p += 16) {
+        {
+            int ns = stage + RING_STAGES - 1;
+            if (ns >= RING_STAGES) ns -= RING_STAGES;
+            issue_loads(p + (RING_STAGES - 1) * 16, ns);
+        }
+        cp_async_wait<RING_STAGES - 1>();
         float sm[2][8];
         uint4 ud[2], uv[2], uk[2];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            ud[h2] = nd[h2];
-            uv[h2] = nv[h2];
-            uk[h2] = nk[h2];
-            unpack8(nq[h2], sm[h2]);
+            const uint32_t st = ring + stage * kStage + h2 * 4 * kVec;
+            ud[h2] = lds16(st);
+            unpack8(lds16(st + kVec), sm[h2]);
+            uk[h2] = lds16(st + 2 * kVec);
+            uv[h2] = lds16(st + 3 * kVec);
         }
-        if (p + 16 < p1) issue_loads(p + 16);
+        if (++stage == RING_STAGES) stage = 0;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) row_softmax(sm[h2]);
         uint32_t a[2][4];
@@ -590,7 +627,8 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, i
     CESM_CHECK_LAUNCH();
     la_finalize_kernel<<<ceil_div(NI * H * LD * LD, 256), 256, 0, st>>>(ws, H, NI);
     CESM_CHECK_LAUNCH();
-    la_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
+    const size_t sh_apply = (size_t)RING_STAGES * APPLY_MT * 2 * 256 * 16;  // 48 KB
+    la_apply_kernel<<<grid, 32 * H, sh_apply, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
                                                     scale);
     CESM_CHECK_LAUNCH();
     (void)HD;
@@ -614,7 +652,13 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
     CESM_CHECK_LAUNCH();
     la_delta_kernel<<<ceil_div(NI * H * LD, 128), 128, 0, st>>>(ws, dctx, delta, H, NI);
     CESM_CHECK_LAUNCH();
-    la_bwd_apply_kernel<<<grid, 32 * H, 0, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
+    const size_t sh_bwd = (size_t)RING_STAGES * 8 * 256 * 16;  // 96 KB
+    static bool bwd_cfg = false;
+    if (!bwd_cfg) {
+        CESM_CHECK_CUDA(cudaFuncSetAttribute(la_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bwd));
+        bwd_cfg = true;
+    }
+    la_bwd_apply_kernel<<<grid, 32 * H, sh_bwd, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
                                                  (__nv_bfloat16*)dqkv, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
