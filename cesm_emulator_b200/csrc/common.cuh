@@ -31,6 +31,18 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// exp(x) as ONE FFMA + ONE MUFU: ex2.approx.ftz(x * log2(e) - shift_l2e).  `__expf` adds a denormal-range
+// fix-up (compare, two scalings, predicate shuffling: ~6 more instructions per element) that the
+// softmax-style users here do not need: results that small flush to zero either way after bf16 rounding.
+static constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// exp(x - m) with m pre-multiplied: m_l2e = m * log2(e)
+__device__ __forceinline__ float exp_sub(float x, float m_l2e) { return ex2_ftz(fmaf(x, kLog2e, -m_l2e)); }
+
 // sigmoid through one MUFU op: sigma(x) = 0.5 * tanh(x / 2) + 0.5 (tanh.approx.f32, ~2^-11 relative
 // error; every consumer rounds to bf16 afterwards).  The exp + rcp form costs two MUFU ops, and the
 // GroupNorm kernels are MUFU/ALU-limited before they are HBM-limited.

@@ -146,7 +146,7 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
     float cmax[8], zsum[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        cmax[i] = (MODE == 0) ? dec_ordered(W.kmax[w * LD + c * 8 + i]) : 0.f;
+        cmax[i] = (MODE == 0) ? dec_ordered(W.kmax[w * LD + c * 8 + i]) * kLog2e : 0.f;
         zsum[i] = 0.f;
     }
     float acc[2][4][4];
@@ -214,18 +214,18 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
             if (MODE == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    f[i] = valid ? __expf(f[i] - cmax[i]) : 0.f;
+                    f[i] = valid ? exp_sub(f[i], cmax[i]) : 0.f;  // cmax holds max * log2(e)
                     zsum[i] += f[i];
                 }
             } else {
                 float m = f[0];
 #pragma unroll
                 for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
-                m = quad_max(m);
+                m = quad_max(m) * kLog2e;
                 float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    f[i] = __expf(f[i] - m);
+                    f[i] = exp_sub(f[i], m);
                     s += f[i];
                 }
                 s = quad_sum(s);
@@ -354,11 +354,11 @@ __device__ __forceinline__ void row_softmax(float (&f)[8]) {
     float m = f[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
-    m = quad_max(m);
+    m = quad_max(m) * kLog2e;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        f[i] = __expf(f[i] - m);
+        f[i] = exp_sub(f[i], m);
         s += f[i];
     }
     const float inv = 1.f / quad_sum(s);
@@ -482,7 +482,7 @@ la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     __shared__ __align__(16) float s_kml[8 * LD], s_del[8 * LD];
     {
         const int col = threadIdx.x;  // blockDim.x == HD
-        s_kml[col] = dec_ordered(W.kmax[col]) + __logf(W.z[col]);
+        s_kml[col] = (dec_ordered(W.kmax[col]) + __logf(W.z[col])) * kLog2e;  // pre-scaled for exp_sub
         s_del[col] = delta[(size_t)ni * HD + col];
     }
     __syncthreads();
@@ -567,7 +567,7 @@ la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
             *reinterpret_cast<float4*>(dl + 4) = *reinterpret_cast<const float4*>(del + 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                kh[i] = __expf(kh[i] - km[i]);
+                kh[i] = exp_sub(kh[i], km[i]);
                 o[h2][i] = kh[i] * (o[h2][i] - dl[i]);
             }
             ukh[h2] = pack8(kh);
