@@ -90,6 +90,8 @@ def load() -> ctypes.CDLL:
     lib.cesm_linattn_ws_floats.restype = ctypes.c_size_t
     lib.cesm_linattn_ws_floats.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.cesm_adamw_partials.restype = ctypes.c_int
+    lib.cesm_set_prezeroed_scratch.restype = None
+    lib.cesm_set_prezeroed_scratch.argtypes = [ctypes.c_int]
     _declare(lib)
     _lib = lib
     return lib
@@ -138,6 +140,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 def exported_symbols() -> list[str]:
     return ["cesm_last_error", "cesm_version", "cesm_launch_count", "cesm_linattn_ws_floats", "cesm_adamw_partials",
+            "cesm_set_prezeroed_scratch",
             *sorted(_SIGNATURES)]
 
 

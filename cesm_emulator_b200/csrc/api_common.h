@@ -26,6 +26,14 @@ void note_launch();
         ::cesm::note_launch();         \
         CESM_CHECK_CUDA(cudaGetLastError()); \
     } while (0)
+// Zero a caller-provided scratch / statistics buffer before the kernels that accumulate into it --
+// unless the caller has promised (cesm_set_prezeroed_scratch) that such buffers arrive zeroed: the
+// training engine carves them from one arena cleared by a single memset per step instead of ~70.
+bool scratch_prezeroed();
+#define CESM_ZERO_SCRATCH(ptr, bytes, st)                                               \
+    do {                                                                                \
+        if (!::cesm::scratch_prezeroed()) CESM_CHECK_CUDA(cudaMemsetAsync((ptr), 0, (bytes), (st))); \
+    } while (0)
 #define CESM_REQUIRE(cond, ...)                                                 \
     do {                                                                        \
         if (!(cond)) return ::cesm::set_error(CESM_ERR_INVALID, __VA_ARGS__);   \

@@ -15,6 +15,8 @@ namespace cesm {
 static thread_local std::string g_last_error;
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_prezeroed{0};
+bool scratch_prezeroed() { return g_prezeroed.load(std::memory_order_relaxed) != 0; }
 
 int set_error(int code, const char* fmt, ...) {
     char buf[1024];
@@ -151,6 +153,7 @@ using namespace cesm;
 
 extern "C" const char* cesm_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* cesm_version(void) { return "cesm_b200 0.1 sm_100a"; }
+extern "C" void cesm_set_prezeroed_scratch(int on) { g_prezeroed.store(on ? 1 : 0, std::memory_order_relaxed); }
 extern "C" long long cesm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +264,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
             p.bn = 1;
             p.m_tiles = p.tiles_w * p.tiles_h * a->n;
         }
-        CESM_CHECK_CUDA(cudaMemsetAsync(a->gn_sums, 0, sizeof(float) * 2 * (a->n / a->gn_frames) * a->gn_groups, st));
+        CESM_ZERO_SCRATCH(a->gn_sums, sizeof(float) * 2 * (a->n / a->gn_frames) * a->gn_groups, st);
     }
 
     // ---- shared-memory plan ----

@@ -551,7 +551,7 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
     CESM_REQUIRE(dim_head == D, "temporal attention kernel needs dim_head == 32 (got %d)", dim_head);
     CESM_REQUIRE(H >= 1 && H <= 8, "temporal attention kernel supports 1..8 heads (got %d)", H);
     cudaStream_t st = as_stream(stream);
-    CESM_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * H * F * F, st));
+    CESM_ZERO_SCRATCH(dbias, sizeof(float) * H * F * F, st);
     if (F <= 4) {
         const long long npix = (long long)B * HW, items = npix * H * 4;
         long long want = (items + 127) / 128;

@@ -45,20 +45,11 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // four independent 16-byte loads in flight per thread (a pure stream: bytes in flight set the rate)
-    const long long stride = (long long)gridDim.x * rows_per_iter;
-    for (long long r = (long long)blockIdx.x * rows_per_iter + threadIdx.x / vec; r < M; r += 4 * stride) {
-        uint4 u[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long rk = r + k * stride;
-            u[k] = rk < M ? __ldg(reinterpret_cast<const uint4*>(x + rk * C + slot * 8)) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), c = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-        }
+    for (long long r = (long long)blockIdx.x * rows_per_iter + threadIdx.x / vec; r < M;
+         r += (long long)gridDim.x * rows_per_iter) {
+        uint4 u = *reinterpret_cast<const uint4*>(x + r * C + slot * 8);
+        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
     }
     __shared__ float red[256][9];
 #pragma unroll
@@ -439,8 +430,8 @@ extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, int ac
     CESM_REQUIRE(C % 8 == 0 && C <= 2048 && 2048 % C == 0, "colsum needs C dividing 2048 (C=%d)", C);
     cudaStream_t st = as_stream(stream);
     if (!accumulate) CESM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
-    long long blocks = (M * (C / 8) + 4 * 256 - 1) / (4 * 256);  // >= one 4-deep trip per thread
-    if (blocks > 148 * 2) blocks = 148 * 2;  // few blocks: each ends with C same-address atomics
+    long long blocks = (M + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
     colsum_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, M, C);
     CESM_CHECK_LAUNCH();

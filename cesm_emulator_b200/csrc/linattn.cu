@@ -617,7 +617,7 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, i
     CESM_REQUIRE(H >= 1 && H <= 8, "linear attention kernel supports 1..8 heads (got %d)", H);
     cudaStream_t st = as_stream(stream);
     const int HD = H * LD;
-    CESM_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * cesm_linattn_ws_floats(NI, H), st));
+    CESM_ZERO_SCRATCH(ws, sizeof(float) * cesm_linattn_ws_floats(NI, H), st);
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
     la_colmax_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, ws, n, H, chunk);
@@ -643,7 +643,7 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
     cudaStream_t st = as_stream(stream);
     float* dctx = scratch;
     float* delta = scratch + (size_t)NI * H * LD * LD;
-    CESM_CHECK_CUDA(cudaMemsetAsync(dctx, 0, sizeof(float) * NI * H * LD * LD, st));
+    CESM_ZERO_SCRATCH(dctx, sizeof(float) * NI * H * LD * LD, st);
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
     const size_t sh = la_context_smem(H);

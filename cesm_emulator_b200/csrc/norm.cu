@@ -615,7 +615,7 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
                            int B, long long P, int C, int G, float eps, int accumulate_params, void* stream) {
     GN_CHECK(C, G);
     cudaStream_t st = as_stream(stream);
-    CESM_CHECK_CUDA(cudaMemsetAsync(csum, 0, sizeof(float) * 3 * B * C, st));
+    CESM_ZERO_SCRATCH(csum, sizeof(float) * 3 * B * C, st);
     const int per_block = kNormThreads / (C / 8) * UNR;
     static const int res_r = resident_blocks(gn_bwd_reduce_kernel, kNormThreads);
     static const int res_a = resident_blocks(gn_bwd_apply_kernel, kNormThreads);

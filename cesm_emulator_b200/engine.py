@@ -244,9 +244,19 @@ class TrainEngine:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self._warm = 0
+        self.arena = K.ZeroArena(dev) if dev.type == "cuda" else None
 
     # the captured region ----------------------------------------------------------------------
     def _step_body(self):
+        if self.arena is None:
+            return self._step_body_inner()
+        try:
+            self.arena.begin()  # one memset; the library's per-call scratch memsets are off until end()
+            self._step_body_inner()
+        finally:
+            self.arena.end()
+
+    def _step_body_inner(self):
         ops.set_grad_sink(self.buckets)
         ops.prepack_all()  # one kernel refreshes every bf16 operand copy of the (just updated) weights
         self.buckets.begin_step()

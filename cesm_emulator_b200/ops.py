@@ -481,11 +481,11 @@ class ResnetBlockFn(torch.autograd.Function):
             res = K.igemm(x, _conv_fwd_weight(meta.cres, wres, cout, c0 + cx1, 1, train), a1=x1, bias=bres)
         F = x.shape[0] // B
         # GroupNorm statistics come out of the conv epilogue (no extra pass over y)
-        sums1 = torch.empty((B, G, 2), dtype=torch.float32, device=x.device)
+        sums1 = K.zero_scratch((B, G, 2), x.device)
         y1 = K.igemm(x, _conv_fwd_weight(meta.c1, w1, cout, c0 + cx1, 3, train), a1=x1, taps=K.TAPS_3x3, bias=b1,
                      gn_sums=sums1, gn_frames=F)
         h1 = K.gn_apply_fwd(y1, sums1, g1w, g1b, film, None, B, G, eps)
-        sums2 = torch.empty((B, G, 2), dtype=torch.float32, device=x.device)
+        sums2 = K.zero_scratch((B, G, 2), x.device)
         y2 = K.igemm(h1, _conv_fwd_weight(meta.c2, w2, cout, cout, 3, train), taps=K.TAPS_3x3, bias=b2,
                      gn_sums=sums2, gn_frames=F)
         out = K.gn_apply_fwd(y2, sums2, g2w, g2b, None, res, B, G, eps)

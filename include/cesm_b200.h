@@ -145,6 +145,12 @@ int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* s
 /* Batched inverse for gradients: for each descriptor, dst (fp32, the parameter-gradient layout)
  * += src[o][t][i] (fp32 packed scratch written by cesm_wgrad) and the scratch is zeroed. */
 int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream);
+/* Scratch / statistics buffers the kernels ACCUMULATE into (igemm gn_sums, cesm_gn_bwd csum, cesm_tattn_bwd
+ * dbias, cesm_linattn_fwd ws, cesm_linattn_bwd scratch) are zeroed by the call itself.  A caller that hands
+ * in already-zeroed memory (the training engine carves them from one arena cleared once per step) switches
+ * those ~70 per-step memsets off with on != 0.  Process-wide; default off. */
+void cesm_set_prezeroed_scratch(int on);
+
 /* Optimizer step of train.py:864-867 + 1078-1083 on FLAT fp32 buffers (every parameter, its gradient and
  * both AdamW moments are views into four contiguous arrays of n floats, 16-byte aligned): global-norm
  * clip (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (|g| + 1e-6)); max_norm <= 0 disables it)
