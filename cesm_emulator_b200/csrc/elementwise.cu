@@ -63,6 +63,76 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
 }
 
 // ------------------------------------------------------------------------------------------------
+// Input conv on the tensor cores: im2col of the two fp32 input planes into bf16 patch rows
+//   [hi(x) 2*KS*KS | lo(x) 2*KS*KS | 1 | 1 | 0 ...]  (KPAD columns),  hi = bf16(x), lo = bf16(x - hi),
+// so that the tcgen05 implicit GEMM (1 tap, K = KPAD) against [w | w | bias_hi | bias_lo | 0] reproduces the
+// fp32-input convolution to ~2^-17 in the inputs (the weights are bf16 like every other layer's) and its
+// weight-gradient kernel yields dW (sum of the hi and lo column blocks) and db (the ones column) from
+// the same patch matrix.  A block stages a 16x16 pixel tile's halo once; a warp then writes one pixel's
+// 2*KPAD bytes per trip, each lane a fixed 8-column chunk whose shared-memory offsets it computed once.
+// ------------------------------------------------------------------------------------------------
+template <int KS, int KPAD>
+__global__ void __launch_bounds__(256)
+input_patches_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
+                     __nv_bfloat16* __restrict__ out, int F, int H, int W) {
+    constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS;
+    static_assert(KPAD % 8 == 0 && KPAD >= 2 * NT + 2 && KPAD / 8 == 32, "one 8-column chunk per lane");
+    __shared__ float sv[2][2][PW][PW];  // [hi | lo][plane][row][col], values already rounded to bf16
+    const int img = blockIdx.z, b = img / F, f = img % F;
+    const int h0 = blockIdx.y * T, w0 = blockIdx.x * T;
+    const float* p0 = in0 + ((size_t)b * f0 + (f0 == 1 ? 0 : f)) * H * W;
+    const float* p1 = in1 + ((size_t)b * f1 + (f1 == 1 ? 0 : f)) * H * W;
+    for (int x = threadIdx.x; x < 2 * PW * PW; x += 256) {
+        const int ci = x / (PW * PW), rr = (x / PW) % PW, cc = x % PW;
+        const int hh = h0 + rr - PAD, ww = w0 + cc - PAD;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = (ci ? p1 : p0)[(size_t)hh * W + ww];
+        const float hi = __bfloat162float(__float2bfloat16(v));
+        sv[0][ci][rr][cc] = hi;
+        sv[1][ci][rr][cc] = __bfloat162float(__float2bfloat16(v - hi));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int off[8];     // >= 0: offset into sv for pixel (0,0); -1: constant 1; -2: constant 0
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = lane * 8 + j;
+        if (k < 2 * NT) {
+            const int part = k / NT, rem = k % NT, ci = rem / (KS * KS), kh = (rem % (KS * KS)) / KS, kw = rem % KS;
+            off[j] = ((part * 2 + ci) * PW + kh) * PW + kw;
+        } else {
+            off[j] = k < 2 * NT + 2 ? -1 : -2;
+        }
+    }
+    __syncthreads();
+    const float* s0 = &sv[0][0][0][0];
+    for (int px = warp; px < T * T; px += 8) {
+        const int ty = px / T, tx = px % T;
+        const int h = h0 + ty, w = w0 + tx;
+        if (h >= H || w >= W) continue;
+        const int base = ty * PW + tx;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? s0[off[j] + base] : (off[j] == -1 ? 1.f : 0.f);
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(out + (((size_t)img * H + h) * W + w) * KPAD + lane * 8) = u;
+    }
+}
+// bf16 GEMM operand [COUT][KPAD] = [w | w | bf16(bias) | bf16(bias - bf16(bias)) | 0]
+__global__ void input_weight_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                         __nv_bfloat16* __restrict__ out, int cout, int nt, int kpad) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cout * kpad) return;
+    const int o = idx / kpad, k = idx % kpad;
+    float v = 0.f;
+    if (k < 2 * nt) v = w[o * nt + (k % nt)];
+    else if (k == 2 * nt) v = bias[o];
+    else if (k == 2 * nt + 1) v = bias[o] - __bfloat162float(__float2bfloat16(bias[o]));
+    out[idx] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------------------------------------
 // 7x7 input conv, 2 input planes (noisy target, condition) -> COUT channels, bf16 NHWC output.
 // Plane p of image (b, f) lives at in_p + (b*fp + (fp == 1 ? 0 : f)) * H*W  (frame broadcast).
 // ------------------------------------------------------------------------------------------------
@@ -434,6 +504,25 @@ extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, int ac
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
     colsum_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, M, C);
+    CESM_CHECK_LAUNCH();
+    return CESM_OK;
+}
+
+extern "C" int cesm_input_patches(const float* in0, const float* in1, int f0, int f1, void* out, int B, int F, int H,
+                                  int W, int ks, int kpad, void* stream) {
+    CESM_REQUIRE(ks == 7 && kpad == 256, "input patch kernel is specialised for 7x7, 256 columns (ks=%d kpad=%d)", ks, kpad);
+    CESM_REQUIRE((f0 == 1 || f0 == F) && (f1 == 1 || f1 == F), "frame counts must be 1 or F");
+    dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B * F);
+    input_patches_kernel<7, 256><<<grid, 256, 0, as_stream(stream)>>>(in0, in1, f0, f1, (__nv_bfloat16*)out, F, H, W);
+    CESM_CHECK_LAUNCH();
+    return CESM_OK;
+}
+
+extern "C" int cesm_input_weight_pack(const float* w, const float* bias, void* out, int cout, int ks, int kpad,
+                                      void* stream) {
+    CESM_REQUIRE(kpad >= 4 * ks * ks + 2, "kpad=%d too small for 2 planes x hi/lo x %dx%d + 2", kpad, ks, ks);
+    input_weight_pack_kernel<<<nblk((long long)cout * kpad, 256), 256, 0, as_stream(stream)>>>(
+        w, bias, (__nv_bfloat16*)out, cout, 2 * ks * ks, kpad);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

@@ -347,6 +347,29 @@ def linattn_bwd(qkv, ws, dout, NI: int, n: int, H: int, D: int, scale: float):
 
 
 # ---- boundary convs -----------------------------------------------------------------------------
+INPUT_KPAD = 256  # columns of the input-conv patch matrix: 2 planes x 49 taps x (hi, lo) + 2 ones + padding
+
+
+def input_patches(in0, in1, B: int, F: int, H: int, W: int, ks: int) -> torch.Tensor:
+    """im2col of the two fp32 input planes (frame broadcast folded in) -> bf16 [B*F, H, W, INPUT_KPAD]."""
+    _req_cuda(in0, in1)
+    f0, f1 = in0.numel() // (B * H * W), in1.numel() // (B * H * W)
+    out = torch.empty((B * F, H, W, INPUT_KPAD), dtype=BF16, device=in0.device)
+    _lib.call("cesm_input_patches", _ptr(in0), _ptr(in1), f0, f1, _ptr(out), B, F, H, W, ks, INPUT_KPAD, _stream(),
+              _meta=_bytes_meta(out))
+    return out
+
+
+def input_weight_pack(w, bias, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[cout, 2, 1, ks, ks] fp32 + bias -> bf16 [cout, INPUT_KPAD] operand matching `input_patches`."""
+    _req_cuda(w, bias)
+    cout, ks = w.shape[0], w.shape[-1]
+    if out is None:
+        out = torch.empty((cout, INPUT_KPAD), dtype=BF16, device=w.device)
+    _lib.call("cesm_input_weight_pack", _ptr(w), _ptr(bias), _ptr(out), cout, ks, INPUT_KPAD, _stream())
+    return out
+
+
 def input_conv_fwd(in0, in1, w, bias, B: int, F: int, H: int, W: int, ks: int):
     _req_cuda(in0, in1, w, bias)
     cout = w.shape[0]

@@ -658,20 +658,30 @@ class InputConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cond, weight, bias, F: int):
+        """Tensor-core path: bf16 (hi, lo) im2col patches x [w | w | bias] through the tcgen05 implicit GEMM
+        (kernels.input_patches / input_weight_pack); the patches are kept for the weight gradient."""
         x, cond = x.contiguous().float(), cond.contiguous().float()
         B, H, W = x.shape[0], x.shape[-2], x.shape[-1]
         ks = weight.shape[-1]
-        out = K.input_conv_fwd(x, cond, weight, bias, B, F, H, W, ks)
-        ctx.save_for_backward(x, cond)
-        ctx.dims = (B, F, H, W, ks)
+        patches = K.input_patches(x, cond, B, F, H, W, ks)
+        out = K.igemm(patches, K.input_weight_pack(weight.detach(), bias.detach()))
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(patches, weight, bias)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        x, cond = ctx.saved_tensors
-        B, F, H, W, ks = ctx.dims
-        dw, db = K.input_conv_wgrad(x, cond, dy.contiguous(), B, F, H, W, ks)
-        return None, None, dw, db, None
+        patches, weight, bias = ctx.saved_tensors
+        nt = weight[0].numel()  # 2 * ks * ks
+        full = K.wgrad(patches, dy.contiguous())[:, 0, :]          # fp32 [cout, KPAD]
+        dw = (full[:, :nt] + full[:, nt:2 * nt]).view_as(weight)   # hi and lo column blocks see the same dy
+        db = full[:, 2 * nt]                                       # the ones column: sum of dy
+        if _direct_all(weight, bias):
+            weight.grad.add_(dw)
+            bias.grad.add_(db)
+            _ready(weight, bias)
+            return None, None, None, None, None
+        return None, None, dw, db.contiguous(), None
 
 
 class OutConvFn(torch.autograd.Function):

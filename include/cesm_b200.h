@@ -232,6 +232,15 @@ int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, float* scratc
  * Output conv (video_net.py:763 + model.py:129-130): 1x1x1, 64 -> 1, evaluated on the centre
  * frame only (the reference computes every frame and then selects frame F//2).
  * ---------------------------------------------------------------------------------------------- */
+/* Tensor-core form of the same input convolution.  cesm_input_patches writes the im2col matrix
+ * bf16 [B*F][H][W][kpad] = [hi(x) | lo(x) | 1 | 1 | 0...] (x = the 2*ks*ks taps of the two fp32 planes, frame
+ * broadcast as above; hi = bf16(x), lo = bf16(x - hi)); cesm_input_weight_pack writes the matching operand
+ * bf16 [cout][kpad] = [w | w | bias_hi | bias_lo | 0].  cesm_igemm (1 tap) of the two is the convolution with
+ * its bias; cesm_wgrad of (patches, dy) is [dW_hi-block | dW_lo-block | db | db | 0]: dW = sum of the two
+ * blocks.  ks = 7, kpad = 256. */
+int cesm_input_patches(const float* in0, const float* in1, int f0, int f1, void* out, int B, int F, int H, int W,
+                       int ks, int kpad, void* stream);
+int cesm_input_weight_pack(const float* w, const float* bias, void* out, int cout, int ks, int kpad, void* stream);
 int cesm_input_conv_fwd(const float* in0, const float* in1, int f0, int f1, const float* w, const float* bias,
                         void* out, int B, int F, int H, int W, int ks, int cout, void* stream);
 int cesm_input_conv_wgrad(const float* in0, const float* in1, int f0, int f1, const void* dy, float* dw, float* db,

@@ -265,6 +265,35 @@ def test_input_conv(cuda, B, Fr, H, W, f0):
     assert err(dw, gw) < 2e-3 and err(db, gb) < 2e-3
 
 
+@pytest.mark.parametrize("B,Fr,H,W,f0", [(2, 3, 32, 32, 1), (1, 1, 48, 72, 1), (2, 3, 20, 36, 3)])
+def test_input_conv_tensor_core_path(cuda, B, Fr, H, W, f0):
+    """ops.InputConvFn: (hi, lo) bf16 im2col patches through the tcgen05 GEMM and its weight-gradient
+    kernel.  Against fp32 conv3d the forward differs only by the bf16 rounding of the weights and of the
+    output; with bf16-representable weights and bias the patch split must recover the fp32 inputs, so the
+    result then matches the old fp32-input CUDA-core kernel to output rounding."""
+    from cesm_emulator_b200 import kernels as K, ops
+    torch.manual_seed(8)
+    x = torch.randn(B, 1, f0, H, W, device=cuda) * 3
+    c = torch.randn(B, 1, Fr, H, W, device=cuda)
+    w = (torch.randn(64, 2, 1, 7, 7, device=cuda) * 0.1).bfloat16().float()
+    b = torch.randn(64, device=cuda)
+    wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = ops.InputConvFn.apply(x, c, wp, bp, Fr)
+    old = K.input_conv_fwd(x, c, w, b, B, Fr, H, W, 7)
+    assert err(out, old) < 6e-3  # one bf16 ulp of the largest output
+    assert (out.float() - old.float()).abs().mean().item() < 2e-3 * old.float().abs().mean().item()
+    dy = rnd((B * Fr, H, W, 64), cuda)
+    gw, gb = torch.autograd.grad(out, [wp, bp], dy)
+    dw, db = K.input_conv_wgrad(x, c, dy, B, Fr, H, W, 7)
+    assert err(gw, dw) < 1e-4 and err(gb, db) < 1e-4
+    # patch layout: [hi | lo | 1 | 1 | 0...], hi + lo == x to ~2^-17
+    pt = K.input_patches(x, c, B, Fr, H, W, 7).float()
+    assert torch.equal(pt[..., 196:198], torch.ones_like(pt[..., 196:198])) and not pt[..., 198:].any()
+    centre = 3 * 7 + 3  # tap (3,3) of plane 0 is the pixel itself
+    xs = x.expand(-1, -1, Fr, -1, -1).reshape(B * Fr, H, W)
+    assert (pt[..., centre] + pt[..., 98 + centre] - xs).abs().max().item() < 1e-4 * 3 * 4
+
+
 def test_output_conv(cuda):
     from cesm_emulator_b200 import kernels as K
     torch.manual_seed(9)
