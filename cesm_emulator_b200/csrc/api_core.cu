@@ -587,8 +587,11 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
     const int units = a->num_taps * (ctot / 64);
     const int base_ctas = ((units + 1) / 2) * (a->cout / block_n);
     const int tiles = ceil_div(a->ow, p.bw) * ceil_div(a->oh, p.bh) * ceil_div(a->n, p.bn);
+    // split-K so that the grid is ONE resident wave (two CTAs per SM; rounding up would leave a second
+    // wave of a few CTAs that costs as much as the first)
     static const int wg_ctas = [] { const char* e = getenv("CESM_WGRAD_CTAS"); return e ? atoi(e) : 2; }();
-    int ksplit = ceil_div(148 * wg_ctas, base_ctas);
+    static const int wg_ceil = [] { const char* e = getenv("CESM_WGRAD_CEIL"); return e ? atoi(e) : 0; }();
+    int ksplit = wg_ceil ? ceil_div(148 * wg_ctas, base_ctas) : (148 * wg_ctas) / base_ctas;
     if (ksplit > tiles) ksplit = tiles;
     if (ksplit < 1) ksplit = 1;
     note_launch();
