@@ -127,7 +127,7 @@ la_colmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, 
 // Each 16-pixel step is staged through a warp-private smem tile and read back with
 // ldmatrix.trans, which yields the pixel-contracted (MN-major) fragments.
 // ------------------------------------------------------------------------------------------------
-static constexpr int CTX_STAGES = 4;
+static constexpr int CTX_STAGES = 3;
 template <int MODE>
 __global__ void __launch_bounds__(256)
 la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
@@ -137,18 +137,25 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
-    // per warp: [CTX_STAGES][2] raw tiles (A source, B) filled by cp.async + one transformed A tile
-    uint8_t* wbase = la_smem + (size_t)w * (2 * CTX_STAGES + 1) * kTileBytes;
+    // per warp: [CTX_STAGES][2] raw tiles (A source, B) filled by cp.async (+ one transformed A tile in
+    // MODE 1); operands go from there into fragments with ldmatrix.trans
+    constexpr int kWarpTiles = 2 * CTX_STAGES + (MODE == 1 ? 1 : 0);
+    uint8_t* wbase = la_smem + (size_t)w * kWarpTiles * kTileBytes;
     __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(wbase + 2 * CTX_STAGES * kTileBytes);
+    const uint32_t sA_addr = smem_u32(sA);
     const uint32_t ring_addr = smem_u32(wbase);
     const LaWs W = la_ws(ws, ni, HD, H);
 
-    float cmax[8], zsum[8];
+    // MODE 0 works in mma-fragment layout: this lane's A registers hold channels d = 16 mt + r + 8 hh
+    // (mt, hh in {0,1}) of pixel pairs, so it needs 4 column maxima and keeps 4 partial Z sums
+    float cmf[2][2], zf[2][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        cmax[i] = (MODE == 0) ? dec_ordered(W.kmax[w * LD + c * 8 + i]) * kLog2e : 0.f;
-        zsum[i] = 0.f;
-    }
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            cmf[mt][hh] = (MODE == 0) ? dec_ordered(W.kmax[w * LD + 16 * mt + r + 8 * hh]) * kLog2e : 0.f;
+            zf[mt][hh] = 0.f;
+        }
     float acc[2][4][4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -166,7 +173,6 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
 
     // ldmatrix lane addresses (fixed): A m-tile mt, B n-tile pair jp
     const int mi = lane >> 3, rr = lane & 7;
-    const uint32_t sA_addr = smem_u32(sA);
     uint32_t a_off[2], b_off[2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) a_off[mt] = (((mi >> 1) * 8 + rr) * SPITCH + 16 * mt + (mi & 1) * 8) * 2;
@@ -197,48 +203,65 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
         __syncwarp();
         const uint32_t st = ring_addr + (step % CTX_STAGES) * 2 * kTileBytes;
         const uint32_t sB_addr = st + kTileBytes;
-        uint4 ua[2];
+        uint32_t af[2][4], bf[2][4];
+        if (MODE == 0) {
+            // exp(k - max) applied in fragment layout: raw k goes ring -> ldmatrix.trans -> registers, with no
+            // second trip through shared memory.  af[mt][i]: channel 16 mt + r + 8 (i & 1), pixels
+            // p + 2c + 8 (i >> 1) + {0, 1}
+            ldmatrix_x4_trans(af[0], st + a_off[0]);
+            ldmatrix_x4_trans(af[1], st + a_off[1]);
+            const bool full = p + 16 <= p1;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const uint32_t off = ((r + 8 * h2) * SPITCH + c * 8) * 2;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(ua[h2].x), "=r"(ua[h2].y), "=r"(ua[h2].z), "=r"(ua[h2].w)
-                         : "r"(st + off));
-        }
-        // ---- transform A ----
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-            const bool valid = (p + r + 8 * h2) < p1;
-            float f[8];
-            unpack8(ua[h2], f);
-            if (MODE == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    f[i] = valid ? exp_sub(f[i], cmax[i]) : 0.f;  // cmax holds max * log2(e)
-                    zsum[i] += f[i];
+                for (int i = 0; i < 4; ++i) {
+                    const float2 x = unpack_bf16x2(af[mt][i]);
+                    float e0 = exp_sub(x.x, cmf[mt][i & 1]), e1 = exp_sub(x.y, cmf[mt][i & 1]);
+                    if (!full) {
+                        const int px = p + 2 * c + 8 * (i >> 1);
+                        e0 = px < p1 ? e0 : 0.f;
+                        e1 = px + 1 < p1 ? e1 : 0.f;
+                    }
+                    zf[mt][i & 1] += e0 + e1;
+                    af[mt][i] = pack_bf16x2(e0, e1);
                 }
-            } else {
+        } else {
+            // scale * softmax_d(q): rows are normalised in the row layout (quad shuffles), staged through a
+            // warp-private tile and read back transposed.  (Doing this in fragment layout like MODE 0 needs
+            // 24 cross-quad shuffles per step and measured slower: 120 vs 88 us at 192x288.)
+            uint4 ua[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const uint32_t off = ((r + 8 * h2) * SPITCH + c * 8) * 2;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(ua[h2].x), "=r"(ua[h2].y), "=r"(ua[h2].z), "=r"(ua[h2].w)
+                             : "r"(st + off));
+            }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const bool valid = (p + r + 8 * h2) < p1;
+                float f[8];
+                unpack8(ua[h2], f);
                 float m = f[0];
 #pragma unroll
                 for (int i = 1; i < 8; ++i) m = fmaxf(m, f[i]);
                 m = quad_max(m) * kLog2e;
-                float s = 0.f;
+                float sum = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     f[i] = exp_sub(f[i], m);
-                    s += f[i];
+                    sum += f[i];
                 }
-                s = quad_sum(s);
-                const float inv = valid ? scale / s : 0.f;
+                sum = quad_sum(sum);
+                const float inv = valid ? scale / sum : 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] *= inv;
+                *reinterpret_cast<uint4*>(sA + (r + 8 * h2) * SPITCH + c * 8) = pack8(f);
             }
-            *reinterpret_cast<uint4*>(sA + (r + 8 * h2) * SPITCH + c * 8) = pack8(f);
+            __syncwarp();
+            ldmatrix_x4_trans(af[0], sA_addr + a_off[0]);
+            ldmatrix_x4_trans(af[1], sA_addr + a_off[1]);
         }
-        __syncwarp();
-        uint32_t af[2][4], bf[2][4];
-        ldmatrix_x4_trans(af[0], sA_addr + a_off[0]);
-        ldmatrix_x4_trans(af[1], sA_addr + a_off[1]);
         ldmatrix_x4_trans(bf[0], sB_addr + b_off[0]);
         ldmatrix_x4_trans(bf[1], sB_addr + b_off[1]);
         __syncwarp();
@@ -263,13 +286,12 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
         }
     if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float z = zsum[i];
-            z += __shfl_xor_sync(0xffffffffu, z, 4);
-            z += __shfl_xor_sync(0xffffffffu, z, 8);
-            z += __shfl_xor_sync(0xffffffffu, z, 16);
-            if (r == 0) atomicAdd(W.z + w * LD + c * 8 + i, z);
-        }
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float z = quad_sum(zf[mt][hh]);  // the 4 lanes of a quad hold different pixels of channel d
+                if (c == 0) atomicAdd(W.z + w * LD + 16 * mt + r + 8 * hh, z);
+            }
     }
 }
 
@@ -598,15 +620,15 @@ static int la_chunk(int n, int NI) {
     return chunk;
 }
 
-static size_t la_context_smem(int H) {
-    // per warp (= head): CTX_STAGES x {A source, B} cp.async tiles + one transformed A tile
+static size_t la_context_smem(int H, int mode) {
+    // per warp (= head): CTX_STAGES x {A source, B} cp.async tiles
     static bool cfg = false;
     if (!cfg) {
-        cudaFuncSetAttribute(la_context_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * CTX_STAGES + 1) * kTileBytes);
+        cudaFuncSetAttribute(la_context_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * CTX_STAGES * kTileBytes);
         cudaFuncSetAttribute(la_context_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (2 * CTX_STAGES + 1) * kTileBytes);
         cfg = true;
     }
-    return (size_t)H * (2 * CTX_STAGES + 1) * kTileBytes;
+    return (size_t)H * (2 * CTX_STAGES + (mode == 1 ? 1 : 0)) * kTileBytes;
 }
 
 extern "C" size_t cesm_linattn_ws_floats(int NI, int H) { return (size_t)NI * (2 * H * LD + (size_t)H * LD * LD); }
@@ -622,7 +644,7 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, i
     dim3 grid(ceil_div(n, chunk), NI);
     la_colmax_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, ws, n, H, chunk);
     CESM_CHECK_LAUNCH();
-    const size_t sh = la_context_smem(H);
+    const size_t sh = la_context_smem(H, 0);
     la_context_kernel<0><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, nullptr, ws, nullptr, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     la_finalize_kernel<<<ceil_div(NI * H * LD * LD, 256), 256, 0, st>>>(ws, H, NI);
@@ -646,7 +668,7 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
     CESM_ZERO_SCRATCH(dctx, sizeof(float) * NI * H * LD * LD, st);
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
-    const size_t sh = la_context_smem(H);
+    const size_t sh = la_context_smem(H, 1);
     la_context_kernel<1><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, n, H,
                                                    chunk, scale);
     CESM_CHECK_LAUNCH();
