@@ -40,6 +40,20 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
 // ------------------------------------------------------------------------------------------------
 static constexpr int UNR = 4;
 static constexpr int PF = 2;   // vectors per tensor per software-pipeline stage in the backward kernels
+static constexpr int GN_STAGES = 3;
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+    return u;
+}
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once stream: keep it out of L1
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -189,31 +203,45 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
     const size_t base = (size_t)b * P * C + slot * 8;
     const long long stride = (long long)gridDim.x * pix_per_iter;
-    // software pipeline: the PF loads of trip i+1 are in flight while trip i is being reduced
-    uint4 nu[PF], nd[PF];
-    auto issue = [&](long long p) {
+    // thread-private cp.async ring ([stage][vector][thread] x 16 B): trips i+1 and i+2 are in flight while
+    // trip i is reduced; a thread reads back only its own copies, so there is no barrier in the loop
+    extern __shared__ __align__(16) uint8_t gn_ring[];
+    const uint32_t ring = smem_u32(gn_ring) + threadIdx.x * 16u;
+    constexpr uint32_t kVec = kNormThreads * 16, kStage = 2 * PF * kVec;
+    auto issue = [&](long long p, int stage) {
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
             const long long pk = p + k * stride;
             if (pk < P) {
-                nu[k] = ld_stream16(x + base + pk * C);
-                nd[k] = ld_stream16(dout + base + pk * C);
-            } else {
-                nu[k] = make_uint4(0, 0, 0, 0);
-                nd[k] = make_uint4(0, 0, 0, 0);  // dout = 0 -> contributes nothing to T0/T1; x = 0 -> nothing to T2
+                cp_async16_cg(ring + stage * kStage + (2 * k) * kVec, x + base + pk * C);
+                cp_async16_cg(ring + stage * kStage + (2 * k + 1) * kVec, dout + base + pk * C);
             }
         }
+        cp_async_commit_group();
     };
     long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix;
-    if (p < P) issue(p);
+#pragma unroll
+    for (int s0 = 0; s0 < GN_STAGES - 1; ++s0) issue(p + (long long)s0 * PF * stride, s0);
+    int stage = 0;
     for (; p < P; p += PF * stride) {
+        {
+            int ns = stage + GN_STAGES - 1;
+            if (ns >= GN_STAGES) ns -= GN_STAGES;
+            issue(p + (long long)(GN_STAGES - 1) * PF * stride, ns);
+        }
+        cp_async_wait_group<GN_STAGES - 1>();
         uint4 u[PF], d[PF];
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
-            u[k] = nu[k];
-            d[k] = nd[k];
+            if (p + k * stride < P) {
+                u[k] = lds16(ring + stage * kStage + (2 * k) * kVec);
+                d[k] = lds16(ring + stage * kStage + (2 * k + 1) * kVec);
+            } else {
+                u[k] = make_uint4(0, 0, 0, 0);
+                d[k] = make_uint4(0, 0, 0, 0);  // dout = 0 -> contributes nothing to T0/T1; x = 0 -> nothing to T2
+            }
         }
-        if (p + PF * stride < P) issue(p + PF * stride);
+        if (++stage == GN_STAGES) stage = 0;
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
             const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
@@ -568,9 +596,9 @@ static int norm_grid(long long work_items, int per_block, int batches = 1, int r
     return (int)blocks;
 }
 template <typename Kern>
-static int resident_blocks(Kern kern, int threads) {
+static int resident_blocks(Kern kern, int threads, int dyn_smem = 0) {
     int per_sm = 0, dev = 0, sms = 148;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 2;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return sms * per_sm;
 }
@@ -617,11 +645,17 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     cudaStream_t st = as_stream(stream);
     CESM_ZERO_SCRATCH(csum, sizeof(float) * 3 * B * C, st);
     const int per_block = kNormThreads / (C / 8) * UNR;
-    static const int res_r = resident_blocks(gn_bwd_reduce_kernel, kNormThreads);
+    constexpr int kRing = GN_STAGES * 2 * PF * kNormThreads * 16;  // 48 KB (+ 9 KB static: needs the opt-in)
+    static bool ring_cfg = false;
+    if (!ring_cfg) {
+        CESM_CHECK_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRing));
+        ring_cfg = true;
+    }
+    static const int res_r = resident_blocks(gn_bwd_reduce_kernel, kNormThreads, kRing);
     static const int res_a = resident_blocks(gn_bwd_apply_kernel, kNormThreads);
     dim3 grid(norm_grid(P, per_block, B, res_r), B);
     dim3 grid_a(norm_grid(P, per_block, B, res_a), B);
-    gn_bwd_reduce_kernel<<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
+    gn_bwd_reduce_kernel<<<grid, kNormThreads, kRing, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
     CESM_CHECK_LAUNCH();
     const bool fused = accumulate_params != 0;  // accumulate mode: the apply kernel adds the parameter gradients
