@@ -136,8 +136,17 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
     const uint32_t tmem_base = *tmem_ptr_gen;
 
     auto tile_coords = [&](int tile, int& n_tile, int& n0, int& oh0, int& ow0) {
-        n_tile = tile / p.m_tiles;          // n-major: concurrently running CTAs share the weight tile
-        int t = tile - n_tile * p.m_tiles;
+        // n-major (streamed weights): concurrently running CTAs share the weight tile.  m-major (resident
+        // weights): neighbouring CTAs write the column tiles of the same rows at the same time, so every
+        // output row is completed in one go instead of in n_tiles passes over the whole tensor.
+        int t;
+        if (p.m_major) {
+            t = tile / p.n_tiles;
+            n_tile = tile - t * p.n_tiles;
+        } else {
+            n_tile = tile / p.m_tiles;
+            t = tile - n_tile * p.m_tiles;
+        }
         const int tw = t % p.tiles_w;
         t /= p.tiles_w;
         const int th = t % p.tiles_h;
@@ -202,7 +211,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = tile / p.m_tiles;
+                const int n_tile = p.m_major ? tile % p.n_tiles : tile / p.m_tiles;
                 for (int ai = 0; ai < a_loads; ++ai)
                     for (int ti = 0; ti < taps_per_a; ++ti) {
                         const int kb = HALO ? ti * cblk + ai : ai;
@@ -233,7 +242,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         const uint32_t b_blk16 = b_blk_bytes >> 4;
         if (p.b_resident) mbar_wait(b_all_bar, 0, 13);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_tile = tile / p.m_tiles;
+            const int n_tile = p.m_major ? tile % p.n_tiles : tile / p.m_tiles;
             if (!(p.dbg & 16)) mbar_wait(t_empty(acc), acc_phase ^ 1u, 14);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;

@@ -44,6 +44,7 @@ def main():
         ("L0 1x1 256->64", 6, 192, 288, 256, 0, 64, 1, False),
         ("L0 1x1 768->64", 6, 192, 288, 768, 0, 64, 1, False),
         ("L1 1x1 128->768", 6, 96, 144, 128, 0, 768, 1, False),
+        ("L2 1x1 256->768", 6, 48, 72, 256, 0, 768, 1, False),
     ]
     only = os.environ.get("CASE")
     plain = os.environ.get("PLAIN")  # no graph, 3 calls: for ncu
