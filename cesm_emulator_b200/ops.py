@@ -558,6 +558,14 @@ class TemporalAttnBlockFn(torch.autograd.Function):
         pos_bias = pos_bias.contiguous().float()
         train = any(ctx.needs_input_grad)
         xn = K.ln_fwd(x, g, eps)
+        if F == 1 and not train:
+            # one frame (every step of the sampling chain): the softmax over a single key is exactly 1, so the
+            # attention output IS v -- the reference computes the same thing the long way (video_net.py:
+            # 444-450: softmax of a 1-element row).  Only the v third of to_qkv is projected; q, k, RoPE, the
+            # position bias and the attention kernel drop out.
+            wv = _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train)[2 * hidden:]
+            v = K.igemm(xn, wv)
+            return K.igemm(v, _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), residual=x)
         qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
         o, lse = K.tattn_fwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
         y = K.igemm(o.view(NI, H_, W_, hidden), _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), residual=x)
