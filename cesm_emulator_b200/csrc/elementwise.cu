@@ -361,7 +361,7 @@ small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
-    for (int b = 0; b < B; ++b) {
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {  // grid.y = B: one warp per (row, output)
         float s = 0.f;
         for (int k = lane; k < K; k += 32) {
             float v = x[(size_t)b * K + k];
@@ -582,7 +582,8 @@ extern "C" int cesm_sinusoidal(const long long* t, float* out, int B, int dim, v
 
 extern "C" int cesm_small_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
                                      int act_silu_in, void* stream) {
-    small_linear_fwd_kernel<<<ceil_div(N, 8), 256, 0, as_stream(stream)>>>(x, W, bias, y, B, K, N, act_silu_in);
+    small_linear_fwd_kernel<<<dim3(ceil_div(N, 8), B < 64 ? B : 64), 256, 0, as_stream(stream)>>>(x, W, bias, y, B, K, N,
+                                                                                              act_silu_in);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

@@ -15,8 +15,17 @@ def main():
     torch.manual_seed(0)
     diff = Diffusion(UNet(**BASELINE_KW), timesteps=1000).to("cuda")
     diff.train()
-    eng = TrainEngine(diff, (B, 1, H, W), (B, 1, K, H, W))
-    eng.x0.normal_(); eng.cond.normal_()
+    if len(sys.argv) > 1 and sys.argv[1] == "sample":  # one reverse-diffusion step of a 16-field batch
+        from cesm_emulator_b200.engine import SampleEngine
+        diff.eval()
+        for p_ in diff.parameters():
+            p_.requires_grad_(False)
+        eng = SampleEngine(diff, (16, 1, H, W))
+        eng.cond.normal_(); eng.x.normal_(); eng.t.fill_(999)
+        eng.step_resident = eng.step
+    else:
+        eng = TrainEngine(diff, (B, 1, H, W), (B, 1, K, H, W))
+        eng.x0.normal_(); eng.cond.normal_()
     for _ in range(6):
         eng.step_resident()
     torch.cuda.synchronize()
