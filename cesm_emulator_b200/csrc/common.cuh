@@ -43,6 +43,40 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // exp(x - m) with m pre-multiplied: m_l2e = m * log2(e)
 __device__ __forceinline__ float exp_sub(float x, float m_l2e) { return ex2_ftz(fmaf(x, kLog2e, -m_l2e)); }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot).  The norm kernels
+// are issue-limited before they are HBM-limited, and bf16x2 unpacks to exactly such pairs.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 tanh2(float2 h) {
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+    return t;
+}
+
 // sigmoid through one MUFU op: sigma(x) = 0.5 * tanh(x / 2) + 0.5 (tanh.approx.f32, ~2^-11 relative
 // error; every consumer rounds to bf16 afterwards).  The exp + rcp form costs two MUFU ops, and the
 // GroupNorm kernels are MUFU/ALU-limited before they are HBM-limited.

@@ -130,6 +130,12 @@ gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
         A[i] = ga;
         Bc[i] = be;
     }
+    float2 A2[4], B2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        A2[i] = make_float2(0.5f * A[2 * i], 0.5f * A[2 * i + 1]);
+        B2[i] = make_float2(0.5f * Bc[2 * i], 0.5f * Bc[2 * i + 1]);
+    }
     const size_t base = (size_t)b * P * C + slot * 8;
     const long long stride = (long long)gridDim.x * pix_per_iter;
     for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
@@ -151,14 +157,11 @@ gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
             uint32_t o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(w[i]);
-                float o0 = silu_f(fmaf(f.x, A[2 * i], Bc[2 * i])), o1 = silu_f(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1]));
-                if (residual) {
-                    const float2 rr = unpack_bf16x2(rw[i]);
-                    o0 += rr.x;
-                    o1 += rr.y;
-                }
-                o[i] = pack_bf16x2(o0, o1);
+                // packed pairs: h = u/2 (A2, B2 are the halved coefficients), silu(u) = h (1 + tanh h)
+                const float2 h = ffma2(unpack_bf16x2(w[i]), A2[i], B2[i]);
+                float2 ov = ffma2(h, tanh2(h), h);
+                if (residual) ov = fadd2(ov, unpack_bf16x2(rw[i]));
+                o[i] = pack_bf16x2(ov.x, ov.y);
             }
             *reinterpret_cast<uint4*>(out + base + pk * C) = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -178,29 +181,8 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;
     const int pix_per_iter = kNormThreads / vec_per_pix;
-    const int g = (slot * 8) / (C / G);
-    const float cnt = (float)P * (float)(C / G);
-    const float mean = sums[((size_t)b * G + g) * 2] / cnt;
-    const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] / cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    float A[8], Bc[8];  // u = x*A + Bc
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = slot * 8 + i;
-        float ga = gamma[c] * rstd, be = beta[c] - mean * rstd * gamma[c];
-        if (film) {
-            const float sc = film[(size_t)b * 2 * C + c] + 1.f, sh = film[(size_t)b * 2 * C + C + c];
-            ga *= sc;
-            be = be * sc + sh;
-        }
-        A[i] = 0.5f * ga;  // u / 2 (see dsilu_R_from_half)
-        Bc[i] = 0.5f * be;
-    }
-    float acc[3][8];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+    // the first ring stages are requested before anything else: the statistics / coefficient loads below
+    // (a chain of dependent global loads, ~2 us) then overlap with them instead of preceding them
     const size_t base = (size_t)b * P * C + slot * 8;
     const long long stride = (long long)gridDim.x * pix_per_iter;
     // thread-private cp.async ring ([stage][vector][thread] x 16 B): trips i+1 and i+2 are in flight while
@@ -222,6 +204,31 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
     long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix;
 #pragma unroll
     for (int s0 = 0; s0 < GN_STAGES - 1; ++s0) issue(p + (long long)s0 * PF * stride, s0);
+    const int g = (slot * 8) / (C / G);
+    const float cnt = (float)P * (float)(C / G);
+    const float mean = sums[((size_t)b * G + g) * 2] / cnt;
+    const float var = fmaxf(sums[((size_t)b * G + g) * 2 + 1] / cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    float A[8], Bc[8];  // u = x*A + Bc
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = slot * 8 + i;
+        float ga = gamma[c] * rstd, be = beta[c] - mean * rstd * gamma[c];
+        if (film) {
+            const float sc = film[(size_t)b * 2 * C + c] + 1.f, sh = film[(size_t)b * 2 * C + C + c];
+            ga *= sc;
+            be = be * sc + sh;
+        }
+        A[i] = 0.5f * ga;  // u / 2 (see dsilu_R_from_half)
+        Bc[i] = 0.5f * be;
+    }
+    float2 A2[4], B2[4], acc0[4], acc1[4], acc2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        A2[i] = make_float2(A[2 * i], A[2 * i + 1]);
+        B2[i] = make_float2(Bc[2 * i], Bc[2 * i + 1]);
+        acc0[i] = acc1[i] = acc2[i] = make_float2(0.f, 0.f);
+    }
     int stage = 0;
     for (; p < P; p += PF * stride) {
         {
@@ -249,18 +256,25 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 f = unpack_bf16x2(w[i]), dd = unpack_bf16x2(dw[i]);
-                // A, Bc hold u/2 coefficients; du = dout * silu'(u) = (dout/2) (1 + R)
-                const float e0 = 0.5f * dd.x, e1 = 0.5f * dd.y;
-                const float du0 = fmaf(e0, dsilu_R_from_half(fmaf(f.x, A[2 * i], Bc[2 * i])), e0);
-                const float du1 = fmaf(e1, dsilu_R_from_half(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1])), e1);
-                acc[0][2 * i] += du0;
-                acc[0][2 * i + 1] += du1;
-                acc[1][2 * i] = fmaf(du0, f.x, acc[1][2 * i]);      // sum du*x; xhat folded in below
-                acc[1][2 * i + 1] = fmaf(du1, f.y, acc[1][2 * i + 1]);
-                acc[2][2 * i] += f.x;
-                acc[2][2 * i + 1] += f.y;
+                // packed pairs; A2, B2 hold u/2 coefficients: h = u/2, t = tanh(h), R = t + h (1 - t^2),
+                // du = dout * silu'(u) = (dout/2) (1 + R)
+                const float2 h = ffma2(f, A2[i], B2[i]);
+                const float2 t = tanh2(h);
+                const float2 R = ffma2(h, ffma2(make_float2(-t.x, -t.y), t, make_float2(1.f, 1.f)), t);
+                const float2 e = fmul2(dd, make_float2(0.5f, 0.5f));
+                const float2 du = ffma2(e, R, e);
+                acc0[i] = fadd2(acc0[i], du);
+                acc1[i] = ffma2(du, f, acc1[i]);  // sum du*x; xhat folded in below
+                acc2[i] = fadd2(acc2[i], f);
             }
         }
+    }
+    float acc[3][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc[0][2 * i] = acc0[i].x; acc[0][2 * i + 1] = acc0[i].y;
+        acc[1][2 * i] = acc1[i].x; acc[1][2 * i + 1] = acc1[i].y;
+        acc[2][2 * i] = acc2[i].x; acc[2][2 * i + 1] = acc2[i].y;
     }
     // sum du*xhat = rstd * (sum du*x - mean * sum du)
 #pragma unroll
@@ -325,6 +339,21 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
         Gs[i] = 0.5f * rstd * gamma[c] * sc;
     }
     const float K1 = rstd * rstd * m2, K0 = rstd * m1 - mean * K1;
+    const size_t base = (size_t)b * P * C + slot * 8;
+    const long long stride = (long long)gridDim.x * pix_per_iter;
+    uint4 nu[PF], nd[PF];
+    auto issue = [&](long long p) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const long long pk = p + k * stride;
+            if (pk < P) {
+                nu[k] = ld_stream16(x + base + pk * C);
+                nd[k] = ld_stream16(dout + base + pk * C);
+            }
+        }
+    };
+    long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix;
+    if (p < P) issue(p);
     // parameter gradients (the formulas of gn_bwd_params_kernel) ACCUMULATED by the first block of each
     // sample: saves a launch per GroupNorm when the caller hands in the parameters' .grad buffers
     if (dgamma != nullptr && blockIdx.x == 0 && (int)threadIdx.x < vec_per_pix) {
@@ -344,21 +373,6 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
                                           rstd * rstd * m2 * (s3[2] - (float)P * mean));
         }
     }
-    const size_t base = (size_t)b * P * C + slot * 8;
-    const long long stride = (long long)gridDim.x * pix_per_iter;
-    uint4 nu[PF], nd[PF];
-    auto issue = [&](long long p) {
-#pragma unroll
-        for (int k = 0; k < PF; ++k) {
-            const long long pk = p + k * stride;
-            if (pk < P) {
-                nu[k] = ld_stream16(x + base + pk * C);
-                nd[k] = ld_stream16(dout + base + pk * C);
-            }
-        }
-    };
-    long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix;
-    if (p < P) issue(p);
     for (; p < P; p += PF * stride) {
         uint4 u[PF], d[PF];
 #pragma unroll
