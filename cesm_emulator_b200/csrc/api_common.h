@@ -39,6 +39,26 @@ bool scratch_prezeroed();
         if (!(cond)) return ::cesm::set_error(CESM_ERR_INVALID, __VA_ARGS__);   \
     } while (0)
 
+// Every kernel is launched with the programmatic-stream-serialization attribute: its CTAs may be scheduled
+// while the preceding kernel of the stream drains (they park in griddepcontrol.wait, see pdl_wait() in
+// common.cuh), which hides launch latency and the CTA ramp between the ~480 back-to-back kernels of a step.
+// CESM_NO_PDL=1 turns the attribute off (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Encode (or fetch from the cache) a bf16 tiled tensor map with SWIZZLE_128B.
 // dims/strides/box follow cuTensorMapEncodeTiled (dim 0 innermost, strides in bytes for dims >= 1).
 int get_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

@@ -15,6 +15,10 @@ namespace cesm {
 static thread_local std::string g_last_error;
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("CESM_NO_PDL"); return !(e && atoi(e)); }();
+    return on;
+}
 static std::atomic<int> g_prezeroed{0};
 bool scratch_prezeroed() { return g_prezeroed.load(std::memory_order_relaxed) != 0; }
 

@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(128)
 tattn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
                  const float* __restrict__ cs, const float* __restrict__ sn, __nv_bfloat16* __restrict__ out,
                  float* __restrict__ lse, int B, int F, int HW, int H, float scale) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)B * F * HW * H;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
@@ -119,6 +121,8 @@ tattn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
                  const float* __restrict__ lse, const __nv_bfloat16* __restrict__ dout,
                  __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int B, int F, int HW, int H,
                  float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sbias[];  // [H*F*F] block-local dbias accumulator when it fits
     const bool use_sh = (H * F * F) <= 2048;
     if (use_sh) {
@@ -269,6 +273,8 @@ __global__ void __launch_bounds__(256, 2)
 tattn_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
                        const float* __restrict__ cs, const float* __restrict__ sn, __nv_bfloat16* __restrict__ out,
                        float* __restrict__ lse, long long npix /* B*HW */, int HW, int H, float scale) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int NV = 3 * F;  // 16-byte vectors per item: (q, k, v) x F frames
     const int c = threadIdx.x & 3;
     const int HD = H * D, ld = 3 * HD;
@@ -370,6 +376,8 @@ tattn_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
                        const float* __restrict__ cs, const float* __restrict__ sn,
                        const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
                        float* __restrict__ dbias, long long npix, int HW, int H, float scale) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sbias[8 * F * F];
     for (int x = threadIdx.x; x < H * F * F; x += blockDim.x) sbias[x] = 0.f;
     __syncthreads();
@@ -523,7 +531,7 @@ extern "C" int cesm_tattn_fwd(const void* qkv, const float* bias, const float* c
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                \
             cfg = true;                                                                                             \
         }                                                                                                           \
-        tattn_small_fwd_kernel<FF><<<blocks, 256, kSm, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn,               \
+        launch_pdl(tattn_small_fwd_kernel<FF>, blocks, 256, kSm, st, (const __nv_bfloat16*)qkv, bias, cs, sn,               \
                                                              (__nv_bfloat16*)out, lse, npix, HW, H, scale);         \
     }
         switch (F) {
@@ -539,7 +547,7 @@ extern "C" int cesm_tattn_fwd(const void* qkv, const float* bias, const float* c
     CESM_REQUIRE(lse != nullptr, "lse is required for F > 4");
     const long long total = (long long)B * F * HW * H;
     const int blocks = (int)((total + 127) / 128);
-    tattn_fwd_kernel<<<blocks, 128, 0, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out, lse, B, F, HW,
+    launch_pdl(tattn_fwd_kernel, blocks, 128, 0, st, (const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out, lse, B, F, HW,
                                              H, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
@@ -568,7 +576,7 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));           \
             cfg = true;                                                                                        \
         }                                                                                                      \
-        tattn_small_bwd_kernel<FF><<<blocks, 128, kSm, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn,          \
+        launch_pdl(tattn_small_bwd_kernel<FF>, blocks, 128, kSm, st, (const __nv_bfloat16*)qkv, bias, cs, sn,          \
                                                              (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, \
                                                              dbias, npix, HW, H, scale);                       \
     }
@@ -586,7 +594,7 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
     const long long total = (long long)B * F * HW * H;
     const int blocks = (int)((total + 127) / 128);
     const size_t sh = (H * F * F <= 2048) ? sizeof(float) * H * F * F : 0;
-    tattn_bwd_kernel<<<blocks, 128, sh, st>>>((const __nv_bfloat16*)qkv, bias, cs, sn, (const __nv_bfloat16*)out, lse,
+    launch_pdl(tattn_bwd_kernel, blocks, 128, sh, st, (const __nv_bfloat16*)qkv, bias, cs, sn, (const __nv_bfloat16*)out, lse,
                                               (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias, B, F, HW, H,
                                               scale);
     CESM_CHECK_LAUNCH();

@@ -115,6 +115,16 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel triggers at its top (so the NEXT kernel's CTAs may be
+// scheduled, run their prologue and park as soon as this kernel's CTAs have all started), and every
+// kernel launched through launch_pdl() waits here before it touches global memory: griddepcontrol.wait
+// returns only when the preceding kernel has completed and flushed.  Both are no-ops for launches
+// without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

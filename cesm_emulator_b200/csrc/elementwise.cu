@@ -17,6 +17,8 @@ struct TapOffsets {
 // dst[o][t][i] (bf16) = src[o*so + i*si + off[t]] (fp32)
 __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int O, int T, int I,
                                    long long so, long long si, TapOffsets taps) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)O * T * I) return;
     const int i = idx % I;
@@ -27,6 +29,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16*
 // dst[o*so + i*si + off[t]] (+)= src[o][t][i]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int T, int I,
                                     long long so, long long si, TapOffsets taps, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)O * T * I) return;
     const int i = idx % I;
@@ -39,6 +43,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
 // out[c] = sum_rows x[row][c]; block handles a strip of rows, thread owns 8 channels
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long M, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int vec = C >> 3;
     const int slot = threadIdx.x % vec;
     const int rows_per_iter = 256 / vec;
@@ -75,6 +81,8 @@ template <int KS, int KPAD>
 __global__ void __launch_bounds__(256)
 input_patches_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
                      __nv_bfloat16* __restrict__ out, int F, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS;
     static_assert(KPAD % 8 == 0 && KPAD >= 2 * NT + 2 && KPAD / 8 == 32, "one 8-column chunk per lane");
     __shared__ float sv[2][2][PW][PW];  // [hi | lo][plane][row][col], values already rounded to bf16
@@ -122,6 +130,8 @@ input_patches_kernel(const float* __restrict__ in0, const float* __restrict__ in
 // bf16 GEMM operand [COUT][KPAD] = [w | w | bf16(bias) | bf16(bias - bf16(bias)) | 0]
 __global__ void input_weight_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                          __nv_bfloat16* __restrict__ out, int cout, int nt, int kpad) {
+    pdl_trigger();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= cout * kpad) return;
     const int o = idx / kpad, k = idx % kpad;
@@ -141,6 +151,8 @@ __global__ void __launch_bounds__(256)
 input_conv_fwd_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
                       const float* __restrict__ w /* [COUT][2][KS][KS] */, const float* __restrict__ bias,
                       __nv_bfloat16* __restrict__ out, int F, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1;
     __shared__ float sw[2 * KS * KS][COUT];
     __shared__ float sin_[2][PW][PW + 1];
@@ -201,6 +213,8 @@ __global__ void __launch_bounds__(256)
 input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
                         const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db, int NI,
                         int F, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     // thread = 4 output channels x TPT taps: 4*TPT FMAs per (4 + TPT) shared-memory reads per pixel
     constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS, CG = COUT / 4, Q = 256 / CG;
     constexpr int TPT = (NT + Q - 1) / Q;  // taps per thread
@@ -276,6 +290,8 @@ input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__
 __global__ void __launch_bounds__(256)
 out_conv_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ eps, int B, int F, int mid, long long HW) {
+    pdl_trigger();
+    pdl_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long pix = t >> 3;
     const int sub = t & 7;
@@ -297,6 +313,8 @@ __global__ void __launch_bounds__(256)
 out_conv_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ deps,
                     __nv_bfloat16* __restrict__ da, float* __restrict__ dw, float* __restrict__ db, int B, int F, int mid,
                     long long HW) {
+    pdl_trigger();
+    pdl_wait();
     const int sub = threadIdx.x & 7;
     float wv[8], acc[8], accb = 0.f;
 #pragma unroll
@@ -346,6 +364,8 @@ out_conv_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict
 // time embedding + small fp32 linears (batch <= a few hundred rows)
 // ------------------------------------------------------------------------------------------------
 __global__ void sinusoidal_kernel(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    pdl_trigger();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * dim) return;
     const int b = idx / dim, i = idx % dim, half = dim / 2;
@@ -358,6 +378,8 @@ __global__ void sinusoidal_kernel(const long long* __restrict__ t, float* __rest
 __global__ void __launch_bounds__(256)
 small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                         float* __restrict__ y, int B, int K, int N, int act) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -376,6 +398,8 @@ small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W
 __global__ void small_linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                           float* __restrict__ dW, float* __restrict__ db, int B, int K, int N, int act,
                                           int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * K) return;
     const int k = idx % K, n = idx / K;
@@ -396,6 +420,8 @@ __global__ void small_linear_wgrad_kernel(const float* __restrict__ x, const flo
 __global__ void __launch_bounds__(256)
 small_linear_dgrad_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ dy,
                           float* __restrict__ dx, int B, int K, int N, int act) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + lane, b = blockIdx.y;
     float s = 0.f;
@@ -421,6 +447,8 @@ small_linear_dgrad_kernel(const float* __restrict__ x, const float* __restrict__
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                 const long long* __restrict__ t, const float* __restrict__ sqrt_ac,
                                 const float* __restrict__ sqrt_1mac, float* __restrict__ xt, long long per, long long total) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const long long tb = t[idx / per];
@@ -430,6 +458,8 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
 __global__ void __launch_bounds__(256)
 mse_fwd_kernel(const float* __restrict__ eps, const float* __restrict__ noise, float* __restrict__ diff,
                float* __restrict__ loss, long long total) {
+    pdl_trigger();
+    pdl_wait();
     float s = 0.f;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -450,6 +480,8 @@ mse_fwd_kernel(const float* __restrict__ eps, const float* __restrict__ noise, f
 // out = in * factor * (*gscale)
 __global__ void scale_by_device_scalar_kernel(const float* __restrict__ in, const float* __restrict__ gscale,
                                               float factor, float* __restrict__ out, long long total) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     out[idx] = in[idx] * factor * gscale[0];
@@ -461,6 +493,8 @@ __global__ void p_sample_kernel(const float* __restrict__ xt, const float* __res
                                 const float* __restrict__ betas, const float* __restrict__ sqrt_1mac,
                                 const float* __restrict__ sqrt_recip_a, const float* __restrict__ post_var,
                                 float* __restrict__ out, long long per, long long total) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const long long tb = t[idx / per];
@@ -480,7 +514,7 @@ extern "C" int cesm_pack_weight(const float* src, void* dst, int O, int T, int I
     TapOffsets taps{};
     for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
     const long long total = (long long)O * T * I;
-    pack_weight_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, O, T, I, so, si, taps);
+    launch_pdl(pack_weight_kernel, nblk(total, 256), 256, 0, as_stream(stream), src, (__nv_bfloat16*)dst, O, T, I, so, si, taps);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -491,7 +525,7 @@ extern "C" int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int
     TapOffsets taps{};
     for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
     const long long total = (long long)O * T * I;
-    unpack_wgrad_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(src, dst, O, T, I, so, si, taps, accumulate);
+    launch_pdl(unpack_wgrad_kernel, nblk(total, 256), 256, 0, as_stream(stream), src, dst, O, T, I, so, si, taps, accumulate);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -503,7 +537,7 @@ extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, int ac
     long long blocks = (M + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
-    colsum_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, M, C);
+    launch_pdl(colsum_kernel, (int)blocks, 256, 0, st, (const __nv_bfloat16*)x, out, M, C);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -513,7 +547,7 @@ extern "C" int cesm_input_patches(const float* in0, const float* in1, int f0, in
     CESM_REQUIRE(ks == 7 && kpad == 256, "input patch kernel is specialised for 7x7, 256 columns (ks=%d kpad=%d)", ks, kpad);
     CESM_REQUIRE((f0 == 1 || f0 == F) && (f1 == 1 || f1 == F), "frame counts must be 1 or F");
     dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B * F);
-    input_patches_kernel<7, 256><<<grid, 256, 0, as_stream(stream)>>>(in0, in1, f0, f1, (__nv_bfloat16*)out, F, H, W);
+    launch_pdl(input_patches_kernel<7, 256>, grid, 256, 0, as_stream(stream), in0, in1, f0, f1, (__nv_bfloat16*)out, F, H, W);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -521,7 +555,7 @@ extern "C" int cesm_input_patches(const float* in0, const float* in1, int f0, in
 extern "C" int cesm_input_weight_pack(const float* w, const float* bias, void* out, int cout, int ks, int kpad,
                                       void* stream) {
     CESM_REQUIRE(kpad >= 4 * ks * ks + 2, "kpad=%d too small for 2 planes x hi/lo x %dx%d + 2", kpad, ks, ks);
-    input_weight_pack_kernel<<<nblk((long long)cout * kpad, 256), 256, 0, as_stream(stream)>>>(
+    launch_pdl(input_weight_pack_kernel, nblk((long long)cout * kpad, 256), 256, 0, as_stream(stream), 
         w, bias, (__nv_bfloat16*)out, cout, 2 * ks * ks, kpad);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
@@ -533,7 +567,7 @@ extern "C" int cesm_input_conv_fwd(const float* in0, const float* in1, int f0, i
     CESM_REQUIRE(ks == 7 && cout == 64, "input conv kernel is specialised for 7x7, 64 channels (ks=%d cout=%d)", ks, cout);
     CESM_REQUIRE((f0 == 1 || f0 == F) && (f1 == 1 || f1 == F), "frame counts must be 1 or F");
     dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B * F);
-    input_conv_fwd_kernel<7, 64><<<grid, 256, 0, as_stream(stream)>>>(in0, in1, f0, f1, w, bias, (__nv_bfloat16*)out, F, H, W);
+    launch_pdl(input_conv_fwd_kernel<7, 64>, grid, 256, 0, as_stream(stream), in0, in1, f0, f1, w, bias, (__nv_bfloat16*)out, F, H, W);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -546,7 +580,7 @@ extern "C" int cesm_input_conv_wgrad(const float* in0, const float* in1, int f0,
     CESM_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * cout, st));
     const int ntiles = ceil_div(W, 16) * ceil_div(H, 16) * B * F;
     const int grid = ntiles < 148 * 2 ? ntiles : 148 * 2;
-    input_conv_wgrad_kernel<7, 64><<<grid, 256, 0, st>>>(in0, in1, f0, f1, (const __nv_bfloat16*)dy, dw, db, B * F, F, H, W);
+    launch_pdl(input_conv_wgrad_kernel<7, 64>, grid, 256, 0, st, in0, in1, f0, f1, (const __nv_bfloat16*)dy, dw, db, B * F, F, H, W);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -555,7 +589,7 @@ extern "C" int cesm_out_conv_fwd(const void* a, const float* w, const float* bia
                                  long long HW, int C, void* stream) {
     CESM_REQUIRE(C == 64, "output conv kernel needs 64 input channels (C=%d)", C);
     const long long threads = (long long)B * HW * 8;
-    out_conv_fwd_kernel<<<nblk(threads, 256), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)a, w, bias, eps, B, F, mid, HW);
+    launch_pdl(out_conv_fwd_kernel, nblk(threads, 256), 256, 0, as_stream(stream), (const __nv_bfloat16*)a, w, bias, eps, B, F, mid, HW);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -568,21 +602,21 @@ extern "C" int cesm_out_conv_bwd(const void* a, const float* w, const float* dep
     CESM_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
     long long blocks = ((long long)B * F * HW * 8 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    out_conv_bwd_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)a, w, deps, (__nv_bfloat16*)da, dw, db, B, F, mid, HW);
+    launch_pdl(out_conv_bwd_kernel, (int)blocks, 256, 0, st, (const __nv_bfloat16*)a, w, deps, (__nv_bfloat16*)da, dw, db, B, F, mid, HW);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
 extern "C" int cesm_sinusoidal(const long long* t, float* out, int B, int dim, void* stream) {
     CESM_REQUIRE(dim >= 4 && dim % 2 == 0, "dim=%d must be even and >= 4", dim);
-    sinusoidal_kernel<<<nblk((long long)B * dim, 128), 128, 0, as_stream(stream)>>>(t, out, B, dim);
+    launch_pdl(sinusoidal_kernel, nblk((long long)B * dim, 128), 128, 0, as_stream(stream), t, out, B, dim);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
 extern "C" int cesm_small_linear_fwd(const float* x, const float* W, const float* bias, float* y, int B, int K, int N,
                                      int act_silu_in, void* stream) {
-    small_linear_fwd_kernel<<<dim3(ceil_div(N, 8), B < 64 ? B : 64), 256, 0, as_stream(stream)>>>(x, W, bias, y, B, K, N,
+    launch_pdl(small_linear_fwd_kernel, dim3(ceil_div(N, 8), B < 64 ? B : 64), 256, 0, as_stream(stream), x, W, bias, y, B, K, N,
                                                                                               act_silu_in);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
@@ -591,11 +625,11 @@ extern "C" int cesm_small_linear_fwd(const float* x, const float* W, const float
 extern "C" int cesm_small_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
                                      int B, int K, int N, int act_silu_in, int accumulate, void* stream) {
     cudaStream_t st = as_stream(stream);
-    small_linear_wgrad_kernel<<<nblk((long long)N * K, 256), 256, 0, st>>>(x, dy, dW, db, B, K, N, act_silu_in,
+    launch_pdl(small_linear_wgrad_kernel, nblk((long long)N * K, 256), 256, 0, st, x, dy, dW, db, B, K, N, act_silu_in,
                                                                            accumulate);
     CESM_CHECK_LAUNCH();
     if (dx) {
-        small_linear_dgrad_kernel<<<dim3(ceil_div(K, 32), B), 256, 0, st>>>(x, W, dy, dx, B, K, N, act_silu_in);
+        launch_pdl(small_linear_dgrad_kernel, dim3(ceil_div(K, 32), B), 256, 0, st, x, W, dy, dx, B, K, N, act_silu_in);
         CESM_CHECK_LAUNCH();
     }
     return CESM_OK;
@@ -604,7 +638,7 @@ extern "C" int cesm_small_linear_bwd(const float* x, const float* W, const float
 extern "C" int cesm_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
                              const float* sqrt_1mac, float* xt, int B, long long per_sample, void* stream) {
     const long long total = (long long)B * per_sample;
-    q_sample_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(x0, noise, t, sqrt_ac, sqrt_1mac, xt, per_sample, total);
+    launch_pdl(q_sample_kernel, nblk(total, 256), 256, 0, as_stream(stream), x0, noise, t, sqrt_ac, sqrt_1mac, xt, per_sample, total);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -615,14 +649,14 @@ extern "C" int cesm_mse_fwd(const float* eps, const float* noise, float* diff, f
     CESM_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
-    mse_fwd_kernel<<<(int)blocks, 256, 0, st>>>(eps, noise, diff, loss, total);
+    launch_pdl(mse_fwd_kernel, (int)blocks, 256, 0, st, eps, noise, diff, loss, total);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
 
 extern "C" int cesm_scale_by_scalar(const float* in, const float* gscale, float factor, float* out, long long total,
                                     void* stream) {
-    scale_by_device_scalar_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(in, gscale, factor, out, total);
+    launch_pdl(scale_by_device_scalar_kernel, nblk(total, 256), 256, 0, as_stream(stream), in, gscale, factor, out, total);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -631,7 +665,7 @@ extern "C" int cesm_p_sample(const float* xt, const float* eps, const float* z, 
                              const float* sqrt_1mac, const float* sqrt_recip_a, const float* post_var, float* out,
                              int B, long long per_sample, void* stream) {
     const long long total = (long long)B * per_sample;
-    p_sample_kernel<<<nblk(total, 256), 256, 0, as_stream(stream)>>>(xt, eps, z, t, betas, sqrt_1mac, sqrt_recip_a,
+    launch_pdl(p_sample_kernel, nblk(total, 256), 256, 0, as_stream(stream), xt, eps, z, t, betas, sqrt_1mac, sqrt_recip_a,
                                                                     post_var, out, per_sample, total);
     CESM_CHECK_LAUNCH();
     return CESM_OK;

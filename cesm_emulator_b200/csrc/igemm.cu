@@ -13,6 +13,7 @@
 //
 // Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
 // warps4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+#include "api_common.h"
 #include "common.cuh"
 #include "igemm.h"
 
@@ -39,6 +40,8 @@ struct IgemmSmem {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(256)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
+    pdl_trigger();
+    pdl_wait();
     using S = IgemmSmem<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -216,7 +219,7 @@ static cudaError_t launch_igemm(const IgemmMaps& maps, const IgemmParams& p, int
         configured = true;
     }
     dim3 grid(m_tiles, p.cout / BLOCK_N, 1);
-    igemm_kernel<BLOCK_N, STAGES><<<grid, 256, S::kTotal, stream>>>(maps, p);
+    launch_pdl(igemm_kernel<BLOCK_N, STAGES>, grid, 256, S::kTotal, stream, maps, p);
     return cudaGetLastError();
 }
 

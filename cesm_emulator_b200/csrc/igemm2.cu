@@ -25,6 +25,7 @@
 // (+ TMEM allocation), 3..10 = epilogue: two groups of four warps (warp w reads TMEM lanes
 // 32*(w%4)..+31), the groups alternating over the 64-column chunks of a tile.
 
+#include "api_common.h"
 #include "common.cuh"
 #include "igemm.h"
 
@@ -76,6 +77,7 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&v)[64])
 template <int BLOCK_N, bool HALO, bool GN>
 __global__ void __launch_bounds__(kIgemm2Threads, 1)
 igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
+    pdl_trigger();  // pdl_wait() sits in the two TMA producers: everything else depends on their data
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -158,6 +160,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
 
     if (warp == 0 && lane == 0) {
         // ===== activation producer =====
+        pdl_wait();  // the preceding kernel has completed: its outputs (our activations) are visible
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -200,6 +203,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         }
     } else if (warp == 1 && lane == 0) {
         // ===== weight producer =====
+        pdl_wait();
         if (p.b_resident) {
             const uint32_t total_bytes = (uint32_t)p.n_tiles * p.num_kb * b_blk_bytes;
             mbar_arrive_expect_tx(b_all_bar, total_bytes);
@@ -525,7 +529,7 @@ static cudaError_t launch_igemm2(const Igemm2Maps& maps, const Igemm2Params& p, 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    igemm2_kernel<BLOCK_N, HALO, GN><<<grid, kIgemm2Threads, smem, stream>>>(maps, p);
+    launch_pdl(igemm2_kernel<BLOCK_N, HALO, GN>, grid, kIgemm2Threads, smem, stream, maps, p);
     return cudaGetLastError();
 }
 

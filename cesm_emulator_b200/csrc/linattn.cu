@@ -92,6 +92,8 @@ __device__ __forceinline__ LaWs la_ws(float* ws, int ni, int HD, int H) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 la_colmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, int n, int H, int rows_per_block) {
+    pdl_trigger();
+    pdl_wait();
     const int HD = H * LD, cpr = HD / 8;
     const int ni = blockIdx.y;
     const int chunk = threadIdx.x % cpr, rl = threadIdx.x / cpr, nrl = blockDim.x / cpr;
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(256)
 la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                   float* __restrict__ ws, float* __restrict__ acc_out /* MODE 1: dctx [NI][H][32][32] */, int n, int H,
                   int chunk, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,6 +301,8 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
 
 // ctx[d][e] /= Z[d]  (forward) -- one thread per element
 __global__ void la_finalize_kernel(float* __restrict__ ws, int H, int NI) {
+    pdl_trigger();
+    pdl_wait();
     const int HD = H * LD;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int per = H * LD * LD;
@@ -309,6 +315,8 @@ __global__ void la_finalize_kernel(float* __restrict__ ws, int H, int NI) {
 // delta[ni][h*32+d] = sum_e ctx[d][e] * dctx[d][e]
 __global__ void la_delta_kernel(float* __restrict__ ws, const float* __restrict__ dctx, float* __restrict__ delta,
                                 int H, int NI) {
+    pdl_trigger();
+    pdl_wait();
     const int HD = H * LD;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // ni*HD + h*32 + d
     if (idx >= NI * HD) return;
@@ -409,6 +417,8 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
 __global__ void __launch_bounds__(256, 3)
 la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int n,
                 int H, int chunk, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -489,6 +499,8 @@ __global__ void __launch_bounds__(256, 2)
 la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     float* __restrict__ ws, const float* __restrict__ dctx, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t la_smem[];
     const int HD = H * LD, ld = 3 * HD;
     const int ni = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -642,15 +654,15 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, i
     CESM_ZERO_SCRATCH(ws, sizeof(float) * cesm_linattn_ws_floats(NI, H), st);
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
-    la_colmax_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv, ws, n, H, chunk);
+    launch_pdl(la_colmax_kernel, grid, 256, 0, st, (const __nv_bfloat16*)qkv, ws, n, H, chunk);
     CESM_CHECK_LAUNCH();
     const size_t sh = la_context_smem(H, 0);
-    la_context_kernel<0><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, nullptr, ws, nullptr, n, H, chunk, scale);
+    launch_pdl(la_context_kernel<0>, grid, 32 * H, sh, st, (const __nv_bfloat16*)qkv, nullptr, ws, nullptr, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
-    la_finalize_kernel<<<ceil_div(NI * H * LD * LD, 256), 256, 0, st>>>(ws, H, NI);
+    launch_pdl(la_finalize_kernel, ceil_div(NI * H * LD * LD, 256), 256, 0, st, ws, H, NI);
     CESM_CHECK_LAUNCH();
     const size_t sh_apply = (size_t)RING_STAGES * APPLY_MT * 2 * 256 * 16;  // 48 KB
-    la_apply_kernel<<<grid, 32 * H, sh_apply, st>>>((const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
+    launch_pdl(la_apply_kernel, grid, 32 * H, sh_apply, st, (const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
                                                     scale);
     CESM_CHECK_LAUNCH();
     (void)HD;
@@ -669,10 +681,10 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
     const size_t sh = la_context_smem(H, 1);
-    la_context_kernel<1><<<grid, 32 * H, sh, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, n, H,
+    launch_pdl(la_context_kernel<1>, grid, 32 * H, sh, st, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, n, H,
                                                    chunk, scale);
     CESM_CHECK_LAUNCH();
-    la_delta_kernel<<<ceil_div(NI * H * LD, 128), 128, 0, st>>>(ws, dctx, delta, H, NI);
+    launch_pdl(la_delta_kernel, ceil_div(NI * H * LD, 128), 128, 0, st, ws, dctx, delta, H, NI);
     CESM_CHECK_LAUNCH();
     const size_t sh_bwd = (size_t)RING_STAGES * 8 * 256 * 16;  // 96 KB
     static bool bwd_cfg = false;
@@ -680,7 +692,7 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
         CESM_CHECK_CUDA(cudaFuncSetAttribute(la_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bwd));
         bwd_cfg = true;
     }
-    la_bwd_apply_kernel<<<grid, 32 * H, sh_bwd, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
+    launch_pdl(la_bwd_apply_kernel, grid, 32 * H, sh_bwd, st, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
                                                  (__nv_bfloat16*)dqkv, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;

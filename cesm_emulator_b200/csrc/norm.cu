@@ -64,6 +64,8 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once stre
 
 __global__ void __launch_bounds__(kNormThreads)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, long long P, int C, int G) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;       // fixed channel vector of this thread
@@ -108,6 +110,8 @@ gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
                     const float* __restrict__ film,  // [B][2C] (scale | shift) or null
                     const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, long long P, int C,
                     int G, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;
@@ -177,6 +181,8 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      const float* __restrict__ sums, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ film, float* __restrict__ csum,
                      long long P, int C, int G, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;
@@ -302,6 +308,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
                     const float* __restrict__ csum, __nv_bfloat16* __restrict__ dx, long long P, int C, int G,
                     float eps, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dfilm,
                     float* __restrict__ dcbias) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;
@@ -413,6 +421,8 @@ __global__ void gn_bwd_params_kernel(const float* __restrict__ csum, const float
                                      float* __restrict__ dbeta, float* __restrict__ dfilm,
                                      float* __restrict__ dcbias, int B, long long P, int C, int G, float eps,
                                      int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const int cpg = C / G, g = c / cpg;
@@ -469,6 +479,8 @@ template <int LPR, int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out,
               long long M, int C, float eps) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, sl = lane % LPR;
     const long long rows_per_blk = 8 * RPW;
@@ -518,6 +530,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, long long M, int C, float eps) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, sl = lane % LPR;
     const long long rows_per_blk = 8 * RPW;
@@ -632,7 +646,7 @@ extern "C" int cesm_gn_stats(const void* x, float* sums, int B, long long P, int
     const int per_block = kNormThreads / (C / 8) * UNR;
     static const int res = resident_blocks(gn_stats_kernel, kNormThreads);
     dim3 grid(norm_grid(P, per_block, B, res), B);
-    gn_stats_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, sums, P, C, G);
+    launch_pdl(gn_stats_kernel, grid, kNormThreads, 0, as_stream(stream), (const __nv_bfloat16*)x, sums, P, C, G);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -644,7 +658,7 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
     const int per_block = kNormThreads / (C / 8) * UNR;
     static const int res = resident_blocks(gn_apply_fwd_kernel, kNormThreads);
     dim3 grid(norm_grid(P, per_block, B, res), B);
-    gn_apply_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>(
+    launch_pdl(gn_apply_fwd_kernel, grid, kNormThreads, 0, as_stream(stream), 
         (const __nv_bfloat16*)x, sums, gamma, beta, film, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, P, C, G,
         eps);
     CESM_CHECK_LAUNCH();
@@ -669,16 +683,16 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     static const int res_a = resident_blocks(gn_bwd_apply_kernel, kNormThreads);
     dim3 grid(norm_grid(P, per_block, B, res_r), B);
     dim3 grid_a(norm_grid(P, per_block, B, res_a), B);
-    gn_bwd_reduce_kernel<<<grid, kNormThreads, kRing, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
+    launch_pdl(gn_bwd_reduce_kernel, grid, kNormThreads, kRing, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
     CESM_CHECK_LAUNCH();
     const bool fused = accumulate_params != 0;  // accumulate mode: the apply kernel adds the parameter gradients
-    gn_bwd_apply_kernel<<<grid_a, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
+    launch_pdl(gn_bwd_apply_kernel, grid_a, kNormThreads, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
                                                        beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps,
                                                        fused ? dgamma : nullptr, dbeta, dfilm, dconv_bias);
     CESM_CHECK_LAUNCH();
     if (!fused) {
-        gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(csum, sums, gamma, beta, film, dgamma, dbeta, dfilm,
+        launch_pdl(gn_bwd_params_kernel, ceil_div(C, 128), 128, 0, st, csum, sums, gamma, beta, film, dgamma, dbeta, dfilm,
                                                                dconv_bias, B, P, C, G, eps, 0);
         CESM_CHECK_LAUNCH();
     }
@@ -690,14 +704,14 @@ static void ln_launch_fwd(int /*grid*/, cudaStream_t st, const void* x, const fl
                           int C, float eps) {
     static const int res = resident_blocks(ln_fwd_kernel<LPR, NV>, 256);
     const int grid = norm_grid(M, 8 * (32 / LPR), 1, res);
-    ln_fwd_kernel<LPR, NV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, (__nv_bfloat16*)out, M, C, eps);
+    launch_pdl(ln_fwd_kernel<LPR, NV>, grid, 256, 0, st, (const __nv_bfloat16*)x, gamma, (__nv_bfloat16*)out, M, C, eps);
 }
 template <int LPR, int NV>
 static void ln_launch_bwd(int /*grid*/, cudaStream_t st, const void* x, const float* gamma, const void* dy,
                           const void* dres, void* dx, float* dgamma, long long M, int C, float eps) {
     static const int res = resident_blocks(ln_bwd_kernel<LPR, NV>, 256);
     const int grid = norm_grid(M, 8 * (32 / LPR), 1, res);
-    ln_bwd_kernel<LPR, NV><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, gamma, (const __nv_bfloat16*)dy,
+    launch_pdl(ln_bwd_kernel<LPR, NV>, grid, 256, 0, st, (const __nv_bfloat16*)x, gamma, (const __nv_bfloat16*)dy,
                                                  (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, M, C, eps);
 }
 // C in {64, 128, 256, 512, 1024}: LPR = min(32, C/8), NV = C / (8*LPR)

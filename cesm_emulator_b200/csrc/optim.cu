@@ -32,6 +32,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int MODE>
 __global__ void __launch_bounds__(kRelayoutThreads)
 relayout_tiled_kernel(const cesm_pack_desc* __restrict__ descs) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float tile[];
     __shared__ int s_off[CESM_MAX_TAPS];
     const cesm_pack_desc& d = descs[blockIdx.y];
@@ -108,6 +110,8 @@ relayout_tiled_kernel(const cesm_pack_desc* __restrict__ descs) {
 static constexpr int kOptThreads = 256;
 __global__ void __launch_bounds__(kOptThreads)
 grad_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials, float* __restrict__ state) {
+    pdl_trigger();
+    pdl_wait();
     float s = 0.f;
     const long long n4 = n >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -139,6 +143,8 @@ __global__ void __launch_bounds__(kOptThreads)
 adamw_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   long long n, const float* __restrict__ partials, int n_partials, float* __restrict__ state, float lr,
                   float beta1, float beta2, float eps, float wd, float max_norm) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_coef;
     if (threadIdx.x < 32) {  // every block re-reduces the partials in the same order
         float t = 0.f;
@@ -198,9 +204,9 @@ static int relayout_launch(const cesm_pack_desc* descs_device, int n, int mode, 
     }
     dim3 grid(32, n);
     if (mode == 0)
-        relayout_tiled_kernel<0><<<grid, kRelayoutThreads, kSmem, st>>>(descs_device);
+        launch_pdl(relayout_tiled_kernel<0>, grid, kRelayoutThreads, kSmem, st, descs_device);
     else
-        relayout_tiled_kernel<1><<<grid, kRelayoutThreads, kSmem, st>>>(descs_device);
+        launch_pdl(relayout_tiled_kernel<1>, grid, kRelayoutThreads, kSmem, st, descs_device);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -225,9 +231,9 @@ extern "C" int cesm_adamw_step(float* p, const float* g, float* m, float* v, lon
                  "adamw_step needs n > 0 and 16-byte aligned flat buffers (n=%lld)", n);
     cudaStream_t st = as_stream(stream);
     const int nb = cesm_adamw_partials();
-    grad_sumsq_kernel<<<nb, kOptThreads, 0, st>>>(g, n, partials, state);
+    launch_pdl(grad_sumsq_kernel, nb, kOptThreads, 0, st, g, n, partials, state);
     CESM_CHECK_LAUNCH();
-    adamw_clip_kernel<<<nb * 2, kOptThreads, 0, st>>>(p, g, m, v, n, partials, nb, state, lr, beta1, beta2, eps,
+    launch_pdl(adamw_clip_kernel, nb * 2, kOptThreads, 0, st, p, g, m, v, n, partials, nb, state, lr, beta1, beta2, eps,
                                                      weight_decay, max_norm);
     CESM_CHECK_LAUNCH();
     return CESM_OK;

@@ -13,6 +13,7 @@
 // Replaces the weight-gradient halves of cuDNN/cuBLAS backward for video_net.py:215, :246, :62,
 // :66, :322-323, :380-381.
 #include <cstdlib>
+#include "api_common.h"
 #include "common.cuh"
 #include "igemm.h"
 
@@ -37,6 +38,7 @@ struct WgradSmem {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
+    pdl_trigger();  // pdl_wait() sits in the TMA producer: MMA and epilogue depend on its data
     using S = WgradSmem<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -87,6 +89,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
+        pdl_wait();
         int um[2], uc[2], udh[2], udw[2];
         for (int i = 0; i < 2; ++i) {
             const int u = u0 + i;
@@ -185,7 +188,7 @@ static cudaError_t launch_wgrad(const WgradMaps& maps, const WgradParams& p, dim
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    wgrad_kernel<BLOCK_N, STAGES><<<grid, 256, S::kTotal, stream>>>(maps, p);
+    launch_pdl(wgrad_kernel<BLOCK_N, STAGES>, grid, 256, S::kTotal, stream, maps, p);
     return cudaGetLastError();
 }
 
