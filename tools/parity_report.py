@@ -20,7 +20,7 @@ def main():
     torch.manual_seed(0)
     unet = UNet(**BASELINE_KW)
     diff = Diffusion(unet).cuda()
-    x0, cond, t, noise = make_inputs(B, K, H, W, seed=5, device="cuda")
+    x0, cond, t, noise = make_inputs(B, K, H, W, seed=int(os.environ.get("SEED", "5")), device="cuda")
     eps, loss, grads = module_loss_and_grads(diff, x0, cond, t, noise)
     ref_eps, ref_loss, ref_grads = oracle_loss_and_grads(unet, BASELINE_KW, x0, cond, t, noise)
     print(f"shape B={B} K={K} {H}x{W}")
