@@ -502,6 +502,39 @@ __global__ void p_sample_kernel(const float* __restrict__ xt, const float* __res
     out[idx] = mean + sqrtf(post_var[tb]) * z[idx];
 }
 
+// ------------------------------------------------------------------------------------------------
+// On-device data path (dataset_single_member.py:168-196): the whole (T, M, H, W) condition and target
+// arrays stay resident in HBM; one launch assembles a batch -- K-frame window gather with the
+// time-reversal frame map folded in, target frame, common spatial crop.  Per-sample plan (host RNG, so
+// the draw order is the reference's): plan[b] = {member, first frame, target frame, crop row, crop col,
+// reverse flag}.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_windows_kernel(const float* __restrict__ cond, const float* __restrict__ tgt, const int* __restrict__ plan,
+                      float* __restrict__ cond_out, float* __restrict__ x0_out, int M, int H, int W, int K, int h,
+                      int w, long long total) {
+    pdl_trigger();
+    pdl_wait();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = idx % w;
+    const int y = (idx / w) % h;
+    const int k = (idx / ((long long)w * h)) % (K + 1);   // plane K is the target
+    const int b = idx / ((long long)w * h * (K + 1));
+    const int* pl = plan + b * 6;
+    const int m = pl[0], t0 = pl[1], ta = pl[2], i0 = pl[3], j0 = pl[4], rev = pl[5];
+    if (k == K) {
+        x0_out[((size_t)b * h + y) * w + x] = tgt[(((size_t)ta * M + m) * H + i0 + y) * W + j0 + x];
+        return;
+    }
+    // time reversal around the centre frame (dataset_single_member.py:178-186): the halves left and
+    // right of the centre are flipped, the centre (anchor) frame stays
+    const int mid = K / 2;
+    int src = k;
+    if (rev) src = k < mid ? mid - 1 - k : (k == mid ? mid : K + mid - k);
+    cond_out[(((size_t)b * K + k) * h + y) * w + x] = cond[(((size_t)(t0 + src) * M + m) * H + i0 + y) * W + j0 + x];
+}
+
 }  // namespace cesm
 
 using namespace cesm;
@@ -538,6 +571,16 @@ extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, int ac
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
     launch_pdl(colsum_kernel, (int)blocks, 256, 0, st, (const __nv_bfloat16*)x, out, M, C);
+    CESM_CHECK_LAUNCH();
+    return CESM_OK;
+}
+
+extern "C" int cesm_gather_windows(const float* cond, const float* tgt, const int* plan, float* cond_out, float* x0_out,
+                                   int B, int T, int M, int H, int W, int K, int h, int w, void* stream) {
+    CESM_REQUIRE(B > 0 && K >= 1 && h > 0 && w > 0 && h <= H && w <= W && T >= K, "bad window shape");
+    const long long total = (long long)B * (K + 1) * h * w;
+    launch_pdl(gather_windows_kernel, nblk(total, 256), 256, 0, as_stream(stream), cond, tgt, plan, cond_out, x0_out, M, H,
+               W, K, h, w, total);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

@@ -347,6 +347,19 @@ def linattn_bwd(qkv, ws, dout, NI: int, n: int, H: int, D: int, scale: float):
 
 
 # ---- boundary convs -----------------------------------------------------------------------------
+def gather_windows(cond, tgt, plan, cond_out, x0_out) -> None:
+    """cond, tgt: fp32 [T, M, H, W] on the device; plan: int32 [B, 6] on the device (see cesm_gather_windows);
+    cond_out: fp32 [B, 1, K, h, w]; x0_out: fp32 [B, 1, h, w] -- both written in place."""
+    _req_cuda(cond, tgt, plan, cond_out, x0_out)
+    assert cond.dtype == tgt.dtype == cond_out.dtype == x0_out.dtype == torch.float32 and plan.dtype == torch.int32
+    assert cond.is_contiguous() and tgt.is_contiguous() and cond_out.is_contiguous() and x0_out.is_contiguous()
+    T, M, H, W = cond.shape
+    B, _, K, h, w = cond_out.shape
+    assert plan.shape == (B, 6) and plan.is_contiguous() and x0_out.shape == (B, 1, h, w) and tgt.shape == cond.shape
+    _lib.call("cesm_gather_windows", _ptr(cond), _ptr(tgt), _ptr(plan), _ptr(cond_out), _ptr(x0_out), B, T, M, H, W, K,
+              h, w, _stream())
+
+
 INPUT_KPAD = 256  # columns of the input-conv patch matrix: 2 planes x 49 taps x (hi, lo) + 2 ones + padding
 
 

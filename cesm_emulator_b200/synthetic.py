@@ -59,25 +59,37 @@ class SyntheticEnsemble:
     def __len__(self) -> int:
         return self.num_units * self.M
 
-    def window(self, idx: int, augment: bool = True):
-        """-> (cond_win [1,K,h,w], x0 [1,h,w]) float32 torch tensors."""
+    def out_hw(self) -> Tuple[int, int]:
+        if self.crop_hw is None:
+            return self.H, self.W
+        return min(self.crop_hw[0], self.H), min(self.crop_hw[1], self.W)
+
+    def plan(self, idx: int, augment: bool = True) -> Tuple[int, int, int, int, int, int]:
+        """The random decisions of one sample, in the reference's draw order (dataset_single_member.py:
+        168-196): -> (member, first frame, target frame, crop row, crop col, time-reverse flag)."""
         m, t0 = idx % self.M, idx // self.M
         anchor = min(t0 + self.K // 2, self.T - 1)
-        times = np.arange(t0, t0 + self.K)
-        cond = self.cond[times, m, 0]            # (K, H, W)
-        x0 = self.tgt[anchor, m]                 # (1, H, W)
-        if augment and self.time_reverse_p > 0 and self._aug.random() < self.time_reverse_p:
-            mid = self.K // 2
-            cond = np.concatenate([cond[:mid][::-1], cond[mid:mid + 1], cond[mid + 1:][::-1]], axis=0)
+        rev = int(augment and self.time_reverse_p > 0 and self._aug.random() < self.time_reverse_p)
         i = j = 0
-        h, w = self.H, self.W
         if self.crop_hw is not None:
-            h, w = min(self.crop_hw[0], self.H), min(self.crop_hw[1], self.W)
+            h, w = self.out_hw()
             if augment:
                 i = 0 if h == self.H else int(self._aug.integers(0, self.H - h + 1))
                 j = 0 if w == self.W else int(self._aug.integers(0, self.W - w + 1))
             else:
                 i, j = (self.H - h) // 2, (self.W - w) // 2
+        return m, t0, anchor, i, j, rev
+
+    def window(self, idx: int, augment: bool = True):
+        """-> (cond_win [1,K,h,w], x0 [1,h,w]) float32 torch tensors."""
+        m, t0, anchor, i, j, rev = self.plan(idx, augment)
+        h, w = self.out_hw()
+        times = np.arange(t0, t0 + self.K)
+        cond = self.cond[times, m, 0]            # (K, H, W)
+        x0 = self.tgt[anchor, m]                 # (1, H, W)
+        if rev:
+            mid = self.K // 2
+            cond = np.concatenate([cond[:mid][::-1], cond[mid:mid + 1], cond[mid + 1:][::-1]], axis=0)
         cond = np.ascontiguousarray(cond[:, i:i + h, j:j + w])[None]
         x0 = np.ascontiguousarray(x0[:, i:i + h, j:j + w])
         return torch.from_numpy(cond), torch.from_numpy(x0)
@@ -90,6 +102,9 @@ class SyntheticEnsemble:
         perm = np.concatenate([perm, perm[: total - len(perm)]])
         return perm[rank:total:world]
 
+    def to_device(self, device) -> "DeviceEnsemble":
+        return DeviceEnsemble(self, device)
+
     def batch(self, indices, augment: bool = True, pin: bool = False):
         """-> (cond [B,1,K,h,w], x0 [B,1,h,w])."""
         cs, xs = zip(*(self.window(int(i), augment) for i in indices))
@@ -97,3 +112,39 @@ class SyntheticEnsemble:
         if pin and torch.cuda.is_available():
             cond, x0 = cond.pin_memory(), x0.pin_memory()
         return cond, x0
+
+
+class DeviceEnsemble:
+    """The on-device data path: both (T, M, H, W) arrays live in HBM (1.9 GB each at
+    the full CESM2-LE shape) and a batch is assembled by ONE kernel (`cesm_gather_windows`) from a 24-byte
+    per-sample plan, instead of numpy gathers on the host plus a 1.7 MB host-to-device copy per step.  The
+    plan is drawn on the host by `SyntheticEnsemble.plan`, so the random stream -- and therefore every
+    batch -- is identical to the host path's (`tests/test_kernels_gpu.py::test_device_data_path`)."""
+
+    def __init__(self, ds: SyntheticEnsemble, device):
+        self.ds = ds
+        self.device = torch.device(device)
+        self.cond = torch.from_numpy(np.ascontiguousarray(ds.cond[:, :, 0])).to(self.device)   # (T, M, H, W)
+        self.tgt = torch.from_numpy(np.ascontiguousarray(ds.tgt[:, :, 0])).to(self.device)
+        self._plan_ring = []   # pinned host plans, rotated so that an in-flight async copy is never overwritten
+        self._plan_dev = None
+        self._turn = 0
+
+    def plan(self, indices, augment: bool = True) -> torch.Tensor:
+        """int32 [B, 6] plan in pinned host memory (one of 8 rotating buffers)."""
+        B = len(indices)
+        if not self._plan_ring or self._plan_ring[0].shape[0] != B:
+            mk = lambda: torch.empty((B, 6), dtype=torch.int32)
+            self._plan_ring = [mk().pin_memory() if torch.cuda.is_available() else mk() for _ in range(8)]
+            self._plan_dev = torch.empty((B, 6), dtype=torch.int32, device=self.device)
+        host = self._plan_ring[self._turn % len(self._plan_ring)]
+        self._turn += 1
+        host.copy_(torch.tensor([self.ds.plan(int(i), augment) for i in indices], dtype=torch.int32))
+        return host
+
+    def batch_into(self, indices, cond_out: torch.Tensor, x0_out: torch.Tensor, augment: bool = True) -> None:
+        """Fill the (static) device buffers cond_out [B,1,K,h,w] / x0_out [B,1,h,w] for these sample indices."""
+        from . import kernels as K
+        host = self.plan(indices, augment)
+        self._plan_dev.copy_(host, non_blocking=True)
+        K.gather_windows(self.cond, self.tgt, self._plan_dev, cond_out, x0_out)

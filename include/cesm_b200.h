@@ -232,6 +232,14 @@ int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, float* scratc
  * Output conv (video_net.py:763 + model.py:129-130): 1x1x1, 64 -> 1, evaluated on the centre
  * frame only (the reference computes every frame and then selects frame F//2).
  * ---------------------------------------------------------------------------------------------- */
+/* On-device data path (dataset_single_member.py:168-196).  cond, tgt: fp32 [T][M][H][W]
+ * resident in device memory.  plan: int32 [B][6] = {member, first window frame, target frame, crop row,
+ * crop col, time-reverse flag} in device memory.  Writes cond_out fp32 [B][K][h][w] (= the reference's
+ * [B,1,K,h,w]) and x0_out fp32 [B][h][w].  With the flag the frames left and right of the centre are flipped
+ * (the reference's centred time reversal). */
+int cesm_gather_windows(const float* cond, const float* tgt, const int* plan, float* cond_out, float* x0_out, int B,
+                        int T, int M, int H, int W, int K, int h, int w, void* stream);
+
 /* Tensor-core form of the same input convolution.  cesm_input_patches writes the im2col matrix
  * bf16 [B*F][H][W][kpad] = [hi(x) | lo(x) | 1 | 1 | 0...] (x = the 2*ks*ks taps of the two fp32 planes, frame
  * broadcast as above; hi = bf16(x), lo = bf16(x - hi)); cesm_input_weight_pack writes the matching operand

@@ -98,13 +98,18 @@ def main(cfg):
         start = load_checkpoint(tcfg["resume"], diffusion, engine, dev)
     save_dir = tcfg.get("save_dir", "runs/exp")
     max_steps = int(tcfg.get("max_steps_per_epoch", 0))
+    # data.on_device (default on): both arrays resident in HBM, batches gathered by one kernel
+    dev_ds = ds.to_device(dev) if cfg.get("data", {}).get("on_device", True) else None
     for epoch in range(start, int(tcfg.get("num_epochs", 1)) + 1):
         idx = ds.shard_indices(epoch, rank, world)
         n_steps = len(idx) // B if not max_steps else min(max_steps, len(idx) // B)
         t0, total = time.time(), torch.zeros((), device=dev)
         for s in range(n_steps):
-            cond, x0 = ds.batch(idx[s * B:(s + 1) * B], pin=True)
-            loss = engine.step(x0, cond)
+            if dev_ds is not None:
+                loss = engine.step_indices(dev_ds, idx[s * B:(s + 1) * B])
+            else:
+                cond, x0 = ds.batch(idx[s * B:(s + 1) * B], pin=True)
+                loss = engine.step(x0, cond)
             total += loss
         mean = (total / max(1, n_steps)).item()  # one host sync per epoch, not per step
         if not (mean == mean and abs(mean) != float("inf")):
