@@ -118,6 +118,7 @@ _SIGNATURES: dict[str, list] = {
     "cesm_linattn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "cesm_linattn_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "cesm_gather_windows": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cesm_qkv_bwd": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P],
     "cesm_input_patches": [_P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "cesm_input_weight_pack": [_P, _P, _P, _I, _I, _I, _P],
     "cesm_input_conv_fwd": [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -189,6 +189,28 @@ def wgrad(x0: torch.Tensor, dy: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
     return dw_
 
 
+def qkv_bwd(dy: torch.Tensor, x: torch.Tensor, wt: torch.Tensor, dw_into: Optional[torch.Tensor] = None):
+    """Fused data + weight gradient of a bias-free C=64 -> cout projection (cesm_qkv_bwd).
+    dy: bf16 [..., cout]; x: bf16 [..., 64]; wt: bf16 [64, cout] (W^T).  -> (dx bf16 like x, dw fp32 [cout, 64]);
+    with `dw_into` (fp32, contiguous [cout, 64] storage, e.g. a parameter's .grad) dW is ACCUMULATED there."""
+    _req_cuda(dy, x, wt, dw_into)
+    assert dy.dtype == BF16 and x.dtype == BF16 and wt.dtype == BF16 and dy.is_contiguous() and x.is_contiguous()
+    cout, cin = dy.shape[-1], x.shape[-1]
+    rows = x.numel() // cin
+    assert dy.numel() // cout == rows and tuple(wt.shape) == (cin, cout) and wt.is_contiguous()
+    dx = torch.empty_like(x)
+    if dw_into is None:
+        dw = torch.zeros((cout, cin), dtype=torch.float32, device=x.device)
+    else:
+        assert dw_into.dtype == torch.float32 and dw_into.is_contiguous() and dw_into.numel() == cout * cin
+        dw = dw_into
+    meta = None
+    if _lib.PROFILER is not None:
+        meta = {"kind": "qkv", "flops": 4.0 * rows * cout * cin, "bytes": 2.0 * rows * (cout + 2 * cin)}
+    _lib.call("cesm_qkv_bwd", _ptr(dy), _ptr(x), _ptr(wt), _ptr(dx), _ptr(dw), cin, rows, cin, cout, _stream(), _meta=meta)
+    return dx, dw
+
+
 def _tap_array(offs: Sequence[int]):
     arr = (ctypes.c_int32 * _lib.CESM_MAX_TAPS)()
     for i, o in enumerate(offs):

@@ -145,6 +145,14 @@ int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* s
 /* Batched inverse for gradients: for each descriptor, dst (fp32, the parameter-gradient layout)
  * += src[o][t][i] (fp32 packed scratch written by cesm_wgrad) and the scratch is zeroed. */
 int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream);
+/* Backward of the q/k/v projection (to_qkv, no bias; video_net.py:322, :380) for 64 input channels: data
+ * gradient and weight gradient in ONE pass over dy (the two separate calls each stream the 768-wide dy from
+ * HBM).  dy: bf16 [rows][cout]; x: bf16 [rows][64] (the projection's input, LN(x)); wt: bf16 [64][cout] = W^T
+ * (the data-gradient operand cesm_pack_weight produces); dx: bf16 [rows][64] (written); dw: fp32, dw[co*dw_so +
+ * ci] += sum_rows dy[row][co] * x[row][ci].  cin == 64, cout a multiple of 128, <= 768. */
+int cesm_qkv_bwd(const void* dy, const void* x, const void* wt, void* dx, float* dw, long long dw_so, long long rows,
+                 int cin, int cout, void* stream);
+
 /* Scratch / statistics buffers the kernels ACCUMULATE into (igemm gn_sums, cesm_gn_bwd csum, cesm_tattn_bwd
  * dbias, cesm_linattn_fwd ws, cesm_linattn_bwd scratch) are zeroed by the call itself.  A caller that hands
  * in already-zeroed memory (the training engine carves them from one arena cleared once per step) switches

@@ -143,3 +143,26 @@ def test_gemm_large_and_streamed_weights(cuda, m, k, n):
     idx = torch.randint(0, m, (4096,), device=cuda)
     ref = a.float().view(m, k)[idx] @ w.float().t()
     assert _err(out.view(m, n)[idx], ref) < 1e-2
+
+
+@pytest.mark.parametrize("rows,cout", [(128 * 5, 768), (1000, 768), (128 * 300 + 17, 768), (4096, 256)])
+def test_fused_qkv_backward(cuda, rows, cout):
+    """cesm_qkv_bwd: data gradient + weight gradient of the C=64 -> cout projection in one pass over dy,
+    against fp32 matmuls of the same bf16 operands (ragged row counts exercise the TMA zero fill and the
+    predicated row stores; two calls accumulate into dW)."""
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(2)
+    dy = (torch.randn(rows, cout, device=cuda) * 0.5).bfloat16()
+    x = torch.randn(rows, 64, device=cuda).bfloat16()
+    w = (torch.randn(cout, 64, device=cuda) * 0.1).bfloat16()      # to_qkv.weight [cout, cin]
+    wt = w.t().contiguous()                                         # data-gradient operand [cin, cout]
+    dx, dw = K.qkv_bwd(dy, x, wt)
+    dx_ref = dy.float() @ w.float()
+    dw_ref = dy.float().t() @ x.float()
+    assert (dx.float() - dx_ref).abs().max().item() <= 1e-2 * dx_ref.abs().max().item()
+    assert (dw - dw_ref).abs().max().item() <= 2e-4 * dw_ref.abs().max().item()
+    base = torch.randn(cout, 64, device=cuda)
+    acc = base.clone()
+    K.qkv_bwd(dy, x, wt, dw_into=acc)
+    K.qkv_bwd(dy, x, wt, dw_into=acc)
+    assert (acc - base - 2 * dw_ref).abs().max().item() <= 4e-4 * dw_ref.abs().max().item()
