@@ -225,6 +225,7 @@ def run_b200(args, H, W, arch_kw):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     B, Kf = args.batch, args.frames
