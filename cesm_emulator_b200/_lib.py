@@ -67,6 +67,12 @@ class PackDesc(Structure):
     ]
 
 
+class FilmDesc(Structure):
+    """Mirror of `cesm_film_desc` (include/cesm_b200.h)."""
+
+    _fields_ = [("W", c_void_p), ("bias", c_void_p), ("dW", c_void_p), ("db", c_void_p), ("N", c_int32), ("n0", c_int32)]
+
+
 class CesmError(RuntimeError):
     pass
 
@@ -117,6 +123,8 @@ _SIGNATURES: dict[str, list] = {
     "cesm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "cesm_linattn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "cesm_linattn_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "cesm_film_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "cesm_film_bwd": [_P, _P, _P, _I, _I, _P, _I, _I, _I, _P],
     "cesm_gather_windows": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "cesm_qkv_bwd": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P],
     "cesm_input_patches": [_P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],

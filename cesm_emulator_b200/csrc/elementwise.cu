@@ -442,6 +442,82 @@ small_linear_dgrad_kernel(const float* __restrict__ x, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// All FiLM projections of the network at once (video_net.py:238-241, one per ResnetBlock): they share the
+// input act(temb) and differ only in their weights, so the ~15 tiny linears of a pass -- and in the
+// backward pass their weight gradients, and the sum of their data gradients -- are ONE launch each over a
+// device table of layers instead of ~45 launches plus the autograd adds of d temb.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int film_find(const cesm_film_desc* __restrict__ L, int n_layers, int n, int& local) {
+    int i = 0;
+    while (i + 1 < n_layers && n >= L[i + 1].n0) ++i;
+    local = n - L[i].n0;
+    return i;
+}
+// y_i[b][j] = sum_k silu(x[b][k]) W_i[j][k] + bias_i[j]; warp per (global output, b)
+__global__ void __launch_bounds__(256)
+film_fwd_kernel(const float* __restrict__ x, const cesm_film_desc* __restrict__ L, float* __restrict__ Y, int n_layers,
+                int n_total, int B, int K) {
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, b = blockIdx.y;
+    if (n >= n_total) return;
+    int j;
+    const cesm_film_desc d = L[film_find(L, n_layers, n, j)];
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(silu_precise(x[(size_t)b * K + k]), d.W[(size_t)j * K + k], s);
+    s = warp_sum(s);
+    if (lane == 0) Y[(size_t)B * d.n0 + (size_t)b * d.N + j] = s + d.bias[j];
+}
+// dW_i[j][k] += sum_b dy_i[b][j] silu(x[b][k]); db_i[j] += sum_b dy_i[b][j]   (thread per (global output, k))
+__global__ void __launch_bounds__(256)
+film_wgrad_kernel(const float* __restrict__ x, const cesm_film_desc* __restrict__ L, const float* __restrict__ DY,
+                  int n_layers, int n_total, int B, int K, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_total * K) return;
+    const int k = idx % K, n = idx / K;
+    int j;
+    const cesm_film_desc d = L[film_find(L, n_layers, n, j)];
+    float s = 0.f, sb = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float g = DY[(size_t)B * d.n0 + (size_t)b * d.N + j];
+        s = fmaf(g, silu_precise(x[(size_t)b * K + k]), s);
+        sb += g;
+    }
+    float* w = d.dW + (size_t)j * K + k;
+    *w = accumulate ? *w + s : s;
+    if (k == 0) d.db[j] = accumulate ? d.db[j] + sb : sb;
+}
+// dx[b][k] += silu'(x[b][k]) * sum_j dy_i[b][j] W_i[j][k] for layer i = blockIdx.z (dx zeroed by the caller);
+// block = 32 k-lanes x 8 output groups
+__global__ void __launch_bounds__(256)
+film_dgrad_kernel(const float* __restrict__ x, const cesm_film_desc* __restrict__ L, const float* __restrict__ DY,
+                  int n_layers, float* __restrict__ dx, int B, int K) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + lane, b = blockIdx.y, i = blockIdx.z;
+    float s = 0.f;
+    if (k < K) {
+        const float* __restrict__ dy = DY + (size_t)B * L[i].n0 + (size_t)b * L[i].N;
+        const float* __restrict__ W = L[i].W;
+        const int N = L[i].N;
+#pragma unroll 4
+        for (int j = w; j < N; j += 8) s = fmaf(__ldg(dy + j), __ldg(W + (size_t)j * K + k), s);
+    }
+    __shared__ float red[8][33];
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && k < K) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][lane];
+        atomicAdd(dx + (size_t)b * K + k, t * dsilu_precise(x[(size_t)b * K + k]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // DDPM elementwise
 // ------------------------------------------------------------------------------------------------
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
@@ -673,6 +749,30 @@ extern "C" int cesm_small_linear_bwd(const float* x, const float* W, const float
     CESM_CHECK_LAUNCH();
     if (dx) {
         launch_pdl(small_linear_dgrad_kernel, dim3(ceil_div(K, 32), B), 256, 0, st, x, W, dy, dx, B, K, N, act_silu_in);
+        CESM_CHECK_LAUNCH();
+    }
+    return CESM_OK;
+}
+
+extern "C" int cesm_film_fwd(const float* x, const cesm_film_desc* layers_device, float* y, int n_layers, int n_total,
+                             int B, int K, void* stream) {
+    CESM_REQUIRE(n_layers > 0 && n_total > 0 && B > 0 && K > 0, "bad FiLM table");
+    launch_pdl(film_fwd_kernel, dim3(ceil_div(n_total, 8), B), 256, 0, as_stream(stream), x, layers_device, y, n_layers,
+               n_total, B, K);
+    CESM_CHECK_LAUNCH();
+    return CESM_OK;
+}
+
+extern "C" int cesm_film_bwd(const float* x, const cesm_film_desc* layers_device, const float* dy, int n_layers,
+                             int n_total, float* dx, int B, int K, int accumulate, void* stream) {
+    CESM_REQUIRE(n_layers > 0 && n_total > 0 && B > 0 && K > 0, "bad FiLM table");
+    cudaStream_t st = as_stream(stream);
+    launch_pdl(film_wgrad_kernel, nblk((long long)n_total * K, 256), 256, 0, st, x, layers_device, dy, n_layers, n_total, B,
+               K, accumulate);
+    CESM_CHECK_LAUNCH();
+    if (dx) {
+        CESM_ZERO_SCRATCH(dx, sizeof(float) * (size_t)B * K, st);
+        launch_pdl(film_dgrad_kernel, dim3(ceil_div(K, 32), B, n_layers), 256, 0, st, x, layers_device, dy, n_layers, dx, B, K);
         CESM_CHECK_LAUNCH();
     }
     return CESM_OK;

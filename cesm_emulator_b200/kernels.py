@@ -479,6 +479,46 @@ def small_linear_bwd(x, W, dy, act_silu_in: bool, need_dx: bool, into=None):
     return dx, dW, db
 
 
+# ---- all FiLM projections of a pass at once -----------------------------------------------------
+def film_table(Ws, bs, dWs=None, dbs=None) -> torch.Tensor:
+    """Device table of `cesm_film_desc` for these layers (static pointers only: cache it)."""
+    n = len(Ws)
+    arr = (_lib.FilmDesc * n)()
+    n0 = 0
+    for i, d in enumerate(arr):
+        d.W, d.bias = Ws[i].data_ptr(), bs[i].data_ptr()
+        d.dW = dWs[i].data_ptr() if dWs is not None else 0
+        d.db = dbs[i].data_ptr() if dbs is not None else 0
+        d.N, d.n0 = Ws[i].shape[0], n0
+        n0 += Ws[i].shape[0]
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(Ws[0].device)
+
+
+def film_fwd(x: torch.Tensor, table: torch.Tensor, Ns) -> list:
+    """-> per-layer fp32 [B, N_i] views of one packed output buffer."""
+    _req_cuda(x, table)
+    B, K = x.shape
+    n_total = int(sum(Ns))
+    y = torch.empty(B * n_total, dtype=torch.float32, device=x.device)
+    _lib.call("cesm_film_fwd", _ptr(x), _ptr(table), _ptr(y), len(Ns), n_total, B, K, _stream())
+    outs, n0 = [], 0
+    for N in Ns:
+        outs.append(y[B * n0:B * (n0 + N)].view(B, N))
+        n0 += N
+    return outs
+
+
+def film_bwd(x: torch.Tensor, table: torch.Tensor, dy_packed: torch.Tensor, Ns, need_dx: bool, accumulate: bool):
+    _req_cuda(x, table, dy_packed)
+    B, K = x.shape
+    n_total = int(sum(Ns))
+    assert dy_packed.numel() == B * n_total and dy_packed.dtype == torch.float32 and dy_packed.is_contiguous()
+    dx = zero_scratch(x.shape, x.device) if need_dx else None  # the per-layer blocks add into it
+    _lib.call("cesm_film_bwd", _ptr(x), _ptr(table), _ptr(dy_packed), len(Ns), n_total, _ptr(dx), B, K, int(accumulate),
+              _stream())
+    return dx
+
+
 # ---- DDPM ---------------------------------------------------------------------------------------
 def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
     _req_cuda(x0, noise, t, sqrt_ac, sqrt_1mac)

@@ -748,6 +748,54 @@ class SmallLinearFn(torch.autograd.Function):
         return dx, dW, db, None
 
 
+_FILM_TABLES: dict = {}  # (parameter pointers, grad pointers or None) -> device descriptor table
+
+
+def _film_table(Ws, bs, direct: bool):
+    key = (tuple(w.data_ptr() for w in Ws), tuple(b.data_ptr() for b in bs),
+           tuple(w.grad.data_ptr() for w in Ws) + tuple(b.grad.data_ptr() for b in bs) if direct else None)
+    tab = _FILM_TABLES.get(key)
+    if tab is None:
+        if len(_FILM_TABLES) > 16:
+            _FILM_TABLES.clear()
+        tab = K.film_table(Ws, bs, [w.grad for w in Ws], [b.grad for b in bs]) if direct else K.film_table(Ws, bs)
+        _FILM_TABLES[key] = tab
+    return tab
+
+
+class FilmAllFn(torch.autograd.Function):
+    """Every ResnetBlock's FiLM projection SiLU -> Linear(time_dim, 2*dim_out) (video_net.py:238-241) in one
+    launch: they all read the same time embedding.  apply(temb, W_0, b_0, W_1, b_1, ...) -> tuple of [B, 2C_i].
+    Backward: one launch for all weight / bias gradients and one for d temb (the sum over layers), instead of
+    ~45 small launches plus autograd's adds."""
+
+    @staticmethod
+    def forward(ctx, temb, *wb):
+        x = temb.contiguous()
+        Ws, bs = list(wb[0::2]), list(wb[1::2])
+        Ns = [w.shape[0] for w in Ws]
+        outs = K.film_fwd(x, _film_table(Ws, bs, False), Ns)
+        ctx.save_for_backward(x, *wb)
+        ctx.Ns = Ns
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        x, wb = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        Ws, bs = list(wb[0::2]), list(wb[1::2])
+        B = x.shape[0]
+        dy = torch.cat([(d if d is not None else x.new_zeros(B, n)).reshape(-1) for d, n in zip(dys, ctx.Ns)])
+        if _direct_all(*Ws, *bs):
+            dx = K.film_bwd(x, _film_table(Ws, bs, True), dy, ctx.Ns, ctx.needs_input_grad[0], accumulate=True)
+            _ready(*Ws, *bs)
+            return (dx,) + (None,) * len(wb)
+        dWs, dbs = [torch.empty_like(w) for w in Ws], [torch.empty_like(b) for b in bs]
+        dx = K.film_bwd(x, K.film_table(Ws, bs, dWs, dbs), dy, ctx.Ns, ctx.needs_input_grad[0], accumulate=False)
+        grads = [None] * len(wb)
+        grads[0::2], grads[1::2] = dWs, dbs
+        return (dx,) + tuple(grads)
+
+
 class MseLossFn(torch.autograd.Function):
     """F.mse_loss(eps, noise) (model.py:208) with the gradient 2*(eps-noise)/N produced on device."""
 

@@ -241,11 +241,11 @@ class ResnetBlock(nn.Module):
         self._meta = ops.BlockMeta(G=groups, eps=self.block1.norm.eps, c1=ops.PackCache(), c2=ops.PackCache(),
                                    cres=ops.PackCache())
 
-    def forward_cl(self, x, B, F, time_emb=None, x1=None):
+    def forward_cl(self, x, B, F, time_emb=None, x1=None, film=None):
         """x1: optional second channels-last source, concatenated after x (U-Net skip).
-        The whole block is one autograd node (ops.ResnetBlockFn)."""
-        film = None
-        if exists(self.mlp):
+        `film`: this block's FiLM vector when the caller has already computed it (the network pass computes
+        all of them in one launch, ops.FilmAllFn).  The whole block is one autograd node (ops.ResnetBlockFn)."""
+        if exists(self.mlp) and film is None:
             assert exists(time_emb), "time emb must be passed in"
             film = ops.SmallLinearFn.apply(time_emb, self.mlp[1].weight, self.mlp[1].bias, True)
         if isinstance(self.res_conv, nn.Identity):
@@ -509,6 +509,14 @@ class UNetModel3D(nn.Module):
             return x
         return mod.forward_cl(x, B, F, **kwargs)
 
+    def _film_blocks(self):
+        """ResnetBlocks with a FiLM projection, in forward order (cached)."""
+        blks = self.__dict__.get("_film_blocks_cache")
+        if blks is None:
+            blks = [m for m in self.modules() if isinstance(m, ResnetBlock) and exists(m.mlp)]
+            self.__dict__["_film_blocks_cache"] = blks
+        return blks
+
     def _time_embedding(self, timesteps, days, years):
         """video_net.py:822-829."""
         emb = self.time_mlp[0](timesteps)
@@ -549,24 +557,29 @@ class UNetModel3D(nn.Module):
         x = self.input_temp_op.forward_cl(x, B, F, pos_bias=pos_bias)
         r = x
         t = self._time_embedding(timesteps, days, years)
+        # every block's FiLM projection of t in ONE launch (they differ only in their weights)
+        fb = self._film_blocks()
+        films = ops.FilmAllFn.apply(t, *[p for blk in fb for p in (blk.mlp[1].weight, blk.mlp[1].bias)]) if fb else ()
+        films = {id(blk): f for blk, f in zip(fb, films)}
+        flm = lambda blk: dict(film=films[id(blk)]) if id(blk) in films else dict(time_emb=t)
 
         h = []
         for block1, block2, spatial_attn, temporal_attn, downsample in self.downs:
-            x = block1.forward_cl(x, B, F, time_emb=t)
-            x = block2.forward_cl(x, B, F, time_emb=t)
+            x = block1.forward_cl(x, B, F, **flm(block1))
+            x = block2.forward_cl(x, B, F, **flm(block2))
             x = self._call(spatial_attn, x, B, F)
             x = temporal_attn.forward_cl(x, B, F, **akw)
             h.append(x)
             x = self._call(downsample, x, B, F)
 
-        x = self.mid_block1.forward_cl(x, B, F, time_emb=t)
+        x = self.mid_block1.forward_cl(x, B, F, **flm(self.mid_block1))
         x = self._call(self.mid_spatial_attn, x, B, F)
         x = self.mid_temporal_attn.forward_cl(x, B, F, **akw)
-        x = self.mid_block2.forward_cl(x, B, F, time_emb=t)
+        x = self.mid_block2.forward_cl(x, B, F, **flm(self.mid_block2))
 
         for block1, block2, spatial_attn, temporal_attn, upsample in self.ups:
-            x = block1.forward_cl(x, B, F, time_emb=t, x1=h.pop())
-            x = block2.forward_cl(x, B, F, time_emb=t)
+            x = block1.forward_cl(x, B, F, x1=h.pop(), **flm(block1))
+            x = block2.forward_cl(x, B, F, **flm(block2))
             x = self._call(spatial_attn, x, B, F)
             x = temporal_attn.forward_cl(x, B, F, **akw)
             x = self._call(upsample, x, B, F)

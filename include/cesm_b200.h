@@ -240,6 +240,24 @@ int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, float* scratc
  * Output conv (video_net.py:763 + model.py:129-130): 1x1x1, 64 -> 1, evaluated on the centre
  * frame only (the reference computes every frame and then selects frame F//2).
  * ---------------------------------------------------------------------------------------------- */
+/* All FiLM projections of a pass in one launch (video_net.py:238-241: SiLU -> Linear(time_dim, 2*dim_out), one
+ * per ResnetBlock, all fed by the same time embedding x [B][K]).  `layers_device`: n_layers descriptors in
+ * DEVICE memory; n0 = running sum of N over the preceding layers, n_total = sum of N.  Outputs and output
+ * gradients are packed layer after layer: layer i owns the contiguous [B][N_i] block at float offset B*n0_i
+ * of y / dy.  cesm_film_fwd: y_i = silu(x) W_i^T + bias_i.  cesm_film_bwd: dW_i, db_i (+= if accumulate) and,
+ * if dx is not NULL, dx = silu'(x) * sum_i dy_i W_i. */
+typedef struct cesm_film_desc {
+    const float* W;      /* [N][K] */
+    const float* bias;   /* [N] */
+    float* dW;           /* [N][K] (backward) */
+    float* db;           /* [N]    (backward) */
+    int32_t N, n0;
+} cesm_film_desc;
+int cesm_film_fwd(const float* x, const cesm_film_desc* layers_device, float* y, int n_layers, int n_total, int B,
+                  int K, void* stream);
+int cesm_film_bwd(const float* x, const cesm_film_desc* layers_device, const float* dy, int n_layers, int n_total,
+                  float* dx, int B, int K, int accumulate, void* stream);
+
 /* On-device data path (dataset_single_member.py:168-196).  cond, tgt: fp32 [T][M][H][W]
  * resident in device memory.  plan: int32 [B][6] = {member, first window frame, target frame, crop row,
  * crop col, time-reverse flag} in device memory.  Writes cond_out fp32 [B][K][h][w] (= the reference's

@@ -467,3 +467,24 @@ def test_device_data_path(cuda, K, crop):
     ref_c, ref_x = host.batch(idx, augment=False)
     dev.batch_into(idx, cond, x0, augment=False)
     assert torch.equal(cond.cpu(), ref_c) and torch.equal(x0.cpu(), ref_x)
+
+
+def test_film_projections_batched(cuda):
+    """ops.FilmAllFn (all FiLM linears of a pass in one launch, one fused backward) against torch."""
+    from cesm_emulator_b200 import ops
+    torch.manual_seed(6)
+    B, Kd = 3, 256
+    Ns = [128, 128, 256, 512, 128]
+    t = torch.randn(B, Kd, device=cuda, requires_grad=True)
+    Ws = [(torch.randn(n, Kd, device=cuda) * 0.05).requires_grad_(True) for n in Ns]
+    bs = [torch.randn(n, device=cuda).requires_grad_(True) for n in Ns]
+    outs = ops.FilmAllFn.apply(t, *[p for w, b in zip(Ws, bs) for p in (w, b)])
+    refs = [F.linear(F.silu(t), w, b) for w, b in zip(Ws, bs)]
+    for o, r in zip(outs, refs):
+        assert o.shape == r.shape and err(o, r) < 1e-5
+    gs = [torch.randn_like(r) for r in refs]
+    loss = sum((o * g).sum() for o, g in zip(outs, gs))
+    got = torch.autograd.grad(loss, [t] + Ws + bs)
+    want = torch.autograd.grad(sum((r * g).sum() for r, g in zip(refs, gs)), [t] + Ws + bs)
+    for a, b_ in zip(got, want):
+        assert err(a, b_) < 1e-5
