@@ -457,7 +457,8 @@ class BlockMeta:
         self.__dict__.update(kw)
 
     def __deepcopy__(self, memo):
-        return BlockMeta(**{k: (PackCache() if isinstance(v, PackCache) else v) for k, v in self.__dict__.items()})
+        return BlockMeta(**{k: (PackCache() if isinstance(v, PackCache) else v) for k, v in self.__dict__.items()
+                            if k != "fold_f1"})
 
 
 class ResnetBlockFn(torch.autograd.Function):
@@ -578,9 +579,16 @@ class TemporalAttnBlockFn(torch.autograd.Function):
             # attention output IS v -- the reference computes the same thing the long way (video_net.py:
             # 444-450: softmax of a 1-element row).  Only the v third of to_qkv is projected; q, k, RoPE, the
             # position bias and the attention kernel drop out.
-            wv = _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train)[2 * hidden:]
-            v = K.igemm(xn, wv)
-            return K.igemm(v, _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), residual=x)
+            # ... and with nothing non-linear between the v projection and to_out, the two linears collapse
+            # into ONE C x C matrix W_out W_v, folded once per weight version: y = x + LN(x) (W_out W_v)^T.
+            key = (_key(wqkv), _key(wout))
+            ent = meta.__dict__.get("fold_f1")
+            if ent is None or ent[0] != key:
+                wv = wqkv.detach().reshape(3 * hidden, C)[2 * hidden:].float()
+                wo = wout.detach().reshape(C, hidden).float()
+                ent = (key, (wo @ wv).to(BF16).contiguous())   # [C out, C in]: the implicit-GEMM operand layout
+                meta.__dict__["fold_f1"] = ent
+            return K.igemm(xn, ent[1], residual=x)
         qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
         o, lse = K.tattn_fwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
         y = K.igemm(o.view(NI, H_, W_, hidden), _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), residual=x)
