@@ -58,8 +58,11 @@ class GradBuckets:
         per_bucket = -(-total // max(1, n_buckets))
         self._bucket_of = {}
         self._pending_init: List[int] = []
+        self.offsets = {}                     # id(param) -> start of its slice in the flat buffers
+        self.registration_order = [p for p in module.parameters() if p.requires_grad]  # what an optimizer sees
         for p in self.params:
             n = p.numel()
+            self.offsets[id(p)] = off
             p.grad = self.flat[off:off + n].view_as(p)
             b = len(self.bounds) - 1
             self._bucket_of[p.data_ptr()] = b
@@ -184,6 +187,7 @@ class FusedAdamW:
 
     def __init__(self, buckets: "GradBuckets", lr, betas, weight_decay, eps, max_grad_norm):
         from . import _lib
+        self._buckets = buckets
         self.g = buckets.flat
         self.p = buckets.flatten_params_()
         self.m = torch.zeros_like(self.p)
@@ -203,12 +207,41 @@ class FusedAdamW:
                      hp["betas"][1], hp["eps"], hp["weight_decay"], self.max_grad_norm)
         ops.invalidate_weight_cache()  # the bf16 operand copies are stale now
 
+    def _slices(self):
+        """(flat offset, numel, shape) of every parameter in REGISTRATION order, i.e. the parameter indexing of
+        a torch optimizer built over `module.parameters()` as the reference does (train.py:1078)."""
+        return [(self._buckets.offsets[id(p)], p.numel(), p.shape) for p in self._buckets.registration_order]
+
     def state_dict(self) -> dict:
-        return {"step": self.state[:1].clone(), "exp_avg": self.m.clone(), "exp_avg_sq": self.v.clone(),
-                "param_groups": [dict(g) for g in self.param_groups]}
+        """torch.optim.AdamW's state-dict format, so that checkpoints interchange with the reference's
+        `optimizer.load_state_dict` (train.py:934-939) and with any torch AdamW over the same module."""
+        step = self.state[0].detach().clone()
+        state = {i: {"step": step.clone(), "exp_avg": self.m[o:o + n].view(shape).clone(),
+                     "exp_avg_sq": self.v[o:o + n].view(shape).clone()}
+                 for i, (o, n, shape) in enumerate(self._slices())}
+        g = self.param_groups[0]
+        group = dict(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=g["weight_decay"], amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     params=list(range(len(state))))
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: dict) -> None:
-        self.state[:1].copy_(sd["step"])
+        if "state" in sd:  # torch format (ours, the reference's, or any torch AdamW over module.parameters())
+            slices = self._slices()
+            steps = []
+            for i, (o, n, shape) in enumerate(slices):
+                st = sd["state"].get(i)
+                if st is None:
+                    continue
+                self.m[o:o + n].view(shape).copy_(st["exp_avg"])
+                self.v[o:o + n].view(shape).copy_(st["exp_avg_sq"])
+                steps.append(float(st["step"]))
+            if steps:
+                self.state[0] = max(steps)
+            for g, src in zip(self.param_groups, sd.get("param_groups", [])):
+                g.update({k: src[k] for k in ("lr", "betas", "eps", "weight_decay") if k in src})
+            return
+        self.state[:1].copy_(sd["step"])  # flat format of earlier checkpoints of this repo
         self.m.copy_(sd["exp_avg"])
         self.v.copy_(sd["exp_avg_sq"])
         for g, src in zip(self.param_groups, sd.get("param_groups", [])):

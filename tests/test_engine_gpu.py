@@ -154,3 +154,50 @@ def test_loss_curve_tracks_fp32_oracle(cuda):
     assert sum(rel) / len(rel) < 1e-2, sum(rel) / len(rel)
     m_c, m_g = sum(cpu[-20:]) / 20, sum(gpu[-20:]) / 20
     assert abs(m_g - m_c) < 1e-2 * m_c, (m_g, m_c)
+
+
+def test_optimizer_state_interchanges_with_torch_adamw(cuda):
+    """FusedAdamW.state_dict() is torch.optim.AdamW's format over module.parameters() (what the reference's
+    train.py saves and loads): it loads into a torch AdamW, a torch AdamW's state loads into the engine, and
+    both continue with the same update."""
+    from cesm_emulator_b200 import ops
+    from cesm_emulator_b200.engine import TrainEngine
+    from cesm_emulator_b200.model import Diffusion, UNet
+    B, K, H, W = 1, 3, 32, 32
+    tiny = dict(BASELINE_KW, ch_mults=(1, 2))
+    torch.manual_seed(0)
+    d = Diffusion(UNet(**tiny)).to(cuda)
+    d.train()
+    hp = dict(lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    eng = TrainEngine(d, (B, 1, H, W), (B, 1, K, H, W), use_graph=False, max_grad_norm=None, **hp)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        eng.step(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, K, H, W, generator=g))
+    sd = eng.opt.state_dict()
+    params = [p for p in d.parameters() if p.requires_grad]
+    assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == len(params)
+    assert all(sd["state"][i]["exp_avg"].shape == p.shape for i, p in enumerate(params))
+    ref = torch.optim.AdamW(params, **hp)
+    ref.load_state_dict(sd)                                   # engine -> torch
+    assert float(ref.state[params[0]]["step"]) == 3.0
+    # same gradient through both optimizers, starting from the same weights and state
+    grads = [torch.randn_like(p) * 1e-2 for p in params]
+    before = [p.detach().clone() for p in params]
+    for p, gr in zip(params, grads):
+        p.grad.copy_(gr)                                      # .grad are views of the engine's flat buffer
+    eng.opt.step()
+    got = [p.detach().clone() for p in params]
+    with torch.no_grad():
+        for p, b0 in zip(params, before):
+            p.copy_(b0)
+    ref.step()
+    for a, b_ in zip(got, params):
+        assert (a - b_).abs().max().item() < 2e-6
+    # torch -> engine: round trip restores the moments exactly
+    eng.opt.m.zero_(); eng.opt.v.zero_()
+    eng.opt.load_state_dict(sd)
+    sd2 = eng.opt.state_dict()
+    for i in sd["state"]:
+        assert torch.equal(sd2["state"][i]["exp_avg"], sd["state"][i]["exp_avg"])
+        assert torch.equal(sd2["state"][i]["exp_avg_sq"], sd["state"][i]["exp_avg_sq"])
+    ops.set_grad_sink(None)
