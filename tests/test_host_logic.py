@@ -96,3 +96,32 @@ def test_grad_buckets_allreduce_world2_gloo():
     ref = torch.cat([p.grad.reshape(-1) for _, p in _ready_order(net.named_parameters())])
     assert torch.allclose(g0, ref, rtol=1e-5, atol=1e-7)
     assert abs(n0 - ref.norm().item()) < 1e-5 * max(1.0, ref.norm().item())
+
+
+def test_window_plan_and_frame_map_match_the_host_gather():
+    """The on-device data path is driven by `SyntheticEnsemble.plan` and a frame map evaluated inside
+    cesm_gather_windows; restated here in numpy (same formula as the kernel: left and right halves around
+    the centre flipped) it must reproduce `window()` for every K, with and without crops."""
+    from cesm_emulator_b200.synthetic import SyntheticEnsemble
+
+    def gather(ds, plan):
+        m, t0, ta, i0, j0, rev = plan
+        h, w = ds.out_hw()
+        K, mid = ds.K, ds.K // 2
+        src = [(mid - 1 - k if k < mid else (mid if k == mid else K + mid - k)) if rev else k for k in range(K)]
+        cond = np.stack([ds.cond[t0 + s, m, 0, i0:i0 + h, j0:j0 + w] for s in src])[None]
+        return cond, ds.tgt[ta, m, :, i0:i0 + h, j0:j0 + w]
+
+    for K, crop in ((2, None), (3, (8, 8)), (4, (6, 10)), (5, None), (7, (8, 12))):
+        kw = dict(members=3, times=12, lat=12, lon=16, seed=3, K=K, crop_hw=crop, time_reverse_p=0.6)
+        a, b = SyntheticEnsemble(**kw), SyntheticEnsemble(**kw)   # two identical random streams
+        flips = 0
+        for idx in list(range(len(a)))[::2]:
+            plan = a.plan(idx)
+            cond, x0 = b.window(idx)
+            gc, gx = gather(a, plan)
+            assert np.array_equal(cond.numpy(), gc) and np.array_equal(x0.numpy(), gx)
+            assert plan[0] == idx % a.M and plan[1] == idx // a.M and plan[2] == min(plan[1] + K // 2, a.T - 1)
+            flips += plan[5]
+        assert flips > 0
+        assert a.plan(5, augment=False)[3:] == (((a.H - a.out_hw()[0]) // 2, (a.W - a.out_hw()[1]) // 2, 0))
