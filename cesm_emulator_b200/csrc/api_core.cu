@@ -393,6 +393,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
     // 64->768 projection at 192x288: 131.5 us n-major, 106.6 us m-major (the output rows are completed in one
     // go instead of in three passes over the 510 MB tensor; tools/bench_igemm.py)
     p.m_major = ((knob_mmajor == 1 && p.b_resident) || knob_mmajor == 2) && p.n_tiles > 1 ? 1 : 0;
+    p.wt_stable = a->wt_stable ? 1 : 0;
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
     note_launch();

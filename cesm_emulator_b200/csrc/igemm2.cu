@@ -203,7 +203,8 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         }
     } else if (warp == 1 && lane == 0) {
         // ===== weight producer =====
-        pdl_wait();
+        // weights re-packed at the top of the step are fetched while the preceding kernel still drains
+        if (!p.wt_stable) pdl_wait();
         if (p.b_resident) {
             const uint32_t total_bytes = (uint32_t)p.n_tiles * p.num_kb * b_blk_bytes;
             mbar_arrive_expect_tx(b_all_bar, total_bytes);

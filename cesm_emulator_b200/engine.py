@@ -288,10 +288,12 @@ class TrainEngine:
             self._step_body_inner()
         finally:
             self.arena.end()
+            K.STABLE_WEIGHT_PTRS = set()
 
     def _step_body_inner(self):
         ops.set_grad_sink(self.buckets)
         ops.prepack_all()  # one kernel refreshes every bf16 operand copy of the (just updated) weights
+        K.STABLE_WEIGHT_PTRS = ops.packed_ptrs()  # nothing rewrites them until the next step
         self.buckets.begin_step()
         loss = self.diffusion.loss(self.x0, self.cond)
         (loss / self.world if self.world > 1 else loss).backward()

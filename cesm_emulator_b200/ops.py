@@ -138,6 +138,11 @@ def prepack_all() -> int:
     return len(live)
 
 
+def packed_ptrs() -> set:
+    """Addresses of every registered packed weight copy (full tensors; slices are not included)."""
+    return {e.out.data_ptr() for e in _ENTRIES if e.wref() is not None}
+
+
 # ------------------------------------------------------------------------------------------------
 # gradient delivery
 # ------------------------------------------------------------------------------------------------

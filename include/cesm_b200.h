@@ -86,6 +86,10 @@ typedef struct cesm_igemm_args {
     float* gn_sums;
     int32_t gn_groups;
     int32_t gn_frames;
+    /* != 0: `wt` was written well before the kernel that precedes this call in the stream (the training
+     * engine re-packs every weight once at the top of a step), so the weight tiles may be fetched while
+     * that kernel is still draining (programmatic dependent launch).  0 is always safe. */
+    int32_t wt_stable;
 } cesm_igemm_args;
 
 int cesm_igemm(const cesm_igemm_args* args, void* stream);

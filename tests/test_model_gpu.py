@@ -29,7 +29,7 @@ GRAD_BARS = {
     # shape: (median bar, min fraction of tensors <= 1e-2, worst-tensor bar).  The worst tensor moves by
     # up to ~1e-2 from run to run (fp32 atomics reorder sums -> individual bf16 roundings flip; two runs of
     # the SAME path differ by 4e-3 median / 2e-2 worst, tools/engine_grad_check.py), hence the headroom.
-    (2, 3, 128, 128): (1e-2, 0.8, 4e-2),   # measured: median 5e-3, 85-89 % <= 1e-2, worst 1.5-2.1e-2
+    (2, 3, 128, 128): (1e-2, 0.75, 4e-2),  # measured over 12 runs: median 5.1-5.6e-3, 81-92 % <= 1e-2, worst 1.6-3.0e-2
     (1, 3, 48, 72): (1e-2, 0.5, 6e-2),     # measured: median 7e-3, worst 2.9-4.1e-2
     (2, 3, 32, 32): (1.2e-2, 0.4, 8e-2),   # measured: median 9e-3, worst 3-6e-2
     (2, 1, 16, 16): (2e-2, 0.3, 9e-2),     # measured: median 1.5e-2, worst 4.4e-2
