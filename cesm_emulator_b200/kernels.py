@@ -77,7 +77,10 @@ class ZeroArena:
         start = self.off
         self.off = start + (n + 63) // 64 * 64  # 256-byte granules
         if self.off > self.buf.numel():
-            raise _lib.CesmError(f"zero arena exhausted ({self.off} > {self.buf.numel()} floats)")
+            # larger batch than the arena was sized for: fall back to an individually zeroed tensor (the
+            # library's own memsets are off while the arena is active, so it MUST arrive zeroed)
+            self.off = start
+            return torch.zeros(tuple(shape), dtype=torch.float32, device=self.buf.device)
         self.high = max(self.high, self.off)
         return self.buf[start:start + n].view(*shape)
 
