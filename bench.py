@@ -428,6 +428,10 @@ def run_sample(args, H, W, arch_kw):
 
 def main():
     args = parse_args()
+    if args.impl == "b200" and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        from cesm_emulator_b200 import build as _build
+        if not _build.LIB_PATH.exists():  # fresh checkout: build artefacts are git-ignored
+            _build.build()
     H, W = (int(v) for v in args.hw.lower().split("x"))
     arch_kw = BASELINE_KW if args.arch == "baseline" else MORE_BLOCKS_KW
     if args.impl == "reference":

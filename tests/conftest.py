@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # A fresh checkout has no libcesm_b200.so (build artefacts are git-ignored): compile it once for the test
+    # session.  The package itself never does this -- a missing library is a hard error there.
+    from cesm_emulator_b200 import build as _build
+    if not _build.LIB_PATH.exists():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc: the tests that need the library will say so
+            sys.stderr.write(f"[conftest] could not build {_build.LIB_PATH.name}: {exc}\n")
 
 
 @pytest.fixture(scope="session")
