@@ -428,10 +428,15 @@ def run_sample(args, H, W, arch_kw):
 
 def main():
     args = parse_args()
-    if args.impl == "b200" and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+    if args.impl == "b200":
         from cesm_emulator_b200 import build as _build
         if not _build.LIB_PATH.exists():  # fresh checkout: build artefacts are git-ignored
-            _build.build()
+            if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+                _build.build()
+            else:  # the other ranks of a torchrun launch wait for rank 0's build
+                t0 = time.time()
+                while not _build.LIB_PATH.exists() and time.time() - t0 < 600:
+                    time.sleep(1.0)
     H, W = (int(v) for v in args.hw.lower().split("x"))
     arch_kw = BASELINE_KW if args.arch == "baseline" else MORE_BLOCKS_KW
     if args.impl == "reference":
