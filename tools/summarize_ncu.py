@@ -23,6 +23,8 @@ def launches(path):
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot = 0.0
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue  # logs that also carry dram__bytes rows (see `traffic`)
         v = float(row["Metric Value"].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(row["Metric Unit"], 1.0)
         name = re.sub(r"\(.*", "", row["Kernel Name"])[:70]
