@@ -59,9 +59,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-// Encode (or fetch from the cache) a bf16 tiled tensor map with SWIZZLE_128B.
+// Encode (or fetch from the cache) a fp16 tiled tensor map with SWIZZLE_128B.
 // dims/strides/box follow cuTensorMapEncodeTiled (dim 0 innermost, strides in bytes for dims >= 1).
-int get_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+int get_tensor_map_h16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

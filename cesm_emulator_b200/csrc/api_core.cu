@@ -73,7 +73,7 @@ struct MapKeyHash {
 static std::mutex g_map_mutex;  // autograd runs backward on its own threads
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
-int get_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+int get_tensor_map_h16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box) {
     CESM_REQUIRE(rank >= 2 && rank <= 4, "tensor map rank %d unsupported", rank);
     CESM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "tensor base %p not 16-byte aligned", base);
@@ -109,7 +109,7 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint
         CESM_REQUIRE(bx[i] >= 1 && bx[i] <= 256, "tensor map box[%d]=%u out of range", i, bx[i]);
     }
     alignas(64) CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(CESM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -331,7 +331,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
             if (!src[s]) continue;
             const uint64_t dims[4] = {(uint64_t)cs[s], (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
             const uint64_t str[3] = {(uint64_t)cs[s] * 2, (uint64_t)a->w * cs[s] * 2, (uint64_t)a->h * a->w * cs[s] * 2};
-            int rc = get_tensor_map_bf16(&maps.a[s], src[s], 4, dims, str, abox);
+            int rc = get_tensor_map_h16(&maps.a[s], src[s], 4, dims, str, abox);
             if (rc) return rc;
             n_amaps = s + 1;
         }
@@ -347,7 +347,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
                 const char* base = static_cast<const char*>(a->a0) + (size_t)(ph * a->w + pw2) * c * 2;
                 const uint64_t dims[4] = {(uint64_t)c, (uint64_t)a->w / 2, (uint64_t)a->h / 2, (uint64_t)a->n};
                 const uint64_t str[3] = {(uint64_t)c * 4, (uint64_t)a->w * c * 4, (uint64_t)a->h * a->w * c * 2};
-                int rc = get_tensor_map_bf16(&maps.a[ph * 2 + pw2], base, 4, dims, str, abox);
+                int rc = get_tensor_map_h16(&maps.a[ph * 2 + pw2], base, 4, dims, str, abox);
                 if (rc) return rc;
             }
         n_amaps = 4;
@@ -364,7 +364,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->cout};
         const uint64_t str[1] = {(uint64_t)ktot * 2};
         const uint32_t bbox[2] = {64u, (uint32_t)block_n};
-        int rc = get_tensor_map_bf16(&maps.b, a->wt, 2, dims, str, bbox);
+        int rc = get_tensor_map_h16(&maps.b, a->wt, 2, dims, str, bbox);
         if (rc) return rc;
     }
     {
@@ -386,7 +386,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
             obox[2] = 1u;
             obox[3] = 1u;
         }
-        int rc = get_tensor_map_bf16(&maps.out, base, 4, dims, str, obox);
+        int rc = get_tensor_map_h16(&maps.out, base, 4, dims, str, obox);
         if (rc) return rc;
     }
     static const int knob_mmajor = [] { const char* e = getenv("CESM_IGEMM_MMAJOR"); return e ? atoi(e) : 1; }();
@@ -415,7 +415,7 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
     CESM_REQUIRE(a->ldo % 8 == 0 && (a->residual == nullptr || a->ldr % 8 == 0), "row pitches must be multiples of 8");
     if (!a->out_fp32 && !(knob_v1() && a->gn_sums == nullptr))
         return igemm2_run(a, as_stream(stream));  // persistent kernel (igemm2.cu)
-    CESM_REQUIRE(a->gn_sums == nullptr, "fused GroupNorm statistics need bf16 output");
+    CESM_REQUIRE(a->gn_sums == nullptr, "fused GroupNorm statistics need fp16 output");
 
     IgemmParams p{};
     p.c0 = a->c0;
@@ -450,7 +450,7 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
             if (!src[s]) continue;
             const uint64_t dims[4] = {(uint64_t)cs[s], (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
             const uint64_t str[3] = {(uint64_t)cs[s] * 2, (uint64_t)a->w * cs[s] * 2, (uint64_t)a->h * a->w * cs[s] * 2};
-            int rc = get_tensor_map_bf16(&amaps[s], src[s], 4, dims, str, box);
+            int rc = get_tensor_map_h16(&amaps[s], src[s], 4, dims, str, box);
             if (rc) return rc;
             n_amaps = s + 1;
         }
@@ -467,7 +467,7 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
                 const char* base = static_cast<const char*>(a->a0) + (size_t)(ph * a->w + pw) * c * 2;
                 const uint64_t dims[4] = {(uint64_t)c, (uint64_t)a->w / 2, (uint64_t)a->h / 2, (uint64_t)a->n};
                 const uint64_t str[3] = {(uint64_t)c * 4, (uint64_t)a->w * c * 4, (uint64_t)a->h * a->w * c * 2};
-                int rc = get_tensor_map_bf16(&amaps[ph * 2 + pw], base, 4, dims, str, box);
+                int rc = get_tensor_map_h16(&amaps[ph * 2 + pw], base, 4, dims, str, box);
                 if (rc) return rc;
             }
         n_amaps = 4;
@@ -486,7 +486,7 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->cout};
         const uint64_t str[1] = {(uint64_t)ktot * 2};
         const uint32_t bbox[2] = {64u, (uint32_t)block_n};
-        int rc = get_tensor_map_bf16(&bmap, a->wt, 2, dims, str, bbox);
+        int rc = get_tensor_map_h16(&bmap, a->wt, 2, dims, str, bbox);
         if (rc) return rc;
     }
     note_launch();
@@ -544,7 +544,7 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
             if (!src[s]) continue;
             const uint64_t dims[4] = {(uint64_t)cs[s], (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
             const uint64_t str[3] = {(uint64_t)cs[s] * 2, (uint64_t)a->w * cs[s] * 2, (uint64_t)a->h * a->w * cs[s] * 2};
-            int rc = get_tensor_map_bf16(&xmaps[s], src[s], 4, dims, str, box);
+            int rc = get_tensor_map_h16(&xmaps[s], src[s], 4, dims, str, box);
             if (rc) return rc;
             n_xmaps = s + 1;
         }
@@ -560,7 +560,7 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
                 const char* base = static_cast<const char*>(a->x0) + (size_t)(ph * a->w + pw) * c * 2;
                 const uint64_t dims[4] = {(uint64_t)c, (uint64_t)a->w / 2, (uint64_t)a->h / 2, (uint64_t)a->n};
                 const uint64_t str[3] = {(uint64_t)c * 4, (uint64_t)a->w * c * 4, (uint64_t)a->h * a->w * c * 2};
-                int rc = get_tensor_map_bf16(&xmaps[ph * 2 + pw], base, 4, dims, str, box);
+                int rc = get_tensor_map_h16(&xmaps[ph * 2 + pw], base, 4, dims, str, box);
                 if (rc) return rc;
             }
         n_xmaps = 4;
@@ -578,7 +578,7 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
         const uint64_t dims[4] = {(uint64_t)co, (uint64_t)a->ow, (uint64_t)a->oh, (uint64_t)a->n};
         const uint64_t str[3] = {(uint64_t)a->y_sw * co * 2, (uint64_t)a->y_sh * a->y_w * co * 2,
                                  (uint64_t)a->y_h * a->y_w * co * 2};
-        int rc = get_tensor_map_bf16(&ymap, base, 4, dims, str, box);
+        int rc = get_tensor_map_h16(&ymap, base, 4, dims, str, box);
         if (rc) return rc;
     }
     const int ctot = a->c0 + a->c1;

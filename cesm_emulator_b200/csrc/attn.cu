@@ -1,4 +1,4 @@
-// Attention cores (bf16 activations, fp32 math).  Head dim is 32 for both attention types
+// Attention cores (fp16 activations, fp32 math).  Head dim is 32 for both attention types
 // (video_net.py:314 dim_head=32; model.py:55 attn_dim_head=32), which these kernels require.
 //
 //  Temporal attention (video_net.py:413-453 + rotary_embedding.py:29-48): per (batch, pixel, head)
@@ -15,25 +15,25 @@ namespace cesm {
 
 static constexpr int D = 32;  // head dim
 
-__device__ __forceinline__ void load32(const __nv_bfloat16* p, float (&f)[D]) {
+__device__ __forceinline__ void load32(const h16* p, float (&f)[D]) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint4 u = __ldg(q + j);
-        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
         f[8 * j + 0] = a.x; f[8 * j + 1] = a.y; f[8 * j + 2] = b.x; f[8 * j + 3] = b.y;
         f[8 * j + 4] = c.x; f[8 * j + 5] = c.y; f[8 * j + 6] = d.x; f[8 * j + 7] = d.y;
     }
 }
-__device__ __forceinline__ void store32(__nv_bfloat16* p, const float (&f)[D]) {
+__device__ __forceinline__ void store32(h16* p, const float (&f)[D]) {
     uint4* q = reinterpret_cast<uint4*>(p);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint4 u;
-        u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-        u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-        u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-        u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+        u.x = pack_h2(f[8 * j + 0], f[8 * j + 1]);
+        u.y = pack_h2(f[8 * j + 2], f[8 * j + 3]);
+        u.z = pack_h2(f[8 * j + 4], f[8 * j + 5]);
+        u.w = pack_h2(f[8 * j + 6], f[8 * j + 7]);
         q[j] = u;
     }
 }
@@ -72,8 +72,8 @@ __device__ __forceinline__ float dot32(const float (&a)[D], const float (&b)[D])
 //   bias: [H][F][F] fp32 ; cs/sn: [F][D/2] fp32 rotary cos/sin ; out: [B*F*HW][H*D] ; lse: [rows][H]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-tattn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
-                 const float* __restrict__ cs, const float* __restrict__ sn, __nv_bfloat16* __restrict__ out,
+tattn_fwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bias,
+                 const float* __restrict__ cs, const float* __restrict__ sn, h16* __restrict__ out,
                  float* __restrict__ lse, int B, int F, int HW, int H, float scale) {
     pdl_trigger();
     pdl_wait();
@@ -116,10 +116,10 @@ tattn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
 
 // One thread per (b, hw, h, r): first acts as query r (dq, dbias), then as key/value r (dk, dv).
 __global__ void __launch_bounds__(128)
-tattn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
-                 const float* __restrict__ cs, const float* __restrict__ sn, const __nv_bfloat16* __restrict__ out,
-                 const float* __restrict__ lse, const __nv_bfloat16* __restrict__ dout,
-                 __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int B, int F, int HW, int H,
+tattn_bwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bias,
+                 const float* __restrict__ cs, const float* __restrict__ sn, const h16* __restrict__ out,
+                 const float* __restrict__ lse, const h16* __restrict__ dout,
+                 h16* __restrict__ dqkv, float* __restrict__ dbias, int B, int F, int HW, int H,
                  float scale) {
     pdl_trigger();
     pdl_wait();
@@ -210,15 +210,15 @@ tattn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict_
 // are reduced with two quad shuffles.  Nothing but qkv (and dout) is read: the backward recomputes
 // the softmax instead of loading out / lse.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+__device__ __forceinline__ void ld8(const h16* p, float (&f)[8]) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+__device__ __forceinline__ void st8(h16* p, const float (&f)[8]) {
     uint4 u;
-    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    u.x = pack_h2(f[0], f[1]); u.y = pack_h2(f[2], f[3]);
+    u.z = pack_h2(f[4], f[5]); u.w = pack_h2(f[6], f[7]);
     *reinterpret_cast<uint4*>(p) = u;
 }
 __device__ __forceinline__ float qsum(float v) {
@@ -263,15 +263,15 @@ __device__ __forceinline__ void ts_wait() { asm volatile("cp.async.wait_group %0
 __device__ __forceinline__ void lds8(uint32_t addr, float (&f)[8]) {
     uint4 u;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 extern __shared__ __align__(16) uint8_t ts_smem[];
 
 template <int F>
 __global__ void __launch_bounds__(256, 2)
-tattn_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
-                       const float* __restrict__ cs, const float* __restrict__ sn, __nv_bfloat16* __restrict__ out,
+tattn_small_fwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bias,
+                       const float* __restrict__ cs, const float* __restrict__ sn, h16* __restrict__ out,
                        float* __restrict__ lse, long long npix /* B*HW */, int HW, int H, float scale) {
     pdl_trigger();
     pdl_wait();
@@ -303,7 +303,7 @@ tattn_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
             const uint32_t st = ring + stage * kStage;
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-                const __nv_bfloat16* row = qkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
+                const h16* row = qkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
                 ts_cp16(st + (3 * f + 0) * kVec, row);
                 ts_cp16(st + (3 * f + 1) * kVec, row + HD);
                 ts_cp16(st + (3 * f + 2) * kVec, row + 2 * HD);
@@ -372,9 +372,9 @@ tattn_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
 // the extra resident warps (12 instead of 8 per SM) that hide the load latency of this pure stream.
 template <int F>
 __global__ void __launch_bounds__(128, (F <= 3 ? 3 : 2))
-tattn_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
+tattn_small_bwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bias,
                        const float* __restrict__ cs, const float* __restrict__ sn,
-                       const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
+                       const h16* __restrict__ dout, h16* __restrict__ dqkv,
                        float* __restrict__ dbias, long long npix, int HW, int H, float scale) {
     pdl_trigger();
     pdl_wait();
@@ -411,7 +411,7 @@ tattn_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
 #pragma unroll
             for (int f = 0; f < F; ++f) {
                 const long long r = (b * F + f) * HW + hw;
-                const __nv_bfloat16* row = qkv + r * ld + h * D + c * 8;
+                const h16* row = qkv + r * ld + h * D + c * 8;
                 ts_cp16(st + (4 * f + 0) * kVec, row);
                 ts_cp16(st + (4 * f + 1) * kVec, row + HD);
                 ts_cp16(st + (4 * f + 2) * kVec, row + 2 * HD);
@@ -490,7 +490,7 @@ tattn_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __res
                 }
             rope8_t(dq, cf[f], sf[f], scale);
             rope8_t(dk, cf[f], sf[f], 1.f);
-            __nv_bfloat16* drow = dqkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
+            h16* drow = dqkv + ((b * F + f) * HW + hw) * ld + h * D + c * 8;
             if (valid) {
                 st8(drow, dq);
                 st8(drow + HD, dk);
@@ -531,8 +531,8 @@ extern "C" int cesm_tattn_fwd(const void* qkv, const float* bias, const float* c
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                \
             cfg = true;                                                                                             \
         }                                                                                                           \
-        launch_pdl(tattn_small_fwd_kernel<FF>, blocks, 256, kSm, st, (const __nv_bfloat16*)qkv, bias, cs, sn,               \
-                                                             (__nv_bfloat16*)out, lse, npix, HW, H, scale);         \
+        launch_pdl(tattn_small_fwd_kernel<FF>, blocks, 256, kSm, st, (const h16*)qkv, bias, cs, sn,               \
+                                                             (h16*)out, lse, npix, HW, H, scale);         \
     }
         switch (F) {
             case 1: TATTN_FWD(1) break;
@@ -547,7 +547,7 @@ extern "C" int cesm_tattn_fwd(const void* qkv, const float* bias, const float* c
     CESM_REQUIRE(lse != nullptr, "lse is required for F > 4");
     const long long total = (long long)B * F * HW * H;
     const int blocks = (int)((total + 127) / 128);
-    launch_pdl(tattn_fwd_kernel, blocks, 128, 0, st, (const __nv_bfloat16*)qkv, bias, cs, sn, (__nv_bfloat16*)out, lse, B, F, HW,
+    launch_pdl(tattn_fwd_kernel, blocks, 128, 0, st, (const h16*)qkv, bias, cs, sn, (h16*)out, lse, B, F, HW,
                                              H, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
@@ -576,8 +576,8 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));           \
             cfg = true;                                                                                        \
         }                                                                                                      \
-        launch_pdl(tattn_small_bwd_kernel<FF>, blocks, 128, kSm, st, (const __nv_bfloat16*)qkv, bias, cs, sn,          \
-                                                             (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, \
+        launch_pdl(tattn_small_bwd_kernel<FF>, blocks, 128, kSm, st, (const h16*)qkv, bias, cs, sn,          \
+                                                             (const h16*)dout, (h16*)dqkv, \
                                                              dbias, npix, HW, H, scale);                       \
     }
         switch (F) {
@@ -594,8 +594,8 @@ extern "C" int cesm_tattn_bwd(const void* qkv, const float* bias, const float* c
     const long long total = (long long)B * F * HW * H;
     const int blocks = (int)((total + 127) / 128);
     const size_t sh = (H * F * F <= 2048) ? sizeof(float) * H * F * F : 0;
-    launch_pdl(tattn_bwd_kernel, blocks, 128, sh, st, (const __nv_bfloat16*)qkv, bias, cs, sn, (const __nv_bfloat16*)out, lse,
-                                              (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias, B, F, HW, H,
+    launch_pdl(tattn_bwd_kernel, blocks, 128, sh, st, (const h16*)qkv, bias, cs, sn, (const h16*)out, lse,
+                                              (const h16*)dout, (h16*)dqkv, dbias, B, F, HW, H,
                                               scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;

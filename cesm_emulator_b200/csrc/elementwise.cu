@@ -1,5 +1,5 @@
 // Small and bandwidth-bound kernels around the tensor-core path:
-//   weight re-layout (fp32 parameter -> bf16 GEMM operand, and fp32 GEMM-layout gradient -> parameter)
+//   weight re-layout (fp32 parameter -> fp16 GEMM operand, and fp32 GEMM-layout gradient -> parameter)
 //   7x7 input conv with fused concat / frame broadcast (video_net.py:808-815, model.py:110-121)
 //   1x1x1 output conv fused with centre-frame selection (video_net.py:763, model.py:129-130)
 //   time embedding + small fp32 linears (video_net.py:101-113, 651-656, 238-241)
@@ -14,8 +14,8 @@ struct TapOffsets {
     int32_t off[CESM_MAX_TAPS];
 };
 
-// dst[o][t][i] (bf16) = src[o*so + i*si + off[t]] (fp32)
-__global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int O, int T, int I,
+// dst[o][t][i] (fp16) = src[o*so + i*si + off[t]] (fp32)
+__global__ void pack_weight_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int T, int I,
                                    long long so, long long si, TapOffsets taps) {
     pdl_trigger();
     pdl_wait();
@@ -24,7 +24,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16*
     const int i = idx % I;
     const int t = (idx / I) % T;
     const int o = idx / ((long long)I * T);
-    dst[idx] = __float2bfloat16(src[o * so + i * si + taps.off[t]]);
+    dst[idx] = __float2half_rn(src[o * so + i * si + taps.off[t]]);
 }
 // dst[o*so + i*si + off[t]] (+)= src[o][t][i]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int T, int I,
@@ -42,7 +42,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
 
 // out[c] = sum_rows x[row][c]; block handles a strip of rows, thread owns 8 channels
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long M, int C) {
+colsum_kernel(const h16* __restrict__ x, float* __restrict__ out, long long M, int C) {
     pdl_trigger();
     pdl_wait();
     const int vec = C >> 3;
@@ -54,7 +54,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
     for (long long r = (long long)blockIdx.x * rows_per_iter + threadIdx.x / vec; r < M;
          r += (long long)gridDim.x * rows_per_iter) {
         uint4 u = *reinterpret_cast<const uint4*>(x + r * C + slot * 8);
-        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
         acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
     }
     __shared__ float red[256][9];
@@ -69,10 +69,10 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
 }
 
 // ------------------------------------------------------------------------------------------------
-// Input conv on the tensor cores: im2col of the two fp32 input planes into bf16 patch rows
-//   [hi(x) 2*KS*KS | lo(x) 2*KS*KS | 1 | 1 | 0 ...]  (KPAD columns),  hi = bf16(x), lo = bf16(x - hi),
+// Input conv on the tensor cores: im2col of the two fp32 input planes into fp16 patch rows
+//   [hi(x) 2*KS*KS | lo(x) 2*KS*KS | 1 | 1 | 0 ...]  (KPAD columns),  hi = fp16(x), lo = fp16(x - hi),
 // so that the tcgen05 implicit GEMM (1 tap, K = KPAD) against [w | w | bias_hi | bias_lo | 0] reproduces the
-// fp32-input convolution to ~2^-17 in the inputs (the weights are bf16 like every other layer's) and its
+// fp32-input convolution to ~2^-17 in the inputs (the weights are fp16 like every other layer's) and its
 // weight-gradient kernel yields dW (sum of the hi and lo column blocks) and db (the ones column) from
 // the same patch matrix.  A block stages a 16x16 pixel tile's halo once; a warp then writes one pixel's
 // 2*KPAD bytes per trip, each lane a fixed 8-column chunk whose shared-memory offsets it computed once.
@@ -80,12 +80,12 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
 template <int KS, int KPAD>
 __global__ void __launch_bounds__(256)
 input_patches_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
-                     __nv_bfloat16* __restrict__ out, int F, int H, int W) {
+                     h16* __restrict__ out, int F, int H, int W) {
     pdl_trigger();
     pdl_wait();
     constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS;
     static_assert(KPAD % 8 == 0 && KPAD >= 2 * NT + 2 && KPAD / 8 == 32, "one 8-column chunk per lane");
-    __shared__ float sv[2][2][PW][PW];  // [hi | lo][plane][row][col], values already rounded to bf16
+    __shared__ float sv[2][2][PW][PW];  // [hi | lo][plane][row][col], values already rounded to fp16
     const int img = blockIdx.z, b = img / F, f = img % F;
     const int h0 = blockIdx.y * T, w0 = blockIdx.x * T;
     const float* p0 = in0 + ((size_t)b * f0 + (f0 == 1 ? 0 : f)) * H * W;
@@ -95,9 +95,9 @@ input_patches_kernel(const float* __restrict__ in0, const float* __restrict__ in
         const int hh = h0 + rr - PAD, ww = w0 + cc - PAD;
         float v = 0.f;
         if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = (ci ? p1 : p0)[(size_t)hh * W + ww];
-        const float hi = __bfloat162float(__float2bfloat16(v));
+        const float hi = __half2float(__float2half_rn(v));
         sv[0][ci][rr][cc] = hi;
-        sv[1][ci][rr][cc] = __bfloat162float(__float2bfloat16(v - hi));
+        sv[1][ci][rr][cc] = __half2float(__float2half_rn(v - hi));
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int off[8];     // >= 0: offset into sv for pixel (0,0); -1: constant 1; -2: constant 0
@@ -122,14 +122,14 @@ input_patches_kernel(const float* __restrict__ in0, const float* __restrict__ in
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? s0[off[j] + base] : (off[j] == -1 ? 1.f : 0.f);
         uint4 u;
-        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        u.x = pack_h2(v[0], v[1]); u.y = pack_h2(v[2], v[3]);
+        u.z = pack_h2(v[4], v[5]); u.w = pack_h2(v[6], v[7]);
         *reinterpret_cast<uint4*>(out + (((size_t)img * H + h) * W + w) * KPAD + lane * 8) = u;
     }
 }
-// bf16 GEMM operand [COUT][KPAD] = [w | w | bf16(bias) | bf16(bias - bf16(bias)) | 0]
+// fp16 GEMM operand [COUT][KPAD] = [w | w | fp16(bias) | fp16(bias - fp16(bias)) | 0]
 __global__ void input_weight_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                         __nv_bfloat16* __restrict__ out, int cout, int nt, int kpad) {
+                                         h16* __restrict__ out, int cout, int nt, int kpad) {
     pdl_trigger();
     pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,19 +138,19 @@ __global__ void input_weight_pack_kernel(const float* __restrict__ w, const floa
     float v = 0.f;
     if (k < 2 * nt) v = w[o * nt + (k % nt)];
     else if (k == 2 * nt) v = bias[o];
-    else if (k == 2 * nt + 1) v = bias[o] - __bfloat162float(__float2bfloat16(bias[o]));
-    out[idx] = __float2bfloat16(v);
+    else if (k == 2 * nt + 1) v = bias[o] - __half2float(__float2half_rn(bias[o]));
+    out[idx] = __float2half_rn(v);
 }
 
 // ------------------------------------------------------------------------------------------------
-// 7x7 input conv, 2 input planes (noisy target, condition) -> COUT channels, bf16 NHWC output.
+// 7x7 input conv, 2 input planes (noisy target, condition) -> COUT channels, fp16 NHWC output.
 // Plane p of image (b, f) lives at in_p + (b*fp + (fp == 1 ? 0 : f)) * H*W  (frame broadcast).
 // ------------------------------------------------------------------------------------------------
 template <int KS, int COUT>
 __global__ void __launch_bounds__(256)
 input_conv_fwd_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
                       const float* __restrict__ w /* [COUT][2][KS][KS] */, const float* __restrict__ bias,
-                      __nv_bfloat16* __restrict__ out, int F, int H, int W) {
+                      h16* __restrict__ out, int F, int H, int W) {
     pdl_trigger();
     pdl_wait();
     constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1;
@@ -197,10 +197,10 @@ input_conv_fwd_kernel(const float* __restrict__ in0, const float* __restrict__ i
 #pragma unroll
         for (int j = 0; j < COUT / 8; ++j) {
             uint4 u;
-            u.x = pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]);
-            u.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
-            u.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
-            u.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+            u.x = pack_h2(acc[8 * j + 0], acc[8 * j + 1]);
+            u.y = pack_h2(acc[8 * j + 2], acc[8 * j + 3]);
+            u.z = pack_h2(acc[8 * j + 4], acc[8 * j + 5]);
+            u.w = pack_h2(acc[8 * j + 6], acc[8 * j + 7]);
             op[j] = u;
         }
     }
@@ -211,7 +211,7 @@ input_conv_fwd_kernel(const float* __restrict__ in0, const float* __restrict__ i
 template <int KS, int COUT>
 __global__ void __launch_bounds__(256)
 input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int f0, int f1,
-                        const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db, int NI,
+                        const h16* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db, int NI,
                         int F, int H, int W) {
     pdl_trigger();
     pdl_wait();
@@ -219,7 +219,7 @@ input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__
     constexpr int T = 16, PAD = KS / 2, PW = T + KS - 1, NT = 2 * KS * KS, CG = COUT / 4, Q = 256 / CG;
     constexpr int TPT = (NT + Q - 1) / Q;  // taps per thread
     __shared__ float sin_[2][PW][PW + 1];
-    __shared__ __align__(16) __nv_bfloat16 sdy[T * T][COUT + 8];
+    __shared__ __align__(16) h16 sdy[T * T][COUT + 8];
     const int cg = threadIdx.x % CG, q = threadIdx.x / CG;
     float acc[TPT][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
     int toff[TPT];  // offset of tap (ci, kh, kw) inside sin_ relative to [0][ty][tx]
@@ -257,7 +257,7 @@ input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__
 #pragma unroll 2
         for (int px = 0; px < T * T; ++px) {
             const uint2 gu = *reinterpret_cast<const uint2*>(&sdy[px][cg * 4]);
-            const float2 g01 = unpack_bf16x2(gu.x), g23 = unpack_bf16x2(gu.y);
+            const float2 g01 = unpack_h2(gu.x), g23 = unpack_h2(gu.y);
             const int poff = (px / T) * (PW + 1) + (px % T);
             if (q == 0) {
                 accb[0] += g01.x; accb[1] += g01.y; accb[2] += g23.x; accb[3] += g23.y;
@@ -288,7 +288,7 @@ input_conv_wgrad_kernel(const float* __restrict__ in0, const float* __restrict__
 
 // eps[b][h][w] = bias + sum_c a[(b*F + mid)][h][w][c] * w[c]   ; 8 lanes per pixel (C == 64)
 __global__ void __launch_bounds__(256)
-out_conv_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+out_conv_fwd_kernel(const h16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ eps, int B, int F, int mid, long long HW) {
     pdl_trigger();
     pdl_wait();
@@ -299,7 +299,7 @@ out_conv_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict
     if (pix < (long long)B * HW) {
         const long long b = pix / HW, p = pix % HW;
         uint4 u = *reinterpret_cast<const uint4*>(a + (((size_t)b * F + mid) * HW + p) * 64 + sub * 8);
-        float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+        float2 x0 = unpack_h2(u.x), x1 = unpack_h2(u.y), x2 = unpack_h2(u.z), x3 = unpack_h2(u.w);
         const float* ww = w + sub * 8;
         s = x0.x * ww[0] + x0.y * ww[1] + x1.x * ww[2] + x1.y * ww[3] + x2.x * ww[4] + x2.y * ww[5] + x3.x * ww[6] + x3.y * ww[7];
     }
@@ -310,8 +310,8 @@ out_conv_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict
 }
 // da[(b,f)][p][c] = (f == mid) ? deps[b][p]*w[c] : 0 ; dw[c] += sum deps*a ; db += sum deps
 __global__ void __launch_bounds__(256)
-out_conv_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ deps,
-                    __nv_bfloat16* __restrict__ da, float* __restrict__ dw, float* __restrict__ db, int B, int F, int mid,
+out_conv_bwd_kernel(const h16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ deps,
+                    h16* __restrict__ da, float* __restrict__ dw, float* __restrict__ db, int B, int F, int mid,
                     long long HW) {
     pdl_trigger();
     pdl_wait();
@@ -332,14 +332,14 @@ out_conv_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict
         if (f == mid) {
             const float g = deps[b * HW + p];
             uint4 u = *reinterpret_cast<const uint4*>(a + pix * 64 + sub * 8);
-            float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+            float2 x0 = unpack_h2(u.x), x1 = unpack_h2(u.y), x2 = unpack_h2(u.z), x3 = unpack_h2(u.w);
             acc[0] += g * x0.x; acc[1] += g * x0.y; acc[2] += g * x1.x; acc[3] += g * x1.y;
             acc[4] += g * x2.x; acc[5] += g * x2.y; acc[6] += g * x3.x; acc[7] += g * x3.y;
             if (sub == 0) accb += g;
-            o.x = pack_bf16x2(g * wv[0], g * wv[1]);
-            o.y = pack_bf16x2(g * wv[2], g * wv[3]);
-            o.z = pack_bf16x2(g * wv[4], g * wv[5]);
-            o.w = pack_bf16x2(g * wv[6], g * wv[7]);
+            o.x = pack_h2(g * wv[0], g * wv[1]);
+            o.y = pack_h2(g * wv[2], g * wv[3]);
+            o.z = pack_h2(g * wv[4], g * wv[5]);
+            o.w = pack_h2(g * wv[6], g * wv[7]);
         }
         *reinterpret_cast<uint4*>(da + pix * 64 + sub * 8) = o;
     }
@@ -623,7 +623,7 @@ extern "C" int cesm_pack_weight(const float* src, void* dst, int O, int T, int I
     TapOffsets taps{};
     for (int t = 0; t < T; ++t) taps.off[t] = tap_off[t];
     const long long total = (long long)O * T * I;
-    launch_pdl(pack_weight_kernel, nblk(total, 256), 256, 0, as_stream(stream), src, (__nv_bfloat16*)dst, O, T, I, so, si, taps);
+    launch_pdl(pack_weight_kernel, nblk(total, 256), 256, 0, as_stream(stream), src, (h16*)dst, O, T, I, so, si, taps);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -646,7 +646,7 @@ extern "C" int cesm_colsum(const void* x, float* out, long long M, int C, int ac
     long long blocks = (M + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
-    launch_pdl(colsum_kernel, (int)blocks, 256, 0, st, (const __nv_bfloat16*)x, out, M, C);
+    launch_pdl(colsum_kernel, (int)blocks, 256, 0, st, (const h16*)x, out, M, C);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -666,7 +666,7 @@ extern "C" int cesm_input_patches(const float* in0, const float* in1, int f0, in
     CESM_REQUIRE(ks == 7 && kpad == 256, "input patch kernel is specialised for 7x7, 256 columns (ks=%d kpad=%d)", ks, kpad);
     CESM_REQUIRE((f0 == 1 || f0 == F) && (f1 == 1 || f1 == F), "frame counts must be 1 or F");
     dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B * F);
-    launch_pdl(input_patches_kernel<7, 256>, grid, 256, 0, as_stream(stream), in0, in1, f0, f1, (__nv_bfloat16*)out, F, H, W);
+    launch_pdl(input_patches_kernel<7, 256>, grid, 256, 0, as_stream(stream), in0, in1, f0, f1, (h16*)out, F, H, W);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -675,7 +675,7 @@ extern "C" int cesm_input_weight_pack(const float* w, const float* bias, void* o
                                       void* stream) {
     CESM_REQUIRE(kpad >= 4 * ks * ks + 2, "kpad=%d too small for 2 planes x hi/lo x %dx%d + 2", kpad, ks, ks);
     launch_pdl(input_weight_pack_kernel, nblk((long long)cout * kpad, 256), 256, 0, as_stream(stream), 
-        w, bias, (__nv_bfloat16*)out, cout, 2 * ks * ks, kpad);
+        w, bias, (h16*)out, cout, 2 * ks * ks, kpad);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -686,7 +686,7 @@ extern "C" int cesm_input_conv_fwd(const float* in0, const float* in1, int f0, i
     CESM_REQUIRE(ks == 7 && cout == 64, "input conv kernel is specialised for 7x7, 64 channels (ks=%d cout=%d)", ks, cout);
     CESM_REQUIRE((f0 == 1 || f0 == F) && (f1 == 1 || f1 == F), "frame counts must be 1 or F");
     dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B * F);
-    launch_pdl(input_conv_fwd_kernel<7, 64>, grid, 256, 0, as_stream(stream), in0, in1, f0, f1, w, bias, (__nv_bfloat16*)out, F, H, W);
+    launch_pdl(input_conv_fwd_kernel<7, 64>, grid, 256, 0, as_stream(stream), in0, in1, f0, f1, w, bias, (h16*)out, F, H, W);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -699,7 +699,7 @@ extern "C" int cesm_input_conv_wgrad(const float* in0, const float* in1, int f0,
     CESM_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * cout, st));
     const int ntiles = ceil_div(W, 16) * ceil_div(H, 16) * B * F;
     const int grid = ntiles < 148 * 2 ? ntiles : 148 * 2;
-    launch_pdl(input_conv_wgrad_kernel<7, 64>, grid, 256, 0, st, in0, in1, f0, f1, (const __nv_bfloat16*)dy, dw, db, B * F, F, H, W);
+    launch_pdl(input_conv_wgrad_kernel<7, 64>, grid, 256, 0, st, in0, in1, f0, f1, (const h16*)dy, dw, db, B * F, F, H, W);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -708,7 +708,7 @@ extern "C" int cesm_out_conv_fwd(const void* a, const float* w, const float* bia
                                  long long HW, int C, void* stream) {
     CESM_REQUIRE(C == 64, "output conv kernel needs 64 input channels (C=%d)", C);
     const long long threads = (long long)B * HW * 8;
-    launch_pdl(out_conv_fwd_kernel, nblk(threads, 256), 256, 0, as_stream(stream), (const __nv_bfloat16*)a, w, bias, eps, B, F, mid, HW);
+    launch_pdl(out_conv_fwd_kernel, nblk(threads, 256), 256, 0, as_stream(stream), (const h16*)a, w, bias, eps, B, F, mid, HW);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -721,7 +721,7 @@ extern "C" int cesm_out_conv_bwd(const void* a, const float* w, const float* dep
     CESM_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
     long long blocks = ((long long)B * F * HW * 8 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    launch_pdl(out_conv_bwd_kernel, (int)blocks, 256, 0, st, (const __nv_bfloat16*)a, w, deps, (__nv_bfloat16*)da, dw, db, B, F, mid, HW);
+    launch_pdl(out_conv_bwd_kernel, (int)blocks, 256, 0, st, (const h16*)a, w, deps, (h16*)da, dw, db, B, F, mid, HW);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

@@ -6,9 +6,9 @@
 //
 //     out[pixel, co] = sum_{tap, ci} A[pixel + tap, ci] * Wt[co, tap, ci]   (+ bias) (+ residual)
 //
-// A is one or two NHWC bf16 activation tensors (two = the U-Net skip concat, never materialised),
+// A is one or two NHWC fp16 activation tensors (two = the U-Net skip concat, never materialised),
 // fetched tile by tile with 4-D TMA boxes; conv zero padding comes from TMA out-of-bounds fill.
-// Wt is bf16 [cout][taps*cin] (K-major).  A 128-pixel x BLOCK_N tile is accumulated in TMEM by a
+// Wt is fp16 [cout][taps*cin] (K-major).  A 128-pixel x BLOCK_N tile is accumulated in TMEM by a
 // single MMA-issuing thread; 4 epilogue warps read TMEM back, fuse bias/residual and store.
 //
 // Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
@@ -20,7 +20,7 @@
 namespace cesm {
 
 static constexpr int kBlockM = 128;
-static constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+static constexpr int kBlockK = 64;  // 64 fp16 = 128 B = one SWIZZLE_128B row
 static constexpr int kUmmaK = 16;
 
 struct IgemmMaps {
@@ -117,7 +117,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+        constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -131,7 +131,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
                 // K step is a 32 B advance of the start address inside the atom.
                 const uint64_t da = make_smem_desc_sw128(sa + k * kUmmaK * 2, 0, 1024);
                 const uint64_t db = make_smem_desc_sw128(sb + k * kUmmaK * 2, 0, 1024);
-                umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+                umma_f16(tmem_base, da, db, idesc, (kb | k) != 0);
             }
             umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
             if (kb == num_kb - 1) umma_commit(tmem_full_bar);
@@ -170,12 +170,12 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
                 }
                 if (p.residual) {
                     const uint4* rp = reinterpret_cast<const uint4*>(
-                        reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.ldr + col);
+                        reinterpret_cast<const h16*>(p.residual) + pix * p.ldr + col);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 u = __ldg(rp + j);
-                        float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
-                               d = unpack_bf16x2(u.w);
+                        float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c2 = unpack_h2(u.z),
+                               d = unpack_h2(u.w);
                         f[j * 8 + 0] += a.x; f[j * 8 + 1] += a.y; f[j * 8 + 2] += b.x; f[j * 8 + 3] += b.y;
                         f[j * 8 + 4] += c2.x; f[j * 8 + 5] += c2.y; f[j * 8 + 6] += d.x; f[j * 8 + 7] += d.y;
                     }
@@ -185,14 +185,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 } else {
-                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col);
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<h16*>(p.out) + pix * p.ldo + col);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 u;
-                        u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                        u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                        u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                        u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        u.x = pack_h2(f[8 * j + 0], f[8 * j + 1]);
+                        u.y = pack_h2(f[8 * j + 2], f[8 * j + 3]);
+                        u.z = pack_h2(f[8 * j + 4], f[8 * j + 5]);
+                        u.w = pack_h2(f[8 * j + 6], f[8 * j + 7]);
                         op[j] = u;
                     }
                 }

@@ -25,7 +25,7 @@ struct IgemmParams {
     int32_t ldo;
     int32_t out_h, out_w, o_sh, o_sw, o_h0, o_w0;
     const float* bias;     // [cout] or null
-    const void* residual;  // bf16, same pixel addressing as out, row pitch ldr; or null
+    const void* residual;  // fp16, same pixel addressing as out, row pitch ldr; or null
     int32_t ldr;
 };
 

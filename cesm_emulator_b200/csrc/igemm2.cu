@@ -19,7 +19,7 @@
 //     the MMAs of tile i+1.
 //   * the epilogue goes TMEM -> registers -> swizzled shared memory -> TMA store (full 128-byte
 //     lines), fusing bias, residual add and -- for the convs that feed a GroupNorm -- the per-sample
-//     per-group sum / sum-of-squares of the bf16-rounded outputs (video_net.py:216).
+//     per-group sum / sum-of-squares of the fp16-rounded outputs (video_net.py:216).
 //
 // Warp roles (352 threads): 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer
 // (+ TMEM allocation), 3..10 = epilogue: two groups of four warps (warp w reads TMEM lanes
@@ -33,7 +33,7 @@ namespace cesm {
 
 static constexpr int kTileM = 128;
 static constexpr int kKBlk = 64;
-static constexpr int kStageRowBytes = 128;                       // 64 bf16
+static constexpr int kStageRowBytes = 128;                       // 64 fp16
 static constexpr int kOutStageBytes = kTileM * kStageRowBytes;   // one 64-column output chunk
 static constexpr int kIgemm2Threads = 352;
 
@@ -237,7 +237,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         // occupies the tensor pipe for only 32 clocks.  Descriptors are therefore not rebuilt per MMA: the
         // constant upper word is hoisted, the 14-bit start-address field is advanced by adds (+2 per
         // 16-element K step = 32 B, + 8 per 128-byte row for the halo tap views).
-        constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+        constexpr uint32_t idesc = make_idesc_f16(kTileM, BLOCK_N, 0, 0);
         const uint64_t desc_hi = make_smem_desc_sw128(0, 0, 1024);   // start-address field = 0
         int a_stage = 0, b_stage = 0, acc = 0;
         uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
@@ -262,7 +262,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
 #pragma unroll
                         for (int k = 0; k < kKBlk / 16; ++k) {
                             if (leader)
-                                umma_bf16(d_tmem, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k),
+                                umma_f16(d_tmem, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k),
                                           idesc, accum);
                             accum = 1;
                         }
@@ -396,7 +396,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                 const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
                 const bool has_res = p.residual != nullptr;
                 const uint4* rp = reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + (valid ? pix : 0) * p.ldr + col);
+                    reinterpret_cast<const h16*>(p.residual) + (valid ? pix : 0) * p.ldr + col);
                 tmem_ld_wait();
                 float sv[16];  // GN: [0..7] per 8-column octet sums of this row, [8..15] sums of squares
 #pragma unroll
@@ -411,24 +411,24 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                     }
                     if (has_res && valid) {
                         const uint4 rr = __ldg(rp + j);
-                        const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y),
-                                     c2 = unpack_bf16x2(rr.z), d = unpack_bf16x2(rr.w);
+                        const float2 a = unpack_h2(rr.x), b = unpack_h2(rr.y),
+                                     c2 = unpack_h2(rr.z), d = unpack_h2(rr.w);
                         f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
                         f[4] += c2.x; f[5] += c2.y; f[6] += d.x; f[7] += d.y;
                     }
                     uint4 u;
-                    u.x = pack_bf16x2(f[0], f[1]);
-                    u.y = pack_bf16x2(f[2], f[3]);
-                    u.z = pack_bf16x2(f[4], f[5]);
-                    u.w = pack_bf16x2(f[6], f[7]);
+                    u.x = pack_h2(f[0], f[1]);
+                    u.y = pack_h2(f[2], f[3]);
+                    u.z = pack_h2(f[4], f[5]);
+                    u.w = pack_h2(f[6], f[7]);
                     const uint32_t addr = my_row + ((j ^ sw7) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z),
                                  "r"(u.w)
                                  : "memory");
                     if (GN) {
-                        // statistics of what the consumer will read: the bf16-rounded values
-                        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z),
-                                     d = unpack_bf16x2(u.w);
+                        // statistics of what the consumer will read: the fp16-rounded values
+                        const float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c2 = unpack_h2(u.z),
+                                     d = unpack_h2(u.w);
                         const float s = ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
                         const float qq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c2.x, c2.x,
                                          fmaf(c2.y, c2.y, fmaf(d.x, d.x, d.y * d.y)))))));

@@ -1,4 +1,4 @@
-// Spatial linear attention core (video_net.py:338-344) for sm_100a, bf16 in / fp32 accumulate.
+// Spatial linear attention core (video_net.py:338-344) for sm_100a, fp16 in / fp32 accumulate.
 //
 // Per image (one frame of one sample) and head, with n pixels and d = e = 32:
 //     qs = scale * softmax_d(q)         (over the 32 features of a pixel)
@@ -24,7 +24,7 @@
 namespace cesm {
 
 static constexpr int LD = 32;        // head dim
-static constexpr int SPITCH = 40;    // bf16 elements per staged row (80 B: conflict-free ldmatrix)
+static constexpr int SPITCH = 40;    // fp16 elements per staged row (80 B: conflict-free ldmatrix)
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -33,7 +33,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 }
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
         "{%0, %1, %2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -47,13 +47,13 @@ __device__ __forceinline__ float dec_ordered(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     uint4 u;
-    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    u.x = pack_h2(f[0], f[1]); u.y = pack_h2(f[2], f[3]);
+    u.z = pack_h2(f[4], f[5]); u.w = pack_h2(f[6], f[7]);
     return u;
 }
 __device__ __forceinline__ float quad_max(float v) {
@@ -76,7 +76,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-static constexpr int kTileBytes = 16 * SPITCH * 2;  // one staged 16-pixel x 32-channel bf16 tile
+static constexpr int kTileBytes = 16 * SPITCH * 2;  // one staged 16-pixel x 32-channel fp16 tile
 
 struct LaWs {  // views into the per-image workspace
     uint32_t* kmax;
@@ -92,7 +92,7 @@ __device__ __forceinline__ LaWs la_ws(float* ws, int ni, int HD, int H) {
 // column max of k over the pixels of each image: thread = 8 channels (16 B), rows strided over the block
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-la_colmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, int n, int H, int rows_per_block) {
+la_colmax_kernel(const h16* __restrict__ qkv, float* __restrict__ ws, int n, int H, int rows_per_block) {
     pdl_trigger();
     pdl_wait();
     const int HD = H * LD, cpr = HD / 8;
@@ -103,7 +103,7 @@ la_colmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
     if (rl < nrl) {
-        const __nv_bfloat16* base = qkv + ((size_t)ni * n) * (3 * HD) + HD + chunk * 8;
+        const h16* base = qkv + ((size_t)ni * n) * (3 * HD) + HD + chunk * 8;
         for (int p = p0 + rl; p < p1; p += nrl) {
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * 3 * HD)), f);
@@ -133,7 +133,7 @@ la_colmax_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, 
 static constexpr int CTX_STAGES = 3;
 template <int MODE>
 __global__ void __launch_bounds__(256)
-la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+la_context_kernel(const h16* __restrict__ qkv, const h16* __restrict__ dout,
                   float* __restrict__ ws, float* __restrict__ acc_out /* MODE 1: dctx [NI][H][32][32] */, int n, int H,
                   int chunk, float scale) {
     pdl_trigger();
@@ -146,7 +146,7 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
     // MODE 1); operands go from there into fragments with ldmatrix.trans
     constexpr int kWarpTiles = 2 * CTX_STAGES + (MODE == 1 ? 1 : 0);
     uint8_t* wbase = la_smem + (size_t)w * kWarpTiles * kTileBytes;
-    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(wbase + 2 * CTX_STAGES * kTileBytes);
+    h16* sA = reinterpret_cast<h16*>(wbase + 2 * CTX_STAGES * kTileBytes);
     const uint32_t sA_addr = smem_u32(sA);
     const uint32_t ring_addr = smem_u32(wbase);
     const LaWs W = la_ws(ws, ni, HD, H);
@@ -170,8 +170,8 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
             for (int k = 0; k < 4; ++k) acc[a][b][k] = 0.f;
 
     const size_t img_row0 = (size_t)ni * n;
-    const __nv_bfloat16* a_base = qkv + img_row0 * ld + (MODE == 0 ? HD : 0) + w * LD + c * 8;
-    const __nv_bfloat16* b_base = (MODE == 0) ? qkv + img_row0 * ld + 2 * HD + w * LD + c * 8
+    const h16* a_base = qkv + img_row0 * ld + (MODE == 0 ? HD : 0) + w * LD + c * 8;
+    const h16* b_base = (MODE == 0) ? qkv + img_row0 * ld + 2 * HD + w * LD + c * 8
                                               : dout + img_row0 * HD + w * LD + c * 8;
     const int b_ld = (MODE == 0) ? ld : HD;
     const int p0 = blockIdx.x * chunk, p1 = min(n, p0 + chunk);
@@ -220,7 +220,7 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float2 x = unpack_bf16x2(af[mt][i]);
+                    const float2 x = unpack_h2(af[mt][i]);
                     float e0 = exp_sub(x.x, cmf[mt][i & 1]), e1 = exp_sub(x.y, cmf[mt][i & 1]);
                     if (!full) {
                         const int px = p + 2 * c + 8 * (i >> 1);
@@ -228,7 +228,7 @@ la_context_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __
                         e1 = px + 1 < p1 ? e1 : 0.f;
                     }
                     zf[mt][i & 1] += e0 + e1;
-                    af[mt][i] = pack_bf16x2(e0, e1);
+                    af[mt][i] = pack_h2(e0, e1);
                 }
         } else {
             // scale * softmax_d(q): rows are normalised in the row layout (quad shuffles), staged through a
@@ -354,12 +354,12 @@ __device__ __forceinline__ void load_bfrag32(const float* __restrict__ M, int g,
 #pragma unroll
             for (int hi = 0; hi < 2; ++hi) {
                 const int k0 = phi32(16 * ks + 8 * hi + 2 * t), k1 = k0 + 1;  // phi keeps (even, odd) pairs adjacent
-                b[ks][j][hi] = TRANS ? pack_bf16x2(M[nn * LD + k0], M[nn * LD + k1])
-                                     : pack_bf16x2(M[k0 * LD + nn], M[k1 * LD + nn]);
+                b[ks][j][hi] = TRANS ? pack_h2(M[nn * LD + k0], M[nn * LD + k1])
+                                     : pack_h2(M[k0 * LD + nn], M[k1 * LD + nn]);
             }
         }
 }
-// A fragments of a 16 x 32 tile whose rows g / g+8 this lane holds as packed bf16 (lo / hi)
+// A fragments of a 16 x 32 tile whose rows g / g+8 this lane holds as packed fp16 (lo / hi)
 __device__ __forceinline__ void rows_to_afrag(const uint4& lo, const uint4& hi, uint32_t (&a)[2][4]) {
     a[0][0] = lo.x; a[0][1] = hi.x; a[0][2] = lo.y; a[0][3] = hi.y;
     a[1][0] = lo.z; a[1][1] = hi.z; a[1][2] = lo.w; a[1][3] = hi.w;
@@ -416,7 +416,7 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
     return u;
 }
 __global__ void __launch_bounds__(256, 3)
-la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int n,
+la_apply_kernel(const h16* __restrict__ qkv, float* __restrict__ ws, h16* __restrict__ out, int n,
                 int H, int chunk, float scale) {
     pdl_trigger();
     pdl_wait();
@@ -429,8 +429,8 @@ la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, _
     load_bfrag32<false>(W.ctx + (size_t)w * LD * LD, r, c, bctx);
     const size_t row0 = (size_t)ni * n;
     const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
-    const __nv_bfloat16* qbase = qkv + row0 * ld + w * LD + c * 8;
-    __nv_bfloat16* obase = out + row0 * HD + w * LD + c * 8;
+    const h16* qbase = qkv + row0 * ld + w * LD + c * 8;
+    h16* obase = out + row0 * HD + w * LD + c * 8;
     // thread-private cp.async ring: [stage][vector][thread] x 16 B; the loads of step i+2 are in flight
     // while step i is computed, and a lane only reads back what it copied itself (no barriers)
     const uint32_t ring = smem_u32(la_smem) + threadIdx.x * 16u;
@@ -497,9 +497,9 @@ la_apply_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ ws, _
 //   dv  = kh dctx
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2)
-la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+la_bwd_apply_kernel(const h16* __restrict__ qkv, const h16* __restrict__ dout,
                     float* __restrict__ ws, const float* __restrict__ dctx, const float* __restrict__ delta,
-                    __nv_bfloat16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
+                    h16* __restrict__ dqkv, int n, int H, int chunk, float scale) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) uint8_t la_smem[];
@@ -525,9 +525,9 @@ la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     const float* del = s_del + w * LD + c * 8;
     const size_t row0 = (size_t)ni * n;
     const int p1 = min(n, (int)(blockIdx.x + 1) * chunk);
-    const __nv_bfloat16* xbase = qkv + row0 * ld + w * LD + c * 8;
-    const __nv_bfloat16* dbase = dout + row0 * HD + w * LD + c * 8;
-    __nv_bfloat16* gbase = dqkv + row0 * ld + w * LD + c * 8;
+    const h16* xbase = qkv + row0 * ld + w * LD + c * 8;
+    const h16* dbase = dout + row0 * HD + w * LD + c * 8;
+    h16* gbase = dqkv + row0 * ld + w * LD + c * 8;
     // thread-private cp.async ring (see la_apply_kernel): 8 x 16 B per lane and step, two steps ahead
     const uint32_t ring = smem_u32(la_smem) + threadIdx.x * 16u;
     constexpr uint32_t kVec = 256 * 16, kStage = 8 * kVec;
@@ -536,7 +536,7 @@ la_bwd_apply_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
                 const int row = min(pp + r + 8 * h2, p1 - 1);
-                const __nv_bfloat16* xg = xbase + (size_t)row * ld;
+                const h16* xg = xbase + (size_t)row * ld;
                 const uint32_t st = ring + stage * kStage + h2 * 4 * kVec;
                 cp_async16(st, dbase + (size_t)row * HD);
                 cp_async16(st + kVec, xg);
@@ -657,15 +657,15 @@ extern "C" int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, i
     CESM_ZERO_SCRATCH(ws, sizeof(float) * cesm_linattn_ws_floats(NI, H), st);
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
-    launch_pdl(la_colmax_kernel, grid, 256, 0, st, (const __nv_bfloat16*)qkv, ws, n, H, chunk);
+    launch_pdl(la_colmax_kernel, grid, 256, 0, st, (const h16*)qkv, ws, n, H, chunk);
     CESM_CHECK_LAUNCH();
     const size_t sh = la_context_smem(H, 0);
-    launch_pdl(la_context_kernel<0>, grid, 32 * H, sh, st, (const __nv_bfloat16*)qkv, nullptr, ws, nullptr, n, H, chunk, scale);
+    launch_pdl(la_context_kernel<0>, grid, 32 * H, sh, st, (const h16*)qkv, nullptr, ws, nullptr, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     launch_pdl(la_finalize_kernel, ceil_div(NI * H * LD * LD, 256), 256, 0, st, ws, H, NI);
     CESM_CHECK_LAUNCH();
     const size_t sh_apply = (size_t)RING_STAGES * APPLY_MT * 2 * 256 * 16;  // 48 KB
-    launch_pdl(la_apply_kernel, grid, 32 * H, sh_apply, st, (const __nv_bfloat16*)qkv, ws, (__nv_bfloat16*)out, n, H, chunk,
+    launch_pdl(la_apply_kernel, grid, 32 * H, sh_apply, st, (const h16*)qkv, ws, (h16*)out, n, H, chunk,
                                                     scale);
     CESM_CHECK_LAUNCH();
     (void)HD;
@@ -684,7 +684,7 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
     const int chunk = la_chunk(n, NI);
     dim3 grid(ceil_div(n, chunk), NI);
     const size_t sh = la_context_smem(H, 1);
-    launch_pdl(la_context_kernel<1>, grid, 32 * H, sh, st, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, n, H,
+    launch_pdl(la_context_kernel<1>, grid, 32 * H, sh, st, (const h16*)qkv, (const h16*)dout, ws, dctx, n, H,
                                                    chunk, scale);
     CESM_CHECK_LAUNCH();
     launch_pdl(la_delta_kernel, ceil_div(NI * H * LD, 128), 128, 0, st, ws, dctx, delta, H, NI);
@@ -695,8 +695,8 @@ extern "C" int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, fl
         CESM_CHECK_CUDA(cudaFuncSetAttribute(la_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bwd));
         bwd_cfg = true;
     }
-    launch_pdl(la_bwd_apply_kernel, grid, 32 * H, sh_bwd, st, (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, ws, dctx, delta,
-                                                 (__nv_bfloat16*)dqkv, n, H, chunk, scale);
+    launch_pdl(la_bwd_apply_kernel, grid, 32 * H, sh_bwd, st, (const h16*)qkv, (const h16*)dout, ws, dctx, delta,
+                                                 (h16*)dqkv, n, H, chunk, scale);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

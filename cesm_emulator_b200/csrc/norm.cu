@@ -1,10 +1,10 @@
-// Bandwidth-bound normalisation kernels (bf16 channels-last activations, fp32 math/statistics).
+// Bandwidth-bound normalisation kernels (fp16 channels-last activations, fp32 math/statistics).
 //
 //  GroupNorm + FiLM + SiLU (+ residual)      reference: video_net.py:216-227 (Block), :265 (+res)
 //  channel LayerNorm (gain only)              reference: video_net.py:78-87
 //
 // Layout: x[b][p][c], p = (frame, row, col) flattened, c fastest.  Every thread owns one 16-byte
-// vector (8 bf16 channels) of a pixel, so global accesses are fully coalesced 128-bit
+// vector (8 fp16 channels) of a pixel, so global accesses are fully coalesced 128-bit
 // transactions; reductions go thread -> shared memory -> one fp32 atomic per (block, slot).
 #include "api_common.h"
 #include "common.cuh"
@@ -16,19 +16,19 @@ static constexpr int kNormThreads = 256;
 struct Vec8 {
     float v[8];
 };
-__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
+__device__ __forceinline__ Vec8 load8(const h16* p) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
     Vec8 r;
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
     return r;
 }
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
+__device__ __forceinline__ void store8(h16* p, const Vec8& r) {
     uint4 u;
-    u.x = pack_bf16x2(r.v[0], r.v[1]);
-    u.y = pack_bf16x2(r.v[2], r.v[3]);
-    u.z = pack_bf16x2(r.v[4], r.v[5]);
-    u.w = pack_bf16x2(r.v[6], r.v[7]);
+    u.x = pack_h2(r.v[0], r.v[1]);
+    u.y = pack_h2(r.v[2], r.v[3]);
+    u.z = pack_h2(r.v[4], r.v[5]);
+    u.w = pack_h2(r.v[6], r.v[7]);
     *reinterpret_cast<uint4*>(p) = u;
 }
 
@@ -63,14 +63,14 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once stre
 }
 
 __global__ void __launch_bounds__(kNormThreads)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, long long P, int C, int G) {
+gn_stats_kernel(const h16* __restrict__ x, float* __restrict__ sums, long long P, int C, int G) {
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y;
     const int vec_per_pix = C >> 3;
     const int slot = threadIdx.x % vec_per_pix;       // fixed channel vector of this thread
     const int pix_per_iter = kNormThreads / vec_per_pix;
-    const __nv_bfloat16* xb = x + (size_t)b * P * C + slot * 8;
+    const h16* xb = x + (size_t)b * P * C + slot * 8;
     const long long stride = (long long)gridDim.x * pix_per_iter;
     float s = 0.f, ss = 0.f;
     for (long long p = (long long)blockIdx.x * pix_per_iter + threadIdx.x / vec_per_pix; p < P; p += UNR * stride) {
@@ -85,7 +85,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, l
             const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(w[i]);
+                const float2 f = unpack_h2(w[i]);
                 s += f.x + f.y;
                 ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
             }
@@ -105,10 +105,10 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, l
 
 // out = silu(((x-mean)*rstd*gamma + beta) * (scale+1) + shift) (+ residual)
 __global__ void __launch_bounds__(kNormThreads)
-gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sums,
+gn_apply_fwd_kernel(const h16* __restrict__ x, const float* __restrict__ sums,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ film,  // [B][2C] (scale | shift) or null
-                    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, long long P, int C,
+                    const h16* __restrict__ residual, h16* __restrict__ out, long long P, int C,
                     int G, float eps) {
     pdl_trigger();
     pdl_wait();
@@ -162,10 +162,10 @@ gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 // packed pairs: h = u/2 (A2, B2 are the halved coefficients), silu(u) = h (1 + tanh h)
-                const float2 h = ffma2(unpack_bf16x2(w[i]), A2[i], B2[i]);
+                const float2 h = ffma2(unpack_h2(w[i]), A2[i], B2[i]);
                 float2 ov = ffma2(h, tanh2(h), h);
-                if (residual) ov = fadd2(ov, unpack_bf16x2(rw[i]));
-                o[i] = pack_bf16x2(ov.x, ov.y);
+                if (residual) ov = fadd2(ov, unpack_h2(rw[i]));
+                o[i] = pack_h2(ov.x, ov.y);
             }
             *reinterpret_cast<uint4*>(out + base + pk * C) = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -177,7 +177,7 @@ gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 //   needs is algebra on these: dz = du*(sc+1), sum dz = (sc+1) T0, sum dz*xhat = (sc+1) T1,
 //   sum du*z = gamma T1 + beta T0.
 __global__ void __launch_bounds__(kNormThreads, 3)
-gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dout,
+gn_bwd_reduce_kernel(const h16* __restrict__ x, const h16* __restrict__ dout,
                      const float* __restrict__ sums, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ film, float* __restrict__ csum,
                      long long P, int C, int G, float eps) {
@@ -261,7 +261,7 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
             const uint32_t dw[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(w[i]), dd = unpack_bf16x2(dw[i]);
+                const float2 f = unpack_h2(w[i]), dd = unpack_h2(dw[i]);
                 // packed pairs; A2, B2 hold u/2 coefficients: h = u/2, t = tanh(h), R = t + h (1 - t^2),
                 // du = dout * silu'(u) = (dout/2) (1 + R)
                 const float2 h = ffma2(f, A2[i], B2[i]);
@@ -302,10 +302,10 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 
 // Backward pass 2: dx = rstd * (gamma*dz - m1 - xhat*m2), m1/m2 = group means of gamma*dz and gamma*dz*xhat.
 __global__ void __launch_bounds__(kNormThreads, 3)
-gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dout,
+gn_bwd_apply_kernel(const h16* __restrict__ x, const h16* __restrict__ dout,
                     const float* __restrict__ sums, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ film,
-                    const float* __restrict__ csum, __nv_bfloat16* __restrict__ dx, long long P, int C, int G,
+                    const float* __restrict__ csum, h16* __restrict__ dx, long long P, int C, int G,
                     float eps, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dfilm,
                     float* __restrict__ dcbias) {
     pdl_trigger();
@@ -398,12 +398,12 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
             uint32_t o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16x2(w[i]), dd = unpack_bf16x2(dw[i]);
+                const float2 f = unpack_h2(w[i]), dd = unpack_h2(dw[i]);
                 // dout silu'(u) Gs = e (1 + R) with e = dout * Gs / 2 (Gs already halved)
                 const float e0 = dd.x * Gs[2 * i], e1 = dd.y * Gs[2 * i + 1];
                 const float o0 = fmaf(e0, dsilu_R_from_half(fmaf(f.x, A[2 * i], Bc[2 * i])), e0) + fmaf(-K1, f.x, -K0);
                 const float o1 = fmaf(e1, dsilu_R_from_half(fmaf(f.y, A[2 * i + 1], Bc[2 * i + 1])), e1) + fmaf(-K1, f.y, -K0);
-                o[i] = pack_bf16x2(o0, o1);
+                o[i] = pack_h2(o0, o1);
             }
             *reinterpret_cast<uint4*>(dx + base + pk * C) = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -477,7 +477,7 @@ __device__ __forceinline__ float sub_sum(float v) {
 
 template <int LPR, int NV>
 __global__ void __launch_bounds__(256)
-ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out,
+ln_fwd_kernel(const h16* __restrict__ x, const float* __restrict__ gamma, h16* __restrict__ out,
               long long M, int C, float eps) {
     pdl_trigger();
     pdl_wait();
@@ -527,9 +527,9 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 // dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (+ dres), g = dy*gamma; dgamma[c] += sum_rows dy*xhat
 template <int LPR, int NV>
 __global__ void __launch_bounds__(256)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-              const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dres,
-              __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, long long M, int C, float eps) {
+ln_bwd_kernel(const h16* __restrict__ x, const float* __restrict__ gamma,
+              const h16* __restrict__ dy, const h16* __restrict__ dres,
+              h16* __restrict__ dx, float* __restrict__ dgamma, long long M, int C, float eps) {
     pdl_trigger();
     pdl_wait();
     constexpr int RPW = 32 / LPR;
@@ -646,7 +646,7 @@ extern "C" int cesm_gn_stats(const void* x, float* sums, int B, long long P, int
     const int per_block = kNormThreads / (C / 8) * UNR;
     static const int res = resident_blocks(gn_stats_kernel, kNormThreads);
     dim3 grid(norm_grid(P, per_block, B, res), B);
-    launch_pdl(gn_stats_kernel, grid, kNormThreads, 0, as_stream(stream), (const __nv_bfloat16*)x, sums, P, C, G);
+    launch_pdl(gn_stats_kernel, grid, kNormThreads, 0, as_stream(stream), (const h16*)x, sums, P, C, G);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }
@@ -659,7 +659,7 @@ extern "C" int cesm_gn_apply_fwd(const void* x, const float* sums, const float* 
     static const int res = resident_blocks(gn_apply_fwd_kernel, kNormThreads);
     dim3 grid(norm_grid(P, per_block, B, res), B);
     launch_pdl(gn_apply_fwd_kernel, grid, kNormThreads, 0, as_stream(stream), 
-        (const __nv_bfloat16*)x, sums, gamma, beta, film, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, P, C, G,
+        (const h16*)x, sums, gamma, beta, film, (const h16*)residual, (h16*)out, P, C, G,
         eps);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
@@ -683,12 +683,12 @@ extern "C" int cesm_gn_bwd(const void* x, const void* dout, const float* sums, c
     static const int res_a = resident_blocks(gn_bwd_apply_kernel, kNormThreads);
     dim3 grid(norm_grid(P, per_block, B, res_r), B);
     dim3 grid_a(norm_grid(P, per_block, B, res_a), B);
-    launch_pdl(gn_bwd_reduce_kernel, grid, kNormThreads, kRing, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums,
+    launch_pdl(gn_bwd_reduce_kernel, grid, kNormThreads, kRing, st, (const h16*)x, (const h16*)dout, sums,
                                                         gamma, beta, film, csum, P, C, G, eps);
     CESM_CHECK_LAUNCH();
     const bool fused = accumulate_params != 0;  // accumulate mode: the apply kernel adds the parameter gradients
-    launch_pdl(gn_bwd_apply_kernel, grid_a, kNormThreads, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, sums, gamma,
-                                                       beta, film, csum, (__nv_bfloat16*)dx, P, C, G, eps,
+    launch_pdl(gn_bwd_apply_kernel, grid_a, kNormThreads, 0, st, (const h16*)x, (const h16*)dout, sums, gamma,
+                                                       beta, film, csum, (h16*)dx, P, C, G, eps,
                                                        fused ? dgamma : nullptr, dbeta, dfilm, dconv_bias);
     CESM_CHECK_LAUNCH();
     if (!fused) {
@@ -704,15 +704,15 @@ static void ln_launch_fwd(int /*grid*/, cudaStream_t st, const void* x, const fl
                           int C, float eps) {
     static const int res = resident_blocks(ln_fwd_kernel<LPR, NV>, 256);
     const int grid = norm_grid(M, 8 * (32 / LPR), 1, res);
-    launch_pdl(ln_fwd_kernel<LPR, NV>, grid, 256, 0, st, (const __nv_bfloat16*)x, gamma, (__nv_bfloat16*)out, M, C, eps);
+    launch_pdl(ln_fwd_kernel<LPR, NV>, grid, 256, 0, st, (const h16*)x, gamma, (h16*)out, M, C, eps);
 }
 template <int LPR, int NV>
 static void ln_launch_bwd(int /*grid*/, cudaStream_t st, const void* x, const float* gamma, const void* dy,
                           const void* dres, void* dx, float* dgamma, long long M, int C, float eps) {
     static const int res = resident_blocks(ln_bwd_kernel<LPR, NV>, 256);
     const int grid = norm_grid(M, 8 * (32 / LPR), 1, res);
-    launch_pdl(ln_bwd_kernel<LPR, NV>, grid, 256, 0, st, (const __nv_bfloat16*)x, gamma, (const __nv_bfloat16*)dy,
-                                                 (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, dgamma, M, C, eps);
+    launch_pdl(ln_bwd_kernel<LPR, NV>, grid, 256, 0, st, (const h16*)x, gamma, (const h16*)dy,
+                                                 (const h16*)dres, (h16*)dx, dgamma, M, C, eps);
 }
 // C in {64, 128, 256, 512, 1024}: LPR = min(32, C/8), NV = C / (8*LPR)
 #define LN_DISPATCH(FN, ...)                                   \

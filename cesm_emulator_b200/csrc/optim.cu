@@ -2,9 +2,10 @@
 // "the next forward can start" is four bandwidth-bound launches over flat fp32 buffers:
 //
 //   relayout_tiled<1>  packed fp32 weight-gradient scratch [O][T][I] -> += parameter-gradient layout
-//   grad_sumsq         per-block partial sums of g^2 (deterministic order), step counter += 1
-//   adamw_clip         global-norm clip coefficient + AdamW on (p, g, m, v), all parameters at once
-//   relayout_tiled<0>  fp32 parameters -> bf16 GEMM-operand copies [O][T][I]
+//   grad_sumsq         per-block partial sums of g^2 (deterministic order)
+//   adamw_clip         loss-scale removal + inf check + global-norm clip + AdamW on (p, g, m, v), all parameters
+//   scaler_update      GradScaler.update(): step count, loss-scale backoff / growth (one warp)
+//   relayout_tiled<0>  fp32 parameters -> fp16 GEMM-operand copies [O][T][I]
 //
 // The two re-layouts are 3-D permutations (conv weight [co][ci][tap] <-> operand [o][tap][i] with
 // (o, i) = (co, ci) or (ci, co)); they go through a shared-memory tile so that both the parameter
@@ -23,7 +24,7 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// MODE 0: dst (bf16 [O][T][I]) = src[o*so + i*si + tap_off[t]]                      (pack)
+// MODE 0: dst (fp16 [O][T][I]) = src[o*so + i*si + tap_off[t]]                      (pack)
 // MODE 1: dst[o*so + i*si + tap_off[t]] += src (fp32 [O][T][I]); src = 0             (un-pack)
 // Requires min(so, si) = T' >= 1 (the parameter's own tap count), tap_off[t] in [0, T'), T' <= 16.
 // A tile is (rows of the outer index) x (32 of the inner index) x (all T' taps): each row is one
@@ -55,7 +56,7 @@ relayout_tiled_kernel(const cesm_pack_desc* __restrict__ descs) {
     }
     // parameter-layout side (fp32) and packed side
     float* __restrict__ par = MODE == 0 ? const_cast<float*>(d.src) : reinterpret_cast<float*>(d.dst);
-    __nv_bfloat16* __restrict__ pk16 = reinterpret_cast<__nv_bfloat16*>(d.dst);       // MODE 0
+    h16* __restrict__ pk16 = reinterpret_cast<h16*>(d.dst);       // MODE 0
     float* __restrict__ pk32 = const_cast<float*>(d.src);                            // MODE 1
     const uint32_t tile_addr = smem_u32(tile);
     for (int tl = blockIdx.x; tl < tiles_in * tiles_out; tl += gridDim.x) {
@@ -83,7 +84,7 @@ relayout_tiled_kernel(const cesm_pack_desc* __restrict__ descs) {
             const long long q = ((long long)o_g * T + t) * I + i_g;
             if (act) {
                 if (MODE == 0) {
-                    pk16[q] = __float2bfloat16(tile[sp]);
+                    pk16[q] = __float2half_rn(tile[sp]);
                 } else {
                     tile[sp] += pk32[q];
                     pk32[q] = 0.f;
@@ -132,33 +133,43 @@ grad_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ 
 #pragma unroll
         for (int i = 0; i < kOptThreads / 32; ++i) t += red[i];
         partials[blockIdx.x] = t;
-        if (blockIdx.x == 0) state[0] += 1.f;  // optimizer step count (read by the AdamW kernel that follows)
     }
 }
 
-// AdamW exactly as torch.optim.AdamW (decoupled decay, bias correction, eps outside the sqrt), with the
-// global-norm clip coefficient min(1, max_norm / (|g| + 1e-6)) (torch.nn.utils.clip_grad_norm_) folded in.
-// state[0] = step count (already incremented), state[1] <- |g| (pre-clip), for logging.
+// Optimizer state vector (fp32, on the device so that a replayed CUDA graph sees every change):
+//   [0] step count   [1] last gradient norm (unscaled, before clipping)   [2] loss scale S
+//   [3] growth tracker   [4] found_inf of the last step   [5] number of skipped steps
+//   [6] learning rate   [7] weight decay   [8] growth interval (0 = static scale)
+// AdamW exactly as torch.optim.AdamW (decoupled decay, bias correction, eps outside the sqrt), with
+// torch.amp.GradScaler's unscale / inf check / skip (train.py:862-867) and the global-norm clip coefficient
+// min(1, max_norm / (|g| + 1e-6)) (torch.nn.utils.clip_grad_norm_, train.py:865) folded in: the gradients in
+// `g` are S times the true ones; a non-finite sum of squares means some gradient overflowed fp16 -> the step
+// is skipped (parameters and moments untouched) and scaler_update_kernel backs S off.
 __global__ void __launch_bounds__(kOptThreads)
 adamw_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                  long long n, const float* __restrict__ partials, int n_partials, float* __restrict__ state, float lr,
-                  float beta1, float beta2, float eps, float wd, float max_norm) {
+                  long long n, const float* __restrict__ partials, int n_partials, float* __restrict__ state,
+                  float beta1, float beta2, float eps, float max_norm) {
     pdl_trigger();
     pdl_wait();
     __shared__ float s_coef;
+    __shared__ int s_skip;
     if (threadIdx.x < 32) {  // every block re-reduces the partials in the same order
         float t = 0.f;
         for (int i = threadIdx.x; i < n_partials; i += 32) t += partials[i];
         t = warp_sum(t);
         if (threadIdx.x == 0) {
-            const float norm = sqrtf(t);
-            s_coef = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+            const float inv_scale = 1.f / state[2];
+            const float norm = sqrtf(t) * inv_scale;
+            s_skip = !isfinite(t);
+            s_coef = (max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f) * inv_scale;
             if (blockIdx.x == 0) state[1] = norm;
         }
     }
     __syncthreads();
+    if (s_skip) return;
     const float coef = s_coef;
-    const float step = state[0];
+    const float step = state[0] + 1.f;  // scaler_update_kernel commits the increment after this kernel
+    const float lr = state[6], wd = state[7];
     const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
     const float step_size = lr / bc1, inv_bc2_sqrt = rsqrtf(bc2), decay = 1.f - lr * wd;
     const long long n4 = n >> 2;
@@ -187,6 +198,37 @@ adamw_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const long long i = (n4 << 2) + threadIdx.x;
         upd(p[i], g[i], m[i], v[i]);
+    }
+}
+
+// torch.amp.GradScaler.update() (backoff 0.5 on overflow, growth 2 every `growth interval` clean steps) and the
+// step-count commit, one warp after the AdamW kernel has finished reading the state.
+__global__ void scaler_update_kernel(const float* __restrict__ partials, int n_partials, float* __restrict__ state) {
+    pdl_trigger();
+    pdl_wait();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < n_partials; i += 32) t += partials[i];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+        if (!isfinite(t)) {
+            state[2] = fmaxf(state[2] * 0.5f, 1.f);
+            state[3] = 0.f;
+            state[4] = 1.f;
+            state[5] += 1.f;
+        } else {
+            state[0] += 1.f;
+            state[4] = 0.f;
+            const float interval = state[8];
+            if (interval > 0.f) {
+                const float tr = state[3] + 1.f;
+                if (tr >= interval) {
+                    state[2] = fminf(state[2] * 2.f, 16777216.f);
+                    state[3] = 0.f;
+                } else {
+                    state[3] = tr;
+                }
+            }
+        }
     }
 }
 
@@ -224,8 +266,7 @@ extern "C" int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, in
 extern "C" int cesm_adamw_partials(void) { return 148 * 4; }
 
 extern "C" int cesm_adamw_step(float* p, const float* g, float* m, float* v, long long n, float* partials,
-                               float* state, float lr, float beta1, float beta2, float eps, float weight_decay,
-                               float max_norm, void* stream) {
+                               float* state, float beta1, float beta2, float eps, float max_norm, void* stream) {
     CESM_REQUIRE(n > 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
                  "adamw_step needs n > 0 and 16-byte aligned flat buffers (n=%lld)", n);
@@ -233,8 +274,10 @@ extern "C" int cesm_adamw_step(float* p, const float* g, float* m, float* v, lon
     const int nb = cesm_adamw_partials();
     launch_pdl(grad_sumsq_kernel, nb, kOptThreads, 0, st, g, n, partials, state);
     CESM_CHECK_LAUNCH();
-    launch_pdl(adamw_clip_kernel, nb * 2, kOptThreads, 0, st, p, g, m, v, n, partials, nb, state, lr, beta1, beta2, eps,
-                                                     weight_decay, max_norm);
+    launch_pdl(adamw_clip_kernel, nb * 2, kOptThreads, 0, st, p, g, m, v, n, partials, nb, state, beta1, beta2, eps,
+                                                     max_norm);
+    CESM_CHECK_LAUNCH();
+    launch_pdl(scaler_update_kernel, 1, 32, 0, st, (const float*)partials, nb, state);
     CESM_CHECK_LAUNCH();
     return CESM_OK;
 }

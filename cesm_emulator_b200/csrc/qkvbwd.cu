@@ -4,7 +4,7 @@
 //     dX[p][ci]  = sum_co dY[p][co] * W[co][ci]           (contraction over the cout = 768 output channels)
 //     dW[co][ci] += sum_p  dY[p][co] * X[p][ci]            (contraction over pixels)
 //
-// dY (bf16 [rows][cout], 1.5 KB per row at cout = 768) is by far the largest operand of both; as two
+// dY (fp16 [rows][cout], 1.5 KB per row at cout = 768) is by far the largest operand of both; as two
 // kernels it was streamed from HBM twice (84 + 87 us at 192x288, each at its own bandwidth roofline).
 // Here a persistent CTA walks 128-pixel row tiles; a tile's dY arrives in 128-channel chunks
 // ([128 px][128 co], two SWIZZLE_128B sub-tiles of 64 channels) and every chunk feeds two tcgen05 MMA
@@ -14,7 +14,7 @@
 //     weight gradient: the chunk as an MN-major A operand (M = co, K = pixels) x the X tile (MN-major B),
 //                      accumulating D2[chunk][128 co][64 ci] over ALL tiles of the CTA.
 // TMEM: D1 double-buffered (2 x 64 columns) + D2 (6 x 64 columns) = 512 columns exactly.
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocation, 4..7 = epilogue (D1 -> bf16 dX rows per
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocation, 4..7 = epilogue (D1 -> fp16 dX rows per
 // tile; D2 -> red.add into dW once at the end).
 #include <cstdlib>
 
@@ -42,7 +42,7 @@ struct QkvBwdMaps {
 struct QkvBwdParams {
     long long rows;
     int tiles, chunks;          // row tiles; cout / 128
-    __nv_bfloat16* dx;          // [rows][64]
+    h16* dx;          // [rows][64]
     float* dw;                  // dW[co * so + ci] (+=)
     long long so;
     int dbg;   // CESM_QKVBWD_DBG bisection bits (0 in production): 1 = no data-gradient MMAs, 2 = no weight-gradient MMAs
@@ -123,8 +123,8 @@ qkv_bwd_kernel(const __grid_constant__ QkvBwdMaps maps, const QkvBwdParams p) {
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the loops, one elected lane issues =====
         const bool leader = elect_one();
-        constexpr uint32_t idesc_dg = make_idesc_bf16(QB_TILE, QB_C, 0, 0);    // K-major A, B
-        constexpr uint32_t idesc_wg = make_idesc_bf16(QB_CHUNK, QB_C, 1, 1);   // MN-major A, B
+        constexpr uint32_t idesc_dg = make_idesc_f16(QB_TILE, QB_C, 0, 0);    // K-major A, B
+        constexpr uint32_t idesc_wg = make_idesc_f16(QB_CHUNK, QB_C, 1, 1);   // MN-major A, B
         const uint64_t dk = make_smem_desc_sw128(0, 0, 1024);                  // K-major SW128
         const uint64_t dmn = make_smem_desc_sw128(0, QB_SUB, 1024);            // MN-major: 64-channel atoms QB_SUB apart
         int st = 0, xs = 0, acc = 0, it = 0;
@@ -145,14 +145,14 @@ qkv_bwd_kernel(const __grid_constant__ QkvBwdMaps maps, const QkvBwdParams p) {
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t ao = a16 + (k >> 2) * (QB_SUB >> 4) + (k & 3) * 2;
                     const uint32_t bo = w16 + (k >> 2) * (QB_WSUB >> 4) + (k & 3) * 2;
-                    if (leader && !(p.dbg & 1)) umma_bf16(d1, dk | (uint64_t)ao, dk | (uint64_t)bo, idesc_dg, (c > 0 || k > 0) ? 1u : 0u);
+                    if (leader && !(p.dbg & 1)) umma_f16(d1, dk | (uint64_t)ao, dk | (uint64_t)bo, idesc_dg, (c > 0 || k > 0) ? 1u : 0u);
                 }
                 // weight gradient: K = 128 pixels = 8 steps of 16 pixels (2048 B)
                 const uint32_t d2 = tmem_d2 + c * 64;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     if (leader && !(p.dbg & 2))
-                        umma_bf16(d2, dmn | (uint64_t)(a16 + k * 128), dmn | (uint64_t)(x16 + k * 128), idesc_wg,
+                        umma_f16(d2, dmn | (uint64_t)(a16 + k * 128), dmn | (uint64_t)(x16 + k * 128), idesc_wg,
                                   (it > 0 || k > 0) ? 1u : 0u);
                 }
                 if (leader) umma_commit(s_empty(st));
@@ -195,10 +195,10 @@ qkv_bwd_kernel(const __grid_constant__ QkvBwdMaps maps, const QkvBwdParams p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 u;
-                        u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                        u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                        u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                        u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                        u.x = pack_h2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                        u.y = pack_h2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                        u.z = pack_h2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                        u.w = pack_h2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
                         dst[j] = u;
                     }
                 }
@@ -256,28 +256,28 @@ extern "C" int cesm_qkv_bwd(const void* dy, const void* x, const void* wt, void*
         const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)rows};
         const uint64_t str[1] = {(uint64_t)cout * 2};
         const uint32_t box[2] = {64u, (uint32_t)QB_TILE};
-        int rc = get_tensor_map_bf16(&maps.dy, dy, 2, dims, str, box);
+        int rc = get_tensor_map_h16(&maps.dy, dy, 2, dims, str, box);
         if (rc) return rc;
     }
     {
         const uint64_t dims[2] = {(uint64_t)cin, (uint64_t)rows};
         const uint64_t str[1] = {(uint64_t)cin * 2};
         const uint32_t box[2] = {64u, (uint32_t)QB_TILE};
-        int rc = get_tensor_map_bf16(&maps.x, x, 2, dims, str, box);
+        int rc = get_tensor_map_h16(&maps.x, x, 2, dims, str, box);
         if (rc) return rc;
     }
     {
         const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)cin};
         const uint64_t str[1] = {(uint64_t)cout * 2};
         const uint32_t box[2] = {64u, (uint32_t)QB_C};
-        int rc = get_tensor_map_bf16(&maps.w, wt, 2, dims, str, box);
+        int rc = get_tensor_map_h16(&maps.w, wt, 2, dims, str, box);
         if (rc) return rc;
     }
     QkvBwdParams p;
     p.rows = rows;
     p.tiles = (int)((rows + QB_TILE - 1) / QB_TILE);
     p.chunks = cout / QB_CHUNK;
-    p.dx = (__nv_bfloat16*)dx;
+    p.dx = (h16*)dx;
     p.dw = dw;
     p.so = dw_so;
     static const int dbg = [] { const char* e = getenv("CESM_QKVBWD_DBG"); return e ? atoi(e) : 0; }();

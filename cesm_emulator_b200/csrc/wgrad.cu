@@ -124,7 +124,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the loop (warp-uniform operands), one elected lane issues;
         // the constant descriptor word is hoisted and only the start-address field advances =====
-        constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+        constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 1, 1);
         const bool leader = elect_one();
         const uint64_t desc_hi = make_smem_desc_sw128(0, kPix * 128, 1024);
         int stage = 0;
@@ -138,7 +138,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
             for (int k = 0; k < kPix / 16; ++k) {
                 // 16 pixels = two 8-row groups = 2048 B further along K
                 if (leader)
-                    umma_bf16(tmem_base, desc_hi | (uint64_t)(sa16 + k * 128), desc_hi | (uint64_t)(sb16 + k * 128), idesc,
+                    umma_f16(tmem_base, desc_hi | (uint64_t)(sa16 + k * 128), desc_hi | (uint64_t)(sb16 + k * 128), idesc,
                               accum);
                 accum = 1;
             }

@@ -1,16 +1,16 @@
 """Training-step and sampling engines: the loop bodies of the reference's train.py / inference.py
 on CUDA streams and graphs.
 
-TrainEngine.step is what `train_one_epoch` does per batch (train.py:829-867) -- loss, backward,
-global-norm clip, AdamW -- with three differences that are deliberate and documented in DESIGN.md:
-  * activations are bf16 (fp32 accumulate) instead of fp16 autocast + GradScaler, so there is no
-    loss scaling;
+TrainEngine.step is what `train_one_epoch` does per batch (train.py:829-867) -- fp16 forward/backward with
+a dynamically scaled loss (autocast + GradScaler, train.py:853-867), unscale + inf check, global-norm clip,
+AdamW, scaler update -- with two differences that are deliberate and documented in DESIGN.md:
   * under torch.distributed the gradients really are averaged over ranks (the reference wraps the
     model in DDP, train.py:1076, but calls `.module.loss`, so its reducer never fires): static
     buckets in expected-ready order are all-reduced with NCCL on a side stream as soon as the last
     gradient of a bucket has been produced, overlapping the rest of the backward pass;
-  * the whole step (RNG draws, forward, backward, all-reduce, clip, AdamW) is captured once into a
-    CUDA graph and replayed: no host syncs, no per-kernel launch latency.
+  * the whole step (RNG draws, forward, backward, all-reduce, unscale, clip, AdamW, loss-scale update) is
+    captured once into a CUDA graph and replayed: the GradScaler logic (found-inf check, skipped step, backoff /
+    growth of the scale) runs on the device, so there are no host syncs and no per-kernel launch latency.
 """
 from __future__ import annotations
 
@@ -47,6 +47,8 @@ class GradBuckets:
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
         order = _ready_order(module.named_parameters())
         self.params = [p for _, p in order]
+        self._named = order
+        self._seen = {}
         # every tensor starts on a 64-byte boundary of the flat buffers (kernels read parameters with
         # 16-byte vector loads); the padding stays zero in the gradient, parameter and moment buffers
         pad = lambda n: (n + 15) // 16 * 16
@@ -130,9 +132,11 @@ class GradBuckets:
     def begin_step(self):
         self.flat.zero_()
         self._pending = list(self._pending_init)
+        self._seen = {}
 
     def _on_grad(self, p):
         b = self._bucket_of[p.data_ptr()]
+        self._seen[id(p)] = True
         self._pending[b] -= 1
         if self._pending[b] == 0:
             self.unpack_bucket(b)
@@ -148,6 +152,15 @@ class GradBuckets:
     def finish_step(self):
         if self.world == 1:
             self.unpack_bucket(None)
+        if self.world > 1:
+            # a parameter that produced no gradient leaves its bucket un-reduced and the replicas diverge
+            # silently (the reference passes find_unused_parameters=True for this, train.py:1076): fail loudly.
+            # Host-side bookkeeping only; during graph capture it is checked once, for the captured step.
+            late = [b for b, n in enumerate(self._pending) if n > 0]
+            if late:
+                names = [n for n, p in self._named if self._bucket_of.get(p.data_ptr()) in late and not self._seen.get(id(p))]
+                raise RuntimeError(f"gradient buckets {late} were never all-reduced: no gradient arrived for {names[:8]}"
+                                   f"{' ...' if len(names) > 8 else ''}")
         if self.world > 1 and self.on_cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
@@ -180,32 +193,63 @@ class GradBuckets:
 
 
 class FusedAdamW:
-    """torch.optim.AdamW semantics (train.py:1078-1083) + clip_grad_norm_ (train.py:865) as two launches of
-    the library's own kernel over flat buffers (`cesm_adamw_step`).  The step counter lives on the device so
-    that a replayed CUDA graph advances the bias correction.  Drop-in for what the engine and train.py use
-    of an optimizer: `step()`, `state_dict()`, `load_state_dict()`, `param_groups[0]["lr"]`."""
+    """torch.optim.AdamW (train.py:1078-1083) + torch.amp.GradScaler (train.py:862-867, 1084) + clip_grad_norm_
+    (train.py:865) as three launches of the library's own kernels over flat buffers (`cesm_adamw_step`).  Step
+    counter, loss scale, growth tracker, learning rate and weight decay live in a small device vector (`state`,
+    layout in include/cesm_b200.h) so that a replayed CUDA graph advances / honours them.  Drop-in for what the
+    engine and train.py use of an optimizer: `step()`, `state_dict()`, `load_state_dict()`,
+    `param_groups[0]["lr"]` (picked up by the next step through `sync_hparams`, also after graph capture)."""
 
-    def __init__(self, buckets: "GradBuckets", lr, betas, weight_decay, eps, max_grad_norm):
+    def __init__(self, buckets: "GradBuckets", lr, betas, weight_decay, eps, max_grad_norm,
+                 init_scale: float = 65536.0, growth_interval: int = 2000):
         from . import _lib
         self._buckets = buckets
         self.g = buckets.flat
         self.p = buckets.flatten_params_()
         self.m = torch.zeros_like(self.p)
         self.v = torch.zeros_like(self.p)
-        self.state = torch.zeros(2, dtype=torch.float32, device=self.p.device)  # [step, last grad norm]
+        st = torch.zeros(K.OPT_STATE_FLOATS, dtype=torch.float32)
+        st[K.OPT_SCALE], st[K.OPT_INTERVAL] = init_scale, growth_interval  # GradScaler() defaults
+        self.state = st.to(self.p.device)
         self.partials = torch.zeros(_lib.load().cesm_adamw_partials(), dtype=torch.float32, device=self.p.device)
         self.param_groups = [dict(lr=lr, betas=tuple(betas), weight_decay=weight_decay, eps=eps)]
         self.max_grad_norm = max_grad_norm
+        self._synced = None    # (lr, weight_decay) last written to the device
+        self._frozen = None    # (betas, eps, max_norm) baked into the first launch / the captured graph
+        self.sync_hparams()
 
     @property
     def grad_norm(self) -> torch.Tensor:
-        return self.state[1]
+        return self.state[K.OPT_NORM]
+
+    @property
+    def loss_scale(self) -> torch.Tensor:
+        """0-dim device view of the current loss scale (multiply the loss by it before backward)."""
+        return self.state[K.OPT_SCALE]
+
+    def sync_hparams(self) -> None:
+        """Bring the device copy of lr / weight decay up to date with `param_groups` (a 8-byte H2D copy, only when
+        they changed; call outside graph capture -- TrainEngine does, before every replay)."""
+        hp = self.param_groups[0]
+        cur = (float(hp["lr"]), float(hp["weight_decay"]))
+        if cur != self._synced:
+            if self.p.is_cuda and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedAdamW: lr / weight_decay changed while a CUDA graph is being captured")
+            self.state[K.OPT_LR:K.OPT_WD + 1].copy_(torch.tensor(cur, dtype=torch.float32))
+            self._synced = cur
+        frozen = (tuple(hp["betas"]), float(hp["eps"]), self.max_grad_norm)
+        if self._frozen is not None and frozen != self._frozen:
+            raise RuntimeError("FusedAdamW: betas / eps / max_grad_norm are fixed after the first step "
+                               f"(were {self._frozen}, now {frozen})")
 
     def step(self) -> None:
         hp = self.param_groups[0]
-        K.adamw_step(self.p, self.g, self.m, self.v, self.partials, self.state, hp["lr"], hp["betas"][0],
-                     hp["betas"][1], hp["eps"], hp["weight_decay"], self.max_grad_norm)
-        ops.invalidate_weight_cache()  # the bf16 operand copies are stale now
+        if not (self.p.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.sync_hparams()
+        self._frozen = (tuple(hp["betas"]), float(hp["eps"]), self.max_grad_norm)
+        K.adamw_step(self.p, self.g, self.m, self.v, self.partials, self.state, hp["betas"][0], hp["betas"][1],
+                     hp["eps"], self.max_grad_norm)
+        ops.invalidate_weight_cache()  # the fp16 operand copies are stale now
 
     def _slices(self):
         """(flat offset, numel, shape) of every parameter in REGISTRATION order, i.e. the parameter indexing of
@@ -223,7 +267,10 @@ class FusedAdamW:
         group = dict(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=g["weight_decay"], amsgrad=False,
                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
                      params=list(range(len(state))))
-        return {"state": state, "param_groups": [group]}
+        # "grad_scaler": torch.amp.GradScaler.state_dict() keys (the reference loads one if present, train.py:940-944)
+        scaler = {"scale": float(self.state[K.OPT_SCALE]), "growth_factor": 2.0, "backoff_factor": 0.5,
+                  "growth_interval": int(self.state[K.OPT_INTERVAL]), "_growth_tracker": int(self.state[K.OPT_TRACKER])}
+        return {"state": state, "param_groups": [group], "grad_scaler": scaler}
 
     def load_state_dict(self, sd: dict) -> None:
         if "state" in sd:  # torch format (ours, the reference's, or any torch AdamW over module.parameters())
@@ -240,12 +287,19 @@ class FusedAdamW:
                 self.state[0] = max(steps)
             for g, src in zip(self.param_groups, sd.get("param_groups", [])):
                 g.update({k: src[k] for k in ("lr", "betas", "eps", "weight_decay") if k in src})
+            sc = sd.get("grad_scaler")
+            if sc:
+                self.state[K.OPT_SCALE] = float(sc["scale"])
+                self.state[K.OPT_TRACKER] = float(sc.get("_growth_tracker", 0))
+                self.state[K.OPT_INTERVAL] = float(sc.get("growth_interval", 2000))
+            self.sync_hparams()
             return
         self.state[:1].copy_(sd["step"])  # flat format of earlier checkpoints of this repo
         self.m.copy_(sd["exp_avg"])
         self.v.copy_(sd["exp_avg_sq"])
         for g, src in zip(self.param_groups, sd.get("param_groups", [])):
             g.update(src)
+        self.sync_hparams()
 
 
 class TrainEngine:
@@ -292,11 +346,15 @@ class TrainEngine:
 
     def _step_body_inner(self):
         ops.set_grad_sink(self.buckets)
-        ops.prepack_all()  # one kernel refreshes every bf16 operand copy of the (just updated) weights
+        ops.prepack_all()  # one kernel refreshes every fp16 operand copy of the (just updated) weights
         K.STABLE_WEIGHT_PTRS = ops.packed_ptrs()  # nothing rewrites them until the next step
         self.buckets.begin_step()
         loss = self.diffusion.loss(self.x0, self.cond)
-        (loss / self.world if self.world > 1 else loss).backward()
+        if isinstance(self.opt, FusedAdamW):
+            # scaler.scale(loss).backward() (train.py:862); /world turns the bucket SUM into the mean
+            (loss * (self.opt.loss_scale * (1.0 / self.world))).backward()
+        else:
+            (loss / self.world if self.world > 1 else loss).backward()
         self.buckets.finish_step()
         if isinstance(self.opt, FusedAdamW):
             self.opt.step()
@@ -325,7 +383,12 @@ class TrainEngine:
             with torch.cuda.graph(self.graph):
                 self._step_body()
             self.launches_per_step = _lib.launch_count() - n0
+        if isinstance(self.opt, FusedAdamW):
+            self.opt.sync_hparams()  # an lr schedule / warm-up changes param_groups between replays
         self.graph.replay()
+        # the replayed optimizer step rewrote the parameters behind torch's back: every cached fp16 operand
+        # copy / F = 1 fold keyed on (pointer, version, epoch) is stale for any eager or eval use that follows
+        ops.invalidate_weight_cache()
 
     # public -----------------------------------------------------------------------------------
     def step_resident(self) -> torch.Tensor:
@@ -411,6 +474,10 @@ class SampleEngine:
         """cond: [B,1,H,W] -> generated field [B,1,H,W] after `steps` (default T) reverse steps."""
         T = self.diffusion.T
         steps = T if steps is None else steps
+        # operands derived from the weights (packed fp16 copies, F = 1 folds) are captured by ADDRESS: bring their
+        # contents up to date with whatever training / load_state_dict did since the graph was captured
+        ops.prepack_all()
+        ops.refresh_folds()
         self.cond.copy_(cond, non_blocking=True)
         self.x.normal_()
         self.t.fill_(T - 1)

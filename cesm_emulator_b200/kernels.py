@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import IgemmArgs
 
-BF16 = torch.bfloat16
+H16 = torch.float16
 
 
 def _stream() -> ctypes.c_void_p:
@@ -108,15 +108,15 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
           out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None,
           out_place: Tuple[int, int, int, int] = (1, 1, 0, 0),
           bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-          out_dtype: torch.dtype = BF16, gn_sums: Optional[torch.Tensor] = None, gn_frames: int = 1):
+          out_dtype: torch.dtype = H16, gn_sums: Optional[torch.Tensor] = None, gn_frames: int = 1):
     """out[n,oh,ow,:] = sum_t A[n, oh*stride+dh_t, ow*stride+dw_t, :] @ wt[:, t, :]^T (+bias)(+residual).
 
-    a0/a1: bf16 [N,H,W,C]; wt: bf16 [cout, len(taps)*(C0+C1)].  `out_hw` is the iterated output
+    a0/a1: fp16 [N,H,W,C]; wt: fp16 [cout, len(taps)*(C0+C1)].  `out_hw` is the iterated output
     grid (defaults to H//stride, W//stride); `out_place` = (o_sh, o_sw, o_h0, o_w0) scatters the
     grid into a larger `out` tensor (transposed-conv phases).
     """
     _req_cuda(a0, a1, wt, out, bias, residual)
-    assert a0.dtype == BF16 and wt.dtype == BF16 and a0.dim() == 4
+    assert a0.dtype == H16 and wt.dtype == H16 and a0.dim() == 4
     n, h, w, c0 = a0.shape
     c1 = 0 if a1 is None else a1.shape[-1]
     cout = wt.shape[0]
@@ -148,7 +148,7 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == cout
     if residual is not None:
-        assert residual.dtype == BF16 and residual.shape[:3] == out.shape[:3]
+        assert residual.dtype == H16 and residual.shape[:3] == out.shape[:3]
     meta = None
     if _lib.PROFILER is not None:
         rows = n * oh * ow
@@ -168,7 +168,7 @@ def wgrad(x0: torch.Tensor, dy: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
     With `into` (an fp32 tensor) and `layout` = (so, si, tap_off) the result is instead ACCUMULATED
     at into.flatten()[co*so + ci*si + tap_off[t]] (e.g. straight into a parameter's .grad)."""
     _req_cuda(x0, x1, dy)
-    assert x0.dtype == BF16 and dy.dtype == BF16 and x0.dim() == 4 and dy.dim() == 4
+    assert x0.dtype == H16 and dy.dtype == H16 and x0.dim() == 4 and dy.dim() == 4
     n, h, w, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
     cout = dy.shape[-1]
@@ -202,10 +202,10 @@ def wgrad(x0: torch.Tensor, dy: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
 
 def qkv_bwd(dy: torch.Tensor, x: torch.Tensor, wt: torch.Tensor, dw_into: Optional[torch.Tensor] = None):
     """Fused data + weight gradient of a bias-free C=64 -> cout projection (cesm_qkv_bwd).
-    dy: bf16 [..., cout]; x: bf16 [..., 64]; wt: bf16 [64, cout] (W^T).  -> (dx bf16 like x, dw fp32 [cout, 64]);
+    dy: fp16 [..., cout]; x: fp16 [..., 64]; wt: fp16 [64, cout] (W^T).  -> (dx fp16 like x, dw fp32 [cout, 64]);
     with `dw_into` (fp32, contiguous [cout, 64] storage, e.g. a parameter's .grad) dW is ACCUMULATED there."""
     _req_cuda(dy, x, wt, dw_into)
-    assert dy.dtype == BF16 and x.dtype == BF16 and wt.dtype == BF16 and dy.is_contiguous() and x.is_contiguous()
+    assert dy.dtype == H16 and x.dtype == H16 and wt.dtype == H16 and dy.is_contiguous() and x.is_contiguous()
     cout, cin = dy.shape[-1], x.shape[-1]
     rows = x.numel() // cin
     assert dy.numel() // cout == rows and tuple(wt.shape) == (cin, cout) and wt.is_contiguous()
@@ -231,11 +231,11 @@ def _tap_array(offs: Sequence[int]):
 
 def pack_weight(src: torch.Tensor, O: int, T: int, I: int, so: int, si: int, tap_off: Sequence[int],
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dst[o][t][i] (bf16) = src.flatten()[o*so + i*si + tap_off[t]]."""
+    """dst[o][t][i] (fp16) = src.flatten()[o*so + i*si + tap_off[t]]."""
     _req_cuda(src)
     assert src.dtype == torch.float32
     if out is None:
-        out = torch.empty((O, T * I), dtype=BF16, device=src.device)
+        out = torch.empty((O, T * I), dtype=H16, device=src.device)
     _lib.call("cesm_pack_weight", _ptr(src), _ptr(out), O, T, I, so, si, _tap_array(tap_off), _stream())
     return out
 
@@ -248,23 +248,26 @@ def unpack_wgrad(src: torch.Tensor, dst: torch.Tensor, O: int, T: int, I: int, s
     return dst
 
 
+OPT_STATE_FLOATS = 16  # CESM_OPT_STATE_FLOATS; layout in include/cesm_b200.h
+OPT_STEP, OPT_NORM, OPT_SCALE, OPT_TRACKER, OPT_FOUND_INF, OPT_SKIPPED, OPT_LR, OPT_WD, OPT_INTERVAL = range(9)
+
+
 def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, partials: torch.Tensor,
-               state: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
-               max_norm: Optional[float]) -> None:
-    """Global-norm clip + AdamW over flat fp32 buffers (see cesm_adamw_step in include/cesm_b200.h)."""
+               state: torch.Tensor, beta1: float, beta2: float, eps: float, max_norm: Optional[float]) -> None:
+    """Loss-scale removal + inf check + global-norm clip + AdamW over flat fp32 buffers, then the scaler update
+    (see cesm_adamw_step in include/cesm_b200.h; lr, weight decay and the loss scale live in `state`)."""
     _req_cuda(p, g, m, v, partials, state)
     for t in (p, g, m, v, partials, state):
         assert t.dtype == torch.float32 and t.is_contiguous()
-    assert p.numel() == g.numel() == m.numel() == v.numel() and state.numel() >= 2
+    assert p.numel() == g.numel() == m.numel() == v.numel() and state.numel() >= OPT_STATE_FLOATS
     assert partials.numel() >= _lib.load().cesm_adamw_partials()
     _lib.call("cesm_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(partials), _ptr(state),
-              float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
-              float(max_norm) if max_norm is not None else 0.0, _stream(),
+              float(beta1), float(beta2), float(eps), float(max_norm) if max_norm is not None else 0.0, _stream(),
               _meta={"bytes": 28.0 * p.numel()})
 
 
 def colsum(x: torch.Tensor, into: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Column sums of bf16 x[..., C]; with `into` (fp32 [C]) the sums are ADDED to it."""
+    """Column sums of fp16 x[..., C]; with `into` (fp32 [C]) the sums are ADDED to it."""
     _req_cuda(x, into)
     C = x.shape[-1]
     out = torch.empty(C, dtype=torch.float32, device=x.device) if into is None else into
@@ -342,7 +345,7 @@ def ln_bwd(x, gamma, dy, dres, eps: float, into: Optional[torch.Tensor] = None):
 def tattn_fwd(qkv, bias, cs, sn, B: int, F: int, HW: int, H: int, D: int, scale: float):
     _req_cuda(qkv, bias, cs, sn)
     rows = B * F * HW
-    out = torch.empty((rows, H * D), dtype=BF16, device=qkv.device)
+    out = torch.empty((rows, H * D), dtype=H16, device=qkv.device)
     # F <= 4: the backward recomputes the softmax, so no log-sum-exp is kept
     lse = torch.empty((rows, H), dtype=torch.float32, device=qkv.device) if F > 4 else None
     _lib.call("cesm_tattn_fwd", _ptr(qkv), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse), B, F, HW, H, D, scale,
@@ -360,11 +363,11 @@ def tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B: int, F: int, HW: int, H: int
 
 
 def linattn_fwd(qkv, NI: int, n: int, H: int, D: int, scale: float):
-    """-> (out bf16 [NI*n, H*D], ws fp32 workspace kept for the backward)."""
+    """-> (out fp16 [NI*n, H*D], ws fp32 workspace kept for the backward)."""
     _req_cuda(qkv)
     dev = qkv.device
     ws = zero_scratch((_lib.load().cesm_linattn_ws_floats(NI, H),), dev)
-    out = torch.empty((NI * n, H * D), dtype=BF16, device=dev)
+    out = torch.empty((NI * n, H * D), dtype=H16, device=dev)
     _lib.call("cesm_linattn_fwd", _ptr(qkv), _ptr(ws), _ptr(out), NI, n, H, D, scale, _stream(),
               _meta=_bytes_meta(qkv, out))
     return out, ws
@@ -397,21 +400,21 @@ INPUT_KPAD = 256  # columns of the input-conv patch matrix: 2 planes x 49 taps x
 
 
 def input_patches(in0, in1, B: int, F: int, H: int, W: int, ks: int) -> torch.Tensor:
-    """im2col of the two fp32 input planes (frame broadcast folded in) -> bf16 [B*F, H, W, INPUT_KPAD]."""
+    """im2col of the two fp32 input planes (frame broadcast folded in) -> fp16 [B*F, H, W, INPUT_KPAD]."""
     _req_cuda(in0, in1)
     f0, f1 = in0.numel() // (B * H * W), in1.numel() // (B * H * W)
-    out = torch.empty((B * F, H, W, INPUT_KPAD), dtype=BF16, device=in0.device)
+    out = torch.empty((B * F, H, W, INPUT_KPAD), dtype=H16, device=in0.device)
     _lib.call("cesm_input_patches", _ptr(in0), _ptr(in1), f0, f1, _ptr(out), B, F, H, W, ks, INPUT_KPAD, _stream(),
               _meta=_bytes_meta(out))
     return out
 
 
 def input_weight_pack(w, bias, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[cout, 2, 1, ks, ks] fp32 + bias -> bf16 [cout, INPUT_KPAD] operand matching `input_patches`."""
+    """[cout, 2, 1, ks, ks] fp32 + bias -> fp16 [cout, INPUT_KPAD] operand matching `input_patches`."""
     _req_cuda(w, bias)
     cout, ks = w.shape[0], w.shape[-1]
     if out is None:
-        out = torch.empty((cout, INPUT_KPAD), dtype=BF16, device=w.device)
+        out = torch.empty((cout, INPUT_KPAD), dtype=H16, device=w.device)
     _lib.call("cesm_input_weight_pack", _ptr(w), _ptr(bias), _ptr(out), cout, ks, INPUT_KPAD, _stream())
     return out
 
@@ -420,7 +423,7 @@ def input_conv_fwd(in0, in1, w, bias, B: int, F: int, H: int, W: int, ks: int):
     _req_cuda(in0, in1, w, bias)
     cout = w.shape[0]
     f0, f1 = in0.numel() // (B * H * W), in1.numel() // (B * H * W)
-    out = torch.empty((B * F, H, W, cout), dtype=BF16, device=in0.device)
+    out = torch.empty((B * F, H, W, cout), dtype=H16, device=in0.device)
     _lib.call("cesm_input_conv_fwd", _ptr(in0), _ptr(in1), f0, f1, _ptr(w), _ptr(bias), _ptr(out), B, F, H, W, ks, cout,
               _stream())
     return out

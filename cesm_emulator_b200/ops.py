@@ -1,8 +1,8 @@
 """torch.autograd.Function wrappers: forward and backward both run in the C ABI kernels.
 
-Internal activation layout is channels-last bf16 `[N, H, W, C]` with N = batch*frames (the
+Internal activation layout is channels-last fp16 `[N, H, W, C]` with N = batch*frames (the
 reference's NCDHW tensors, permuted once at the network boundary).  Parameters stay fp32 in the
-reference's layouts; the bf16 GEMM operand copies (forward layout and data-gradient layout) live in
+reference's layouts; the fp16 GEMM operand copies (forward layout and data-gradient layout) live in
 a registry (`PackCache`) and are refreshed by ONE batched kernel per optimizer step.
 
 Two granularities are offered:
@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from . import kernels as K
 
-BF16 = torch.bfloat16
+H16 = torch.float16
 
 # sub-pixel decomposition of a k4/s2/p1 transposed conv: output phase -> [(input offset, kernel index)]
 _PHASE_TAPS = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}
@@ -43,7 +43,7 @@ def _phase(ph: int, pw: int):
 
 
 # ------------------------------------------------------------------------------------------------
-# packed bf16 operand copies of the fp32 parameters
+# packed fp16 operand copies of the fp32 parameters
 # ------------------------------------------------------------------------------------------------
 # Fused / capturable optimizers update parameters without bumping `Tensor._version`, so validity is
 # also keyed on a global epoch that every torch optimizer step advances.
@@ -76,7 +76,7 @@ def _key(weight: torch.Tensor):
 
 
 class PackCache:
-    """Per-layer view of the packed-operand registry: `get(weight, tag, spec)` returns the bf16 copy
+    """Per-layer view of the packed-operand registry: `get(weight, tag, spec)` returns the fp16 copy
     `dst[o][t][i] = weight.flatten()[src_off + o*so + i*si + taps[t]]`, re-packing it (in place, so
     the address is stable for CUDA graphs) when the parameter changed.  While a training step is
     being captured, a copy that was not refreshed by `prepack_all()` in this step is always
@@ -93,7 +93,7 @@ class PackCache:
             ent = _PackEntry()
             ent.wref = weakref.ref(weight)
             ent.src_off, ent.O, ent.T, ent.I, ent.so, ent.si, ent.taps = spec
-            ent.out = torch.empty((ent.O, ent.T * ent.I), dtype=BF16, device=weight.device)
+            ent.out = torch.empty((ent.O, ent.T * ent.I), dtype=H16, device=weight.device)
             ent.key, ent.serial = None, -1
             self._d[tag] = ent
             _ENTRIES.append(ent)
@@ -136,6 +136,39 @@ def prepack_all() -> int:
     for e in live:
         e.key, e.serial = _key(e.wref()), _PREPACK_SERIAL[0]
     return len(live)
+
+
+# F = 1 inference fold  W_out W_v  of a temporal-attention block (see TemporalAttnBlockFn.forward): one
+# [C, C] fp16 operand per block, rebuilt IN PLACE (stable address for captured sampling graphs) whenever the
+# weights changed; `refresh_folds()` lets an engine bring every fold up to date outside its graph.
+_FOLDS: list = []
+
+
+def _fold_f1(meta, wqkv, wout, hidden: int, C: int) -> torch.Tensor:
+    key = (_key(wqkv), _key(wout))
+    ent = meta.__dict__.get("fold_f1")
+    if ent is None or ent[1].device != wqkv.device:
+        ent = [None, torch.empty((C, C), dtype=H16, device=wqkv.device), weakref.ref(wqkv), weakref.ref(wout), hidden]
+        meta.__dict__["fold_f1"] = ent
+        _FOLDS.append(ent)
+    if ent[0] != key:
+        wv = wqkv.detach().reshape(3 * hidden, C)[2 * hidden:].float()
+        wo = wout.detach().reshape(C, hidden).float()
+        ent[1].copy_(wo @ wv)   # [C out, C in]: the implicit-GEMM operand layout
+        ent[0] = key
+    return ent[1]
+
+
+def refresh_folds() -> None:
+    live = [e for e in _FOLDS if e[2]() is not None and e[3]() is not None]
+    _FOLDS[:] = live
+    for e in live:
+        wqkv, wout = e[2](), e[3]()
+        key = (_key(wqkv), _key(wout))
+        if e[0] != key:
+            C, hidden = e[1].shape[0], e[4]
+            e[1].copy_(wout.detach().reshape(C, hidden).float() @ wqkv.detach().reshape(3 * hidden, C)[2 * hidden:].float())
+            e[0] = key
 
 
 def packed_ptrs() -> set:
@@ -310,7 +343,7 @@ class UpsampleFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, cache: PackCache):
         x = x.contiguous()
         n, h, w, c = x.shape
-        out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+        out = torch.empty((n, 2 * h, 2 * w, c), dtype=H16, device=x.device)
         # [ci][t][co] = W[ci, co, kh, kw] for the data gradient (a stride-2 conv of dy)
         train = any(ctx.needs_input_grad)
         ctx.wd = cache.get(weight, "dgrad", (0, c, 16, c, c * 16, 16, list(range(16))), train) if train else None
@@ -586,14 +619,7 @@ class TemporalAttnBlockFn(torch.autograd.Function):
             # position bias and the attention kernel drop out.
             # ... and with nothing non-linear between the v projection and to_out, the two linears collapse
             # into ONE C x C matrix W_out W_v, folded once per weight version: y = x + LN(x) (W_out W_v)^T.
-            key = (_key(wqkv), _key(wout))
-            ent = meta.__dict__.get("fold_f1")
-            if ent is None or ent[0] != key:
-                wv = wqkv.detach().reshape(3 * hidden, C)[2 * hidden:].float()
-                wo = wout.detach().reshape(C, hidden).float()
-                ent = (key, (wo @ wv).to(BF16).contiguous())   # [C out, C in]: the implicit-GEMM operand layout
-                meta.__dict__["fold_f1"] = ent
-            return K.igemm(xn, ent[1], residual=x)
+            return K.igemm(xn, _fold_f1(meta, wqkv, wout, hidden, C), residual=x)
         qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
         o, lse = K.tattn_fwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
         y = K.igemm(o.view(NI, H_, W_, hidden), _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), residual=x)
@@ -688,11 +714,11 @@ class SpatialAttnBlockFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 class InputConvFn(torch.autograd.Function):
     """cat([x, cond_map], dim=1) -> Conv3d(2, C, (1,k,k)) with frame broadcast folded in
-    (video_net.py:808-815, model.py:110-121).  x/cond: fp32 [B,1,Fx,H,W]; out: bf16 [B*F,H,W,C]."""
+    (video_net.py:808-815, model.py:110-121).  x/cond: fp32 [B,1,Fx,H,W]; out: fp16 [B*F,H,W,C]."""
 
     @staticmethod
     def forward(ctx, x, cond, weight, bias, F: int):
-        """Tensor-core path: bf16 (hi, lo) im2col patches x [w | w | bias] through the tcgen05 implicit GEMM
+        """Tensor-core path: fp16 (hi, lo) im2col patches x [w | w | bias] through the tcgen05 implicit GEMM
         (kernels.input_patches / input_weight_pack); the patches are kept for the weight gradient."""
         x, cond = x.contiguous().float(), cond.contiguous().float()
         B, H, W = x.shape[0], x.shape[-2], x.shape[-1]
@@ -720,7 +746,7 @@ class InputConvFn(torch.autograd.Function):
 
 class OutConvFn(torch.autograd.Function):
     """Conv3d(C, 1, 1) evaluated on the centre frame (video_net.py:763 + model.py:129-130).
-    a: bf16 [B*F, H, W, 64] -> fp32 [B, 1, H, W]."""
+    a: fp16 [B*F, H, W, 64] -> fp32 [B, 1, H, W]."""
 
     @staticmethod
     def forward(ctx, a, weight, bias, B: int, F: int, mid: int):
@@ -829,12 +855,12 @@ class MseLossFn(torch.autograd.Function):
 # layout helpers (network boundary and module-level drop-in calls only)
 # ------------------------------------------------------------------------------------------------
 def to_cl(x: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
-    """[B, C, F, H, W] (any float dtype) -> bf16 [B*F, H, W, C] contiguous, plus (B, F)."""
+    """[B, C, F, H, W] (any float dtype) -> fp16 [B*F, H, W, C] contiguous, plus (B, F)."""
     B, C, F, H, W = x.shape
-    return x.permute(0, 2, 3, 4, 1).reshape(B * F, H, W, C).to(BF16).contiguous(), B, F
+    return x.permute(0, 2, 3, 4, 1).reshape(B * F, H, W, C).to(H16).contiguous(), B, F
 
 
 def from_cl(y: torch.Tensor, B: int, F: int) -> torch.Tensor:
-    """bf16 [B*F, H, W, C] -> [B, C, F, H, W] view."""
+    """fp16 [B*F, H, W, C] -> [B, C, F, H, W] view."""
     n, H, W, C = y.shape
     return y.view(B, F, H, W, C).permute(0, 4, 1, 2, 3)

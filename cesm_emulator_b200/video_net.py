@@ -7,7 +7,7 @@ forward/backward runs through the sm_100a kernels of libcesm_b200.so (see ops.py
 nn.Linear / nn.GroupNorm / nn.Embedding appear below only as PARAMETER HOLDERS with the
 reference's initialisers; their aten forward is never called.
 
-Internal activation layout: channels-last bf16 `[B*F, H, W, C]`.  Every module offers
+Internal activation layout: channels-last fp16 `[B*F, H, W, C]`.  Every module offers
   * `forward(x, ...)`     -- the reference's signature on [B, C, F, H, W] tensors (layout is
                              converted at this boundary), and
   * `forward_cl(x, B, F)` -- the same computation on the internal layout, which is what
@@ -398,7 +398,7 @@ class Attention(nn.Module):
         if x.dim() != 4:
             raise ValueError(f"expected [b, n_seq, f, c], got {tuple(x.shape)}")
         b, n, f, c = x.shape
-        xc = x.permute(0, 2, 1, 3).reshape(b * f, n, 1, c).to(torch.bfloat16).contiguous()
+        xc = x.permute(0, 2, 1, 3).reshape(b * f, n, 1, c).to(torch.float16).contiguous()
         y = self.forward_cl(xc, b, f, pos_bias=pos_bias, focus_present_mask=focus_present_mask)
         return y.view(b, f, n, c).permute(0, 2, 1, 3).to(x.dtype)
 

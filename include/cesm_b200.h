@@ -8,7 +8,7 @@
  * for.  Conventions shared by every function:
  *
  *   - plain C types only: raw DEVICE pointers, sizes, and an opaque `stream` (a cudaStream_t);
- *   - activations are bf16, channels-last: [N, H, W, C] with N = batch*frames (NDHWC flattened);
+ *   - activations are fp16, channels-last: [N, H, W, C] with N = batch*frames (NDHWC flattened);
  *   - parameters / parameter gradients / statistics are fp32;
  *   - the library owns no tensor memory: callers (PyTorch's caching allocator) own every buffer;
  *   - no implicit synchronisation, nothing on the default stream, CUDA-graph capturable;
@@ -62,27 +62,27 @@ long long cesm_launch_count(void);
  * Constraints: c0, c1, cout multiples of 64; stride in {1, 2}; stride 2 needs c1 == 0 and even h, w.
  */
 typedef struct cesm_igemm_args {
-    const void* a0; /* bf16 [n, h, w, c0] */
-    const void* a1; /* bf16 [n, h, w, c1] or NULL */
+    const void* a0; /* fp16 [n, h, w, c0] */
+    const void* a1; /* fp16 [n, h, w, c1] or NULL */
     int32_t c0, c1;
     int32_t n, h, w;
     int32_t stride;
     int32_t num_taps;
     int32_t tap_dh[CESM_MAX_TAPS];
     int32_t tap_dw[CESM_MAX_TAPS];
-    const void* wt; /* bf16 [cout, num_taps*(c0+c1)] */
+    const void* wt; /* fp16 [cout, num_taps*(c0+c1)] */
     int32_t cout;
     int32_t oh, ow; /* output pixels iterated per image */
-    void* out;      /* bf16 (or fp32 if out_fp32) */
+    void* out;      /* fp16 (or fp32 if out_fp32) */
     int32_t out_fp32;
     int32_t ldo;
     int32_t out_h, out_w, o_sh, o_sw, o_h0, o_w0;
     const float* bias;    /* fp32 [cout] or NULL */
-    const void* residual; /* bf16, addressed like out with pitch ldr, or NULL */
+    const void* residual; /* fp16, addressed like out with pitch ldr, or NULL */
     int32_t ldr;
     /* Optional fused GroupNorm statistics (video_net.py:216): if gn_sums != NULL it is zeroed and then
      * receives, per sample b = image / gn_frames and group g of cout / gn_groups channels,
-     * (sum, sum of squares) of the bf16-rounded outputs: fp32 [n / gn_frames][gn_groups][2]. */
+     * (sum, sum of squares) of the fp16-rounded outputs: fp32 [n / gn_frames][gn_groups][2]. */
     float* gn_sums;
     int32_t gn_groups;
     int32_t gn_frames;
@@ -98,7 +98,7 @@ int cesm_igemm(const cesm_igemm_args* args, void* stream);
  * Weight gradient of the implicit GEMM above, contracted over pixels on tcgen05 tensor cores:
  *     dw[co, t, ci] = sum_{n, oh, ow}  dy[n, oh, ow, co] * X[n, oh*stride + tap_dh[t], ow*stride + tap_dw[t], ci]
  * X = concat(x0, x1) as in cesm_igemm.  dy pixel (n, oh, ow) is row
- * ((n*y_h + oh*y_sh + y_h0)*y_w + ow*y_sw + y_w0) of a bf16 [*, cout] matrix (sub-pixel phases of
+ * ((n*y_h + oh*y_sh + y_h0)*y_w + ow*y_sw + y_w0) of a fp16 [*, cout] matrix (sub-pixel phases of
  * a transposed conv).  dw is fp32 [cout, num_taps, c0+c1] and is overwritten (see dw_so for the
  * accumulate-in-place form).
  *
@@ -129,7 +129,7 @@ typedef struct cesm_wgrad_args {
 int cesm_wgrad(const cesm_wgrad_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Weight re-layout.  dst[o][t][i] (bf16) = src[o*so + i*si + tap_off[t]] (fp32): turns a PyTorch
+ * Weight re-layout.  dst[o][t][i] (fp16) = src[o*so + i*si + tap_off[t]] (fp32): turns a PyTorch
  * conv / linear parameter into the [cout][taps][cin] operand of cesm_igemm (forward, or flipped /
  * transposed for the data gradient).  cesm_unpack_wgrad is the inverse scatter for fp32 gradients
  * produced by cesm_wgrad (accumulate != 0 adds into dst).
@@ -137,7 +137,7 @@ int cesm_wgrad(const cesm_wgrad_args* args, void* stream);
 int cesm_pack_weight(const float* src, void* dst, int O, int T, int I, long long so, long long si,
                      const int32_t* tap_off, void* stream);
 /* One launch re-packs many parameters: `descs_device` is an array of n descriptors in DEVICE memory
- * (the training engine refreshes every bf16 operand copy with it once per optimizer step). */
+ * (the training engine refreshes every fp16 operand copy with it once per optimizer step). */
 typedef struct cesm_pack_desc {
     const float* src;
     void* dst;
@@ -151,8 +151,8 @@ int cesm_pack_weights_batched(const cesm_pack_desc* descs_device, int n, void* s
 int cesm_unpack_wgrads_batched(const cesm_pack_desc* descs_device, int n, void* stream);
 /* Backward of the q/k/v projection (to_qkv, no bias; video_net.py:322, :380) for 64 input channels: data
  * gradient and weight gradient in ONE pass over dy (the two separate calls each stream the 768-wide dy from
- * HBM).  dy: bf16 [rows][cout]; x: bf16 [rows][64] (the projection's input, LN(x)); wt: bf16 [64][cout] = W^T
- * (the data-gradient operand cesm_pack_weight produces); dx: bf16 [rows][64] (written); dw: fp32, dw[co*dw_so +
+ * HBM).  dy: fp16 [rows][cout]; x: fp16 [rows][64] (the projection's input, LN(x)); wt: fp16 [64][cout] = W^T
+ * (the data-gradient operand cesm_pack_weight produces); dx: fp16 [rows][64] (written); dw: fp32, dw[co*dw_so +
  * ci] += sum_rows dy[row][co] * x[row][ci].  cin == 64, cout a multiple of 128, <= 768. */
 int cesm_qkv_bwd(const void* dy, const void* x, const void* wt, void* dx, float* dw, long long dw_so, long long rows,
                  int cin, int cout, void* stream);
@@ -163,30 +163,37 @@ int cesm_qkv_bwd(const void* dy, const void* x, const void* wt, void* dx, float*
  * those ~70 per-step memsets off with on != 0.  Process-wide; default off. */
 void cesm_set_prezeroed_scratch(int on);
 
-/* Optimizer step of train.py:864-867 + 1078-1083 on FLAT fp32 buffers (every parameter, its gradient and
- * both AdamW moments are views into four contiguous arrays of n floats, 16-byte aligned): global-norm
- * clip (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (|g| + 1e-6)); max_norm <= 0 disables it)
- * folded into torch.optim.AdamW's update.  `partials`: fp32 scratch of cesm_adamw_partials() floats.
- * `state`: fp32[2] in device memory -- [0] step count, incremented by the call (so that a CUDA-graph
- * replay advances the bias correction), [1] <- pre-clip gradient norm.  Two launches, no host sync. */
+/* Optimizer step of train.py:862-867 + 1078-1084 on FLAT fp32 buffers (every parameter, its gradient and
+ * both AdamW moments are views into four contiguous arrays of n floats, 16-byte aligned):
+ * torch.amp.GradScaler's unscale / inf check / skip / update (the gradients arrive multiplied by the loss
+ * scale S because the activations and gradient stream are fp16, as under the reference's autocast),
+ * global-norm clip (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (|g| + 1e-6)); max_norm <= 0
+ * disables it) and torch.optim.AdamW's update, all on the device so that a CUDA-graph replay advances them.
+ * `partials`: fp32 scratch of cesm_adamw_partials() floats.
+ * `state`: fp32[CESM_OPT_STATE_FLOATS] in device memory:
+ *   [0] step count (incremented by every non-skipped call)   [1] <- unscaled pre-clip gradient norm
+ *   [2] loss scale S (halved after an overflow, doubled after [8] clean steps; set 1 for unscaled gradients)
+ *   [3] growth tracker   [4] <- 1 if this call found a non-finite gradient and skipped the update
+ *   [5] skipped-step count   [6] learning rate   [7] weight decay   [8] growth interval (0: static scale)
+ * Three launches, no host sync. */
+#define CESM_OPT_STATE_FLOATS 16
 int cesm_adamw_partials(void);
 int cesm_adamw_step(float* p, const float* g, float* m, float* v, long long n, float* partials, float* state,
-                    float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
-                    void* stream);
+                    float beta1, float beta2, float eps, float max_norm, void* stream);
 int cesm_unpack_wgrad(const float* src, float* dst, int O, int T, int I, long long so, long long si,
                       const int32_t* tap_off, int accumulate, void* stream);
-/* out[c] (+)= sum over rows of bf16 x[M][C] (bias gradients).  `accumulate` != 0 here and in the other
+/* out[c] (+)= sum over rows of fp16 x[M][C] (bias gradients).  `accumulate` != 0 here and in the other
  * backward entry points adds into the parameter-gradient outputs instead of overwriting them, which
  * lets the caller pass the parameter's .grad buffer directly. */
 int cesm_colsum(const void* x, float* out, long long M, int C, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * GroupNorm + FiLM + SiLU (+ residual), video_net.py:216-227 and :265.   x: bf16 [B][P][C],
+ * GroupNorm + FiLM + SiLU (+ residual), video_net.py:216-227 and :265.   x: fp16 [B][P][C],
  * P = frames*H*W (statistics couple the frames of a sample, as nn.GroupNorm on a 5-D tensor does).
  *   sums  : fp32 [B][G][2]  (sum, sum of squares), written by cesm_gn_stats
  *   film  : fp32 [B][2C] = (scale | shift) from the time-embedding MLP, or NULL
  *   out   = silu(((x-mean)*rstd*gamma+beta)*(scale+1)+shift) (+ residual)
- * cesm_gn_bwd returns dx (bf16), dgamma/dbeta [C], dfilm [B][2C] (if film) and, if dconv_bias is not
+ * cesm_gn_bwd returns dx (fp16), dgamma/dbeta [C], dfilm [B][2C] (if film) and, if dconv_bias is not
  * NULL, dconv_bias[c] = sum over samples and pixels of dx -- the bias gradient of the convolution
  * that produced x (video_net.py:215), from the same per-channel sums.  csum is fp32 scratch [B][C][3].
  * ---------------------------------------------------------------------------------------------- */
@@ -197,7 +204,7 @@ int cesm_gn_bwd(const void* x, const void* dout, const float* sums, const float*
                 const float* film, float* csum, void* dx, float* dgamma, float* dbeta, float* dfilm,
                 float* dconv_bias, int B, long long P, int C, int G, float eps, int accumulate_params, void* stream);
 
-/* Channel LayerNorm with gain only, video_net.py:78-87.  x, out, dy, dres, dx: bf16 [M][C],
+/* Channel LayerNorm with gain only, video_net.py:78-87.  x, out, dy, dres, dx: fp16 [M][C],
  * C in {64, 128, 256, 512, 1024}.
  * bwd: dx = LN'(dy) (+ dres if not NULL); dgamma fp32 [C] is overwritten. */
 int cesm_ln_fwd(const void* x, const float* gamma, void* out, long long M, int C, float eps, void* stream);
@@ -207,8 +214,8 @@ int cesm_ln_bwd(const void* x, const float* gamma, const void* dy, const void* d
 /* ------------------------------------------------------------------------------------------------
  * Temporal attention core, video_net.py:413-453 + rotary_embedding.py:29-48, fused:
  * q*scale -> RoPE(q), RoPE(k) -> q.k + rel-pos bias -> online softmax over frames -> .v
- *   qkv : bf16 [B*F*HW][3*H*32] (q | k | v), row = (b*F + f)*HW + pixel
- *   bias: fp32 [H][F][F];  cs, sn: fp32 [F][16] rotary cos / sin;  out: bf16 [B*F*HW][H*32]
+ *   qkv : fp16 [B*F*HW][3*H*32] (q | k | v), row = (b*F + f)*HW + pixel
+ *   bias: fp32 [H][F][F];  cs, sn: fp32 [F][16] rotary cos / sin;  out: fp16 [B*F*HW][H*32]
  *   lse : fp32 [B*F*HW][H] log-sum-exp saved for the backward.  For F <= 4 (the training window
  *         K=3 and the one-frame sampling call) a register-resident kernel is used whose backward
  *         recomputes the softmax from qkv: lse may then be NULL in fwd, and out / lse NULL in bwd.
@@ -222,12 +229,12 @@ int cesm_tattn_bwd(const void* qkv, const float* bias, const float* cs, const fl
 /* ------------------------------------------------------------------------------------------------
  * Spatial linear attention core, video_net.py:338-344, per image (frame) of n pixels and head:
  * qs = scale*softmax(q) over d, kh = softmax(k) over the n pixels, ctx = kh^T v, out = qs ctx.
- * Both contractions run as warp-level bf16 tensor-core tiles; the softmaxed operands are
+ * Both contractions run as warp-level fp16 tensor-core tiles; the softmaxed operands are
  * recomputed from qkv where needed, so only q, k, v, out (and their gradients) touch HBM.
- *   qkv: bf16 [NI*n][3*H*32];  out: bf16 [NI*n][H*32];  1 <= H <= 8
+ *   qkv: fp16 [NI*n][3*H*32];  out: fp16 [NI*n][H*32];  1 <= H <= 8
  *   ws : fp32 [cesm_linattn_ws_floats(NI, H)], written by fwd and read by bwd; per image it
  *        holds the column maxima of k (order-encoded), Z = sum_p exp(k - max) and ctx [H][32][32]
- *   bwd: scratch fp32 [NI*H*32*32 + NI*H*32]; dqkv: bf16 [NI*n][3*H*32]
+ *   bwd: scratch fp32 [NI*H*32*32 + NI*H*32]; dqkv: fp16 [NI*n][3*H*32]
  * ---------------------------------------------------------------------------------------------- */
 size_t cesm_linattn_ws_floats(int NI, int H);
 int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, int n, int H, int dim_head, float scale,
@@ -239,7 +246,7 @@ int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, float* scratc
  * Network boundary convs.
  * Input conv (video_net.py:808-815 + model.py:110-121): 7x7, the two fp32 input planes (noisy
  * target, condition) are read in place -- channel concat and frame broadcast (f0/f1 = 1 or F frames
- * per sample) are folded into the kernel.  out: bf16 [B*F][H][W][64].  Only the weight gradient
+ * per sample) are folded into the kernel.  out: fp16 [B*F][H][W][64].  Only the weight gradient
  * exists (network inputs need no gradient).
  * Output conv (video_net.py:763 + model.py:129-130): 1x1x1, 64 -> 1, evaluated on the centre
  * frame only (the reference computes every frame and then selects frame F//2).
@@ -271,9 +278,9 @@ int cesm_gather_windows(const float* cond, const float* tgt, const int* plan, fl
                         int T, int M, int H, int W, int K, int h, int w, void* stream);
 
 /* Tensor-core form of the same input convolution.  cesm_input_patches writes the im2col matrix
- * bf16 [B*F][H][W][kpad] = [hi(x) | lo(x) | 1 | 1 | 0...] (x = the 2*ks*ks taps of the two fp32 planes, frame
- * broadcast as above; hi = bf16(x), lo = bf16(x - hi)); cesm_input_weight_pack writes the matching operand
- * bf16 [cout][kpad] = [w | w | bias_hi | bias_lo | 0].  cesm_igemm (1 tap) of the two is the convolution with
+ * fp16 [B*F][H][W][kpad] = [hi(x) | lo(x) | 1 | 1 | 0...] (x = the 2*ks*ks taps of the two fp32 planes, frame
+ * broadcast as above; hi = fp16(x), lo = fp16(x - hi)); cesm_input_weight_pack writes the matching operand
+ * fp16 [cout][kpad] = [w | w | bias_hi | bias_lo | 0].  cesm_igemm (1 tap) of the two is the convolution with
  * its bias; cesm_wgrad of (patches, dy) is [dW_hi-block | dW_lo-block | db | db | 0]: dW = sum of the two
  * blocks.  ks = 7, kpad = 256. */
 int cesm_input_patches(const float* in0, const float* in1, int f0, int f1, void* out, int B, int F, int H, int W,

@@ -46,12 +46,19 @@ def oracle_loss_and_grads(unet, unet_kwargs, x0, cond, t, noise, T=1000):
     return eps, loss, grads
 
 
-def module_loss_and_grads(diffusion, x0, cond, t, noise):
+# The activations and the gradient stream are fp16 (the reference's autocast dtype, train.py:853), so -- exactly as
+# in the reference's step (train.py:862-864: scaler.scale(loss).backward(); scaler.unscale_(opt)) -- the loss is
+# scaled before backward and the fp32 parameter gradients are unscaled afterwards.  65536 is GradScaler's
+# initial scale.
+LOSS_SCALE = 65536.0
+
+
+def module_loss_and_grads(diffusion, x0, cond, t, noise, loss_scale=LOSS_SCALE):
     diffusion.zero_grad(set_to_none=True)
     x_t, _ = diffusion.q_sample(x0, t, noise)
     eps = diffusion.model(x_t, cond, t)
     from cesm_emulator_b200 import ops
     loss = ops.MseLossFn.apply(eps, noise)
-    loss.backward()
-    grads = {k: p.grad for k, p in diffusion.model.named_parameters() if p.grad is not None}
+    (loss * loss_scale).backward()
+    grads = {k: p.grad / loss_scale for k, p in diffusion.model.named_parameters() if p.grad is not None}
     return eps.detach(), loss.detach(), grads

@@ -16,7 +16,7 @@ def _err(a, b):
 
 
 def _rand(shape, dev, scale=1.0):
-    return (torch.randn(shape, device=dev) * scale).to(torch.bfloat16)
+    return (torch.randn(shape, device=dev) * scale).to(torch.float16)
 
 
 @pytest.mark.parametrize("m,k,n", [(128, 64, 64), (1000, 128, 128), (4096, 256, 768), (300, 512, 256), (77, 64, 64)])
@@ -86,7 +86,7 @@ def test_upsample_convT4x4s2(cuda, n, h, w, c):
     x = _rand((n, h, w, c), cuda)
     wt = _rand((c, c, 4, 4), cuda, 0.05)  # [cin, cout, kh, kw] (ConvTranspose layout)
     bias = torch.randn(c, device=cuda)
-    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=cuda)
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float16, device=cuda)
     # out[2m+ph] = sum_ih x[ih] * w[kh], kh = 2m+ph+1-2ih  ->  ph=0: (dh=0,kh=1),(dh=-1,kh=3); ph=1: (dh=1,kh=0),(dh=0,kh=2)
     sel = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}
     for ph in (0, 1):
@@ -152,9 +152,9 @@ def test_fused_qkv_backward(cuda, rows, cout):
     predicated row stores; two calls accumulate into dW)."""
     from cesm_emulator_b200 import kernels as K
     torch.manual_seed(2)
-    dy = (torch.randn(rows, cout, device=cuda) * 0.5).bfloat16()
-    x = torch.randn(rows, 64, device=cuda).bfloat16()
-    w = (torch.randn(cout, 64, device=cuda) * 0.1).bfloat16()      # to_qkv.weight [cout, cin]
+    dy = (torch.randn(rows, cout, device=cuda) * 0.5).half()
+    x = torch.randn(rows, 64, device=cuda).half()
+    w = (torch.randn(cout, 64, device=cuda) * 0.1).half()      # to_qkv.weight [cout, cin]
     wt = w.t().contiguous()                                         # data-gradient operand [cin, cout]
     dx, dw = K.qkv_bwd(dy, x, wt)
     dx_ref = dy.float() @ w.float()

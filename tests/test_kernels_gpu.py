@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from oracle import cesm_oracle as O
 
 pytestmark = pytest.mark.gpu
-BF = torch.bfloat16
+BF = torch.float16
 
 
 def err(a, b):
@@ -275,7 +275,7 @@ def test_input_conv_tensor_core_path(cuda, B, Fr, H, W, f0):
     torch.manual_seed(8)
     x = torch.randn(B, 1, f0, H, W, device=cuda) * 3
     c = torch.randn(B, 1, Fr, H, W, device=cuda)
-    w = (torch.randn(64, 2, 1, 7, 7, device=cuda) * 0.1).bfloat16().float()
+    w = (torch.randn(64, 2, 1, 7, 7, device=cuda) * 0.1).half().float()
     b = torch.randn(64, device=cuda)
     wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     out = ops.InputConvFn.apply(x, c, wp, bp, Fr)

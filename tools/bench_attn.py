@@ -7,8 +7,8 @@ def main():
     NI, n, H, D = 6, 192 * 288, 8, 32
     B, F = 2, 3
     torch.manual_seed(0)
-    qkv = torch.randn(NI * n, 3 * H * D, device="cuda").bfloat16()
-    dout = torch.randn(NI * n, H * D, device="cuda").bfloat16()
+    qkv = torch.randn(NI * n, 3 * H * D, device="cuda").half()
+    dout = torch.randn(NI * n, H * D, device="cuda").half()
     bias = torch.randn(H, F, F, device="cuda")
     freqs = (1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))).cuda()
     ang = torch.arange(F, device="cuda", dtype=torch.float32)[:, None] * freqs[None]

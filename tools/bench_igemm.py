@@ -51,13 +51,13 @@ def main():
     for name, n, h, w, c0, c1, cout, taps, gn in cases:
         if only and only not in name:
             continue
-        x0 = torch.randn(n, h, w, c0, device=dev).bfloat16()
-        x1 = torch.randn(n, h, w, c1, device=dev).bfloat16() if c1 else None
-        wt = (torch.randn(cout, taps * (c0 + c1), device=dev) * 0.05).bfloat16()
+        x0 = torch.randn(n, h, w, c0, device=dev).half()
+        x1 = torch.randn(n, h, w, c1, device=dev).half() if c1 else None
+        wt = (torch.randn(cout, taps * (c0 + c1), device=dev) * 0.05).half()
         bias = torch.randn(cout, device=dev)
         tp = K.TAPS_3x3 if taps == 9 else K.TAPS_1x1
         sums = torch.empty(2, 8, 2, device=dev) if gn else None
-        out = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(n, h, w, cout, device=dev, dtype=torch.float16)
         if plain:
             for _ in range(3):
                 K.igemm(x0, wt, a1=x1, taps=tp, bias=bias, out=out, gn_sums=sums, gn_frames=3)

@@ -12,9 +12,9 @@ def main():
     for name, hw, C in (("L0 C64", 192 * 288, 64), ("L0 C128", 192 * 288, 128), ("L1 C128", 96 * 144, 128), ("L2 C256", 48 * 72, 256)):
         P = F * hw
         torch.manual_seed(0)
-        x = torch.randn(B * P, C, device="cuda").bfloat16()
-        dout = torch.randn(B * P, C, device="cuda").bfloat16()
-        res = torch.randn(B * P, C, device="cuda").bfloat16()
+        x = torch.randn(B * P, C, device="cuda").half()
+        dout = torch.randn(B * P, C, device="cuda").half()
+        res = torch.randn(B * P, C, device="cuda").half()
         gamma = torch.randn(C, device="cuda"); beta = torch.randn(C, device="cuda")
         film = torch.randn(B, 2 * C, device="cuda") * 0.1
         lg = torch.randn(C, device="cuda")

@@ -8,9 +8,9 @@ for name, n, h, w in (("L0", 6, 192, 288), ("L1", 6, 96, 144), ("L2", 6, 48, 72)
     if name != "L0":
         break  # C = 64 only at L0 (the fused kernel is specialised for 64 input channels)
     rows, cout = n * h * w, 768
-    dy = torch.randn(n, h, w, cout, device="cuda").bfloat16()
-    x = torch.randn(n, h, w, 64, device="cuda").bfloat16()
-    wt = (torch.randn(64, cout, device="cuda") * 0.1).bfloat16()
+    dy = torch.randn(n, h, w, cout, device="cuda").half()
+    x = torch.randn(n, h, w, 64, device="cuda").half()
+    wt = (torch.randn(64, cout, device="cuda") * 0.1).half()
     into = torch.zeros(cout, 1, 64, device="cuda")
     acc = torch.zeros(cout, 64, device="cuda")
     t_d = timeit(lambda: K.igemm(dy, wt))

@@ -27,8 +27,8 @@ def main():
     for name, n, h, w, cin, cout, taps in cases:
         if only and only not in name:
             continue
-        x = torch.randn(n, h, w, cin, device=dev).bfloat16()
-        dy = torch.randn(n, h, w, cout, device=dev).bfloat16()
+        x = torch.randn(n, h, w, cin, device=dev).half()
+        dy = torch.randn(n, h, w, cout, device=dev).half()
         tp = K.TAPS_3x3 if taps == 9 else K.TAPS_1x1
         into = torch.zeros(cout, taps, cin, device=dev)
         layout = (taps * cin, 1, [t * cin for t in range(taps)])

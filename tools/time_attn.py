@@ -24,8 +24,8 @@ def main():
     for name, n in (("L0", 192 * 288), ("L1", 96 * 144), ("L2", 48 * 72)):
         NI = B * F
         torch.manual_seed(0)
-        qkv = torch.randn(NI * n, 3 * H * D, device="cuda").bfloat16()
-        dout = torch.randn(NI * n, H * D, device="cuda").bfloat16()
+        qkv = torch.randn(NI * n, 3 * H * D, device="cuda").half()
+        dout = torch.randn(NI * n, H * D, device="cuda").half()
         bias = torch.randn(H, F, F, device="cuda")
         freqs = (1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))).cuda()
         ang = torch.arange(F, device="cuda", dtype=torch.float32)[:, None] * freqs[None]
