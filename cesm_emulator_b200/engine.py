@@ -423,6 +423,7 @@ class SampleEngine:
         self.shape = tuple(shape)
         self.x = torch.zeros(self.shape, dtype=torch.float32, device=dev)
         self.cond = torch.zeros(self.shape, dtype=torch.float32, device=dev)
+        self.z = torch.zeros(self.shape, dtype=torch.float32, device=dev)
         self.t = torch.zeros((self.shape[0],), dtype=torch.long, device=dev)
         self.arena = K.ZeroArena(dev) if dev.type == "cuda" else None
         self.use_graph = use_graph
@@ -442,8 +443,8 @@ class SampleEngine:
         d = self.diffusion
         with torch.no_grad():
             eps = d.model(self.x, self.cond, self.t)
-            z = torch.randn_like(self.x)
-            self.x.copy_(K.p_sample(self.x, eps, z, self.t, d.betas, d.sqrt_one_minus_alphas_cumprod,
+            self.z.normal_()  # model.py:181 randn_like; kept in a static buffer so that a caller can read the draw
+            self.x.copy_(K.p_sample(self.x, eps, self.z, self.t, d.betas, d.sqrt_one_minus_alphas_cumprod,
                                     d.sqrt_recip_alphas, d.posterior_variance))
             self.t.sub_(1)
 

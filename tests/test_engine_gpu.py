@@ -20,11 +20,11 @@ def _make(cuda):
 
 
 def test_engine_gradients_match_autograd_and_oracle(cuda):
-    """bf16 + fp32 atomics make two runs of the SAME path differ by ~4e-3 median / ~2e-2 worst per
-    gradient tensor (tools/engine_grad_check.py), so the engine is held to the oracle with the bars of
-    test_model_gpu.GRAD_BARS and to the autograd path at noise level."""
+    """The engine's gradient delivery (flat buffer, batched un-pack, block-level nodes, loss scale) against the
+    plain autograd path and the fp32 oracle: every tensor within the 1e-2 contract of the oracle, and within
+    run-to-run noise (fp32 atomics) of the autograd path."""
     import numpy as np
-    from _parity import oracle_loss_and_grads
+    from _parity import LOSS_SCALE, oracle_loss_and_grads
     from cesm_emulator_b200 import ops
     from cesm_emulator_b200.engine import TrainEngine
     B, K, H, W = 2, 3, 32, 48
@@ -35,8 +35,8 @@ def test_engine_gradients_match_autograd_and_oracle(cuda):
     ops.set_grad_sink(None)
     d.zero_grad(set_to_none=True)
     loss_ref = d.loss(x0, cond, t=t, noise=noise)
-    loss_ref.backward()
-    ref = {k: p.grad.clone() for k, p in d.named_parameters() if p.grad is not None}
+    (loss_ref * LOSS_SCALE).backward()
+    ref = {k: p.grad / LOSS_SCALE for k, p in d.named_parameters() if p.grad is not None}
     _, loss_o, og = oracle_loss_and_grads(d.model, BASELINE_KW, x0, cond, t, noise)
     og = {"model." + k: v for k, v in og.items()}
     # engine, eager, no clipping, lr = 0 so that the weights stay put; fixed (t, noise)
@@ -47,12 +47,14 @@ def test_engine_gradients_match_autograd_and_oracle(cuda):
         loss = eng.step(x0, cond)
         assert abs(loss.item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
         assert abs(loss.item() - loss_o.item()) < 1e-2 * abs(loss_o.item())
-        got = {k: p.grad for k, p in d.named_parameters() if p.requires_grad}
+        # the engine leaves S * gradient in the flat buffer (the AdamW kernel unscales); S did not change (no overflow)
+        assert eng.opt.state[4].item() == 0 and eng.opt.loss_scale.item() == LOSS_SCALE
+        got = {k: p.grad / LOSS_SCALE for k, p in d.named_parameters() if p.requires_grad}
         assert set(got) == set(ref) == set(og)
         vs_auto = np.array([rel_err(got[k], ref[k]) for k in ref])
         vs_orac = np.array([rel_err(got[k], og[k]) for k in ref])
-        assert np.median(vs_auto) < 1e-2 and vs_auto.max() < 6e-2, (rep, np.median(vs_auto), vs_auto.max())
-        assert np.median(vs_orac) < 1.2e-2 and vs_orac.max() < 7e-2, (rep, np.median(vs_orac), vs_orac.max())
+        assert vs_auto.max() < 3e-3, (rep, np.median(vs_auto), vs_auto.max())
+        assert vs_orac.max() < 1e-2, (rep, np.median(vs_orac), vs_orac.max())
     del d.loss
     ops.set_grad_sink(None)
 
@@ -72,10 +74,10 @@ def test_graph_replay_matches_eager(cuda):
         if use_graph:
             assert eng.graph is not None and eng.launches_per_step > 100
         ops.set_grad_sink(None)
-    # identical RNG stream, weights and data; bf16 + atomics give tiny run-to-run differences that
+    # identical RNG stream, weights and data; fp32 atomics give tiny run-to-run differences that
     # AdamW's normalised updates amplify slightly over 5 steps
     for a, b in zip(losses[False], losses[True]):
-        assert abs(a - b) < 2e-2 * abs(a), (losses[False], losses[True])
+        assert abs(a - b) < 5e-3 * abs(a), (losses[False], losses[True])
     assert all(l == l and l < 10 for l in losses[True])
 
 
@@ -89,27 +91,38 @@ def test_sample_engine_runs_reverse_chain(cuda):
     assert y.shape == (2, 1, 32, 32) and torch.isfinite(y).all()
     assert eng.graph is not None and eng.launches_per_step > 50
     assert int(eng.t[0].item()) == d.T - 1 - 6
-    # the graph-replayed step equals the module's p_sample with the same noise
+    # one graph-replayed reverse step against the fp32 ORACLE's p_sample (model.py:168-183): the engine draws its
+    # own noise z on the device (kept in eng.z), which is handed to the oracle
+    from oracle import cesm_oracle as O
+    sd = {k: v.detach().float().cpu() for k, v in d.model.state_dict().items()}
+    cfg, buf = O.OracleConfig.from_unet_kwargs(**BASELINE_KW), O.diffusion_buffers(1000)
     torch.manual_seed(9)
     x = torch.randn(2, 1, 32, 32, device=cuda)
-    t = torch.full((2,), 500, device=cuda, dtype=torch.long)
-    z = torch.randn_like(x)
-    ref = d.p_sample(x, cond, t, noise=z)
+    t = torch.tensor([500, 37], device=cuda, dtype=torch.long)
     eng.x.copy_(x); eng.cond.copy_(cond); eng.t.copy_(t)
-    eng2 = copy.copy(eng)  # same buffers; check determinism of the eps path through eager body
+    eng.step()                                     # graph replay: x <- p_sample(x), t <- t - 1
+    z = eng.z.clone()                              # the noise the replayed step drew on the device
+    assert z.abs().max() > 1 and abs(z.mean().item()) < 0.2
     with torch.no_grad():
-        eps = d.model(eng.x, eng.cond, eng.t)
-    from cesm_emulator_b200 import kernels as K
-    got = K.p_sample(eng.x, eps, z, eng.t, d.betas, d.sqrt_one_minus_alphas_cumprod, d.sqrt_recip_alphas,
-                     d.posterior_variance)
-    assert rel_err(got, ref) < 1e-3
-    assert eng2.shape == eng.shape
+        ref = O.p_sample(sd, cfg, buf, x.cpu(), cond.cpu(), t.cpu(), z.cpu())
+    assert eng.t.tolist() == [499, 36]
+    assert rel_err(eng.x, ref) < 1e-2, rel_err(eng.x, ref)
+    # and a short chain end to end against the oracle's chain driven with the engine's own noise sequence
+    eng.x.copy_(x); eng.t.fill_(5)
+    xs = x.cpu().clone()
+    for tt in range(5, -1, -1):
+        eng.step()
+        with torch.no_grad():
+            xs = O.p_sample(sd, cfg, buf, xs, cond.cpu(), torch.full((2,), tt, dtype=torch.long), eng.z.cpu())
+    assert rel_err(eng.x, xs) < 1e-2, rel_err(eng.x, xs)
 
 
 def test_loss_curve_tracks_fp32_oracle(cuda):
-    """north_star: bf16 path vs fp32 reference, loss within 1 % while training.  60 AdamW steps here
-    (tools/loss_curve_parity.py runs 200: mean |rel diff| 0.38 %, last-20-step mean 0.14 %,
-    profiles/r01_loss_curve_parity_200steps.txt); same data, (t, noise), clip and optimizer on both sides."""
+    """north_star: 16-bit path vs fp32 reference, loss within 1 % while training.  60 steps of the reference's
+    own AMP loop (train.py:853-867: scaler.scale(loss).backward(); scaler.unscale_; clip_grad_norm_; scaler.step;
+    scaler.update) with STOCK torch.amp.GradScaler + torch AdamW over this repo's modules, against the fp32 oracle
+    with the same data, (t, noise), clip and optimizer (tools/loss_curve_parity.py runs 200 steps at
+    config/baseline's crop: profiles/r02_loss_curve_parity_200steps.txt)."""
     from cesm_emulator_b200 import ops
     from cesm_emulator_b200.model import Diffusion, UNet
     from cesm_emulator_b200.synthetic import SyntheticEnsemble
@@ -129,14 +142,18 @@ def test_loss_curve_tracks_fp32_oracle(cuda):
     sd = {k: v.detach().float().cpu().clone() for k, v in diff.model.state_dict().items()}
     params = [p for p in diff.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, **hp)
+    scaler = torch.amp.GradScaler("cuda")
     gpu = []
     for cond, x0, t, noise in batches:
         opt.zero_grad(set_to_none=True)
         loss = diff.loss(x0.to(cuda), cond.to(cuda), t=t.to(cuda), noise=noise.to(cuda))
-        loss.backward()
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
         torch.nn.utils.clip_grad_norm_(params, 1.0)
-        opt.step()
+        scaler.step(opt)
+        scaler.update()
         gpu.append(loss.item())
+    assert scaler.get_scale() == 65536.0  # no overflow, no skipped step
     cfg, buf = O.OracleConfig.from_unet_kwargs(**BASELINE_KW), O.diffusion_buffers(1000)
     names = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith("rotary_emb.freqs")]
     leaves = [sd[k].requires_grad_(True) for k in names]
@@ -151,7 +168,8 @@ def test_loss_curve_tracks_fp32_oracle(cuda):
         cpu.append(loss.item())
     rel = [abs(a - b) / abs(b) for a, b in zip(gpu, cpu)]
     assert cpu[-1] < 0.5 * cpu[0]                      # it actually trains
-    assert sum(rel) / len(rel) < 1e-2, sum(rel) / len(rel)
+    assert sum(rel) / len(rel) < 5e-3, sum(rel) / len(rel)
+    assert max(rel) < 2e-2, max(rel)
     m_c, m_g = sum(cpu[-20:]) / 20, sum(gpu[-20:]) / 20
     assert abs(m_g - m_c) < 1e-2 * m_c, (m_g, m_c)
 
@@ -175,7 +193,8 @@ def test_optimizer_state_interchanges_with_torch_adamw(cuda):
         eng.step(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, K, H, W, generator=g))
     sd = eng.opt.state_dict()
     params = [p for p in d.parameters() if p.requires_grad]
-    assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == len(params)
+    assert set(sd) == {"state", "param_groups", "grad_scaler"} and len(sd["state"]) == len(params)
+    assert sd["grad_scaler"]["scale"] == 65536.0
     assert all(sd["state"][i]["exp_avg"].shape == p.shape for i, p in enumerate(params))
     ref = torch.optim.AdamW(params, **hp)
     ref.load_state_dict(sd)                                   # engine -> torch
@@ -184,8 +203,10 @@ def test_optimizer_state_interchanges_with_torch_adamw(cuda):
     grads = [torch.randn_like(p) * 1e-2 for p in params]
     before = [p.detach().clone() for p in params]
     for p, gr in zip(params, grads):
-        p.grad.copy_(gr)                                      # .grad are views of the engine's flat buffer
+        p.grad.copy_(gr * 65536.0)                            # .grad are views of the engine's flat buffer (scaled)
     eng.opt.step()
+    for p, gr in zip(params, grads):
+        p.grad.copy_(gr)
     got = [p.detach().clone() for p in params]
     with torch.no_grad():
         for p, b0 in zip(params, before):
@@ -221,3 +242,81 @@ def test_scratch_arena_overflow_falls_back(cuda):
         ops.set_grad_sink(None)
     for a, b in zip(*losses):
         assert abs(a - b) < 2e-3 * abs(a), losses
+
+
+def test_weights_stay_fresh_across_train_eval_train(cuda):
+    """Graph-replayed optimizer steps rewrite the parameters behind torch's back; every cached operand derived
+    from them (packed fp16 copies, the F = 1 fold W_out W_v) must follow.  train -> eval(F=1) -> train -> eval
+    in one process must equal a fresh model that loads the same state dict, for the eager module call AND for a
+    SampleEngine graph captured before the second round of training."""
+    from cesm_emulator_b200 import ops
+    from cesm_emulator_b200.engine import SampleEngine, TrainEngine
+    from cesm_emulator_b200.model import Diffusion, UNet
+    B, K, H, W = 1, 3, 32, 32
+    tiny = dict(BASELINE_KW, ch_mults=(1, 2))
+    torch.manual_seed(0)
+    d = Diffusion(UNet(**tiny)).to(cuda)
+    eng = TrainEngine(d, (B, 1, H, W), (B, 1, K, H, W), lr=1e-2)   # large lr: the weights move visibly
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 1, H, W, generator=g).to(cuda)
+    c = torch.randn(2, 1, H, W, generator=g).to(cuda)
+    t = torch.tensor([400, 3], device=cuda)
+    samp = None
+
+    def fresh_eps():
+        torch.manual_seed(0)
+        f = Diffusion(UNet(**tiny)).to(cuda)
+        f.load_state_dict(d.state_dict())
+        f.eval()
+        with torch.no_grad():
+            return f.model(x, c, t)
+
+    outs = []
+    for rnd in range(2):
+        d.train()
+        for _ in range(4):  # 2 eager warm-ups + capture + replays in round 0; replays only in round 1
+            eng.step(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, K, H, W, generator=g))
+        assert eng.graph is not None
+        d.eval()
+        with torch.no_grad():
+            got = d.model(x, c, t)
+        ref = fresh_eps()
+        assert rel_err(got, ref) < 1e-5, (rnd, rel_err(got, ref))
+        outs.append(got)
+        if samp is None:
+            samp = SampleEngine(d, (2, 1, H, W))
+        torch.manual_seed(5)
+        y = samp.sample(c, steps=3)
+        torch.manual_seed(5)
+        y_ref = SampleEngine(d, (2, 1, H, W)).sample(c, steps=3)   # captured now, with the current weights
+        assert rel_err(y, y_ref) < 1e-5, (rnd, rel_err(y, y_ref))
+    assert rel_err(outs[1], outs[0]) > 1e-3   # training really changed the network between the two evals
+    ops.set_grad_sink(None)
+
+
+def test_lr_change_after_capture_is_honoured(cuda):
+    """param_groups[0]["lr"] written between graph replays reaches the captured AdamW kernel (device state)."""
+    from cesm_emulator_b200 import ops
+    from cesm_emulator_b200.engine import TrainEngine
+    from cesm_emulator_b200.model import Diffusion, UNet
+    B, K, H, W = 1, 3, 32, 32
+    tiny = dict(BASELINE_KW, ch_mults=(1, 2))
+    torch.manual_seed(0)
+    d = Diffusion(UNet(**tiny)).to(cuda)
+    d.train()
+    eng = TrainEngine(d, (B, 1, H, W), (B, 1, K, H, W), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    x0, cond = torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, K, H, W, generator=g)
+    for _ in range(3):
+        eng.step(x0, cond)
+    assert eng.graph is not None
+    w = next(p for n, p in d.named_parameters() if n.endswith("mid_block1.block1.proj.weight"))
+    eng.opt.param_groups[0]["lr"] = 0.0
+    eng.opt.param_groups[0]["weight_decay"] = 0.0
+    before = w.detach().clone()
+    eng.step(x0, cond)
+    assert torch.equal(w.detach(), before)          # lr = 0: the replayed step leaves the weights alone
+    eng.opt.param_groups[0]["lr"] = 1e-3
+    eng.step(x0, cond)
+    assert not torch.equal(w.detach(), before)
+    ops.set_grad_sink(None)

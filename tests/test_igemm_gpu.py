@@ -1,8 +1,8 @@
 """GPU parity of the tcgen05 implicit-GEMM kernel (csrc/igemm.cu) through the C ABI.
 
-Reference = torch fp32 conv / matmul on the SAME bf16-rounded inputs, so the only differences
-are accumulation order and the final bf16 rounding of the output: tolerance 1e-2 * max|ref|
-(bf16 has 8 mantissa bits: one rounding is <= 2^-9 = 2e-3 relative).
+Reference = torch fp32 conv / matmul on the SAME fp16-rounded inputs, so the only differences
+are accumulation order and the final fp16 rounding of the output: tolerance 2e-3 * max|ref|
+(fp16 has 11 significand bits: one rounding is <= 2^-11 = 4.9e-4 relative).
 """
 import pytest
 import torch
@@ -29,7 +29,7 @@ def test_plain_gemm(cuda, m, k, n):
     res = _rand((1, 1, m, n), cuda)
     out = K.igemm(a, w, bias=bias, residual=res)
     ref = a.float().view(m, k) @ w.float().t() + bias + res.float().view(m, n)
-    assert _err(out.view(m, n), ref) < 1e-2
+    assert _err(out.view(m, n), ref) < 2e-3
     out32 = K.igemm(a, w, out_dtype=torch.float32)
     ref32 = a.float().view(m, k) @ w.float().t()
     assert _err(out32.view(m, n), ref32) < 1e-4
@@ -47,7 +47,7 @@ def test_conv3x3(cuda, n, h, w, cin, cout):
     wg = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
     out = K.igemm(x, wg, taps=K.TAPS_3x3, bias=bias)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
-    assert _err(out, ref) < 1e-2
+    assert _err(out, ref) < 2e-3
 
 
 def test_conv3x3_concat(cuda):
@@ -60,7 +60,7 @@ def test_conv3x3_concat(cuda):
     out = K.igemm(x0, wg, a1=x1, taps=K.TAPS_3x3)
     xin = torch.cat([x0, x1], -1).float().permute(0, 3, 1, 2)
     ref = F.conv2d(xin, wt.float(), None, padding=1).permute(0, 2, 3, 1)
-    assert _err(out, ref) < 1e-2
+    assert _err(out, ref) < 2e-3
 
 
 @pytest.mark.parametrize("n,h,w,c", [(2, 128, 128, 64), (3, 64, 64, 128), (2, 192, 288, 64), (2, 16, 16, 256)])
@@ -75,7 +75,7 @@ def test_downsample_conv4x4s2(cuda, n, h, w, c):
     out = K.igemm(x, wg, taps=taps, stride=2, bias=bias)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
     assert out.shape == ref.shape
-    assert _err(out, ref) < 1e-2
+    assert _err(out, ref) < 2e-3
 
 
 @pytest.mark.parametrize("n,h,w,c", [(2, 32, 32, 128), (3, 64, 64, 64), (2, 48, 72, 128)])
@@ -99,13 +99,13 @@ def test_upsample_convT4x4s2(cuda, n, h, w, c):
             wg = torch.stack(wcols, 1).reshape(c, 4 * c).contiguous()
             K.igemm(x, wg, taps=taps, out=out, out_hw=(h, w), out_place=(2, 2, ph, pw), bias=bias)
     ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
-    assert _err(out, ref) < 1e-2
+    assert _err(out, ref) < 2e-3
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,frames", [(6, 64, 64, 64, 64, 3), (6, 48, 72, 128, 128, 3), (4, 16, 24, 64, 256, 2),
                                                     (2, 192, 288, 64, 64, 1), (6, 8, 8, 128, 128, 3)])
 def test_conv3x3_fused_groupnorm_stats_and_flipped_taps(cuda, n, h, w, cin, cout, frames):
-    """Persistent kernel extras: (a) the per-sample per-group (sum, sum of squares) of the bf16
+    """Persistent kernel extras: (a) the per-sample per-group (sum, sum of squares) of the fp16
     outputs from the epilogue equal those of the stored tensor; (b) the data-gradient form
     (negated taps, residual added in the epilogue) matches conv_transpose."""
     from cesm_emulator_b200 import kernels as K
@@ -118,7 +118,7 @@ def test_conv3x3_fused_groupnorm_stats_and_flipped_taps(cuda, n, h, w, cin, cout
     sums = torch.full((n // frames, G, 2), 123.0, device=cuda)
     out = K.igemm(x, wg, taps=K.TAPS_3x3, bias=bias, gn_sums=sums, gn_frames=frames)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
-    assert _err(out, ref) < 1e-2
+    assert _err(out, ref) < 2e-3
     o = out.float().view(n // frames, frames * h * w, G, cout // G)
     want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
     assert _err(sums, want) < 1e-4
@@ -129,7 +129,7 @@ def test_conv3x3_fused_groupnorm_stats_and_flipped_taps(cuda, n, h, w, cin, cout
     wd = wt.permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous()
     dx = K.igemm(dy, wd, taps=[(-a, -b) for a, b in K.TAPS_3x3], residual=r)
     ref_dx = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1) + r.float()
-    assert _err(dx, ref_dx) < 1e-2
+    assert _err(dx, ref_dx) < 2e-3
 
 
 @pytest.mark.parametrize("m,k,n", [(331776, 64, 768), (82944, 256, 128), (20736, 256, 256), (1000, 1024, 64)])
@@ -142,13 +142,13 @@ def test_gemm_large_and_streamed_weights(cuda, m, k, n):
     out = K.igemm(a, w)
     idx = torch.randint(0, m, (4096,), device=cuda)
     ref = a.float().view(m, k)[idx] @ w.float().t()
-    assert _err(out.view(m, n)[idx], ref) < 1e-2
+    assert _err(out.view(m, n)[idx], ref) < 2e-3
 
 
 @pytest.mark.parametrize("rows,cout", [(128 * 5, 768), (1000, 768), (128 * 300 + 17, 768), (4096, 256)])
 def test_fused_qkv_backward(cuda, rows, cout):
     """cesm_qkv_bwd: data gradient + weight gradient of the C=64 -> cout projection in one pass over dy,
-    against fp32 matmuls of the same bf16 operands (ragged row counts exercise the TMA zero fill and the
+    against fp32 matmuls of the same fp16 operands (ragged row counts exercise the TMA zero fill and the
     predicated row stores; two calls accumulate into dW)."""
     from cesm_emulator_b200 import kernels as K
     torch.manual_seed(2)

@@ -1,8 +1,8 @@
 """GPU parity of every non-GEMM kernel and of the tcgen05 weight-gradient kernel, through the C ABI.
 
 Each check feeds the CUDA kernel and a torch fp32 restatement (oracle functions where they exist)
-the SAME bf16-rounded inputs.  Tolerances (relative to max|ref|): 1e-2 for bf16 outputs (one or
-two bf16 roundings of 2^-9 each plus fp32 reassociation), 2e-3 for fp32 outputs.
+the SAME fp16-rounded inputs.  Tolerances (relative to max|ref|): 2e-3 for fp16 outputs (one or two fp16
+roundings of 2^-12 each plus fp32 reassociation) unless a test states otherwise, 2e-3 for fp32 outputs.
 """
 import math
 
@@ -139,14 +139,14 @@ def test_groupnorm_fwd_bwd(cuda, B, P, C, film, res):
         y = y * (flr[:, :C, None] + 1) + flr[:, C:, None]
     y = F.silu(y).transpose(1, 2)
     ref = y + (r.float() if res else 0)
-    assert err(out, ref) < 1e-2
+    assert err(out, ref) < 2e-3
     grads = torch.autograd.grad(y, [xr, gr, br] + ([flr] if film else []), dout.float())
-    assert err(dx, grads[0]) < 1e-2
+    assert err(dx, grads[0]) < 2e-3
     assert err(dg, grads[1]) < 2e-3 and err(db, grads[2]) < 2e-3
     if film:
         assert err(dfl, grads[3]) < 2e-3
     # bias gradient of the producing conv = sum over samples and pixels of dx (here of the exact dx)
-    assert err(dcb, grads[0].sum(dim=(0, 1))) < 5e-3
+    assert err(dcb, grads[0].sum(dim=(0, 1))) < 2e-3
     # accumulate mode (the engine hands in the parameters' .grad views): the apply kernel adds the
     # parameter gradients itself, on top of what is already there
     base = [torch.randn(C, device=cuda) for _ in range(3)]
@@ -170,12 +170,12 @@ def test_layernorm_fwd_bwd(cuda, M, C):
     dx, dg = K.ln_bwd(x, gamma, dy, dres, 1e-5)
     xr, gr = x.float().requires_grad_(True), gamma.clone().requires_grad_(True)
     y = O.channel_layer_norm(xr.t()[None], gr[None, :, None])[0].t()
-    assert err(out, y) < 1e-2
+    assert err(out, y) < 2e-3
     gx, gg = torch.autograd.grad(y, [xr, gr], dy.float())
-    assert err(dx, gx + dres.float()) < 1e-2
+    assert err(dx, gx + dres.float()) < 2e-3
     assert err(dg, gg) < 2e-3
     dx2, _ = K.ln_bwd(x, gamma, dy, None, 1e-5)
-    assert err(dx2, gx) < 1e-2
+    assert err(dx2, gx) < 2e-3
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,10 +210,10 @@ def test_temporal_attention_core(cuda, B, Fr, HW, H):
     dqkv, dbias = K.tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B, Fr, HW, H, D, D ** -0.5)
     qr, br = qkv.float().requires_grad_(True), bias.clone().requires_grad_(True)
     ref = _tattn_ref(qr, br, freqs, B, Fr, HW, H, D)
-    assert err(out, ref) < 1e-2
+    assert err(out, ref) < 2e-3
     gq, gb = torch.autograd.grad(ref, [qr, br], dout.float())
-    assert err(dqkv, gq) < 1.5e-2
-    assert err(dbias, gb) < 1e-2
+    assert err(dqkv, gq) < 3e-3
+    assert err(dbias, gb) < 2e-3
 
 
 def _linattn_ref(qkv, NI, n, H, D):
@@ -237,9 +237,9 @@ def test_linear_attention_core(cuda, NI, n, H):
     dqkv = K.linattn_bwd(qkv, ws, dout, NI, n, H, D, D ** -0.5)
     qr = qkv.float().requires_grad_(True)
     ref = _linattn_ref(qr, NI, n, H, D)
-    assert err(out, ref) < 1.5e-2
+    assert err(out, ref) < 3e-3
     (g,) = torch.autograd.grad(ref, qr, dout.float())
-    assert err(dqkv, g) < 2e-2
+    assert err(dqkv, g) < 3e-3
 
 
 # ------------------------------------------------------------------------------------------------
@@ -258,7 +258,7 @@ def test_input_conv(cuda, B, Fr, H, W, f0):
     xin = torch.cat([x.expand(-1, -1, Fr, -1, -1), c], dim=1)
     ref = F.conv3d(xin, wr, br, padding=(0, 3, 3))  # [B,64,F,H,W]
     ref_cl = ref.permute(0, 2, 3, 4, 1).reshape(B * Fr, H, W, 64)
-    assert err(out, ref_cl) < 1e-2
+    assert err(out, ref_cl) < 2e-3
     dy = rnd((B * Fr, H, W, 64), cuda)
     dw, db = K.input_conv_wgrad(x, c, dy, B, Fr, H, W, 7)
     gw, gb = torch.autograd.grad(ref_cl, [wr, br], dy.float())
@@ -267,9 +267,9 @@ def test_input_conv(cuda, B, Fr, H, W, f0):
 
 @pytest.mark.parametrize("B,Fr,H,W,f0", [(2, 3, 32, 32, 1), (1, 1, 48, 72, 1), (2, 3, 20, 36, 3)])
 def test_input_conv_tensor_core_path(cuda, B, Fr, H, W, f0):
-    """ops.InputConvFn: (hi, lo) bf16 im2col patches through the tcgen05 GEMM and its weight-gradient
-    kernel.  Against fp32 conv3d the forward differs only by the bf16 rounding of the weights and of the
-    output; with bf16-representable weights and bias the patch split must recover the fp32 inputs, so the
+    """ops.InputConvFn: (hi, lo) fp16 im2col patches through the tcgen05 GEMM and its weight-gradient
+    kernel.  Against fp32 conv3d the forward differs only by the fp16 rounding of the weights and of the
+    output; with fp16-representable weights and bias the patch split must recover the fp32 inputs, so the
     result then matches the old fp32-input CUDA-core kernel to output rounding."""
     from cesm_emulator_b200 import kernels as K, ops
     torch.manual_seed(8)
@@ -280,7 +280,7 @@ def test_input_conv_tensor_core_path(cuda, B, Fr, H, W, f0):
     wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     out = ops.InputConvFn.apply(x, c, wp, bp, Fr)
     old = K.input_conv_fwd(x, c, w, b, B, Fr, H, W, 7)
-    assert err(out, old) < 6e-3  # one bf16 ulp of the largest output
+    assert err(out, old) < 1e-3  # one fp16 ulp of the largest output
     assert (out.float() - old.float()).abs().mean().item() < 2e-3 * old.float().abs().mean().item()
     dy = rnd((B * Fr, H, W, 64), cuda)
     gw, gb = torch.autograd.grad(out, [wp, bp], dy)
@@ -413,8 +413,17 @@ def test_batched_relayouts_match_single(cuda):
         assert not s_.any()
 
 
-@pytest.mark.parametrize("n,max_norm", [(10_001, 1.0), (4096, None), (1_234_567, 0.05)])
-def test_fused_adamw_matches_torch(cuda, n, max_norm):
+def _opt_state(cuda, lr, wd, scale=1.0, interval=0):
+    from cesm_emulator_b200 import kernels as K
+    st = torch.zeros(K.OPT_STATE_FLOATS)
+    st[K.OPT_LR], st[K.OPT_WD], st[K.OPT_SCALE], st[K.OPT_INTERVAL] = lr, wd, scale, interval
+    return st.to(cuda)
+
+
+@pytest.mark.parametrize("n,max_norm,scale", [(10_001, 1.0, 1.0), (4096, None, 65536.0), (1_234_567, 0.05, 1024.0)])
+def test_fused_adamw_matches_torch(cuda, n, max_norm, scale):
+    """cesm_adamw_step against torch.optim.AdamW + clip_grad_norm_ (train.py:865, 1078-1083); the kernel is handed
+    gradients multiplied by the loss scale and must unscale them first (GradScaler.unscale_, train.py:864)."""
     from cesm_emulator_b200 import _lib, kernels as K
     torch.manual_seed(1)
     hp = dict(lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-4, eps=1e-8)
@@ -422,7 +431,7 @@ def test_fused_adamw_matches_torch(cuda, n, max_norm):
     ref = torch.nn.Parameter(p0.clone())
     opt = torch.optim.AdamW([ref], **hp)
     p, m, v = p0.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
-    state = torch.zeros(2, device=cuda)
+    state = _opt_state(cuda, hp["lr"], hp["weight_decay"], scale)
     partials = torch.zeros(_lib.load().cesm_adamw_partials(), device=cuda)
     for step in range(4):
         g = torch.randn(n, device=cuda) * (0.5 + step)
@@ -431,11 +440,51 @@ def test_fused_adamw_matches_torch(cuda, n, max_norm):
         if max_norm is not None:
             torch.nn.utils.clip_grad_norm_([ref], max_norm)
         opt.step()
-        K.adamw_step(p, g, m, v, partials, state, hp["lr"], *hp["betas"], hp["eps"], hp["weight_decay"], max_norm)
-        assert state[0].item() == step + 1
-        assert abs(state[1].item() - norm.item()) < 1e-4 * norm.item()
+        K.adamw_step(p, g * scale, m, v, partials, state, *hp["betas"], hp["eps"], max_norm)
+        assert state[K.OPT_STEP].item() == step + 1 and state[K.OPT_FOUND_INF].item() == 0
+        assert abs(state[K.OPT_NORM].item() - norm.item()) < 1e-4 * norm.item()
         assert (p - ref.data).abs().max().item() < 2e-6, step
+        if step == 1:  # a new learning rate written to the device state is honoured by the next call
+            for gr in opt.param_groups:
+                gr["lr"] = 5e-4
+            state[K.OPT_LR] = 5e-4
     assert err(m, opt.state[ref]["exp_avg"]) < 1e-4 and err(v, opt.state[ref]["exp_avg_sq"]) < 1e-4
+
+
+def test_fused_adamw_follows_grad_scaler(cuda):
+    """The device-side loss-scale logic against torch.amp.GradScaler driving torch AdamW (train.py:862-867,
+    1084): an overflowing gradient skips the update and halves the scale; `growth_interval` clean steps double it."""
+    from cesm_emulator_b200 import _lib, kernels as K
+    torch.manual_seed(2)
+    n, interval = 5000, 3
+    hp = dict(lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    p0 = torch.randn(n, device=cuda)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], **hp)
+    scaler = torch.amp.GradScaler("cuda", init_scale=65536.0, growth_interval=interval)
+    p, m, v = p0.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    state = _opt_state(cuda, hp["lr"], hp["weight_decay"], 65536.0, interval)
+    partials = torch.zeros(_lib.load().cesm_adamw_partials(), device=cuda)
+    overflow_at = {2, 7}
+    for step in range(12):
+        g = torch.randn(n, device=cuda) * 0.1
+        S = scaler.get_scale()
+        assert state[K.OPT_SCALE].item() == S, (step, state[K.OPT_SCALE].item(), S)
+        gs = g * S
+        if step in overflow_at:
+            gs[step] = float("inf")
+        ref.grad = gs.clone()
+        # torch flow (scaler.scale(loss).backward() produced gs)
+        scaler._per_optimizer_states.clear()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        scaler.step(opt)
+        scaler.update()
+        K.adamw_step(p, gs, m, v, partials, state, *hp["betas"], hp["eps"], 1.0)
+        assert state[K.OPT_FOUND_INF].item() == float(step in overflow_at)
+        assert (p - ref.data).abs().max().item() < 2e-6, step
+    assert state[K.OPT_SKIPPED].item() == 2 and state[K.OPT_STEP].item() == 10
+    assert state[K.OPT_SCALE].item() == scaler.get_scale()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -4,11 +4,14 @@ one-frame inference call, sampling step) against
   (2) the fp32 CPU oracle (oracle/cesm_oracle.py, itself pinned to the reference) run on the
       module's own weights with the same inputs.
 
-Tolerances, as max|got-ref|/max|ref| per tensor (north_star: bf16 activations vs fp32 reference,
-<= 1e-2 on forward outputs and gradients; loss within 1 %):
-  forward eps, eps_f1, loss : 1e-2
-  parameter gradients       : see GRAD_BARS below (measured values are printed by
-                              tools/parity_report.py and recorded in DESIGN.md)
+Tolerances, as max|got-ref|/max|ref| PER TENSOR -- north_star's contract (16-bit activations vs the
+fp32 reference: <= 1e-2 on forward outputs and on every gradient tensor; loss within 1 %):
+  forward eps, eps_f1, loss : FWD_TOL  = 1e-2   (measured on B200: 0.9-1.2e-3)
+  EVERY parameter gradient  : GRAD_TOL = 1e-2   (measured: median 8e-4, worst tensor 2-4e-3)
+No tensor is exempted, and every case runs several input seeds (all must pass): the measured values sit
+3-10x inside the bars (profiles/r02_parity_matrix.txt), so a pass does not depend on the seed or on the
+order in which fp32 atomics happened to land.  Gradients are taken the way the reference takes them under
+autocast: scaled loss, unscaled fp32 parameter gradients (_parity.LOSS_SCALE, train.py:862-864).
 """
 import numpy as np
 import pytest
@@ -19,21 +22,23 @@ from _parity import (BASELINE_KW, load_golden, make_inputs, module_loss_and_grad
 pytestmark = pytest.mark.gpu
 
 FWD_TOL = 1e-2
-# Gradient bars per shape: (median, fraction of tensors <= 1e-2, worst tensor).  The training shape
-# of config/baseline (B=2, K=3, 128x128) is held to the north_star bar; at tiny grids the deepest
-# level has only 4x4..8x8 pixels, so bf16 rounding of the gradient stream is averaged over far
-# fewer terms and the worst tensors (GroupNorm/FiLM gradients at the bottleneck) rise to a few 1e-2.
-# For comparison stock torch bf16 autocast at 64x64: median 8.8e-3, 56 % of tensors <= 1e-2, worst
-# 2.9e-2.
-GRAD_BARS = {
-    # shape: (median bar, min fraction of tensors <= 1e-2, worst-tensor bar).  The worst tensor moves by
-    # up to ~1e-2 from run to run (fp32 atomics reorder sums -> individual bf16 roundings flip; two runs of
-    # the SAME path differ by 4e-3 median / 2e-2 worst, tools/engine_grad_check.py), hence the headroom.
-    (2, 3, 128, 128): (1e-2, 0.75, 4e-2),  # measured over 12 runs: median 5.1-5.6e-3, 81-92 % <= 1e-2, worst 1.6-3.0e-2
-    (1, 3, 48, 72): (1e-2, 0.5, 6e-2),     # measured: median 7e-3, worst 2.9-4.1e-2
-    (2, 3, 32, 32): (1.2e-2, 0.4, 8e-2),   # measured: median 9e-3, worst 3-6e-2
-    (2, 1, 16, 16): (2e-2, 0.3, 9e-2),     # measured: median 1.5e-2, worst 4.4e-2
-}
+GRAD_TOL = 1e-2
+SEEDS = (5, 6, 7)
+# (B, K, H, W): config/baseline's training crop, the smoke shape, two tiny grids (deepest level 4x4 / 8x8 pixels)
+SHAPES = [(2, 3, 128, 128), (1, 3, 48, 72), (2, 3, 32, 32), (2, 1, 16, 16)]
+
+
+def _check_against_oracle(diff, unet_kw, B, K, H, W, seed, cuda):
+    x0, cond, t, noise = make_inputs(B, K, H, W, seed=seed, device=cuda)
+    eps, loss, grads = module_loss_and_grads(diff, x0, cond, t, noise)
+    ref_eps, ref_loss, ref_grads = oracle_loss_and_grads(diff.model, unet_kw, x0, cond, t, noise)
+    assert rel_err(eps, ref_eps) < FWD_TOL, (seed, rel_err(eps, ref_eps))
+    assert abs(loss.item() - ref_loss.item()) < 1e-2 * abs(ref_loss.item())
+    assert set(grads) == set(ref_grads)
+    errs = {k: rel_err(grads[k], ref_grads[k]) for k in grads}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < GRAD_TOL, (seed, worst, errs[worst], float(np.median(list(errs.values()))))
+    return rel_err(eps, ref_eps), errs
 
 
 @pytest.fixture(scope="module")
@@ -59,7 +64,7 @@ def test_forward_loss_grads_match_reference_golden(cuda, baseline):
     assert set(names) == set(grads)
     for k in names:
         ref_norm = float(g["gradnorm/" + k])
-        assert abs(grads[k].float().norm().item() - ref_norm) < 3e-2 * ref_norm + 1e-8, k
+        assert abs(grads[k].float().norm().item() - ref_norm) < 1e-2 * ref_norm + 1e-8, k
     # inference-shaped call: 4-D cond, F = 1 (inference.py:221-229)
     baseline.eval()
     with torch.no_grad():
@@ -68,21 +73,20 @@ def test_forward_loss_grads_match_reference_golden(cuda, baseline):
     assert rel_err(eps_f1, torch.from_numpy(g["eps_f1"])) < FWD_TOL
 
 
-@pytest.mark.parametrize("B,K,H,W", sorted(GRAD_BARS))
+@pytest.mark.parametrize("B,K,H,W", SHAPES)
 def test_every_gradient_against_oracle(cuda, baseline, B, K, H, W):
-    x0, cond, t, noise = make_inputs(B, K, H, W, seed=5, device=cuda)
-    eps, loss, grads = module_loss_and_grads(baseline, x0, cond, t, noise)
-    ref_eps, ref_loss, ref_grads = oracle_loss_and_grads(baseline.model, BASELINE_KW, x0, cond, t, noise)
-    assert rel_err(eps, ref_eps) < FWD_TOL
-    assert abs(loss.item() - ref_loss.item()) < 1e-2 * abs(ref_loss.item())
-    assert set(grads) == set(ref_grads)
-    errs = {k: rel_err(grads[k], ref_grads[k]) for k in grads}
-    worst = max(errs, key=errs.get)
-    vals = np.array(sorted(errs.values()))
-    med_bar, frac_bar, worst_bar = GRAD_BARS[(B, K, H, W)]
-    assert np.median(vals) < med_bar, (np.median(vals), worst, errs[worst])
-    assert (vals <= 1e-2).mean() >= frac_bar, ((vals <= 1e-2).mean(), worst, errs[worst])
-    assert errs[worst] < worst_bar, (worst, errs[worst])
+    for seed in SEEDS:
+        _check_against_oracle(baseline, BASELINE_KW, B, K, H, W, seed, cuda)
+
+
+def test_parity_is_reproducible_run_to_run(cuda, baseline):
+    """Three runs of the same step: statistics are accumulated with fp32 atomics, so the runs need not be bitwise
+    equal, but they must agree far inside the parity bar (a pass / fail must not depend on the run)."""
+    x0, cond, t, noise = make_inputs(2, 3, 64, 64, seed=5, device=cuda)
+    runs = [module_loss_and_grads(baseline, x0, cond, t, noise) for _ in range(3)]
+    for eps, loss, grads in runs[1:]:
+        assert rel_err(eps, runs[0][0]) < 2e-3
+        assert max(rel_err(grads[k], runs[0][2][k]) for k in grads) < 3e-3
 
 
 def test_p_sample_step_matches_oracle(cuda, baseline):
@@ -111,53 +115,48 @@ def test_reference_style_module_calls(cuda, baseline):
     with torch.no_grad():
         got = blk(x, temb)
         ref = O.resnet_block(sd, "downs.0.0.", x.cpu(), temb.cpu(), 8)
-        assert rel_err(got, ref) < 2e-2
+        assert rel_err(got, ref) < 3e-3
         got = net.downs[0][2](x)
         ref = O.spatial_attention_block(sd, "downs.0.2.", x.cpu(), 8)
-        assert rel_err(got, ref) < 2e-2
+        assert rel_err(got, ref) < 3e-3
         pb = net.time_rel_pos_bias(3, device=cuda)
         got = net.downs[0][3](x, pos_bias=pb)
         ref = O.temporal_attention_block(sd, "downs.0.3.", x.cpu(), 8, pb.cpu())
-        assert rel_err(got, ref) < 2e-2
+        assert rel_err(got, ref) < 3e-3
         got = net.downs[0][4](x)
         ref = torch.nn.functional.conv3d(x.cpu(), sd["downs.0.4.weight"], sd["downs.0.4.bias"], stride=(1, 2, 2),
                                          padding=(0, 1, 1))
-        assert rel_err(got, ref) < 2e-2
+        assert rel_err(got, ref) < 3e-3
         full = net(x[:, :1], torch.tensor([3, 900], device=cuda), cond_map=x[:, 1:2])
         cfg = O.OracleConfig.from_unet_kwargs(**BASELINE_KW)
         ref = O.unet3d_forward({"net." + k: v for k, v in sd.items()}, cfg, x[:, :1].cpu(), torch.tensor([3, 900]),
                                x[:, 1:2].cpu())
-        assert full.shape == ref.shape and rel_err(full, ref) < 2e-2
+        assert full.shape == ref.shape and rel_err(full, ref) < FWD_TOL
 
 
-def _parity_case(cuda, unet_kw, B, K, H, W, med_bar, worst_bar, fwd_bar=FWD_TOL):
+def _fresh(cuda, unet_kw):
     from cesm_emulator_b200 import ops
     from cesm_emulator_b200.model import Diffusion, UNet
     ops.set_grad_sink(None)
     torch.manual_seed(0)
     diff = Diffusion(UNet(**unet_kw), timesteps=1000).to(cuda)
     diff.train()
-    x0, cond, t, noise = make_inputs(B, K, H, W, seed=8, device=cuda)
-    eps, loss, grads = module_loss_and_grads(diff, x0, cond, t, noise)
-    ref_eps, ref_loss, ref_grads = oracle_loss_and_grads(diff.model, unet_kw, x0, cond, t, noise)
-    assert rel_err(eps, ref_eps) < fwd_bar
-    assert abs(loss.item() - ref_loss.item()) < 1e-2 * abs(ref_loss.item())
-    assert set(grads) == set(ref_grads)
-    vals = np.array([rel_err(grads[k], ref_grads[k]) for k in grads])
-    assert np.median(vals) < med_bar and vals.max() < worst_bar, (np.median(vals), vals.max())
+    return diff
 
 
 def test_more_blocks_architecture_against_oracle(cuda):
     """config/more_blocks: ch_mults [1,2,4,8] -> a fourth level with 512 channels (and the level-0
-    temporal attention going through `temporal_op`, video_net.py:701)."""
+    temporal attention going through `temporal_op`, video_net.py:701), at its configured 64x64 crop."""
     kw = dict(in_channels=2, out_channels=1, base_ch=64, ch_mults=(1, 2, 4, 8), num_res_blocks=6, time_dim=124,
               groups=8, dropout=0.0, use_checkpoint=True)
-    # the deeper stack (two more ResnetBlocks / attention pairs each way) sits right at 1e-2 on the forward
-    # output (measured 0.9-1.02e-2 run to run), hence 1.5e-2 here
-    _parity_case(cuda, kw, B=2, K=3, H=64, W=64, med_bar=1.5e-2, worst_bar=9e-2, fwd_bar=1.5e-2)
+    diff = _fresh(cuda, kw)
+    for seed in (8, 9):
+        _check_against_oracle(diff, kw, 2, 3, 64, 64, seed, cuda)
 
 
 def test_long_window_temporal_attention_against_oracle(cuda):
     """BASELINE.json configs[4]: a longer condition window (K = 12 frames > 4 selects the streaming
     online-softmax temporal-attention kernels and the log-bucketed part of the relative-position table)."""
-    _parity_case(cuda, BASELINE_KW, B=1, K=12, H=16, W=16, med_bar=2e-2, worst_bar=9e-2, fwd_bar=1.5e-2)
+    diff = _fresh(cuda, BASELINE_KW)
+    for seed in (8, 9):
+        _check_against_oracle(diff, BASELINE_KW, 1, 12, 16, 16, seed, cuda)

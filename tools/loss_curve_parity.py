@@ -2,10 +2,11 @@
 
 Trains the same initial weights on the same synthetic batches with the same (t, noise) draws twice:
   * fp32 CPU oracle (oracle/cesm_oracle.py) + torch AdamW + global-norm clip  -- the reference's step
-  * the B200 path (bf16 kernels through the C ABI) + the same optimizer settings
-and prints the per-step relative loss difference.
+  * the B200 path (fp16 kernels through the C ABI) driven by the reference's own AMP loop (train.py:853-867:
+    stock torch.amp.GradScaler + torch AdamW + clip_grad_norm_) with the same optimizer settings
+and prints the per-step relative loss difference (mean / last-20 / max).
 
-    python tools/loss_curve_parity.py [steps=200] [H=32] [W=32] [B=2]
+    python tools/loss_curve_parity.py [steps=200] [H=128] [W=128] [B=2]      (config/baseline's crop and batch)
 """
 import os
 import sys
@@ -20,8 +21,8 @@ from _parity import BASELINE_KW  # noqa: E402
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-    H = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-    W = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+    H = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    W = int(sys.argv[3]) if len(sys.argv) > 3 else 128
     B = int(sys.argv[4]) if len(sys.argv) > 4 else 2
     from cesm_emulator_b200 import ops
     from cesm_emulator_b200.model import Diffusion, UNet
@@ -47,14 +48,18 @@ def main():
     init = {k: v.detach().float().cpu().clone() for k, v in diff.model.state_dict().items()}
     params = [p for p in diff.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, **hp)
+    scaler = torch.amp.GradScaler("cuda")
     gpu_losses = []
     for cond, x0, t, noise in batches:
         opt.zero_grad(set_to_none=True)
         loss = diff.loss(x0.cuda(), cond.cuda(), t=t.cuda(), noise=noise.cuda())
-        loss.backward()
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
         torch.nn.utils.clip_grad_norm_(params, 1.0)
-        opt.step()
+        scaler.step(opt)
+        scaler.update()
         gpu_losses.append(loss.item())
+    print(f"b200 path done: final loss scale {scaler.get_scale():.0f} (65536 = no overflow / skipped step)", flush=True)
 
     # ---- fp32 CPU oracle ----
     cfg = O.OracleConfig.from_unet_kwargs(**BASELINE_KW)
