@@ -7,7 +7,8 @@
 A "step" is one training step (Diffusion.loss forward + backward, gradient all-reduce when N > 1,
 global-norm clip, AdamW) on one synthetic batch.  Workload (BASELINE.json configs[1]): the
 config/baseline model, K=3 condition frames, full 192x288 grid, per-GPU batch 2 (train.batch_size),
-bf16 activations with fp32 accumulation and fp32 master weights.  One JSON line is printed by rank 0.
+fp16 activations / gradients (the reference's autocast dtype, train.py:853) with dynamic loss scaling, fp32
+accumulation and fp32 master weights.  One JSON line is printed by rank 0.
 
   value    : samples/s over all N GPUs, inputs already resident in HBM (CUDA events, max over ranks)
   e2e      : the same metric through the public API (TrainEngine.step) with pinned HOST batches
@@ -18,6 +19,11 @@ bf16 activations with fp32 accumulation and fp32 master weights.  One JSON line 
              for the whole step (algorithmic FLOPs per sample from SURVEY.md section 8(d))
   cpu_baseline : the CPU oracle (a port of the reference's fp32 algorithm) timed on this box's
              host cores on a bounded sample, N=1 only
+  gpu_comparator : the same port run on THIS GPU by stock PyTorch (cuDNN / cuBLAS / aten) under
+             torch.autocast(fp16), same shape, CUDA-event timed, N=1 only
+  extra    : BASELINE.json's other two numbers, measured the same way at this N: ensemble-generation
+             fields/s (SampleEngine, fields sharded over ranks) and config/more_blocks training
+  ranks_in_sync : N > 1: every rank holds bit-identical parameters after the timed steps
 """
 from __future__ import annotations
 
@@ -58,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--no-gpu-comparator", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the ensemble-generation and more_blocks side measurements")
     ap.add_argument("--kernel-table", default="", help="write the per-kernel breakdown to this file")
     return ap.parse_args()
 
@@ -133,66 +141,136 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(arch_kw, frames, H, W, threads, steps, warmup):
-    """Seconds per fwd+bwd of one sample (B=1) at H x W on `threads` host threads (fp32)."""
+def _oracle_setup(arch_kw, threads):
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from _parity import make_inputs
     from oracle import cesm_oracle as O
-    from cesm_emulator_b200.model import UNet
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    unet = UNet(**arch_kw)  # parameter container only: the oracle consumes its state_dict on the CPU
-    sd = {k: v.detach().float() for k, v in unet.state_dict().items()}
     cfg = O.OracleConfig.from_unet_kwargs(**arch_kw)
-    buf = O.diffusion_buffers(1000)
-    x0, cond, t, noise = make_inputs(1, frames, H, W, seed=1234)
+    sd = O.random_state_dict(cfg, seed=0)   # reference key/shape layout; the product package is not imported here
+    return O, cfg, sd, O.diffusion_buffers(1000)
+
+
+def _oracle_inputs(B, frames, H, W, seed=1234):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, frames, H, W, generator=g),
+            torch.randint(0, 1000, (B,), generator=g), torch.randn(B, 1, H, W, generator=g))
+
+
+def cpu_reference_step_time(arch_kw, frames, B, H, W, threads, steps, warmup):
+    """Seconds per training step (loss fwd + bwd, global-norm clip, AdamW: train.py:858-867 in fp32) of a batch of B
+    samples at H x W on `threads` host threads."""
+    import torch
+    O, cfg, sd, buf = _oracle_setup(arch_kw, threads)
+    names = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith("rotary_emb.freqs")]
+    leaves = [sd[k].requires_grad_(True) for k in names]
+    opt = torch.optim.AdamW(leaves, lr=2e-4, weight_decay=1e-4)
+    x0, cond, t, noise = _oracle_inputs(B, frames, H, W)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.loss_and_grads(sd, cfg, buf, x0, cond, t, noise)
+        _, grads = O.loss_and_grads(sd, cfg, buf, x0, cond, t, noise)
+        for k, p in zip(names, leaves):
+            p.grad = grads[k]
+        torch.nn.utils.clip_grad_norm_(leaves, 1.0)
+        opt.step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     return sum(times) / len(times)
 
 
-def pick_cpu_sample(H, W, budget_s, n_steps, arch_kw, frames, threads):
-    """Choose a crop (a power-of-two fraction of the grid) so that n_steps oracle steps fit the budget."""
+def pick_cpu_sample(B, H, W, budget_s, n_steps, arch_kw, frames, threads):
+    """The largest per-step sample of the workload whose n_steps fit the budget: the full batch on the full grid,
+    else one sample on the full grid, else one sample on a power-of-two fraction of the grid.  -> (b, h, w, frac)"""
     probe_h, probe_w = max(16, H // 8), max(16, W // 8)
-    # 2 probe steps: first is cold
-    t_probe = cpu_reference_step_time(arch_kw, frames, probe_h, probe_w, threads, steps=1, warmup=1)
+    t_probe = cpu_reference_step_time(arch_kw, frames, 1, probe_h, probe_w, threads, steps=1, warmup=1)
     per_pixel = t_probe / (probe_h * probe_w)
-    frac = 1
-    while per_pixel * (H // frac) * (W // frac) * n_steps > budget_s and frac < 8:
-        frac *= 2
-    return H // frac, W // frac, frac
+    for b, frac in ((B, 1), (1, 1), (1, 2), (1, 4), (1, 8)):
+        if per_pixel * b * (H // frac) * (W // frac) * n_steps <= budget_s or frac == 8:
+            return b, H // frac, W // frac, frac
 
 
 def run_reference(args, H, W, arch_kw):
+    """The reference arm: the reference's algorithm for the same step on this box's host cores (the reference is
+    pure PyTorch and cannot travel to the GPU box, so this is the oracle port -- pinned to the reference's outputs
+    by tests/golden).  `config` states what actually ran; nothing is extrapolated when the full batch fits."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     n_steps = args.steps + args.warmup
-    h, w, frac = pick_cpu_sample(H, W, budget_s=150.0, n_steps=n_steps, arch_kw=arch_kw, frames=args.frames,
-                                 threads=threads)
-    sec = cpu_reference_step_time(arch_kw, args.frames, h, w, threads, steps=args.steps, warmup=args.warmup)
-    sec_full = sec * (H * W) / (h * w)  # cost is linear in pixels (convs, linear attention, per-pixel temporal attention)
-    value = 1.0 / sec_full
-    sample = (f"oracle port of the reference fp32 algorithm, fwd+bwd of 1 sample at {h}x{w}"
-              + (f" (1/{frac * frac} of the {H}x{W} grid, time scaled by pixel count)" if frac > 1 else "")
-              + f", {args.steps} timed steps after {args.warmup} warm-up")
+    B = args.batch
+    b, h, w, frac = pick_cpu_sample(B, H, W, budget_s=300.0, n_steps=n_steps, arch_kw=arch_kw, frames=args.frames,
+                                    threads=threads)
+    sec = cpu_reference_step_time(arch_kw, args.frames, b, h, w, threads, steps=args.steps, warmup=args.warmup)
+    full = (b, h, w) == (B, H, W)
+    value = b / (sec * (H * W) / (h * w))     # samples/s; frac > 1: scaled by pixel count (cost is linear in pixels)
+    sample = (f"oracle port of the reference fp32 step (loss fwd+bwd, clip, AdamW), {b} sample(s) at {h}x{w} per step"
+              + ("" if frac == 1 else f" (1/{frac * frac} of the {H}x{W} grid; samples/s scaled by pixel count)")
+              + f", {args.steps} timed steps after {args.warmup} warm-up, {threads} threads")
+    cfg = workload_config(args, H, W, b)
+    cfg["parallelism"] = "host cores (1 process)" if not full else cfg["parallelism"]
+    if not full:
+        cfg["sample"] = {"per_step_batch": b, "grid": [h, w], "scaled_by_pixels": frac > 1}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, H, W, 1),
+        "config": {**cfg, "cuda_graph": False, "l2": "host arm: caches as the host leaves them"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_comparator(arch_kw, frames, B, H, W, dev, steps=5, warmup=3):
+    """SURVEY.md section 8(d) "GPU comparator": the reference's algorithm (oracle port = the same torch calls the
+    reference modules make) executed by STOCK PyTorch on this GPU -- cuDNN convolutions, cuBLAS matmuls, aten
+    normalisation / softmax / elementwise kernels -- under torch.autocast(fp16) as the reference trains
+    (train.py:853), plus clip_grad_norm_ and fused torch AdamW.  None of this repo's kernels run here."""
+    import torch
+    O, cfg, sd, buf = _oracle_setup(arch_kw, os.cpu_count() or 1)
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    buf = {k: v.to(dev) for k, v in buf.items()}
+    names = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith("rotary_emb.freqs")]
+    leaves = [sd[k].requires_grad_(True) for k in names]
+    opt = torch.optim.AdamW(leaves, lr=2e-4, weight_decay=1e-4, fused=True)
+    x0, cond, t, noise = (v.to(dev) for v in _oracle_inputs(B, frames, H, W))
+    torch.backends.cudnn.benchmark = True
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.float16):
+            loss = O.diffusion_loss(sd, cfg, buf, x0, cond, t, noise)
+        (loss * 65536.0).backward()
+        for p in leaves:
+            p.grad.mul_(1.0 / 65536.0)
+        torch.nn.utils.clip_grad_norm_(leaves, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    ms /= steps
+    mem = torch.cuda.max_memory_allocated(dev) / 2**30
+    del sd, leaves, opt
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "what": "oracle port of the reference step on this GPU through stock PyTorch "
+                    f"{torch.__version__} (cuDNN/cuBLAS/aten) under torch.autocast(float16), eager, B={B} K={frames} {H}x{W}",
+            "peak_mem_gib": round(mem, 1)}
 
 
 def workload_config(args, H, W, per_gpu_batch):
@@ -285,6 +363,15 @@ def run_b200(args, H, W, arch_kw):
     ms_e2e, _ = timed(e2e_step)
     clocks = sampler.stop() if rank == 0 else None
 
+    in_sync = None
+    if world > 1:
+        # every rank must hold bit-identical parameters after the same all-reduced updates (train.py:1076)
+        bits = eng.opt.p.view(torch.int32).to(torch.int64)
+        sig = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        in_sync = all(torch.equal(sigs[0], x) for x in sigs)
+
     samples = B * world * args.steps
     value = samples / (ms_res * 1e-3)
     e2e_value = samples / (ms_e2e * 1e-3)
@@ -315,7 +402,7 @@ def run_b200(args, H, W, arch_kw):
         peak = peaks["bf16_tflops_sustained"]
         ach = ig_fl / (ig_ms * 1e-3) / 1e12
         traffic = None  # DRAM bytes per launch of the same kernels, from the committed ncu pass of this workload
-        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_traffic_final.json")
+        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_step_traffic.json")
         if args.arch == "baseline" and (B, Kf, H, W) == (2, 3, 192, 288) and os.path.exists(tj):
             tk = [v for k, v in json.load(open(tj)).items() if "igemm2_kernel" in k]
             traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in tk) / max(1, sum(v["launches"] for v in tk))
@@ -323,7 +410,7 @@ def run_b200(args, H, W, arch_kw):
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                     "launches_per_step": ig_calls, "share_of_kernel_time": ig_ms / total_ms, "traffic": traffic,
-                    "traffic_source": "profiles/r01_step_traffic_final.txt (ncu dram__bytes_read+write, mean per launch)",
+                    "traffic_source": "profiles/r02_step_traffic.txt (ncu dram__bytes_read+write, mean per launch)",
                     "algorithmic_bytes_per_launch": sum(v["bytes"] for v in ig) / max(1, ig_calls),
                     "step_achieved": step_tf, "step_frac": (step_tf / peak) if step_tf else None}
         lines = [f"{'kernel':40s} {'calls':>6s} {'ms':>9s} {'share':>7s} {'TFLOP/s':>9s} {'GB/s':>9s}"]
@@ -338,28 +425,40 @@ def run_b200(args, H, W, arch_kw):
             with open(args.kernel_table, "w") as f:
                 f.write(f"# bench.py kernel pass: arch={args.arch} B={B} K={Kf} grid={H}x{W}\n" + text + "\n")
 
-    cpu_baseline = None
+    cpu_baseline = comparator = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        h, w, frac = pick_cpu_sample(H, W, budget_s=25.0, n_steps=1, arch_kw=arch_kw, frames=Kf, threads=threads)
-        sec = cpu_reference_step_time(arch_kw, Kf, h, w, threads, steps=1, warmup=0)
-        sec_full = sec * (H * W) / (h * w)
-        cpu_baseline = {"value": 1.0 / sec_full, "unit": "samples/s", "cores": threads, "kind": "port",
-                        "sample": f"oracle port (fp32 torch CPU) fwd+bwd of 1 sample at {h}x{w}"
-                                  + (f", 1/{frac * frac} of the grid, time scaled by pixel count" if frac > 1 else "")
-                                  + ", 1 timed step after a small-grid warm-up"}
+        b, h, w, frac = pick_cpu_sample(1, H, W, budget_s=25.0, n_steps=4, arch_kw=arch_kw, frames=Kf, threads=threads)
+        sec = cpu_reference_step_time(arch_kw, Kf, b, h, w, threads, steps=3, warmup=1)
+        cpu_baseline = {"value": b / (sec * (H * W) / (h * w)), "unit": "samples/s", "cores": threads, "kind": "port",
+                        "sample": f"oracle port (fp32 torch CPU) of the step (loss fwd+bwd, clip, AdamW), {b} sample at {h}x{w}"
+                                  + (f", 1/{frac * frac} of the grid, scaled by pixel count" if frac > 1 else "")
+                                  + ", mean of 3 timed steps after 1 warm-up"}
+    if rank == 0 and world == 1 and not args.no_gpu_comparator:
+        try:
+            comparator = gpu_comparator(arch_kw, Kf, B, H, W, dev)
+        except Exception as exc:  # e.g. out of memory next to the engines: report, do not hide
+            comparator = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+    # ---- BASELINE.json's other two numbers at this N (untimed by the driver; same event timing) --------
+    extra = {}
+    if not args.no_extra:
+        extra["ensemble_gen"] = measure_sampling(args, H, W, BASELINE_KW, dev, rank, world, steps=10, warmup=3)
+        extra["more_blocks"] = measure_more_blocks(args, dev, rank, world, peaks, steps=5, warmup=3)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {**workload_config(args, H, W, B), "cuda_graph": not args.no_graph,
                        "l2": "256 MiB buffer zeroed between steps (L2 is 126 MB); per-step activations >> L2"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "launches_per_step": eng.launches_per_step,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_comparator": comparator,
+            "extra": extra, "ranks_in_sync": in_sync,
+            "loss_scale": {"final": float(eng.opt.state[2]), "skipped_steps": int(eng.opt.state[5])},
             "loss_first_last": [losses[0], losses[-1]] if losses else None,
         }
         print(json.dumps(line), flush=True)
@@ -374,13 +473,116 @@ def run_b200(args, H, W, arch_kw):
         os._exit(0)
 
 
-def run_sample(args, H, W, arch_kw):
-    """Secondary metric (BASELINE.json: "ensemble-gen fields/s"): reverse-diffusion steps for a batch of
-    independent fields (inference.py:217-232 -> model.py:186-194), one CUDA-graph replay per step.
-    A step = one UNet call (F = 1) + fused p_sample update; fields/s = batch / (T * step time), T = 1000."""
+def measure_sampling(args, H, W, arch_kw, dev, rank, world, steps, warmup, B=16):
+    """BASELINE.json's second metric, "ensemble-gen fields/s": reverse-diffusion steps for a batch of independent
+    fields (inference.py:217-232 -> model.py:186-194), one CUDA-graph replay per step, fields sharded over ranks
+    (each rank its own batch, no collective inside the chain).  A step = one UNet call (F = 1) + fused p_sample
+    update; fields/s = world * batch / (T * step time), T = 1000, step time = max over ranks."""
     import torch
+    import torch.distributed as dist
+    from cesm_emulator_b200 import ops
     from cesm_emulator_b200.engine import SampleEngine
     from cesm_emulator_b200.model import Diffusion, UNet
+    ops.set_grad_sink(None)
+    torch.manual_seed(0)
+    diff = Diffusion(UNet(**arch_kw), timesteps=1000).to(dev)
+    diff.eval()
+    for p_ in diff.parameters():
+        p_.requires_grad_(False)
+    eng = SampleEngine(diff, (B, 1, H, W), use_graph=not args.no_graph)
+    torch.manual_seed(4321 + rank)   # every rank generates different fields
+    eng.cond.normal_()
+    eng.x.normal_()
+    eng.t.fill_(999)
+    for _ in range(1 + warmup):
+        eng.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    finite = bool(torch.isfinite(eng.x).all())
+    gflop = 178.5 * (H * W) / (192 * 288) if arch_kw is BASELINE_KW else None  # SURVEY 8(d): per UNet call per field
+    peaks = load_peaks()
+    tf = gflop * B / ms if gflop else None
+    out = {"metric": "ensemble-gen fields/s (1000-step DDPM chain)", "value": B * world / (1000 * ms * 1e-3),
+           "unit": "fields/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+           "fields_per_gpu_batch": B, "grid": [H, W], "frames": 1, "finite": finite,
+           "note": f"{steps} timed reverse steps of a {B}-field batch per GPU (fields sharded over ranks, no collective); "
+                   "value extrapolated to the full 1000-step chain",
+           "launches_per_step": eng.launches_per_step,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["bf16_tflops_sustained"] if tf else None,
+                        "note": "whole reverse step: algorithmic 178.5 GFLOP per field per UNet call at 192x288"}}
+    del eng, diff
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_more_blocks(args, dev, rank, world, peaks, steps, warmup):
+    """BASELINE.json configs[2]: config/more_blocks (ch_mults [1,2,4,8]) training at its own crop and batch
+    (config/more_blocks: 64x64, batch_size 64 per GPU, K = 3), data-parallel over the same ranks."""
+    import torch
+    import torch.distributed as dist
+    from cesm_emulator_b200 import ops
+    from cesm_emulator_b200.engine import TrainEngine
+    from cesm_emulator_b200.model import Diffusion, UNet
+    B, Kf, H, W = 64, 3, 64, 64
+    ops.set_grad_sink(None)
+    torch.manual_seed(0)
+    diff = Diffusion(UNet(**MORE_BLOCKS_KW), timesteps=1000).to(dev)
+    diff.train()
+    eng = TrainEngine(diff, (B, 1, H, W), (B, 1, Kf, H, W), use_graph=not args.no_graph)
+    torch.manual_seed(99 + rank)
+    eng.x0.normal_()
+    eng.cond.normal_()
+    for _ in range(3 + warmup):
+        eng.step_resident()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        flush.zero_()
+        eng.step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        torch.cuda.synchronize()
+    tf = GFLOP_PER_PIXEL["more_blocks"] * H * W * B / ms
+    out = {"metric": "train samples/s (more_blocks cfg)", "value": B * world / (ms * 1e-3), "unit": "samples/s",
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "per_gpu_batch": B, "grid": [H, W],
+           "frames": Kf, "loss": float(eng.loss), "launches_per_step": eng.launches_per_step,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["bf16_tflops_sustained"],
+                        "note": "whole step: algorithmic 137.5 GFLOP per sample (SURVEY 8(d)) / step time"}}
+    for h in eng.buckets._hooks:
+        h.remove()
+    ops.set_grad_sink(None)
+    del eng, diff
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sample(args, H, W, arch_kw):
+    """`--workload sample`: the ensemble-generation measurement as the headline line (torchrun for N > 1)."""
+    import torch
+    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -388,42 +590,21 @@ def run_sample(args, H, W, arch_kw):
     rank = int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     B = args.batch if args.batch != 2 else 16  # inference.py:180 default batch_size 16
-    torch.manual_seed(0)
-    diff = Diffusion(UNet(**arch_kw), timesteps=1000).to(dev)
-    diff.eval()
-    for p_ in diff.parameters():
-        p_.requires_grad_(False)
-    eng = SampleEngine(diff, (B, 1, H, W), use_graph=not args.no_graph)
-    eng.cond.normal_()
-    eng.x.normal_()
-    eng.t.fill_(999)
-    for _ in range(3 + args.warmup):
-        eng.step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        eng.step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    out = measure_sampling(args, H, W, arch_kw, dev, rank, world, steps=args.steps, warmup=args.warmup, B=B)
     if rank == 0:
-        gflop = 178.5 * (H * W) / (192 * 288) if args.arch == "baseline" else None  # per UNet call per field
-        peaks = load_peaks()
-        tf = gflop * B / ms if gflop else None
-        print(json.dumps({
-            "metric": "ensemble-gen fields/s (1000-step DDPM chain)", "value": B * world / (1000 * ms * 1e-3),
-            "unit": "fields/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"config/{args.arch} sampling: {args.steps} timed reverse steps of a {B}-field batch, "
-                                   f"{H}x{W}, F=1; value extrapolated to the full 1000-step chain",
-                       "fields_per_batch": B, "grid": [H, W], "cuda_graph": not args.no_graph},
-            "gpu_launches": eng.launches_per_step * args.steps, "launches_per_step": eng.launches_per_step,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["bf16_tflops_sustained"] if tf else None, "traffic": None,
-                         "note": "whole reverse step: algorithmic 178.5 GFLOP per field per UNet call"},
-        }), flush=True)
+        out.update({"higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+                    "config": {"workload": f"config/{args.arch} sampling, {B} fields per GPU batch, {H}x{W}, F=1",
+                               "cuda_graph": not args.no_graph},
+                    "gpu_launches": out["launches_per_step"] * args.steps})
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 def main():

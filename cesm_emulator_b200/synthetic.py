@@ -126,7 +126,12 @@ class DeviceEnsemble:
         self.device = torch.device(device)
         self.cond = torch.from_numpy(np.ascontiguousarray(ds.cond[:, :, 0])).to(self.device)   # (T, M, H, W)
         self.tgt = torch.from_numpy(np.ascontiguousarray(ds.tgt[:, :, 0])).to(self.device)
-        self._plan_ring = []   # pinned host plans, rotated so that an in-flight async copy is never overwritten
+        # pinned host plans in a ring; each slot carries the CUDA event recorded after the H2D copy that read it,
+        # and the host waits on that event before rewriting the slot.  The training loop never syncs inside an
+        # epoch, so without this the host can run more than a ring ahead of the stream-ordered copies and
+        # overwrite a plan that has not been read yet (torn / repeated batches).
+        self._plan_ring = []
+        self._plan_events = []
         self._plan_dev = None
         self._turn = 0
 
@@ -135,9 +140,15 @@ class DeviceEnsemble:
         B = len(indices)
         if not self._plan_ring or self._plan_ring[0].shape[0] != B:
             mk = lambda: torch.empty((B, 6), dtype=torch.int32)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)   # nothing may still be reading the old ring
             self._plan_ring = [mk().pin_memory() if torch.cuda.is_available() else mk() for _ in range(8)]
+            self._plan_events = [None] * len(self._plan_ring)
             self._plan_dev = torch.empty((B, 6), dtype=torch.int32, device=self.device)
-        host = self._plan_ring[self._turn % len(self._plan_ring)]
+        slot = self._turn % len(self._plan_ring)
+        host = self._plan_ring[slot]
+        if self._plan_events[slot] is not None:
+            self._plan_events[slot].synchronize()     # the copy issued 8 batches ago has consumed this buffer
         self._turn += 1
         host.copy_(torch.tensor([self.ds.plan(int(i), augment) for i in indices], dtype=torch.int32))
         return host
@@ -146,5 +157,10 @@ class DeviceEnsemble:
         """Fill the (static) device buffers cond_out [B,1,K,h,w] / x0_out [B,1,h,w] for these sample indices."""
         from . import kernels as K
         host = self.plan(indices, augment)
+        slot = (self._turn - 1) % len(self._plan_ring)
         self._plan_dev.copy_(host, non_blocking=True)
+        if self.device.type == "cuda":
+            ev = self._plan_events[slot] or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._plan_events[slot] = ev
         K.gather_windows(self.cond, self.tgt, self._plan_dev, cond_out, x0_out)

@@ -375,3 +375,90 @@ def loss_and_grads(sd: StateDict, cfg: OracleConfig, buf: Dict[str, Tensor], x0:
     names = [k for k, v in leaves.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
     return loss.detach(), {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, grads)}
+
+
+# --------------------------------------------------------------------------------------------
+# a state dict of the reference's layout without the reference (timing legs of bench.py)
+# --------------------------------------------------------------------------------------------
+def random_state_dict(cfg: OracleConfig, seed: int = 0, time_dim: Optional[int] = None, pre: str = "net.") -> StateDict:
+    """Random weights in the key / shape layout of model.UNet(...).state_dict() (video_net.py:562-764, SURVEY.md
+    section 8(b)); scales follow PyTorch's default fan-in initialisation so that activations stay O(1).  Used where
+    only the arithmetic is timed (bench.py's CPU / stock-PyTorch legs): the product package is not imported there."""
+    g = torch.Generator().manual_seed(seed)
+    sd: StateDict = {}
+    dim, heads, dh = cfg.model_dim, cfg.attn_heads, cfg.attn_dim_head
+    hidden, sp_hidden = heads * dh, heads * cfg.spatial_dim_head
+    tdim = dim * 4 if time_dim is None else time_dim  # video_net.py:650
+    ks = cfg.init_kernel_size
+
+    def w(key, *shape, fan_in=None):
+        fan = fan_in if fan_in is not None else max(1, int(torch.tensor(shape[1:]).prod()))
+        bound = 1.0 / math.sqrt(fan)
+        sd[pre + key] = (torch.rand(*shape, generator=g) * 2 - 1) * bound
+
+    def conv(key, cout, cin, kh, kw, bias=True):
+        w(key + ".weight", cout, cin, 1, kh, kw)
+        if bias:
+            w(key + ".bias", cout, fan_in=cin * kh * kw)
+
+    def temporal(key, c):
+        sd[pre + key + ".fn.norm.gamma"] = torch.ones(1, c, 1, 1, 1)
+        w(key + ".fn.fn.fn.to_qkv.weight", 3 * hidden, c)
+        w(key + ".fn.fn.fn.to_out.weight", c, hidden)
+        sd[pre + key + ".fn.fn.fn.rotary_emb.freqs"] = 1.0 / (10000 ** (torch.arange(0, min(32, dh), 2).float() / min(32, dh)))
+
+    def spatial(key, c):
+        sd[pre + key + ".fn.norm.gamma"] = torch.ones(1, c, 1, 1, 1)
+        w(key + ".fn.fn.to_qkv.weight", 3 * sp_hidden, c, 1, 1)
+        w(key + ".fn.fn.to_out.weight", c, sp_hidden, 1, 1)
+        w(key + ".fn.fn.to_out.bias", c, fan_in=sp_hidden)
+
+    def resnet(key, cin, cout, temb=True):
+        if temb:
+            w(key + ".mlp.1.weight", 2 * cout, tdim)
+            w(key + ".mlp.1.bias", 2 * cout, fan_in=tdim)
+        conv(key + ".block1.proj", cout, cin, 3, 3)
+        sd[pre + key + ".block1.norm.weight"], sd[pre + key + ".block1.norm.bias"] = torch.ones(cout), torch.zeros(cout)
+        conv(key + ".block2.proj", cout, cout, 3, 3)
+        sd[pre + key + ".block2.norm.weight"], sd[pre + key + ".block2.norm.bias"] = torch.ones(cout), torch.zeros(cout)
+        if cin != cout:
+            conv(key + ".res_conv", cout, cin, 1, 1)
+
+    cin0 = cfg.n_vars + (1 if cfg.cond_map else 0)
+    conv("input_conv", dim, cin0, ks, ks)
+    sd[pre + "time_rel_pos_bias.relative_attention_bias.weight"] = torch.randn(cfg.rel_pos_num_buckets, heads, generator=g)
+    temporal("input_temp_op", dim)
+    w("time_mlp.1.weight", tdim, dim)
+    w("time_mlp.1.bias", tdim, fan_in=dim)
+    w("time_mlp.3.weight", tdim, tdim)
+    w("time_mlp.3.bias", tdim, fan_in=tdim)
+    dims = cfg.dims
+    in_out = list(zip(dims[:-1], dims[1:]))
+    n = len(in_out)
+    for i, (ci, co) in enumerate(in_out):
+        last = i >= n - 1
+        resnet(f"downs.{i}.0", ci, co)
+        resnet(f"downs.{i}.1", co, co)
+        if cfg.use_sparse_linear_attn:
+            spatial(f"downs.{i}.2", co)
+        temporal(f"downs.{i}.3", co)
+        if not last:
+            conv(f"downs.{i}.4", co, co, 4, 4)
+    mid = dims[-1]
+    resnet("mid_block1", mid, mid)
+    temporal("mid_temporal_attn", mid)
+    resnet("mid_block2", mid, mid)
+    for i, (ci, co) in enumerate(reversed(in_out)):
+        last = i >= n - 1
+        resnet(f"ups.{i}.0", co * 2, ci)
+        resnet(f"ups.{i}.1", ci, ci)
+        if cfg.use_sparse_linear_attn:
+            spatial(f"ups.{i}.2", ci)
+        temporal(f"ups.{i}.3", ci)
+        if not last:
+            # ConvTranspose3d weight is [cin, cout, 1, 4, 4] (video_net.py:65-66)
+            w(f"ups.{i}.4.weight", ci, ci, 1, 4, 4)
+            w(f"ups.{i}.4.bias", ci, fan_in=ci * 16)
+    resnet("out_conv.0", dim * 2, dim, temb=False)
+    conv("out_conv.1", cfg.n_vars, dim, 1, 1)
+    return sd

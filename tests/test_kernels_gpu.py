@@ -518,6 +518,31 @@ def test_device_data_path(cuda, K, crop):
     assert torch.equal(cond.cpu(), ref_c) and torch.equal(x0.cpu(), ref_x)
 
 
+def test_device_data_path_survives_host_run_ahead(cuda):
+    """The training loop never syncs inside an epoch: the host may issue dozens of batches while the GPU is still
+    busy with the first.  Every batch must still be the one the host path would have produced (the pinned plan
+    ring is guarded by events; a bare 8-slot ring was overwritten before its async copies ran)."""
+    from cesm_emulator_b200.synthetic import SyntheticEnsemble
+    kw = dict(members=3, times=12, lat=24, lon=40, seed=5, K=3, crop_hw=(16, 24), time_reverse_p=0.5)
+    host, ds = SyntheticEnsemble(**kw), SyntheticEnsemble(**kw)
+    dev = ds.to_device(cuda)
+    B, n = 4, 40
+    g = torch.Generator().manual_seed(2)
+    idxs = [torch.randint(0, len(ds), (B,), generator=g).tolist() for _ in range(n)]
+    refs = [host.batch(i) for i in idxs]
+    conds = [torch.empty(B, 1, 3, 16, 24, device=cuda) for _ in range(n)]
+    x0s = [torch.empty(B, 1, 16, 24, device=cuda) for _ in range(n)]
+    big = torch.randn(8192, 8192, device=cuda)
+    torch.cuda.synchronize()
+    for _ in range(20):          # ~tens of ms of queued GPU work: the stream lags far behind the host
+        big = big @ big * 1e-4
+    for i in range(n):
+        dev.batch_into(idxs[i], conds[i], x0s[i])
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert torch.equal(conds[i].cpu(), refs[i][0]) and torch.equal(x0s[i].cpu(), refs[i][1]), i
+
+
 def test_film_projections_batched(cuda):
     """ops.FilmAllFn (all FiLM linears of a pass in one launch, one fused backward) against torch."""
     from cesm_emulator_b200 import ops

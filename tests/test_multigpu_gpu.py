@@ -1,0 +1,31 @@
+"""Hardware multi-GPU correctness (reference train.py:1076): needs >= 2 GPUs
+(`gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu`); skipped on a 1-GPU box.  The record of
+the last run on 2 and 8 B200s is profiles/r02_multigpu_correctness.txt."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_replicas_in_sync_and_gradient_equals_global_batch(cuda):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_mgpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("MGPU_RESULT ")][-1]
+    res = json.loads(line[len("MGPU_RESULT "):])
+    assert res["world"] == world and res["ranks_in_sync"] is True, res
+    assert res["skipped_steps"] == 0
+    assert all(l == l and l < 10 for l in res["losses_rank0"])
+    assert res["grad_vs_global_batch"]["max"] < 3e-3, res
+    assert res["local_only_vs_global_batch_median"] > 5e-2, res   # different data: a missing all-reduce would show

@@ -55,6 +55,8 @@ def save_checkpoint(path, epoch, diffusion, engine, cfg):
         "optimizer": engine.opt.state_dict(),
         "config": cfg,
     }
+    if "grad_scaler" in ckpt["optimizer"]:  # GradScaler.state_dict() layout; the reference loads "scaler" if present (train.py:940-944)
+        ckpt["scaler"] = dict(ckpt["optimizer"]["grad_scaler"])
     os.makedirs(os.path.dirname(path), exist_ok=True)
     torch.save(ckpt, path)
 
@@ -116,7 +118,9 @@ def main(cfg):
             raise RuntimeError(f"Non-finite loss at epoch {epoch}: {mean}")  # train.py:860-861
         if rank == 0:
             dt = time.time() - t0
-            print(f"epoch {epoch}: loss {mean:.5f}  {n_steps * B * world / dt:.1f} samples/s ({world} GPU)")
+            st = engine.opt.state.tolist()
+            print(f"epoch {epoch}: loss {mean:.5f}  {n_steps * B * world / dt:.1f} samples/s ({world} GPU)  "
+                  f"loss scale {st[2]:.0f}, {int(st[5])} skipped step(s)")
             if epoch % int(tcfg.get("save_every", 10)) == 0:
                 save_checkpoint(os.path.join(save_dir, "checkpoints", f"ckpt_epoch_{epoch}.pt"), epoch, diffusion,
                                 engine, cfg)
