@@ -428,7 +428,7 @@ def run_b200(args, H, W, arch_kw):
     cpu_baseline = comparator = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        b, h, w, frac = pick_cpu_sample(1, H, W, budget_s=25.0, n_steps=4, arch_kw=arch_kw, frames=Kf, threads=threads)
+        b, h, w, frac = pick_cpu_sample(1, H, W, budget_s=40.0, n_steps=4, arch_kw=arch_kw, frames=Kf, threads=threads)
         sec = cpu_reference_step_time(arch_kw, Kf, b, h, w, threads, steps=3, warmup=1)
         cpu_baseline = {"value": b / (sec * (H * W) / (h * w)), "unit": "samples/s", "cores": threads, "kind": "port",
                         "sample": f"oracle port (fp32 torch CPU) of the step (loss fwd+bwd, clip, AdamW), {b} sample at {h}x{w}"

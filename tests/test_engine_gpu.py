@@ -53,7 +53,9 @@ def test_engine_gradients_match_autograd_and_oracle(cuda):
         assert set(got) == set(ref) == set(og)
         vs_auto = np.array([rel_err(got[k], ref[k]) for k in ref])
         vs_orac = np.array([rel_err(got[k], og[k]) for k in ref])
-        assert vs_auto.max() < 3e-3, (rep, np.median(vs_auto), vs_auto.max())
+        # two runs of the same arithmetic are not bitwise equal (fp32 atomics land in a different order, individual
+        # fp16 roundings flip and the difference spreads): measured median 6e-4, worst tensor 3.5e-3
+        assert np.median(vs_auto) < 1.5e-3 and vs_auto.max() < 6e-3, (rep, np.median(vs_auto), vs_auto.max())
         assert vs_orac.max() < 1e-2, (rep, np.median(vs_orac), vs_orac.max())
     del d.loss
     ops.set_grad_sink(None)
@@ -281,7 +283,9 @@ def test_weights_stay_fresh_across_train_eval_train(cuda):
         with torch.no_grad():
             got = d.model(x, c, t)
         ref = fresh_eps()
-        assert rel_err(got, ref) < 1e-5, (rnd, rel_err(got, ref))
+        # run-to-run noise (atomics order -> flipped fp16 roundings) is ~3e-4; a stale operand after 4 steps at
+        # lr = 1e-2 moves the output by O(1)
+        assert rel_err(got, ref) < 2e-3, (rnd, rel_err(got, ref))
         outs.append(got)
         if samp is None:
             samp = SampleEngine(d, (2, 1, H, W))
@@ -289,8 +293,8 @@ def test_weights_stay_fresh_across_train_eval_train(cuda):
         y = samp.sample(c, steps=3)
         torch.manual_seed(5)
         y_ref = SampleEngine(d, (2, 1, H, W)).sample(c, steps=3)   # captured now, with the current weights
-        assert rel_err(y, y_ref) < 1e-5, (rnd, rel_err(y, y_ref))
-    assert rel_err(outs[1], outs[0]) > 1e-3   # training really changed the network between the two evals
+        assert rel_err(y, y_ref) < 2e-3, (rnd, rel_err(y, y_ref))
+    assert rel_err(outs[1], outs[0]) > 5e-2   # training really changed the network between the two evals
     ops.set_grad_sink(None)
 
 

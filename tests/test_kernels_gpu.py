@@ -462,6 +462,7 @@ def test_fused_adamw_follows_grad_scaler(cuda):
     ref = torch.nn.Parameter(p0.clone())
     opt = torch.optim.AdamW([ref], **hp)
     scaler = torch.amp.GradScaler("cuda", init_scale=65536.0, growth_interval=interval)
+    scaler.scale(torch.zeros(1, device=cuda))  # lazy initialisation of the scale tensor
     p, m, v = p0.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
     state = _opt_state(cuda, hp["lr"], hp["weight_decay"], 65536.0, interval)
     partials = torch.zeros(_lib.load().cesm_adamw_partials(), device=cuda)
@@ -475,7 +476,6 @@ def test_fused_adamw_follows_grad_scaler(cuda):
             gs[step] = float("inf")
         ref.grad = gs.clone()
         # torch flow (scaler.scale(loss).backward() produced gs)
-        scaler._per_optimizer_states.clear()
         scaler.unscale_(opt)
         torch.nn.utils.clip_grad_norm_([ref], 1.0)
         scaler.step(opt)
