@@ -192,12 +192,29 @@ class KernelProfiler:
 
 
 PROFILER = None  # set to a KernelProfiler to time every call
+# CESM_NVTX=1: every C-ABI call is wrapped in an NVTX range named after the entry point (plus the profiler
+# `kind`, e.g. "cesm_igemm/9tap"), so nsys / ncu --nvtx timelines and `ncu --nvtx-include` filters speak the C ABI's
+# vocabulary.  Ranges pushed during CUDA-graph capture annotate the capture, not the replays: profile with
+# use_graph=False (bench.py --no-graph) for per-call ranges.
+NVTX = bool(int(__import__("os").environ.get("CESM_NVTX", "0")))
+
+
+def _nvtx_call(lib, name, args, meta):
+    from torch.cuda import nvtx
+    nvtx.range_push(name if not meta or "kind" not in meta else f"{name}/{meta['kind']}")
+    try:
+        check(getattr(lib, name)(*args), name)
+    finally:
+        nvtx.range_pop()
 
 
 def call(name: str, *args, _meta=None) -> None:
     lib = load()
     prof = PROFILER
     if prof is None:
+        if NVTX:
+            _nvtx_call(lib, name, args, _meta)
+            return
         check(getattr(lib, name)(*args), name)
         return
     import torch

@@ -61,7 +61,9 @@ class GradBuckets:
         self._bucket_of = {}
         self._pending_init: List[int] = []
         self.offsets = {}                     # id(param) -> start of its slice in the flat buffers
-        self.registration_order = [p for p in module.parameters() if p.requires_grad]  # what an optimizer sees
+        # what the reference's optimizer sees: AdamW(diffusion.parameters()) (train.py:1078) -- EVERY parameter in
+        # registration order, including the frozen rotary `freqs` (index 3), which holds an index but never a state
+        self.registration_order = list(module.parameters())
         for p in self.params:
             n = p.numel()
             self.offsets[id(p)] = off
@@ -252,9 +254,10 @@ class FusedAdamW:
         ops.invalidate_weight_cache()  # the fp16 operand copies are stale now
 
     def _slices(self):
-        """(flat offset, numel, shape) of every parameter in REGISTRATION order, i.e. the parameter indexing of
-        a torch optimizer built over `module.parameters()` as the reference does (train.py:1078)."""
-        return [(self._buckets.offsets[id(p)], p.numel(), p.shape) for p in self._buckets.registration_order]
+        """index -> (flat offset, numel, shape) for every TRAINABLE parameter, indexed as a torch optimizer built over
+        `module.parameters()` indexes them (the reference's AdamW, train.py:1078: frozen parameters keep their slot)."""
+        return {i: (self._buckets.offsets[id(p)], p.numel(), p.shape)
+                for i, p in enumerate(self._buckets.registration_order) if id(p) in self._buckets.offsets}
 
     def state_dict(self) -> dict:
         """torch.optim.AdamW's state-dict format, so that checkpoints interchange with the reference's
@@ -262,11 +265,11 @@ class FusedAdamW:
         step = self.state[0].detach().clone()
         state = {i: {"step": step.clone(), "exp_avg": self.m[o:o + n].view(shape).clone(),
                      "exp_avg_sq": self.v[o:o + n].view(shape).clone()}
-                 for i, (o, n, shape) in enumerate(self._slices())}
+                 for i, (o, n, shape) in self._slices().items()}
         g = self.param_groups[0]
         group = dict(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=g["weight_decay"], amsgrad=False,
                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
-                     params=list(range(len(state))))
+                     params=list(range(len(self._buckets.registration_order))))
         # "grad_scaler": torch.amp.GradScaler.state_dict() keys (the reference loads one if present, train.py:940-944)
         scaler = {"scale": float(self.state[K.OPT_SCALE]), "growth_factor": 2.0, "backoff_factor": 0.5,
                   "growth_interval": int(self.state[K.OPT_INTERVAL]), "_growth_tracker": int(self.state[K.OPT_TRACKER])}
@@ -276,7 +279,7 @@ class FusedAdamW:
         if "state" in sd:  # torch format (ours, the reference's, or any torch AdamW over module.parameters())
             slices = self._slices()
             steps = []
-            for i, (o, n, shape) in enumerate(slices):
+            for i, (o, n, shape) in slices.items():
                 st = sd["state"].get(i)
                 if st is None:
                     continue

@@ -194,14 +194,17 @@ def test_optimizer_state_interchanges_with_torch_adamw(cuda):
     for _ in range(3):
         eng.step(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, K, H, W, generator=g))
     sd = eng.opt.state_dict()
-    params = [p for p in d.parameters() if p.requires_grad]
-    assert set(sd) == {"state", "param_groups", "grad_scaler"} and len(sd["state"]) == len(params)
+    params = list(d.parameters())   # the reference's AdamW(diffusion.parameters()) (train.py:1078): frozen freqs included
+    trainable = [i for i, p in enumerate(params) if p.requires_grad]
+    assert set(sd) == {"state", "param_groups", "grad_scaler"} and sorted(sd["state"]) == trainable
+    assert len(sd["param_groups"][0]["params"]) == len(params)
     assert sd["grad_scaler"]["scale"] == 65536.0
-    assert all(sd["state"][i]["exp_avg"].shape == p.shape for i, p in enumerate(params))
+    assert all(sd["state"][i]["exp_avg"].shape == params[i].shape for i in trainable)
     ref = torch.optim.AdamW(params, **hp)
     ref.load_state_dict(sd)                                   # engine -> torch
     assert float(ref.state[params[0]]["step"]) == 3.0
     # same gradient through both optimizers, starting from the same weights and state
+    params = [p for p in params if p.requires_grad]
     grads = [torch.randn_like(p) * 1e-2 for p in params]
     before = [p.detach().clone() for p in params]
     for p, gr in zip(params, grads):

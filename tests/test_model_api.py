@@ -116,3 +116,47 @@ def test_c_abi_exports_every_declared_symbol():
     assert sorted(_lib.exported_symbols()) == declared
     lib.cesm_version.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.cesm_version()
+
+
+def test_loads_a_checkpoint_written_by_the_reference():
+    """tests/golden/ref_ckpt_tiny.pt was saved by the UNMODIFIED reference classes with train.py:1154-1165's
+    layout (tests/golden/make_ref_checkpoint.py).  This repo's resume path (train.load_checkpoint, the
+    train.py:915-946 semantics) must take it as is: every key lands (strict), the buffers match, the epoch
+    advances, the optimizer state indexes the same parameters, and the loaded weights compute what the
+    reference computed (checked through the fp32 oracle; the CUDA path needs channel counts that are
+    multiples of 64, so the GPU side of checkpoint interchange is tests/test_engine_gpu.py's job)."""
+    import os
+    import numpy as np
+    import torch
+    import train as train_entry
+    from cesm_emulator_b200.model import Diffusion
+    from oracle import cesm_oracle as O
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    ckpt = torch.load(os.path.join(gold, "ref_ckpt_tiny.pt"), map_location="cpu", weights_only=False)
+    assert set(ckpt) == {"epoch", "model", "diffusion_buffers", "optimizer", "config"}
+    diffusion = Diffusion(train_entry.build_model_from_config(ckpt["config"]["unet"]), timesteps=1000)
+    start = train_entry.load_checkpoint(os.path.join(gold, "ref_ckpt_tiny.pt"), diffusion, engine=None, device="cpu")
+    assert start == ckpt["epoch"] + 1
+    ours = diffusion.model.state_dict()
+    assert set(ours) == set(ckpt["model"])
+    for k, v in ckpt["model"].items():
+        assert torch.equal(ours[k], v), k
+    for k, v in ckpt["diffusion_buffers"].items():
+        assert torch.equal(getattr(diffusion, k), v), k
+    # optimizer: torch AdamW over this repo's module.parameters() accepts the reference's optimizer state
+    params = list(diffusion.parameters())   # train.py:1078: AdamW(diffusion.parameters()), frozen rotary freqs included
+    opt = torch.optim.AdamW(params, lr=2e-4)
+    opt.load_state_dict(ckpt["optimizer"])
+    z = np.load(os.path.join(gold, "ref_ckpt_tiny_expect.npz"))
+    assert len(opt.state_dict()["state"]) == int(z["n_params"]) == len([p for p in params if p.requires_grad])
+    assert 3 not in opt.state_dict()["state"] and not params[3].requires_grad  # rotary_emb.freqs holds index 3, no state
+    assert torch.equal(opt.state[params[0]]["exp_avg"], torch.from_numpy(z["exp_avg_0"]))
+    assert opt.state[params[0]]["exp_avg"].shape == params[0].shape
+    # the loaded weights reproduce the reference's outputs
+    cfg = O.OracleConfig.from_unet_kwargs(**{**ckpt["config"]["unet"], "ch_mults": tuple(ckpt["config"]["unet"]["ch_mults"])})
+    sd = {k: v.float() for k, v in ours.items()}
+    with torch.no_grad():
+        eps = O.unet_forward(sd, cfg, torch.from_numpy(z["x_t"]), torch.from_numpy(z["cond"]), torch.from_numpy(z["t"]))
+        eps1 = O.unet_forward(sd, cfg, torch.from_numpy(z["x_t"]), torch.from_numpy(z["cond"][:, :, 1]), torch.from_numpy(z["t"]))
+    assert (eps - torch.from_numpy(z["eps"])).abs().max() < 2e-5 * np.abs(z["eps"]).max()
+    assert (eps1 - torch.from_numpy(z["eps_f1"])).abs().max() < 2e-5 * np.abs(z["eps_f1"]).max()
