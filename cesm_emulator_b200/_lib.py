@@ -96,6 +96,7 @@ def load() -> ctypes.CDLL:
     lib.cesm_linattn_ws_floats.restype = ctypes.c_size_t
     lib.cesm_linattn_ws_floats.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.cesm_adamw_partials.restype = ctypes.c_int
+    lib.cesm_tattn_long_max_frames.restype = ctypes.c_int
     lib.cesm_set_prezeroed_scratch.restype = None
     lib.cesm_set_prezeroed_scratch.argtypes = [ctypes.c_int]
     _declare(lib)
@@ -121,6 +122,8 @@ _SIGNATURES: dict[str, list] = {
     "cesm_ln_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P],
     "cesm_tattn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "cesm_tattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "cesm_tattn_long_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "cesm_tattn_long_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "cesm_linattn_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "cesm_linattn_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "cesm_film_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
@@ -152,7 +155,7 @@ def _declare(lib: ctypes.CDLL) -> None:
 
 def exported_symbols() -> list[str]:
     return ["cesm_last_error", "cesm_version", "cesm_launch_count", "cesm_linattn_ws_floats", "cesm_adamw_partials",
-            "cesm_set_prezeroed_scratch",
+            "cesm_set_prezeroed_scratch", "cesm_tattn_long_max_frames",
             *sorted(_SIGNATURES)]
 
 

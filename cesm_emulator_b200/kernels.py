@@ -342,11 +342,40 @@ def ln_bwd(x, gamma, dy, dres, eps: float, into: Optional[torch.Tensor] = None):
 
 
 # ---- attention cores ----------------------------------------------------------------------------
+LONG_WINDOW_MAX = 128  # cesm_tattn_long_max_frames(): frames of one pixel column that fit in shared memory
+
+
+def _bias_to_diag(bias: torch.Tensor) -> torch.Tensor:
+    """[H, F, F] Toeplitz relative-position bias (video_net.py:302-310: a function of key - query) -> [H, 2F-1] with
+    diag[h][d + F - 1] = bias[h][i][i + d]: first column (d < 0, reversed) then first row (d >= 0)."""
+    return torch.cat([bias[:, 1:, 0].flip(1), bias[:, 0, :]], dim=1).contiguous()
+
+
+def _diag_to_bias_grad(ddiag: torch.Tensor, F: int) -> torch.Tensor:
+    """The per-diagonal bias gradient as an [H, F, F] tensor with each diagonal's sum placed on its first element:
+    every consumer of d(bias) here sums over a diagonal anyway (the bucket of an entry depends on key - query only),
+    so the embedding-table gradient is the same as with the element-wise gradient."""
+    H = ddiag.shape[0]
+    g = torch.zeros((H, F, F), dtype=ddiag.dtype, device=ddiag.device)
+    g[:, 0, :] = ddiag[:, F - 1:]
+    g[:, 1:, 0] = ddiag[:, :F - 1].flip(1)
+    return g
+
+
 def tattn_fwd(qkv, bias, cs, sn, B: int, F: int, HW: int, H: int, D: int, scale: float):
+    """F <= 4: register-resident kernel, `bias` may be any [H, F, F].  F > 4: the shared-memory / tensor-core flash
+    kernel (cesm_tattn_long_fwd), which takes the bias by diagonal: `bias` must be Toeplitz (RelativePositionBias)."""
     _req_cuda(qkv, bias, cs, sn)
     rows = B * F * HW
     out = torch.empty((rows, H * D), dtype=H16, device=qkv.device)
-    # F <= 4: the backward recomputes the softmax, so no log-sum-exp is kept
+    if 4 < F <= LONG_WINDOW_MAX:
+        lse = torch.empty((rows, H), dtype=torch.float32, device=qkv.device)
+        _lib.call("cesm_tattn_long_fwd", _ptr(qkv), _ptr(_bias_to_diag(bias)), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse),
+                  B, F, HW, H, D, scale, _stream(),
+                  _meta={"kind": f"F{F}", "bytes": float(qkv.numel() * 2 + out.numel() * 2),
+                         "flops": 4.0 * rows * H * F * D * 2})
+        return out, lse
+    # F <= 4: the backward recomputes the softmax, so no log-sum-exp is kept.  F > 128: the streaming kernel.
     lse = torch.empty((rows, H), dtype=torch.float32, device=qkv.device) if F > 4 else None
     _lib.call("cesm_tattn_fwd", _ptr(qkv), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse), B, F, HW, H, D, scale,
               _stream(), _meta=_bytes_meta(qkv, out))
@@ -356,6 +385,13 @@ def tattn_fwd(qkv, bias, cs, sn, B: int, F: int, HW: int, H: int, D: int, scale:
 def tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B: int, F: int, HW: int, H: int, D: int, scale: float):
     _req_cuda(qkv, bias, cs, sn, out, lse, dout)
     dqkv = torch.empty_like(qkv)
+    if 4 < F <= LONG_WINDOW_MAX:
+        ddiag = zero_scratch((H, 2 * F - 1), qkv.device)
+        _lib.call("cesm_tattn_long_bwd", _ptr(qkv), _ptr(_bias_to_diag(bias)), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse),
+                  _ptr(dout), _ptr(dqkv), _ptr(ddiag), B, F, HW, H, D, scale, _stream(),
+                  _meta={"kind": f"F{F}", "bytes": float(qkv.numel() * 4 + dout.numel() * 4),
+                         "flops": 14.0 * B * F * HW * H * F * D * 2})
+        return dqkv, _diag_to_bias_grad(ddiag, F)
     dbias = zero_scratch((H, F, F), qkv.device)
     _lib.call("cesm_tattn_bwd", _ptr(qkv), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), _ptr(lse), _ptr(dout), _ptr(dqkv),
               _ptr(dbias), B, F, HW, H, D, scale, _stream(), _meta=_bytes_meta(qkv, dout, dqkv))

@@ -226,6 +226,19 @@ int cesm_tattn_bwd(const void* qkv, const float* bias, const float* cs, const fl
                    const float* lse, const void* dout, void* dqkv, float* dbias, int B, int F, int HW, int H,
                    int dim_head, float scale, void* stream);
 
+/* Long windows (F > 4, up to 128 frames; BASELINE.json configs[4]): the same computation, flash style.  A CTA
+ * stages every frame of one pixel column in shared memory once and one warp per head runs the F x F attention on
+ * the tensor cores (mma.sync m16n8k16), instead of each query re-reading all keys / values from global memory.
+ * The relative-position bias of video_net.py:302-310 depends on (key - query) only, so it is passed by diagonal:
+ *   bias_diag : fp32 [H][2F-1], bias_diag[h][d + F - 1] = bias[h][i][i + d];  dbias_diag likewise (zeroed by the call).
+ * lse is always written (fwd) / read (bwd). */
+int cesm_tattn_long_max_frames(void);
+int cesm_tattn_long_fwd(const void* qkv, const float* bias_diag, const float* cs, const float* sn, void* out,
+                        float* lse, int B, int F, int HW, int H, int dim_head, float scale, void* stream);
+int cesm_tattn_long_bwd(const void* qkv, const float* bias_diag, const float* cs, const float* sn, const void* out,
+                        const float* lse, const void* dout, void* dqkv, float* dbias_diag, int B, int F, int HW, int H,
+                        int dim_head, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Spatial linear attention core, video_net.py:338-344, per image (frame) of n pixels and head:
  * qs = scale*softmax(q) over d, kh = softmax(k) over the n pixels, ctx = kh^T v, out = qs ctx.

@@ -195,13 +195,31 @@ def _tattn_ref(qkv, bias, freqs, B, Fr, HW, H, D):
     return out.permute(0, 2, 1, 3).reshape(B * Fr * HW, H * D)
 
 
-@pytest.mark.parametrize("B,Fr,HW,H", [(2, 3, 64, 8), (1, 1, 100, 8), (2, 12, 33, 8), (1, 40, 16, 4)])
+def _toeplitz_bias(H, Fr, dev):
+    """A bias of RelativePositionBias's structure (video_net.py:302-310): a function of key - query per head."""
+    diag = torch.randn(H, 2 * Fr - 1, device=dev)
+    i = torch.arange(Fr, device=dev)
+    return diag[:, (i[None, :] - i[:, None]) + Fr - 1].contiguous(), diag
+
+
+def _fold_diagonals(g, Fr):
+    """[H, F, F] -> [H, 2F-1]: sums over entries with the same key - query."""
+    i = torch.arange(Fr, device=g.device)
+    idx = ((i[None, :] - i[:, None]) + Fr - 1).reshape(-1)
+    return torch.zeros(g.shape[0], 2 * Fr - 1, device=g.device, dtype=g.dtype).index_add_(1, idx, g.reshape(g.shape[0], -1))
+
+
+@pytest.mark.parametrize("B,Fr,HW,H", [(2, 3, 64, 8), (1, 1, 100, 8), (2, 12, 33, 8), (1, 40, 16, 4), (1, 16, 64, 8),
+                                       (1, 32, 40, 8), (2, 64, 24, 8), (1, 128, 6, 8), (1, 100, 5, 2), (1, 5, 300, 8)])
 def test_temporal_attention_core(cuda, B, Fr, HW, H):
+    """F <= 4: the register-resident kernels with an arbitrary [H, F, F] bias.  F > 4: the shared-memory / mma.sync
+    flash kernels (csrc/tattn_long.cu), which take the relative-position bias by diagonal -- Toeplitz bias, and its
+    gradient compared per diagonal (the only form any consumer uses: buckets depend on key - query)."""
     from cesm_emulator_b200 import kernels as K
     torch.manual_seed(6)
     D = 32
     qkv = rnd((B * Fr * HW, 3 * H * D), cuda)
-    bias = torch.randn(H, Fr, Fr, device=cuda)
+    bias = torch.randn(H, Fr, Fr, device=cuda) if Fr <= 4 else _toeplitz_bias(H, Fr, cuda)[0]
     freqs = (1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))).to(cuda)
     ang = torch.arange(Fr, device=cuda, dtype=torch.float32)[:, None] * freqs[None]
     cs, sn = ang.cos().contiguous(), ang.sin().contiguous()
@@ -213,7 +231,20 @@ def test_temporal_attention_core(cuda, B, Fr, HW, H):
     assert err(out, ref) < 2e-3
     gq, gb = torch.autograd.grad(ref, [qr, br], dout.float())
     assert err(dqkv, gq) < 3e-3
-    assert err(dbias, gb) < 2e-3
+    if Fr <= 4:
+        assert err(dbias, gb) < 2e-3
+    else:
+        assert err(_fold_diagonals(dbias, Fr), _fold_diagonals(gb, Fr)) < 3e-3
+        lse_ref = torch.logsumexp(_tattn_scores(qr.detach(), bias, freqs, B, Fr, HW, H, D), dim=-1)  # [B, HW, H, F]
+        assert err(lse.view(B, Fr, HW, H).permute(0, 2, 3, 1), lse_ref) < 2e-3
+
+
+def _tattn_scores(qkv, bias, freqs, B, Fr, HW, H, D):
+    x = qkv.view(B, Fr, HW, 3 * H * D).permute(0, 2, 1, 3)
+    q, k, _ = (t.reshape(B, HW, Fr, H, D).transpose(-2, -3) for t in x.chunk(3, dim=-1))
+    ang = O.rotary_angles(freqs, Fr)
+    q, k = O.apply_rotary(q * D ** -0.5, ang), O.apply_rotary(k, ang)
+    return torch.einsum("...hid,...hjd->...hij", q, k) + bias
 
 
 def _linattn_ref(qkv, NI, n, H, D):

@@ -48,7 +48,7 @@ def main():
     init = {k: v.detach().float().cpu().clone() for k, v in diff.model.state_dict().items()}
     params = [p for p in diff.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, **hp)
-    scaler = torch.amp.GradScaler("cuda")
+    scaler = torch.amp.GradScaler("cuda", init_scale=float(os.environ.get("INIT_SCALE", "65536")))
     gpu_losses = []
     for cond, x0, t, noise in batches:
         opt.zero_grad(set_to_none=True)
@@ -80,6 +80,14 @@ def main():
             print(f"step {i:4d}  oracle {cpu_losses[-1]:.6f}  b200 {gpu_losses[i]:.6f}  "
                   f"rel {abs(gpu_losses[i] - cpu_losses[-1]) / abs(cpu_losses[-1]):.2e}", flush=True)
     rel = [abs(a - b) / abs(b) for a, b in zip(gpu_losses, cpu_losses)]
+    if os.environ.get("DUMP"):
+        import json
+        with open(os.environ["DUMP"], "w") as f:
+            json.dump({"oracle": cpu_losses, "b200": gpu_losses}, f)
+    srel = sorted(rel)
+    print(f"per-step |rel diff|: median {srel[len(srel) // 2]:.3e}  p90 {srel[int(0.9 * len(srel))]:.3e}; "
+          f"per-step |abs diff|: mean {sum(abs(a - b) for a, b in zip(gpu_losses, cpu_losses)) / steps:.3e}; "
+          f"mean loss over all steps oracle {sum(cpu_losses) / steps:.6f} b200 {sum(gpu_losses) / steps:.6f}")
     mean_c, mean_g = sum(cpu_losses[-20:]) / 20, sum(gpu_losses[-20:]) / 20
     print(f"steps {steps} grid {H}x{W} B={B}: max rel diff {max(rel):.3e}, mean rel diff {sum(rel)/len(rel):.3e}, "
           f"last-20 mean oracle {mean_c:.6f} b200 {mean_g:.6f} (rel {abs(mean_g-mean_c)/mean_c:.2e}); "
