@@ -445,6 +445,8 @@ def run_b200(args, H, W, arch_kw):
     if not args.no_extra:
         extra["ensemble_gen"] = measure_sampling(args, H, W, BASELINE_KW, dev, rank, world, steps=10, warmup=3)
         extra["more_blocks"] = measure_more_blocks(args, dev, rank, world, peaks, steps=5, warmup=3)
+        if rank == 0 and world == 1:
+            extra["long_window_attention"] = measure_long_window_attention(dev, H, W)
 
     if rank == 0:
         line = {
@@ -528,6 +530,60 @@ def measure_sampling(args, H, W, arch_kw, dev, rank, world, steps, warmup, B=16)
     return out
 
 
+def measure_long_window_attention(dev, H, W, frames=(32, 64, 128), heads=8, steps=5):
+    """BASELINE.json configs[4]: the temporal-attention core in isolation on the full
+    grid for multi-decade windows, B = 1: q|k|v [F*H*W, 768] fp16 -> out [F*H*W, 256] (cesm_tattn_long_fwd / _bwd).
+    HBM-bound: algorithmic bytes = q|k|v + out forward (2 KB per row); q|k|v, out, dout, dq|dk|dv backward (4 KB per
+    row) against the measured copy bandwidth; tensor work (mma.sync) is reported beside it."""
+    import torch
+    from cesm_emulator_b200 import kernels as K
+    peaks = load_peaks()
+    D, HW, res = 32, H * W, {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for F in frames:
+        rows = F * HW
+        torch.manual_seed(F)
+        qkv = (torch.randn(rows, 3 * heads * D, device=dev) * 0.5).half()
+        dout = (torch.randn(rows, heads * D, device=dev) * 0.1).half()
+        diag = torch.randn(heads, 2 * F - 1, device=dev) * 0.1
+        i = torch.arange(F, device=dev)
+        bias = diag[:, (i[None, :] - i[:, None]) + F - 1].contiguous()
+        freqs = (1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))).to(dev)
+        ang = torch.arange(F, device=dev, dtype=torch.float32)[:, None] * freqs[None]
+        cs, sn = ang.cos().contiguous(), ang.sin().contiguous()
+        out, lse = K.tattn_fwd(qkv, bias, cs, sn, 1, F, HW, heads, D, D ** -0.5)     # warm-up
+        K.tattn_bwd(qkv, bias, cs, sn, out, lse, dout, 1, F, HW, heads, D, D ** -0.5)
+        torch.cuda.synchronize()
+        t = {}
+        for name, fn in (("fwd", lambda: K.tattn_fwd(qkv, bias, cs, sn, 1, F, HW, heads, D, D ** -0.5)),
+                         ("bwd", lambda: K.tattn_bwd(qkv, bias, cs, sn, out, lse, dout, 1, F, HW, heads, D, D ** -0.5))):
+            ms = 0.0
+            for _ in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms += e0.elapsed_time(e1)
+            t[name] = ms / steps
+        by_f = rows * (3 + 1) * heads * D * 2.0
+        by_b = rows * (3 + 1 + 1 + 3) * heads * D * 2.0
+        fl_f = 4.0 * rows * heads * F * D            # QK^T + PV
+        fl_b = 14.0 * rows * heads * F * D           # 7 F x F x 32 contractions (S and dP recomputed in both passes)
+        res[f"F{F}"] = {
+            "rows": rows, "fwd_ms": t["fwd"], "bwd_ms": t["bwd"],
+            "fwd_rows_per_s": rows / (t["fwd"] * 1e-3), "bwd_rows_per_s": rows / (t["bwd"] * 1e-3),
+            "roofline_fwd": {"bound": "hbm", "achieved": by_f / t["fwd"] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": by_f / t["fwd"] / 1e6 / peaks["hbm_gbs"], "tensor_tflops": fl_f / t["fwd"] / 1e9},
+            "roofline_bwd": {"bound": "hbm", "achieved": by_b / t["bwd"] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": by_b / t["bwd"] / 1e6 / peaks["hbm_gbs"], "tensor_tflops": fl_b / t["bwd"] / 1e9}}
+        del qkv, dout, out, lse
+        torch.cuda.empty_cache()
+    return {"metric": "temporal attention core, long windows (rows = frames x pixels)", "grid": [H, W], "heads": heads,
+            "batch": 1, "steps": steps, "by_frames": res}
+
+
 def measure_more_blocks(args, dev, rank, world, peaks, steps, warmup):
     """BASELINE.json configs[2]: config/more_blocks (ch_mults [1,2,4,8]) training at its own crop and batch
     (config/more_blocks: 64x64, batch_size 64 per GPU, K = 3), data-parallel over the same ranks."""
@@ -595,6 +651,32 @@ def run_sample(args, H, W, arch_kw):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch if args.batch != 2 else 16  # inference.py:180 default batch_size 16
     out = measure_sampling(args, H, W, arch_kw, dev, rank, world, steps=args.steps, warmup=args.warmup, B=B)
+    if rank == 0 and args.kernel_table:
+        # untimed instrumented reverse step: per-C-ABI-call device time
+        from cesm_emulator_b200 import _lib
+        from cesm_emulator_b200.engine import SampleEngine
+        from cesm_emulator_b200.model import Diffusion, UNet
+        torch.manual_seed(0)
+        diff = Diffusion(UNet(**arch_kw), timesteps=1000).to(dev)
+        diff.eval()
+        eng = SampleEngine(diff, (B, 1, H, W), use_graph=False)
+        eng.cond.normal_(); eng.x.normal_(); eng.t.fill_(999)
+        eng.step()
+        torch.cuda.synchronize()
+        _lib.PROFILER = _lib.KernelProfiler()
+        eng.step()
+        table = _lib.PROFILER.summary()
+        _lib.PROFILER = None
+        total_ms = sum(v["ms"] for v in table.values())
+        lines = [f"# bench.py --workload sample kernel pass: arch={args.arch} fields={B} grid={H}x{W}",
+                 f"{'kernel':40s} {'calls':>6s} {'ms':>9s} {'share':>7s} {'TFLOP/s':>9s} {'GB/s':>9s}"]
+        for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
+            tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] else 0.0
+            gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] else 0.0
+            lines.append(f"{k:40s} {v['calls']:6d} {v['ms']:9.3f} {v['ms'] / total_ms:7.1%} {tf:9.1f} {gb:9.1f}")
+        lines.append(f"{'total (instrumented eager step)':40s} {sum(v['calls'] for v in table.values()):6d} {total_ms:9.3f}")
+        with open(args.kernel_table, "w") as f:
+            f.write("\n".join(lines) + "\n")
     if rank == 0:
         out.update({"higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
                     "config": {"workload": f"config/{args.arch} sampling, {B} fields per GPU batch, {H}x{W}, F=1",

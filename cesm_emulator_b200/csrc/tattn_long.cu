@@ -72,18 +72,23 @@ struct Geo {
 };
 
 // Stage rows r < F of one pixel column: `parts` runs of HG*64 bytes per row, `part_stride` halfs apart in global.
+// One warp per row (rows strided over the warps), lanes over the row's 16-byte chunks: no integer divisions.
 __device__ __forceinline__ void stage_rows(uint32_t dst, int pitch_h, const h16* __restrict__ src, long long row0,
                                            long long row_stride, int ld, int parts, int part_stride, int HG, int F, int Fp) {
     const int cpr = HG * 4;                       // 16-byte chunks per part per row
-    const int per_row = parts * cpr;
-    for (int idx = threadIdx.x; idx < Fp * per_row; idx += blockDim.x) {
-        const int r = idx / per_row, c = idx - r * per_row;
-        const int part = c / cpr, ch = c - part * cpr;
-        const uint32_t d = dst + (uint32_t)(r * pitch_h + part * HG * 32 + ch * 8) * 2u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < Fp; r += nw) {
+        const uint32_t drow = dst + (uint32_t)(r * pitch_h) * 2u;
         if (r < F) {
-            cp16(d, src + (row0 + (long long)r * row_stride) * ld + part * part_stride + ch * 8);
+            const h16* srow = src + (row0 + (long long)r * row_stride) * ld;
+            for (int part = 0; part < parts; ++part)
+                for (int ch = lane; ch < cpr; ch += 32)
+                    cp16(drow + (uint32_t)(part * HG * 32 + ch * 8) * 2u, srow + part * part_stride + ch * 8);
         } else {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d), "r"(0u) : "memory");
+            for (int part = 0; part < parts; ++part)
+                for (int ch = lane; ch < cpr; ch += 32)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(drow + (uint32_t)(part * HG * 32 + ch * 8) * 2u), "r"(0u)
+                                 : "memory");
         }
     }
 }
@@ -243,12 +248,12 @@ tattn_long_fwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bia
             store_tile(o, tile, g.pq, mt * 16, w * D, lane);   // over this tile's (consumed) q rows
         }
         __syncthreads();
-        // out rows: HG*64 contiguous bytes per frame
+        // out rows: HG*64 contiguous bytes per frame (one warp per row, lanes over 16-byte chunks)
         const int cpr = g.HG * 4;
-        for (int idx = threadIdx.x; idx < g.F * cpr; idx += blockDim.x) {
-            const int r = idx / cpr, ch = idx - r * cpr;
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + (size_t)(r * g.pq + ch * 8) * 2);
-            *reinterpret_cast<uint4*>(out + (row0 + (long long)r * g.HW) * (g.H * D) + h0 * D + ch * 8) = v;
+        for (int r = w; r < g.F; r += (int)(blockDim.x >> 5)) {
+            h16* orow = out + (row0 + (long long)r * g.HW) * (g.H * D) + h0 * D;
+            for (int ch = lane; ch < cpr; ch += 32)
+                *reinterpret_cast<uint4*>(orow + ch * 8) = *reinterpret_cast<const uint4*>(smem + (size_t)(r * g.pq + ch * 8) * 2);
         }
     }
 }
@@ -273,6 +278,8 @@ tattn_long_bwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bia
     float* gd = bd + g.HG * 2 * g.Fp;                              // [HG][2*Fp] its gradient (whole kernel)
     float* s_lse = gd + g.HG * 2 * g.Fp;                           // [HG][Fp]
     float* s_dl = s_lse + g.HG * g.Fp;                             // [HG][Fp] delta_i = dO_i . O_i
+    const int ps = g.Fp + 4;                                       // pitch of the per-warp dS scratch
+    float* s_ds = s_dl + g.HG * g.Fp;                              // [HG][16][Fp + 4]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h0 = blockIdx.y * g.HG;
     const int ld = 3 * g.H * D, lo = g.H * D;
@@ -286,6 +293,7 @@ tattn_long_bwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bia
     float* gw = gd + w * 2 * g.Fp + (g.Fp - 1);
     float* lw = s_lse + w * g.Fp;
     float* dw = s_dl + w * g.Fp;
+    float* sw = s_ds + w * 16 * ps;
     for (long long pix = blockIdx.x; pix < npix; pix += gridDim.x) {
         const long long b = pix / g.HW, hw = pix - b * g.HW;
         const long long row0 = b * g.F * g.HW + hw;
@@ -340,12 +348,23 @@ tattn_long_bwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bia
                 s[nt][1] = p1 * (dp[nt][1] - e0);
                 s[nt][2] = p2 * (dp[nt][2] - e1);
                 s[nt][3] = p3 * (dp[nt][3] - e1);
-                // bias gradient by diagonal (key - query); masked entries are exact zeros
-                if (v0 && c0) atomicAdd(gw + (j - i0), s[nt][0]);
-                if (v0 && c1) atomicAdd(gw + (j + 1 - i0), s[nt][1]);
-                if (v1 && c0) atomicAdd(gw + (j - i1), s[nt][2]);
-                if (v1 && c1) atomicAdd(gw + (j + 1 - i1), s[nt][3]);
+                // dS tile -> this warp's scratch (row-major fp32) for the per-diagonal bias gradient below
+                *reinterpret_cast<float2*>(sw + gq * ps + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
+                *reinterpret_cast<float2*>(sw + (gq + 8) * ps + nt * 8 + 2 * t) = make_float2(s[nt][2], s[nt][3]);
             }
+            // bias gradient by diagonal (key - query): each diagonal of the 16 x Fp tile belongs to ONE lane, which
+            // sums its <= 16 entries (masked entries are exact zeros) and adds them to the warp's own table: no atomics
+            __syncwarp();
+            for (int d = lane; d < g.Fp + 15; d += 32) {
+                float acc = 0.f;
+#pragma unroll
+                for (int v = 0; v < 16; ++v) {
+                    const int c = v + d - 15;
+                    if (c >= 0 && c < g.Fp) acc += sw[v * ps + c];
+                }
+                gw[d - 15 - mt * 16] += acc;
+            }
+            __syncwarp();
             float dq[4][4];
             gemm_pv<NT>(dq, s, tile, g.pq, g.HG * D + w * D, lane);                // dQ_rot = dS K
             // undo RoPE (transpose of the rotation) and the scale; pairs (2m, 2m+1) are adjacent fragment columns
@@ -421,16 +440,18 @@ tattn_long_bwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bia
             store_tile(dv, tile, g.pq, jt * 16, 2 * g.HG * D + w * D, lane);       // ... and v rows
         }
         __syncthreads();
-        // dq | dk | dv rows out: three runs of HG*64 bytes per frame
+        // dq | dk | dv rows out: three runs of HG*64 bytes per frame (one warp per row)
         const int cpr = g.HG * 4;
-        for (int idx = threadIdx.x; idx < g.F * 3 * cpr; idx += blockDim.x) {
-            const int r = idx / (3 * cpr), c = idx - r * 3 * cpr;
-            const int part = c / cpr, ch = c - part * cpr;
-            uint4 v;
-            if (part == 0) v = *reinterpret_cast<const uint4*>(smem + (size_t)g.Fp * g.pq * 2 + (size_t)g.Fp * g.po * 2 +
-                                                               (size_t)(r * g.po + ch * 8) * 2);
-            else v = *reinterpret_cast<const uint4*>(smem + (size_t)(r * g.pq + part * g.HG * D + ch * 8) * 2);
-            *reinterpret_cast<uint4*>(dqkv + (row0 + (long long)r * g.HW) * ld + part * g.H * D + h0 * D + ch * 8) = v;
+        const uint8_t* sdq = smem + (size_t)g.Fp * g.pq * 2 + (size_t)g.Fp * g.po * 2;
+        for (int r = w; r < g.F; r += (int)(blockDim.x >> 5)) {
+            h16* grow = dqkv + (row0 + (long long)r * g.HW) * ld + h0 * D;
+            for (int ch = lane; ch < cpr; ch += 32) {
+                *reinterpret_cast<uint4*>(grow + ch * 8) = *reinterpret_cast<const uint4*>(sdq + (size_t)(r * g.po + ch * 8) * 2);
+                *reinterpret_cast<uint4*>(grow + g.H * D + ch * 8) =
+                    *reinterpret_cast<const uint4*>(smem + (size_t)(r * g.pq + g.HG * D + ch * 8) * 2);
+                *reinterpret_cast<uint4*>(grow + 2 * g.H * D + ch * 8) =
+                    *reinterpret_cast<const uint4*>(smem + (size_t)(r * g.pq + 2 * g.HG * D + ch * 8) * 2);
+            }
         }
     }
     __syncthreads();
@@ -443,7 +464,8 @@ tattn_long_bwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bia
 
 static size_t fwd_smem(const Geo& g) { return (size_t)g.Fp * g.pq * 2 + (size_t)g.HG * 2 * g.Fp * 4; }
 static size_t bwd_smem(const Geo& g) {
-    return (size_t)g.Fp * g.pq * 2 + 2 * (size_t)g.Fp * g.po * 2 + (size_t)g.HG * 2 * g.Fp * 4 * 2 + (size_t)g.HG * g.Fp * 4 * 2;
+    return (size_t)g.Fp * g.pq * 2 + 2 * (size_t)g.Fp * g.po * 2 + (size_t)g.HG * 2 * g.Fp * 4 * 2 + (size_t)g.HG * g.Fp * 4 * 2 +
+           (size_t)g.HG * 16 * (g.Fp + 4) * 4;
 }
 static Geo make_geo(int F, int HW, int H, int HG) {
     Geo g;

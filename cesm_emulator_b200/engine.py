@@ -137,6 +137,12 @@ class GradBuckets:
         self._seen = {}
 
     def _on_grad(self, p):
+        # A parameter whose gradient was written directly (ops._direct) reports through ready(); torch ALSO runs
+        # its post-accumulate hook (measured on 2 B200s: every direct parameter reported twice, the buckets
+        # reached zero after half of their gradients and were all-reduced early -- replicas diverged).  Count
+        # each parameter once per step.
+        if id(p) in self._seen:
+            return
         b = self._bucket_of[p.data_ptr()]
         self._seen[id(p)] = True
         self._pending[b] -= 1

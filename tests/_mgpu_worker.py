@@ -86,8 +86,12 @@ def main():
     worst = max(errs, key=errs.get)
     out["grad_vs_global_batch"] = {"max": errs[worst], "worst": worst,
                                    "median": sorted(errs.values())[len(errs) // 2], "tensors": len(errs)}
+    bad = sorted((k for k in errs if errs[k] > 1e-2), key=errs.get, reverse=True)
+    out["bad_tensors"] = {k: [errs[k], float(g_ddp[k].norm()), float(g_one[k].norm())] for k in bad[:40]}
+    out["n_bad"] = len(bad)
     # the per-rank gradient alone must NOT match (the data differ): the check above is not vacuous
     g_local = grads_of(solo, mine, B)
+    out["bad_vs_half_local"] = {k: rel_err(g_ddp[k], 0.5 * g_local[k]) for k in bad[:40]}
     out["local_only_vs_global_batch_median"] = sorted(rel_err(g_local[k], g_one[k]) for k in g_one)[len(g_one) // 2]
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(out), flush=True)

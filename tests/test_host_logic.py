@@ -64,7 +64,15 @@ def _bucket_worker(rank, world, port, q):
         torch.manual_seed(100 + rank)  # different data per rank
         x = torch.randn(5, 6)
         buckets.begin_step()
+        # engine mode: a parameter whose gradient is written directly reports through ready() AND torch runs its
+        # post-accumulate hook as well (seen on 2 B200s: buckets were all-reduced after half of their gradients).
+        # Emulate the double report: a backward hook on the first layer's output calls ready() for the LAST
+        # layer's parameters right after autograd accumulated them -- they must be counted once.
+        last = list(net[4].parameters())
+        h = net[2].register_full_backward_hook(lambda *_: [buckets.ready(p) for p in last])
         (net(x).pow(2).mean() / world).backward()   # mean over ranks == sum of (loss / world)
+        h.remove()
+        assert buckets._pending == [0] * buckets.n_buckets, buckets._pending
         buckets.finish_step()
         norm = buckets.clip_(1e9)
         # the flat buffer pads every tensor to a 64-byte boundary: compare the per-parameter views
