@@ -69,7 +69,11 @@ def _bucket_worker(rank, world, port, q):
         # Emulate the double report: a backward hook on the first layer's output calls ready() for the LAST
         # layer's parameters right after autograd accumulated them -- they must be counted once.
         last = list(net[4].parameters())
-        h = net[2].register_full_backward_hook(lambda *_: [buckets.ready(p) for p in last])
+        def report_again(*_):
+            for p in last:
+                buckets.ready(p)
+
+        h = net[2].register_full_backward_hook(report_again)
         (net(x).pow(2).mean() / world).backward()   # mean over ranks == sum of (loss / world)
         h.remove()
         assert buckets._pending == [0] * buckets.n_buckets, buckets._pending
