@@ -398,6 +398,39 @@ def tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B: int, F: int, HW: int, H: int
     return dqkv, dbias
 
 
+_NO_FUSED_TATTN = bool(int(__import__("os").environ.get("CESM_NO_FUSED_TATTN", "0")))  # A/B measurements only
+
+
+def tattn_proj_ok(C: int, F: int, HW: int, H: int, D: int) -> bool:
+    """Shapes the fused projection + attention kernels (csrc/tattn_proj.cu) take."""
+    return C == 64 and 1 <= F <= 3 and HW % 16 == 0 and H == 8 and D == 32 and not _NO_FUSED_TATTN
+
+
+def tattn_proj_fwd(xn, wqkv_packed, bias, cs, sn, B: int, F: int, HW: int, H: int, D: int, scale: float):
+    """o = attention(xn Wq^T, xn Wk^T, xn Wv^T) for F <= 3 frames without materialising q|k|v.
+    xn: fp16 [B*F*HW, 64]; wqkv_packed: fp16 [768, 64] -> fp16 [B*F*HW, 256]."""
+    _req_cuda(xn, wqkv_packed, bias, cs, sn)
+    assert xn.dtype == H16 and wqkv_packed.dtype == H16 and tuple(wqkv_packed.shape) == (3 * H * D, 64)
+    rows = B * F * HW
+    out = torch.empty((rows, H * D), dtype=H16, device=xn.device)
+    _lib.call("cesm_tattn_proj_fwd", _ptr(xn), _ptr(wqkv_packed), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(out), B, F, HW, H, D,
+              64, scale, _stream(),
+              _meta={"kind": "fused", "flops": 2.0 * rows * 64 * 3 * H * D, "bytes": float(rows * (64 + H * D) * 2)})
+    return out
+
+
+def tattn_proj_bwd(xn, wqkv_packed, bias, cs, sn, dout, B: int, F: int, HW: int, H: int, D: int, scale: float):
+    """-> (dqkv fp16 [B*F*HW, 768], dbias fp32 [H, F, F]); q, k, v are recomputed from xn."""
+    _req_cuda(xn, wqkv_packed, bias, cs, sn, dout)
+    rows = B * F * HW
+    dqkv = torch.empty((rows, 3 * H * D), dtype=H16, device=xn.device)
+    dbias = zero_scratch((H, F, F), xn.device)
+    _lib.call("cesm_tattn_proj_bwd", _ptr(xn), _ptr(wqkv_packed), _ptr(bias), _ptr(cs), _ptr(sn), _ptr(dout), _ptr(dqkv),
+              _ptr(dbias), B, F, HW, H, D, 64, scale, _stream(),
+              _meta={"kind": "fused", "flops": 2.0 * rows * 64 * 3 * H * D, "bytes": float(rows * (64 + H * D + 3 * H * D) * 2)})
+    return dqkv, dbias
+
+
 def linattn_fwd(qkv, NI: int, n: int, H: int, D: int, scale: float):
     """-> (out fp16 [NI*n, H*D], ws fp32 workspace kept for the backward)."""
     _req_cuda(qkv)

@@ -620,22 +620,33 @@ class TemporalAttnBlockFn(torch.autograd.Function):
             # ... and with nothing non-linear between the v projection and to_out, the two linears collapse
             # into ONE C x C matrix W_out W_v, folded once per weight version: y = x + LN(x) (W_out W_v)^T.
             return K.igemm(xn, _fold_f1(meta, wqkv, wout, hidden, C), residual=x)
-        qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
-        o, lse = K.tattn_fwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
+        wq = _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train)
+        fused = K.tattn_proj_ok(C, F, H_ * W_, heads, D)
+        if fused:
+            # 64 input channels, F <= 3: q|k|v never reach HBM (csrc/tattn_proj.cu); the backward recomputes them from xn
+            qkv, lse = None, None
+            o = K.tattn_proj_fwd(xn.view(-1, C), wq, pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
+        else:
+            qkv = K.igemm(xn, wq)
+            o, lse = K.tattn_fwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
         y = K.igemm(o.view(NI, H_, W_, hidden), _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), residual=x)
         ctx.wdq = _conv_dgrad_weights(meta.cq, wqkv, 3 * hidden, C, 0, 1, train)[0]
         ctx.wdo = _conv_dgrad_weights(meta.co, wout, C, hidden, 0, 1, train)[0]
-        if F <= 4:
-            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, gamma)
-        else:
-            ctx.save_for_backward(x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, gamma, lse)
+        ctx.wq_fwd = wq if fused else None   # the packed operand (a cache buffer, valid until the next optimizer step)
+        saved = [x, g, xn, o, pos_bias, cs, sn, wqkv, wout, gamma]
+        if not fused:
+            saved.append(qkv)
+            if F > 4:
+                saved.append(lse)
+        ctx.save_for_backward(*saved)
         ctx.cfg, ctx.gshape = (B, F, heads, D, eps), gamma.shape
         return y
 
     @staticmethod
     def backward(ctx, dy):
         saved = ctx.saved_tensors
-        x, g, xn, qkv, o, pos_bias, cs, sn, wqkv, wout, gamma = saved[:11]
+        x, g, xn, o, pos_bias, cs, sn, wqkv, wout, gamma = saved[:10]
+        qkv = saved[10] if len(saved) > 10 else None
         lse = saved[11] if len(saved) > 11 else None
         B, F, heads, D, eps = ctx.cfg
         hidden = heads * D
@@ -643,8 +654,12 @@ class TemporalAttnBlockFn(torch.autograd.Function):
         dy = dy.contiguous()
         do = K.igemm(dy, ctx.wdo)
         dwout = _conv_wgrad(wout, o.view(NI, H_, W_, hidden), None, dy, 1)
-        dqkv, dbias = K.tattn_bwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, o if F > 4 else None, lse,
-                                  do.view(-1, hidden), B, F, H_ * W_, heads, D, D ** -0.5)
+        if ctx.wq_fwd is not None:
+            dqkv, dbias = K.tattn_proj_bwd(xn.view(-1, C), ctx.wq_fwd, pos_bias, cs, sn, do.view(-1, hidden), B, F, H_ * W_,
+                                           heads, D, D ** -0.5)
+        else:
+            dqkv, dbias = K.tattn_bwd(qkv.view(-1, 3 * hidden), pos_bias, cs, sn, o if F > 4 else None, lse,
+                                      do.view(-1, hidden), B, F, H_ * W_, heads, D, D ** -0.5)
         dqkv4 = dqkv.view(NI, H_, W_, 3 * hidden)
         dxn, dwqkv = _qkv_backward(wqkv, ctx.wdq, xn, dqkv4)
         # + dy: the residual branch, added in the LN-backward epilogue

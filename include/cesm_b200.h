@@ -226,6 +226,18 @@ int cesm_tattn_bwd(const void* qkv, const float* bias, const float* cs, const fl
                    const float* lse, const void* dout, void* dqkv, float* dbias, int B, int F, int HW, int H,
                    int dim_head, float scale, void* stream);
 
+/* Short windows (F <= 3: the training window) FUSED WITH THE q/k/v PROJECTION, 64 input channels, 8 heads of 32
+ * (csrc/tattn_proj.cu): out = attention(xn Wq^T, xn Wk^T, xn Wv^T) with q, k, v never written to memory; the backward
+ * recomputes them from xn and writes dq|dk|dv for cesm_qkv_bwd.
+ *   xn  : fp16 [B*F*HW][64] = LayerNorm(x);  wqkv: fp16 [768][64] (to_qkv.weight as cesm_pack_weight lays it out)
+ *   bias: fp32 [8][F][F];  cs, sn: fp32 [F][16];  out / dout: fp16 [B*F*HW][256];  dqkv: fp16 [B*F*HW][768]
+ *   dbias: fp32 [8][F][F], zeroed by the call.  HW must be a multiple of 16. */
+int cesm_tattn_proj_fwd(const void* xn, const void* wqkv, const float* bias, const float* cs, const float* sn, void* out,
+                        int B, int F, int HW, int H, int dim_head, int cin, float scale, void* stream);
+int cesm_tattn_proj_bwd(const void* xn, const void* wqkv, const float* bias, const float* cs, const float* sn,
+                        const void* dout, void* dqkv, float* dbias, int B, int F, int HW, int H, int dim_head, int cin,
+                        float scale, void* stream);
+
 /* Long windows (F > 4, up to 128 frames; BASELINE.json configs[4]): the same computation, flash style.  A CTA
  * stages every frame of one pixel column in shared memory once and one warp per head runs the F x F attention on
  * the tensor cores (mma.sync m16n8k16), instead of each query re-reading all keys / values from global memory.

@@ -239,6 +239,38 @@ def test_temporal_attention_core(cuda, B, Fr, HW, H):
         assert err(lse.view(B, Fr, HW, H).permute(0, 2, 3, 1), lse_ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,Fr,HW", [(2, 3, 64), (1, 3, 48 * 72), (1, 2, 160), (3, 1, 32), (2, 3, 16)])
+def test_temporal_attention_fused_with_projection(cuda, B, Fr, HW):
+    """csrc/tattn_proj.cu: o = attention(xn Wq^T, xn Wk^T, xn Wv^T) without materialising q|k|v, and its recomputing
+    backward (-> dq|dk|dv, d bias), against the fp32 torch restatement of projection + attention on the same
+    fp16-rounded xn / W (video_net.py:403-453)."""
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(7)
+    H, D, C = 8, 32, 64
+    rows = B * Fr * HW
+    xn = rnd((rows, C), cuda)
+    w = rnd((3 * H * D, C), cuda, 0.15)
+    bias = torch.randn(H, Fr, Fr, device=cuda)
+    freqs = (1.0 / (10000 ** (torch.arange(0, D, 2).float() / D))).to(cuda)
+    ang = torch.arange(Fr, device=cuda, dtype=torch.float32)[:, None] * freqs[None]
+    cs, sn = ang.cos().contiguous(), ang.sin().contiguous()
+    dout = rnd((rows, H * D), cuda)
+    out = K.tattn_proj_fwd(xn, w, bias, cs, sn, B, Fr, HW, H, D, D ** -0.5)
+    dqkv, dbias = K.tattn_proj_bwd(xn, w, bias, cs, sn, dout, B, Fr, HW, H, D, D ** -0.5)
+    xr, wr, br = xn.float().requires_grad_(True), w.float().requires_grad_(True), bias.clone().requires_grad_(True)
+    qkv_ref = xr @ wr.t()
+    qkv_ref.retain_grad()
+    ref = _tattn_ref(qkv_ref, br, freqs, B, Fr, HW, H, D)
+    assert err(out, ref) < 2e-3
+    ref.backward(dout.float())
+    assert err(dqkv, qkv_ref.grad) < 3e-3
+    assert err(dbias, br.grad) < 3e-3
+    # and the unfused kernels on the materialised projection agree (same arithmetic, q|k|v rounded to fp16 in between)
+    qkv = K.igemm(xn.view(1, 1, rows, C), w).view(rows, 3 * H * D)
+    out2, _ = K.tattn_fwd(qkv, bias, cs, sn, B, Fr, HW, H, D, D ** -0.5)
+    assert err(out, out2) < 3e-3
+
+
 def _tattn_scores(qkv, bias, freqs, B, Fr, HW, H, D):
     x = qkv.view(B, Fr, HW, 3 * H * D).permute(0, 2, 1, 3)
     q, k, _ = (t.reshape(B, HW, Fr, H, D).transpose(-2, -3) for t in x.chunk(3, dim=-1))
