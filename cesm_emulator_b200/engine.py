@@ -479,15 +479,18 @@ class SampleEngine:
             self.t.copy_(t_keep)
         self.graph.replay()
 
+    def refresh_operands(self) -> None:
+        """Operands derived from the weights (packed fp16 copies, F = 1 folds) are captured by ADDRESS: bring their
+        contents up to date with whatever training / load_state_dict did since the graph was captured."""
+        ops.prepack_all()
+        ops.refresh_folds()
+
     @torch.no_grad()
     def sample(self, cond: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
         """cond: [B,1,H,W] -> generated field [B,1,H,W] after `steps` (default T) reverse steps."""
         T = self.diffusion.T
         steps = T if steps is None else steps
-        # operands derived from the weights (packed fp16 copies, F = 1 folds) are captured by ADDRESS: bring their
-        # contents up to date with whatever training / load_state_dict did since the graph was captured
-        ops.prepack_all()
-        ops.refresh_folds()
+        self.refresh_operands()
         self.cond.copy_(cond, non_blocking=True)
         self.x.normal_()
         self.t.fill_(T - 1)

@@ -398,12 +398,17 @@ def tattn_bwd(qkv, bias, cs, sn, out, lse, dout, B: int, F: int, HW: int, H: int
     return dqkv, dbias
 
 
-_NO_FUSED_TATTN = bool(int(__import__("os").environ.get("CESM_NO_FUSED_TATTN", "0")))  # A/B measurements only
+# Measured on B200 at the bench workload (profiles/r02_fused_tattn_ab.txt): the fused forward beats projection +
+# attention core (-0.26 ms per step: 510 MB per block never written or re-read), but its recomputing backward is
+# issue-bound at 8 warps per SM (255 registers) and loses more than that (+0.56 ms) against the HBM-bound stream
+# kernel it replaces.  So the fused kernels serve forward-only calls (evaluation with K > 1 frames); a training step
+# takes them only with CESM_FUSED_TATTN_TRAIN=1.
+_FUSED_TATTN_TRAIN = bool(int(__import__("os").environ.get("CESM_FUSED_TATTN_TRAIN", "0")))
 
 
-def tattn_proj_ok(C: int, F: int, HW: int, H: int, D: int) -> bool:
-    """Shapes the fused projection + attention kernels (csrc/tattn_proj.cu) take."""
-    return C == 64 and 1 <= F <= 3 and HW % 16 == 0 and H == 8 and D == 32 and not _NO_FUSED_TATTN
+def tattn_proj_ok(C: int, F: int, HW: int, H: int, D: int, train: bool = False) -> bool:
+    """Shapes / modes the fused projection + attention kernels (csrc/tattn_proj.cu) take."""
+    return C == 64 and 1 <= F <= 3 and HW % 16 == 0 and H == 8 and D == 32 and (_FUSED_TATTN_TRAIN or not train)
 
 
 def tattn_proj_fwd(xn, wqkv_packed, bias, cs, sn, B: int, F: int, HW: int, H: int, D: int, scale: float):

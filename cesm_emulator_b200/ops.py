@@ -621,9 +621,10 @@ class TemporalAttnBlockFn(torch.autograd.Function):
             # into ONE C x C matrix W_out W_v, folded once per weight version: y = x + LN(x) (W_out W_v)^T.
             return K.igemm(xn, _fold_f1(meta, wqkv, wout, hidden, C), residual=x)
         wq = _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train)
-        fused = K.tattn_proj_ok(C, F, H_ * W_, heads, D)
+        fused = K.tattn_proj_ok(C, F, H_ * W_, heads, D, train)
         if fused:
-            # 64 input channels, F <= 3: q|k|v never reach HBM (csrc/tattn_proj.cu); the backward recomputes them from xn
+            # 64 input channels, F <= 3, forward-only by default (see kernels.tattn_proj_ok): q|k|v never reach HBM
+            # (csrc/tattn_proj.cu); when used in a training step the backward recomputes them from xn
             qkv, lse = None, None
             o = K.tattn_proj_fwd(xn.view(-1, C), wq, pos_bias, cs, sn, B, F, H_ * W_, heads, D, D ** -0.5)
         else:

@@ -290,13 +290,17 @@ def test_weights_stay_fresh_across_train_eval_train(cuda):
         # lr = 1e-2 moves the output by O(1)
         assert rel_err(got, ref) < 2e-3, (rnd, rel_err(got, ref))
         outs.append(got)
+        # the graph captured in round 0 must see round 1's weights: one replayed reverse step against the module's
+        # own p_sample (eager, fresh operands) with the noise the replay drew
         if samp is None:
             samp = SampleEngine(d, (2, 1, H, W))
-        torch.manual_seed(5)
-        y = samp.sample(c, steps=3)
-        torch.manual_seed(5)
-        y_ref = SampleEngine(d, (2, 1, H, W)).sample(c, steps=3)   # captured now, with the current weights
-        assert rel_err(y, y_ref) < 2e-3, (rnd, rel_err(y, y_ref))
+            samp.sample(c, steps=2)                # captures the graph with the weights of round 0
+        samp.refresh_operands()
+        samp.x.copy_(x); samp.cond.copy_(c); samp.t.copy_(t)
+        samp.step()
+        with torch.no_grad():
+            y_ref = d.p_sample(x, c, t, noise=samp.z)
+        assert rel_err(samp.x, y_ref) < 2e-3, (rnd, rel_err(samp.x, y_ref))
     assert rel_err(outs[1], outs[0]) > 5e-2   # training really changed the network between the two evals
     ops.set_grad_sink(None)
 
