@@ -222,7 +222,7 @@ def run_reference(args, H, W, arch_kw):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def gpu_comparator(arch_kw, frames, B, H, W, dev, steps=5, warmup=3):
@@ -463,7 +463,7 @@ def run_b200(args, H, W, arch_kw):
             "loss_scale": {"final": float(eng.opt.state[2]), "skipped_steps": int(eng.opt.state[5])},
             "loss_first_last": [losses[0], losses[-1]] if losses else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Tear-down: the captured graphs hold NCCL kernels, and destroying the communicator under them
         # can block; everything is measured and printed, so synchronise, meet at a barrier and leave.
@@ -682,15 +682,33 @@ def run_sample(args, H, W, arch_kw):
                     "config": {"workload": f"config/{args.arch} sampling, {B} fields per GPU batch, {H}x{W}, F=1",
                                "cuda_graph": not args.no_graph},
                     "gpu_launches": out["launches_per_step"] * args.steps})
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
         os._exit(0)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints (NCCL's version
+    banner, torchrun notices) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # fd 1 -> stderr for C libraries and stray prints; emit() writes the JSON line to the saved fd
     if args.impl == "b200":
         from cesm_emulator_b200 import build as _build
         if not _build.LIB_PATH.exists():  # fresh checkout: build artefacts are git-ignored
