@@ -183,7 +183,7 @@ def cpu_reference_step_time(arch_kw, frames, B, H, W, threads, steps, warmup):
 def pick_cpu_sample(B, H, W, budget_s, n_steps, arch_kw, frames, threads):
     """The largest per-step sample of the workload whose n_steps fit the budget: the full batch on the full grid,
     else one sample on the full grid, else one sample on a power-of-two fraction of the grid.  -> (b, h, w, frac)"""
-    probe_h, probe_w = max(16, H // 8), max(16, W // 8)
+    probe_h, probe_w = max(16, H // 4), max(16, W // 4)   # small grids overestimate the per-pixel cost: probe at 1/16
     t_probe = cpu_reference_step_time(arch_kw, frames, 1, probe_h, probe_w, threads, steps=1, warmup=1)
     per_pixel = t_probe / (probe_h * probe_w)
     for b, frac in ((B, 1), (1, 1), (1, 2), (1, 4), (1, 8)):
@@ -201,7 +201,7 @@ def run_reference(args, H, W, arch_kw):
     threads = os.cpu_count() or 1
     n_steps = args.steps + args.warmup
     B = args.batch
-    b, h, w, frac = pick_cpu_sample(B, H, W, budget_s=300.0, n_steps=n_steps, arch_kw=arch_kw, frames=args.frames,
+    b, h, w, frac = pick_cpu_sample(B, H, W, budget_s=330.0, n_steps=n_steps, arch_kw=arch_kw, frames=args.frames,
                                     threads=threads)
     sec = cpu_reference_step_time(arch_kw, args.frames, b, h, w, threads, steps=args.steps, warmup=args.warmup)
     full = (b, h, w) == (B, H, W)
@@ -314,7 +314,7 @@ def run_b200(args, H, W, arch_kw):
     eng = TrainEngine(diff, (B, 1, H, W), (B, 1, Kf, H, W), use_graph=not args.no_graph)
 
     # synthetic (member, time, lat, lon, channel) ensemble; a small pool of pinned host batches
-    ds = SyntheticEnsemble(members=4, times=8, lat=H, lon=W, seed=1234 + rank, K=Kf)
+    ds = SyntheticEnsemble(members=4, times=max(8, Kf + 5), lat=H, lon=W, seed=1234 + rank, K=Kf)
     idx = ds.shard_indices(0, rank, world)
     pool = [ds.batch(idx[(i * B + torch.arange(B).numpy()) % len(idx)], pin=True) for i in range(4)]
     torch.manual_seed(1234 + rank)

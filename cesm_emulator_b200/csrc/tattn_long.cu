@@ -231,20 +231,20 @@ tattn_long_fwd_kernel(const h16* __restrict__ qkv, const float* __restrict__ bia
             }
             l0 = quad_sum(l0);
             l1 = quad_sum(l1);
-            const float r0 = 1.f / l0, r1 = 1.f / l1;
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                s[nt][0] *= r0;
-                s[nt][1] *= r0;
-                s[nt][2] *= r1;
-                s[nt][3] *= r1;
-            }
+            const float r0 = 1.f / l0, r1 = 1.f / l1;   // applied to the 16 x 32 output tile, not to the 16 x F probabilities
             if (t == 0) {
                 if (i0 < g.F) lse[(row0 + (long long)i0 * g.HW) * g.H + h0 + w] = m0 + __logf(l0);
                 if (i1 < g.F) lse[(row0 + (long long)i1 * g.HW) * g.H + h0 + w] = m1 + __logf(l1);
             }
             float o[4][4];
             gemm_pv<NT>(o, s, tile, g.pq, 2 * g.HG * D + w * D, lane);
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) {
+                o[nd][0] *= r0;
+                o[nd][1] *= r0;
+                o[nd][2] *= r1;
+                o[nd][3] *= r1;
+            }
             store_tile(o, tile, g.pq, mt * 16, w * D, lane);   // over this tile's (consumed) q rows
         }
         __syncthreads();

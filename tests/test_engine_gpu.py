@@ -331,3 +331,38 @@ def test_lr_change_after_capture_is_honoured(cuda):
     eng.step(x0, cond)
     assert not torch.equal(w.detach(), before)
     ops.set_grad_sink(None)
+
+
+def test_train_and_inference_entry_points(cuda, tmp_path):
+    """The reference's CLI surface end to end on the GPU: `train.py --config config/baseline --set ...` (a few
+    graph-replayed steps with the on-device loss scaler, checkpoint in the reference's layout incl. the scaler state),
+    then `inference.py --ckpt ...` (SampleEngine reverse steps) on that checkpoint."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import json
+    run = str(tmp_path / "run")
+    cfg = json.load(open(os.path.join(root, "config", "baseline")))
+    cfg["dataset"]["crop_hw"] = [32, 32]          # --set parses scalars only (utils_conf.py, as the reference's)
+    cfg_path = str(tmp_path / "baseline_small")
+    json.dump(cfg, open(cfg_path, "w"))
+    sets = ["train.num_epochs=1", "train.max_steps_per_epoch=6", "train.save_every=1", f"train.save_dir={run}",
+            "data.synthetic.lat=32", "data.synthetic.lon=48", "data.synthetic.members=2", "data.synthetic.times=8"]
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, os.path.join(root, "train.py"), "--config", cfg_path, "--set", *sets],
+                       capture_output=True, text=True, cwd=root, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "loss scale 65536" in r.stdout and "0 skipped step(s)" in r.stdout, r.stdout
+    ckpt_path = os.path.join(run, "checkpoints", "final.pt")
+    ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+    assert {"epoch", "model", "diffusion_buffers", "optimizer", "config", "scaler"} <= set(ckpt)   # train.py:1154-1165 (+ scaler)
+    assert ckpt["scaler"]["scale"] == 65536.0 and len(ckpt["model"]) == 233
+    out = str(tmp_path / "pred.npy")
+    r = subprocess.run([sys.executable, os.path.join(root, "inference.py"), "--ckpt", ckpt_path, "--steps", "3",
+                        "--batch_size", "2", "--members", "2", "--times", "2", "--out", out],
+                       capture_output=True, text=True, cwd=root, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    pred = np.load(out)
+    assert pred.shape == (2, 2, 32, 48) and np.isfinite(pred).all()
