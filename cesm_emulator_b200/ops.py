@@ -29,6 +29,25 @@ H16 = torch.float16
 _PHASE_TAPS = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}
 
 
+# `ctx.needs_input_grad` is True for a parameter that requires grad even when the call is made under torch.no_grad()
+# (and grad mode is always off INSIDE Function.forward), so "will this forward be back-propagated?" has to be read
+# at the call site: every Function here goes through _Fn.apply, which records the caller's grad mode.  Without it a
+# no-grad call on a trainable model packs data-gradient operands it never uses and -- at F = 1 -- misses the folded
+# temporal-attention path that sampling relies on.
+_OUTER_GRAD = [True]
+
+
+class _Fn(torch.autograd.Function):
+    @classmethod
+    def apply(cls, *args, **kwargs):
+        _OUTER_GRAD[0] = torch.is_grad_enabled()
+        return super().apply(*args, **kwargs)
+
+
+def _train(ctx) -> bool:
+    return _OUTER_GRAD[0] and any(ctx.needs_input_grad)
+
+
 def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return None if t is None else t.contiguous()
 
@@ -260,7 +279,7 @@ def _conv_wgrad(weight, x0, x1, dy, ks: int):
 # ------------------------------------------------------------------------------------------------
 # op-level: convolutions / linears on the tcgen05 implicit GEMM
 # ------------------------------------------------------------------------------------------------
-class ConvFn(torch.autograd.Function):
+class ConvFn(_Fn):
     """Stride-1 conv with a square k x k kernel (k in {1, 3}) or a linear layer, over one or two
     concatenated channels-last sources, with fused bias and residual.
 
@@ -275,7 +294,7 @@ class ConvFn(torch.autograd.Function):
         c0 = x0.shape[-1]
         c1 = 0 if x1 is None else x1.shape[-1]
         assert weight.numel() == cout * (c0 + c1) * ksize * ksize, (weight.shape, c0, c1, ksize)
-        train = any(ctx.needs_input_grad)
+        train = _train(ctx)
         wt = _conv_fwd_weight(cache, weight, cout, c0 + c1, ksize, train)
         ctx.wd = _conv_dgrad_weights(cache, weight, cout, c0, c1, ksize, train)
         y = K.igemm(x0, wt, a1=x1, taps=_sq_taps(ksize), bias=bias, residual=residual)
@@ -301,7 +320,7 @@ class ConvFn(torch.autograd.Function):
         return dx0, dx1, dwt, db, dres, None, None
 
 
-class DownsampleFn(torch.autograd.Function):
+class DownsampleFn(_Fn):
     """Conv3d(dim, dim, (1,4,4), (1,2,2), (0,1,1)) -- video_net.py:61-62."""
 
     TAPS = [(kh - 1, kw - 1) for kh in range(4) for kw in range(4)]
@@ -310,7 +329,7 @@ class DownsampleFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, cache: PackCache):
         x = x.contiguous()
         c = x.shape[-1]
-        train = any(ctx.needs_input_grad)
+        train = _train(ctx)
         wt = cache.get(weight, "fwd", (0, c, 16, c, c * 16, 16, list(range(16))), train)
         # data gradient: four sub-pixel phases, [ci][t][co] = W[co, ci, kh_t, kw_t]
         ctx.wd = {(ph, pw): cache.get(weight, ("dgrad", ph, pw), (0, c, 4, c, 16, c * 16, _phase(ph, pw)[1]), train)
@@ -336,7 +355,7 @@ class DownsampleFn(torch.autograd.Function):
         return dx, dwt, db, None
 
 
-class UpsampleFn(torch.autograd.Function):
+class UpsampleFn(_Fn):
     """ConvTranspose3d(dim, dim, (1,4,4), (1,2,2), (0,1,1)) as four sub-pixel 2x2 convs -- video_net.py:65-66."""
 
     @staticmethod
@@ -345,7 +364,7 @@ class UpsampleFn(torch.autograd.Function):
         n, h, w, c = x.shape
         out = torch.empty((n, 2 * h, 2 * w, c), dtype=H16, device=x.device)
         # [ci][t][co] = W[ci, co, kh, kw] for the data gradient (a stride-2 conv of dy)
-        train = any(ctx.needs_input_grad)
+        train = _train(ctx)
         ctx.wd = cache.get(weight, "dgrad", (0, c, 16, c, c * 16, 16, list(range(16))), train) if train else None
         for ph in (0, 1):
             for pw in (0, 1):
@@ -379,7 +398,7 @@ class UpsampleFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # op-level: normalisation
 # ------------------------------------------------------------------------------------------------
-class GroupNormSiLUFn(torch.autograd.Function):
+class GroupNormSiLUFn(_Fn):
     """GroupNorm -> optional FiLM (x*(scale+1)+shift) -> SiLU -> optional residual add
     (video_net.py:221-227, :265).  x: [B*F, H, W, C]; film: fp32 [B, 2C]."""
 
@@ -401,7 +420,7 @@ class GroupNormSiLUFn(torch.autograd.Function):
         return dx, dgamma, dbeta, dfilm, (dout if has_res else None), None, None, None
 
 
-class LayerNormFn(torch.autograd.Function):
+class LayerNormFn(_Fn):
     """Channel LayerNorm with gain only (video_net.py:84-87); gamma is the [1,C,1,1,1] parameter."""
 
     @staticmethod
@@ -422,7 +441,7 @@ class LayerNormFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # op-level: attention cores
 # ------------------------------------------------------------------------------------------------
-class TemporalAttnCoreFn(torch.autograd.Function):
+class TemporalAttnCoreFn(_Fn):
     """q*scale, RoPE, q.k + bias, softmax over frames, .v (video_net.py:413-453).  qkv: [B*F*HW, 3*H*D]."""
 
     @staticmethod
@@ -448,7 +467,7 @@ class TemporalAttnCoreFn(torch.autograd.Function):
         return dqkv, dbias, None, None, None, None, None, None, None
 
 
-class RelPosBiasFn(torch.autograd.Function):
+class RelPosBiasFn(_Fn):
     """Embedding gather of the T5 bucket table -> [heads, n, n] (video_net.py:302-310).  The
     table has 32 x heads entries; gather and scatter-add are index ops on a few hundred floats."""
 
@@ -466,7 +485,7 @@ class RelPosBiasFn(torch.autograd.Function):
         return dw, None
 
 
-class LinearAttnCoreFn(torch.autograd.Function):
+class LinearAttnCoreFn(_Fn):
     """softmax(q) over d, softmax(k) over pixels, ctx = k^T v, out = ctx^T q (video_net.py:338-344)."""
 
     @staticmethod
@@ -499,7 +518,7 @@ class BlockMeta:
                             if k != "fold_f1"})
 
 
-class ResnetBlockFn(torch.autograd.Function):
+class ResnetBlockFn(_Fn):
     """video_net.py:254-265 as one node:  out = Block2(Block1(cat(x, x1); film)) + res(cat(x, x1)),
     Block = conv(1,3,3) + bias -> GroupNorm -> FiLM -> SiLU, res = 1x1x1 conv or identity.
 
@@ -513,7 +532,7 @@ class ResnetBlockFn(torch.autograd.Function):
         c0 = x.shape[-1]
         cx1 = 0 if x1 is None else x1.shape[-1]
         cout = w1.shape[0]
-        train = any(ctx.needs_input_grad)
+        train = _train(ctx)
         if wres is None:
             res = x
         else:
@@ -597,7 +616,7 @@ def _qkv_backward(wqkv, wdq, xn, dqkv4):
     return K.igemm(dqkv4, wdq), _conv_wgrad(wqkv, xn, None, dqkv4, 1)
 
 
-class TemporalAttnBlockFn(torch.autograd.Function):
+class TemporalAttnBlockFn(_Fn):
     """Residual(PreNorm(EinopsToAndFrom(Attention))) (video_net.py:69-98, 357-454) as one node:
     y = to_out(attn(to_qkv(LN(x)))) + x.
     args: x, gamma [1,C,1,1,1], wqkv, wout, pos_bias, cs, sn, B, F, meta(heads, dim_head, eps, cq, co)."""
@@ -610,7 +629,7 @@ class TemporalAttnBlockFn(torch.autograd.Function):
         hidden = heads * D
         g = gamma.reshape(-1)
         pos_bias = pos_bias.contiguous().float()
-        train = any(ctx.needs_input_grad)
+        train = _train(ctx)
         xn = K.ln_fwd(x, g, eps)
         if F == 1 and not train:
             # one frame (every step of the sampling chain): the softmax over a single key is exactly 1, so the
@@ -674,7 +693,7 @@ class TemporalAttnBlockFn(torch.autograd.Function):
         return dx, dgamma, dwqkv, dwout, dbias, None, None, None, None, None
 
 
-class SpatialAttnBlockFn(torch.autograd.Function):
+class SpatialAttnBlockFn(_Fn):
     """Residual(PreNorm(SpatialLinearAttention)) (video_net.py:313-347) as one node.
     args: x, gamma, wqkv [3*hidden, C, 1, 1], wout [C, hidden, 1, 1], bout [C], meta."""
 
@@ -685,7 +704,7 @@ class SpatialAttnBlockFn(torch.autograd.Function):
         heads, D, eps = meta.heads, meta.dim_head, meta.eps
         hidden = heads * D
         g = gamma.reshape(-1)
-        train = any(ctx.needs_input_grad)
+        train = _train(ctx)
         xn = K.ln_fwd(x, g, eps)
         qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
         o, ws = K.linattn_fwd(qkv.view(-1, 3 * hidden), NI, H_ * W_, heads, D, D ** -0.5)
@@ -728,7 +747,7 @@ class SpatialAttnBlockFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # network boundary
 # ------------------------------------------------------------------------------------------------
-class InputConvFn(torch.autograd.Function):
+class InputConvFn(_Fn):
     """cat([x, cond_map], dim=1) -> Conv3d(2, C, (1,k,k)) with frame broadcast folded in
     (video_net.py:808-815, model.py:110-121).  x/cond: fp32 [B,1,Fx,H,W]; out: fp16 [B*F,H,W,C]."""
 
@@ -741,7 +760,7 @@ class InputConvFn(torch.autograd.Function):
         ks = weight.shape[-1]
         patches = K.input_patches(x, cond, B, F, H, W, ks)
         out = K.igemm(patches, K.input_weight_pack(weight.detach(), bias.detach()))
-        if any(ctx.needs_input_grad):
+        if _train(ctx):
             ctx.save_for_backward(patches, weight, bias)
         return out
 
@@ -760,7 +779,7 @@ class InputConvFn(torch.autograd.Function):
         return None, None, dw, db.contiguous(), None
 
 
-class OutConvFn(torch.autograd.Function):
+class OutConvFn(_Fn):
     """Conv3d(C, 1, 1) evaluated on the centre frame (video_net.py:763 + model.py:129-130).
     a: fp16 [B*F, H, W, 64] -> fp32 [B, 1, H, W]."""
 
@@ -780,7 +799,7 @@ class OutConvFn(torch.autograd.Function):
         return da, dw, db, None, None, None
 
 
-class SmallLinearFn(torch.autograd.Function):
+class SmallLinearFn(_Fn):
     """fp32 y = act(x) W^T + b for the time-embedding MLP and FiLM projections
     (video_net.py:651-656, 238-241); act = SiLU on the input when `act_in`."""
 
@@ -818,7 +837,7 @@ def _film_table(Ws, bs, direct: bool):
     return tab
 
 
-class FilmAllFn(torch.autograd.Function):
+class FilmAllFn(_Fn):
     """Every ResnetBlock's FiLM projection SiLU -> Linear(time_dim, 2*dim_out) (video_net.py:238-241) in one
     launch: they all read the same time embedding.  apply(temb, W_0, b_0, W_1, b_1, ...) -> tuple of [B, 2C_i].
     Backward: one launch for all weight / bias gradients and one for d temb (the sum over layers), instead of
@@ -851,7 +870,7 @@ class FilmAllFn(torch.autograd.Function):
         return (dx,) + tuple(grads)
 
 
-class MseLossFn(torch.autograd.Function):
+class MseLossFn(_Fn):
     """F.mse_loss(eps, noise) (model.py:208) with the gradient 2*(eps-noise)/N produced on device."""
 
     @staticmethod
