@@ -351,7 +351,7 @@ def run_b200(args, H, W, arch_kw):
         return ms, _lib.launch_count() - n0
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("CESM_BENCH_NO_SAMPLER"):
         sampler.start()
     ms_res, eager_launches = timed(lambda i: eng.step_resident())
     losses = []
