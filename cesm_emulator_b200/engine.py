@@ -147,6 +147,8 @@ class GradBuckets:
         self._seen[id(p)] = True
         self._pending[b] -= 1
         if self._pending[b] == 0:
+            if self.on_cuda and ops._SIDE[0] is not None:
+                torch.cuda.current_stream().wait_stream(ops._SIDE[0])   # weight gradients issued on the side stream
             self.unpack_bucket(b)
             bucket = self.flat[self.bounds[b]:self.bounds[b + 1]]
             if not self.on_cuda:  # host tensors (gloo): used by the CPU tests of the bucket logic
@@ -158,6 +160,8 @@ class GradBuckets:
                 dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.pg)
 
     def finish_step(self):
+        if self.on_cuda:
+            ops.join_side_stream()
         if self.world == 1:
             self.unpack_bucket(None)
         if self.world > 1:
@@ -341,6 +345,9 @@ class TrainEngine:
         self.launches_per_step = 0
         self._warm = 0
         self.arena = K.ZeroArena(dev) if dev.type == "cuda" else None
+        # weight gradients on a second stream (ops._on_side); CESM_NO_SIDE_STREAM=1 keeps everything on one stream
+        self.side_stream = (torch.cuda.Stream(device=dev)
+                            if dev.type == "cuda" and not int(__import__("os").environ.get("CESM_NO_SIDE_STREAM", "0")) else None)
 
     # the captured region ----------------------------------------------------------------------
     def _step_body(self):
@@ -352,9 +359,11 @@ class TrainEngine:
         finally:
             self.arena.end()
             K.STABLE_WEIGHT_PTRS = set()
+            ops.set_side_stream(None)
 
     def _step_body_inner(self):
         ops.set_grad_sink(self.buckets)
+        ops.set_side_stream(self.side_stream)
         ops.prepack_all()  # one kernel refreshes every fp16 operand copy of the (just updated) weights
         K.STABLE_WEIGHT_PTRS = ops.packed_ptrs()  # nothing rewrites them until the next step
         self.buckets.begin_step()

@@ -222,6 +222,53 @@ def _ready(*params) -> None:
         _GRAD_SINK[0].ready(p)
 
 
+# Leaf-gradient side stream (engine mode only).  Weight gradients are not on the backward pass's critical chain: they
+# are launched on a second stream that forks from the main one where their inputs become available and joins before
+# the optimizer (TrainEngine).  At the coarse U-Net levels most kernels have a nearly empty last wave; work from the
+# other stream fills those SMs (measured: 11.44 -> 11.03 ms per step, profiles/r02_side_stream_ab.txt).  Inputs are
+# kept alive until the join (`_SIDE_KEEP`), so no block is recycled under a kernel that is still reading it -- eagerly
+# or inside a captured graph.  (A third stream for the ResnetBlocks' 1x1 residual convolutions, forward and backward,
+# was tried as well: no further gain.)
+_SIDE = [None]       # torch.cuda.Stream or None
+_SIDE_KEEP: list = []
+
+
+def set_side_stream(stream) -> None:
+    _SIDE[0] = stream
+    _SIDE_KEEP.clear()
+
+
+def join_side_stream() -> None:
+    """Main stream waits for everything issued on the side stream; the kept inputs may be released."""
+    side = _SIDE[0]
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
+    _SIDE_KEEP.clear()
+
+
+class _on_side:
+    """`with _on_side(tensors...):` -- run the enclosed launches on the side stream (if one is set and the gradient
+    sink is active), after everything already queued on the current stream."""
+
+    def __init__(self, *tensors):
+        self.side = _SIDE[0] if _GRAD_SINK[0] is not None else None
+        self.tensors = tensors
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            _SIDE_KEEP.append(self.tensors)
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def _wgrad_into_param(weight, x0, x1, dy, taps, so, si, tap_off, last: bool = True,
                       into: Optional[torch.Tensor] = None, **kw):
     """Weight gradient accumulated by the tcgen05 kernel's epilogue directly in `weight`'s own layout:
@@ -229,13 +276,14 @@ def _wgrad_into_param(weight, x0, x1, dy, taps, so, si, tap_off, last: bool = Tr
     T = len(taps)
     if _direct(weight):
         sink = _GRAD_SINK[0]
-        if T == 1:  # same layout as the kernel's packed output: coalesced atomics straight into .grad
-            K.wgrad(x0, dy, x1=x1, taps=taps, into=weight.grad, layout=(so, si, tap_off), **kw)
-        else:       # accumulate into a persistent packed scratch; the sink un-packs a whole bucket at once
-            cout = dy.shape[-1]
-            ctot = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
-            scratch = sink.scratch(weight, tuple(tap_off), (cout, T, ctot, so, si, list(tap_off)))
-            K.wgrad(x0, dy, x1=x1, taps=taps, into=scratch, layout=(T * ctot, 1, [t * ctot for t in range(T)]), **kw)
+        with _on_side(x0, x1, dy):
+            if T == 1:  # same layout as the kernel's packed output: coalesced atomics straight into .grad
+                K.wgrad(x0, dy, x1=x1, taps=taps, into=weight.grad, layout=(so, si, tap_off), **kw)
+            else:       # accumulate into a persistent packed scratch; the sink un-packs a whole bucket at once
+                cout = dy.shape[-1]
+                ctot = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
+                scratch = sink.scratch(weight, tuple(tap_off), (cout, T, ctot, so, si, list(tap_off)))
+                K.wgrad(x0, dy, x1=x1, taps=taps, into=scratch, layout=(T * ctot, 1, [t * ctot for t in range(T)]), **kw)
         if last:
             sink.ready(weight)
         return None
@@ -594,7 +642,8 @@ class ResnetBlockFn(_Fn):
                 dx1 = K.igemm(dy1, ctx.wd1[1], taps=ntaps, residual=r1)
             dwres = _conv_wgrad(wres, x, x1, dout, 1)
             if _direct_all(bres):
-                K.colsum(dout, into=bres.grad)
+                with _on_side(dout):
+                    K.colsum(dout, into=bres.grad)
                 _ready(bres)
             else:
                 dbres = K.colsum(dout)
@@ -726,7 +775,8 @@ class SpatialAttnBlockFn(_Fn):
         do = K.igemm(dy, ctx.wdo)
         dwout = _conv_wgrad(wout, o.view(NI, H_, W_, hidden), None, dy, 1)
         if _direct_all(bout):
-            K.colsum(dy, into=bout.grad)
+            with _on_side(dy):
+                K.colsum(dy, into=bout.grad)
             _ready(bout)
             dbout = None
         else:
