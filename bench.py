@@ -390,6 +390,7 @@ def run_b200(args, H, W, arch_kw):
         for h in eng.buckets._hooks:
             h.remove()
         prof_eng = TrainEngine(diff, (B, 1, H, W), (B, 1, Kf, H, W), use_graph=False)
+        prof_eng.side_stream = None   # per-call event timing wants one stream: no overlap between bracketed calls
         prof_eng.x0.copy_(eng.x0)
         prof_eng.cond.copy_(eng.cond)
         prof_eng.step_resident()
