@@ -317,6 +317,17 @@ def _conv_dgrad_weights(cache: PackCache, weight, cout: int, c0: int, c1: int, k
     return w0, w1
 
 
+def _bias_grad(bias, dy):
+    """Column sums of dy as the gradient of a conv bias: added straight into bias.grad on the side stream in engine
+    mode (returns None), else returned for autograd to accumulate."""
+    if bias is not None and _direct_all(bias):
+        with _on_side(dy):
+            K.colsum(dy, into=bias.grad)
+        _ready(bias)
+        return None
+    return K.colsum(dy)
+
+
 def _conv_wgrad(weight, x0, x1, dy, ks: int):
     cout = weight.shape[0]
     ctot = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
@@ -384,6 +395,7 @@ class DownsampleFn(_Fn):
                   for ph in (0, 1) for pw in (0, 1)} if train else None
         y = K.igemm(x, wt, taps=DownsampleFn.TAPS, stride=2, bias=bias)
         ctx.save_for_backward(x, weight)
+        ctx.bias_ref = bias
         return y
 
     @staticmethod
@@ -399,7 +411,7 @@ class DownsampleFn(_Fn):
         if ctx.needs_input_grad[1]:
             dwt = _wgrad_into_param(weight, x, None, dy, DownsampleFn.TAPS, c * 16, 16, list(range(16)), stride=2)
         if ctx.needs_input_grad[2]:
-            db = K.colsum(dy)
+            db = _bias_grad(ctx.bias_ref, dy)
         return dx, dwt, db, None
 
 
@@ -421,6 +433,7 @@ class UpsampleFn(_Fn):
                 wt = cache.get(weight, ("fwd", ph, pw), (0, c, 4, c, 16, c * 16, koff), train)
                 K.igemm(x, wt, taps=taps, out=out, out_hw=(h, w), out_place=(2, 2, ph, pw), bias=bias)
         ctx.save_for_backward(x, weight)
+        ctx.bias_ref = bias
         return out
 
     @staticmethod
@@ -439,7 +452,7 @@ class UpsampleFn(_Fn):
                 dwt = _wgrad_into_param(weight, x, None, dy, taps, 16, c * 16, koff, last=(n_ph == 3), into=into,
                                         grid_hw=(h, w), dy_place=(2, 2, ph, pw))
         if ctx.needs_input_grad[2]:
-            db = K.colsum(dy)
+            db = _bias_grad(ctx.bias_ref, dy)
         return dx, dwt, db, None
 
 
