@@ -51,6 +51,27 @@ class SyntheticEnsemble:
         self.tgt = self._z(np.ascontiguousarray(np.transpose(tgt, (1, 0, 4, 2, 3))))
         self.num_units = max(1, self.T - self.K + 1)
 
+    @classmethod
+    def from_arrays(cls, cond: np.ndarray, tgt: np.ndarray, K: int = 3, crop_hw: Optional[Tuple[int, int]] = None,
+                    time_reverse_p: float = 0.5, seed: int = 1234) -> "SyntheticEnsemble":
+        """Wrap existing `(T, M, 1, H, W)` arrays (the constructor arguments of the reference's dataset class,
+        dataset_single_member.py:30-44) instead of generating fields; the arrays are used as they are."""
+        if cond.ndim != 5 or tgt.ndim != 5:
+            raise ValueError("Expect (T, M, 1, H, W)")       # dataset_single_member.py:42
+        if cond.shape != tgt.shape:
+            raise ValueError("cond/tgt shapes must match")   # :43
+        if K < 2:
+            raise ValueError("K must be >= 2")
+        self = cls.__new__(cls)
+        self.T, self.M, _, self.H, self.W = cond.shape
+        self.K, self.crop_hw, self.time_reverse_p = int(K), crop_hw, float(time_reverse_p)
+        self._aug = np.random.default_rng(seed + 1)
+        self.cond_mtllc = None
+        self.cond = np.ascontiguousarray(cond, dtype=np.float32)
+        self.tgt = np.ascontiguousarray(tgt, dtype=np.float32)
+        self.num_units = max(1, self.T - self.K + 1)
+        return self
+
     @staticmethod
     def _z(a: np.ndarray) -> np.ndarray:
         a = a.astype(np.float32)

@@ -1,15 +1,16 @@
 #!/usr/bin/env python
 """Ensemble generation entry point (reference: inference.py:174-284).
 
-    python inference.py --ckpt runs/exp/checkpoints/final.pt [--batch_size 16] [--steps 1000] [--out pred.npy]
+    python inference.py --ckpt runs/exp/checkpoints/final.pt [--batch_size 16] [--steps 1000] [--out pred.npy | pred.nc]
     torchrun --standalone --nproc_per_node=8 inference.py --ckpt ...
 
 `predict_temperature_from_emissions` keeps the reference's flow: rebuild UNet/Diffusion from
 ckpt["config"], flatten the condition (T, M, 1, H, W) -> (N, 1, H, W), and run the full reverse chain
 per batch of independent fields (inference.py:217-232).  Here each chain step is one CUDA-graph replay
 (cesm_emulator_b200.engine.SampleEngine) and, under torchrun, the N fields are sharded over ranks.
-Condition data comes from the synthetic ensemble; output is a (T, M, H, W) float32 array (.npy) instead
-of NetCDF (xarray is not a dependency of the hot path).
+Condition data comes from the synthetic ensemble; output is a (T, M, H, W) float32 array, written as .npy or
+-- `--out x.nc` -- as the reference's NetCDF product (`TREFHT_pred`, inference.py:260-281) in classic NetCDF-3
+through scipy (xarray / netCDF4 are not in this image).
 """
 import argparse
 import os
@@ -64,6 +65,35 @@ def predict_temperature_from_emissions(diffusion, cond_tm1hw: np.ndarray, batch_
     return out.reshape(T, M, H, W).numpy()
 
 
+def write_prediction_netcdf(path, pred_tmhw: np.ndarray, stack_coord=None, member_coord=None, lat=None, lon=None,
+                            stack_dim="year", member_dim="member_id", lat_name="lat", lon_name="lon", attrs=None):
+    """The reference's output product (inference.py:239-281): variable `TREFHT_pred` with dims
+    (year, member_id, lat, lon), coordinate variables and the description / units attributes.  xarray and
+    netCDF4 are not in this image, so the file is written as classic NetCDF-3 by scipy
+    (`xr.open_dataset` reads it with its scipy engine)."""
+    from scipy.io import netcdf_file
+    T, M, H, W = pred_tmhw.shape
+    coords = [(stack_dim, stack_coord, T), (member_dim, member_coord, M), (lat_name, lat, H), (lon_name, lon, W)]
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    with netcdf_file(path, "w", version=2) as f:
+        for name, vals, n in coords:
+            f.createDimension(name, n)
+            vals = np.arange(n) if vals is None else np.asarray(vals)
+            if vals.shape != (n,):
+                raise ValueError(f"coordinate {name} has shape {vals.shape}, expected ({n},)")
+            vals = vals.astype(np.float64 if vals.dtype.kind == "f" else np.int32)
+            v = f.createVariable(name, vals.dtype, (name,))
+            v[:] = vals
+        v = f.createVariable("TREFHT_pred", np.float32, (stack_dim, member_dim, lat_name, lon_name))
+        v[:] = np.asarray(pred_tmhw, dtype=np.float32)
+        v.description = "Predicted near-surface air temperature from emissions via diffusion model"
+        v.units = "standardized"
+        for k, val in (attrs or {}).items():
+            setattr(v, k, val)
+
+
 def _cli():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ckpt", required=True)
@@ -86,7 +116,10 @@ def _cli():
                            seed=syn.get("seed", 1234))
     pred = predict_temperature_from_emissions(diffusion, ds.cond, a.batch_size, a.steps, rank, world, dev)
     if rank == 0:
-        np.save(a.out, pred)
+        if a.out.endswith(".nc"):
+            write_prediction_netcdf(a.out, pred, attrs={"checkpoint": os.path.abspath(a.ckpt), "cond_var": "synthetic"})
+        else:
+            np.save(a.out, pred)
         print(f"wrote {a.out} {pred.shape}")
     if world > 1:
         dist.destroy_process_group()

@@ -359,10 +359,13 @@ def test_train_and_inference_entry_points(cuda, tmp_path):
     ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
     assert {"epoch", "model", "diffusion_buffers", "optimizer", "config", "scaler"} <= set(ckpt)   # train.py:1154-1165 (+ scaler)
     assert ckpt["scaler"]["scale"] == 65536.0 and len(ckpt["model"]) == 233
-    out = str(tmp_path / "pred.npy")
+    out = str(tmp_path / "pred.nc")     # the reference's NetCDF product (inference.py:260-281)
     r = subprocess.run([sys.executable, os.path.join(root, "inference.py"), "--ckpt", ckpt_path, "--steps", "3",
                         "--batch_size", "2", "--members", "2", "--times", "2", "--out", out],
                        capture_output=True, text=True, cwd=root, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    pred = np.load(out)
+    from scipy.io import netcdf_file
+    with netcdf_file(out, "r", mmap=False) as f:
+        assert f.variables["TREFHT_pred"].dimensions == ("year", "member_id", "lat", "lon")
+        pred = np.array(f.variables["TREFHT_pred"][:])
     assert pred.shape == (2, 2, 32, 48) and np.isfinite(pred).all()

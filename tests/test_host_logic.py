@@ -137,3 +137,86 @@ def test_window_plan_and_frame_map_match_the_host_gather():
             flips += plan[5]
         assert flips > 0
         assert a.plan(5, augment=False)[3:] == (((a.H - a.out_hw()[0]) // 2, (a.W - a.out_hw()[1]) // 2, 0))
+
+
+# ------------------------------------------------------------------------------------------------
+# the data path pinned to the REFERENCE's dataset class (fixture: tests/golden/make_dataset_golden.py)
+# ------------------------------------------------------------------------------------------------
+def _dataset_fixture():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_windows.npz"))
+    T, M, H, W = (int(v) for v in g["shape"])
+    rng = np.random.default_rng(int(g["seed"]))
+    cond = rng.standard_normal((T, M, 1, H, W)).astype(np.float32)
+    tgt = rng.standard_normal((T, M, 1, H, W)).astype(np.float32)
+    return g, cond, tgt
+
+
+class _ScriptedDraws:
+    """Stands in for the augmentation generator: replays crop origins (and 'never reverse')."""
+
+    def __init__(self, origins):
+        self.vals = [int(v) for ij in origins for v in ij]
+
+    def random(self):
+        return 1.0
+
+    def integers(self, lo, hi):
+        v = self.vals.pop(0)
+        assert lo <= v < hi
+        return v
+
+
+def test_windows_match_reference_dataset_class():
+    """`SyntheticEnsemble.window` returns what WindowedAllMembersDataset_random (dataset_single_member.py:168-196,
+    the class train.py:990 builds) returns for the same arrays: indexing, centre target, centre-preserving time
+    reversal, centre / clamped / random crops (the random origins replayed from the reference's own draws)."""
+    from cesm_emulator_b200.synthetic import SyntheticEnsemble
+    g, cond, tgt = _dataset_fixture()
+
+    def all_windows(ds, augment):
+        cs, xs = zip(*(ds.window(i, augment) for i in range(len(ds))))
+        return np.stack([c.numpy() for c in cs]), np.stack([x.numpy() for x in xs])
+
+    for K in (3, 4, 5):
+        ds = SyntheticEnsemble.from_arrays(cond, tgt, K=K, time_reverse_p=0.0)
+        assert len(ds) == g[f"plain_K{K}_cond"].shape[0]
+        c, x = all_windows(ds, True)
+        assert np.array_equal(c, g[f"plain_K{K}_cond"]) and np.array_equal(x, g[f"plain_K{K}_x0"])
+        ds = SyntheticEnsemble.from_arrays(cond, tgt, K=K, time_reverse_p=1.0)
+        c, x = all_windows(ds, True)
+        assert np.array_equal(c, g[f"rev_K{K}_cond"]) and np.array_equal(x, g[f"rev_K{K}_x0"])
+    ds = SyntheticEnsemble.from_arrays(cond, tgt, K=3, crop_hw=(8, 10), time_reverse_p=0.0)
+    c, x = all_windows(ds, False)     # augment=False = the reference's crop_mode="center"
+    assert np.array_equal(c, g["center_crop_cond"]) and np.array_equal(x, g["center_crop_x0"])
+    ds = SyntheticEnsemble.from_arrays(cond, tgt, K=3, crop_hw=(64, 10), time_reverse_p=0.0)
+    c, x = all_windows(ds, False)
+    assert np.array_equal(c, g["clamped_crop_cond"]) and np.array_equal(x, g["clamped_crop_x0"])
+    ds = SyntheticEnsemble.from_arrays(cond, tgt, K=3, crop_hw=(8, 10), time_reverse_p=0.5)
+    ds._aug = _ScriptedDraws(g["random_crop_origin"])
+    c, x = all_windows(ds, True)
+    assert np.array_equal(c, g["random_crop_cond"]) and np.array_equal(x, g["random_crop_x0"])
+    with pytest.raises(ValueError):
+        SyntheticEnsemble.from_arrays(cond, tgt[:-1])
+    with pytest.raises(ValueError):
+        SyntheticEnsemble.from_arrays(cond, tgt, K=1)
+
+
+def test_prediction_netcdf_product(tmp_path):
+    """inference.py:260-281: variable name, dims, coordinates and attributes of the output file."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from scipy.io import netcdf_file
+    from inference import write_prediction_netcdf
+    pred = np.random.default_rng(0).standard_normal((3, 2, 4, 6)).astype(np.float32)
+    path = str(tmp_path / "out" / "pred.nc")
+    write_prediction_netcdf(path, pred, stack_coord=[1850, 1851, 1852], lat=np.linspace(-90, 90, 4),
+                            attrs={"cond_var": "CO2_em_anthro"})
+    with netcdf_file(path, "r", mmap=False) as f:
+        v = f.variables["TREFHT_pred"]
+        assert v.dimensions == ("year", "member_id", "lat", "lon")
+        assert np.array_equal(v[:], pred)
+        assert v.units == b"standardized" and v.cond_var == b"CO2_em_anthro"
+        assert list(f.variables["year"][:]) == [1850, 1851, 1852]
+        assert np.allclose(f.variables["lat"][:], np.linspace(-90, 90, 4))
+        assert list(f.variables["member_id"][:]) == [0, 1] and f.variables["lon"].shape == (6,)
+    with pytest.raises(ValueError):
+        write_prediction_netcdf(path, pred, lat=[0.0, 1.0])

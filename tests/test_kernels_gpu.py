@@ -581,6 +581,29 @@ def test_device_data_path(cuda, K, crop):
     assert torch.equal(cond.cpu(), ref_c) and torch.equal(x0.cpu(), ref_x)
 
 
+def test_device_data_path_matches_reference_dataset_class(cuda):
+    """The gather kernel against windows produced by the REFERENCE's dataset class (dataset_single_member.py:
+    168-196; fixture written by tests/golden/make_dataset_golden.py from the imported class)."""
+    from cesm_emulator_b200.synthetic import SyntheticEnsemble
+    from test_host_logic import _ScriptedDraws, _dataset_fixture
+    g, cond_np, tgt_np = _dataset_fixture()
+    cases = [(3, None, 0.0, True, "plain_K3"), (4, None, 1.0, True, "rev_K4"), (5, None, 1.0, True, "rev_K5"),
+             (3, (8, 10), 0.0, False, "center_crop"), (3, (64, 10), 0.0, False, "clamped_crop"),
+             (3, (8, 10), 0.5, True, "random_crop")]
+    for K, crop, p, augment, key in cases:
+        ds = SyntheticEnsemble.from_arrays(cond_np, tgt_np, K=K, crop_hw=crop, time_reverse_p=p)
+        if key == "random_crop":
+            ds._aug = _ScriptedDraws(g["random_crop_origin"])
+        dev = ds.to_device(cuda)
+        h, w = ds.out_hw()
+        n = len(ds)
+        cond = torch.empty(n, 1, K, h, w, device=cuda)
+        x0 = torch.empty(n, 1, h, w, device=cuda)
+        dev.batch_into(list(range(n)), cond, x0, augment=augment)
+        assert np.array_equal(cond.cpu().numpy(), g[key + "_cond"]), key
+        assert np.array_equal(x0.cpu().numpy(), g[key + "_x0"]), key
+
+
 def test_device_data_path_survives_host_run_ahead(cuda):
     """The training loop never syncs inside an epoch: the host may issue dozens of batches while the GPU is still
     busy with the first.  Every batch must still be the one the host path would have produced (the pinned plan
