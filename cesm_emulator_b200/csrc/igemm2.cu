@@ -29,6 +29,16 @@
 #include "common.cuh"
 #include "igemm.h"
 
+#include <type_traits>
+
+// Bisection knobs (CESM_IGEMM_DBG bits: 2 = no epilogue, 4 = no MMAs, 16 = no accumulator hand-over, 32 = no
+// activation loads) exist only in builds with -DCESM_IGEMM_DEBUG (CESM_NVCC_EXTRA); production code carries none.
+#ifdef CESM_IGEMM_DEBUG
+#define IGEMM2_DBG(x) (x)
+#else
+#define IGEMM2_DBG(x) 0
+#endif
+
 namespace cesm {
 
 static constexpr int kTileM = 128;
@@ -169,7 +179,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             for (int ai = 0; ai < a_loads; ++ai) {
                 mbar_wait(a_empty(stage), phase ^ 1u, 11);
                 const uint32_t dst = a_base + stage * p.a_stage_bytes;
-                if (p.dbg & 32) {  // bisection: no activation traffic at all
+                if (IGEMM2_DBG(p.dbg) & 32) {  // bisection: no activation traffic at all
                     mbar_arrive(a_full(stage));
                     if (++stage == p.a_stages) {
                         stage = 0;
@@ -231,94 +241,91 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             }
         }
     } else if (warp == 2) {
-        // ===== MMA issuer (the whole warp walks the loops; one elected lane issues) =====
-        const bool leader = elect_one();
-        // One thread issues every MMA, so its instruction stream is on the critical path: a 128x64x16 MMA
-        // occupies the tensor pipe for only 32 clocks.  Descriptors are therefore not rebuilt per MMA: the
-        // constant upper word is hoisted, the 14-bit start-address field is advanced by adds (+2 per
-        // 16-element K step = 32 B, + 8 per 128-byte row for the halo tap views).
-        constexpr uint32_t idesc = make_idesc_f16(kTileM, BLOCK_N, 0, 0);
-        const uint64_t desc_hi = make_smem_desc_sw128(0, 0, 1024);   // start-address field = 0
-        int a_stage = 0, b_stage = 0, acc = 0;
-        uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
-        uint32_t tap_rows8[9];  // HALO: ((1+dh)*pw + (1+dw)) * 8 = row offset of the tap view in 16-byte units
+        // ===== MMA issuer: ONE elected thread runs the whole loop =====
+        // A 128x64x16 MMA occupies the tensor pipe for 32 clocks, so the issuing thread's own instruction stream is
+        // on the critical path (round 2: the previous loop -- all 32 lanes walking it, a predicate per MMA, the
+        // resident / streamed and bisection branches re-evaluated per tap -- spent ~50 instructions per tap and
+        // held every MMA to >= 90 clocks).  Here the resident and streamed variants are separate instantiations
+        // of one generic lambda, descriptors are a constant upper word OR a 14-bit start-address field advanced by
+        // adds (+2 per 16-element K step = 32 B, +8 per 128-byte row for the halo tap views), and only the first
+        // MMA of a tile carries a run-time accumulate flag.
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_f16(kTileM, BLOCK_N, 0, 0);
+            const uint64_t desc_hi = make_smem_desc_sw128(0, 0, 1024);   // start-address field = 0
+            uint32_t tap_rows8[9];  // HALO: ((1+dh)*pw + (1+dw)) * 8 = row offset of the tap view in 16-byte units
 #pragma unroll
-        for (int ti = 0; ti < 9; ++ti) tap_rows8[ti] = HALO ? ((1 + p.tap_dh[ti]) * pw + (1 + p.tap_dw[ti])) * 8 : 0;
-        const uint32_t b_blk16 = b_blk_bytes >> 4;
-        if (p.b_resident) mbar_wait(b_all_bar, 0, 13);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_tile = p.m_major ? tile % p.n_tiles : tile / p.m_tiles;
-            if (!(p.dbg & 16)) mbar_wait(t_empty(acc), acc_phase ^ 1u, 14);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-            const uint32_t b_tile16 = (b_base >> 4) + n_tile * p.num_kb * b_blk16;  // resident weights of this n tile
-            uint32_t accum = 0;
-            for (int ai = 0; ai < a_loads; ++ai) {
-                mbar_wait(a_full(a_stage), a_phase, 15);
-                tc_fence_after();
-                const uint32_t sa16 = (a_base + a_stage * p.a_stage_bytes) >> 4;
-                auto issue_tap = [&](uint32_t a16, uint32_t b16) {
-                    if (!(p.dbg & 4)) {  // bisection knob: CESM_IGEMM_DBG=4 issues no MMAs
+            for (int ti = 0; ti < 9; ++ti)
+                tap_rows8[ti] = HALO ? ((1 + p.tap_dh[ti]) * pw + (1 + p.tap_dw[ti])) * 8 : 0;
+            const uint32_t b_blk16 = b_blk_bytes >> 4;
+            const uint32_t a_stage16 = p.a_stage_bytes >> 4;
+            const uint32_t a_base16 = a_base >> 4, b_base16 = b_base >> 4;
+            const uint32_t tap_b16 = cblk * b_blk16;        // HALO, resident: weight-block stride between taps
+            const uint32_t tile_b16 = p.num_kb * b_blk16;   // resident: stride between n tiles
+            const int n_a_stages = p.a_stages, n_b_stages = p.b_stages, n_tiles = p.n_tiles, m_tiles = p.m_tiles;
+            const bool m_major = p.m_major != 0;
+            const int dbg = IGEMM2_DBG(p.dbg);
+            auto mma4 = [&](uint32_t d_tmem, uint32_t a16, uint32_t b16, uint32_t first_accum) {
+                if (dbg & 4) return;  // bisection knob (debug builds only): no MMAs
 #pragma unroll
-                        for (int k = 0; k < kKBlk / 16; ++k) {
-                            if (leader)
-                                umma_f16(d_tmem, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k),
-                                          idesc, accum);
-                            accum = 1;
-                        }
-                    }
-                };
-                if (HALO) {
+                for (int k = 0; k < kKBlk / 16; ++k)
+                    umma_f16(d_tmem, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k), idesc,
+                             k == 0 ? first_accum : 1u);
+            };
+            auto run = [&](auto resident_tag) {
+                constexpr bool RES = decltype(resident_tag)::value;
+                int a_stage = 0, b_stage = 0, acc = 0;
+                uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+                if (RES) mbar_wait(b_all_bar, 0, 13);
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int n_tile = m_major ? tile % n_tiles : tile / m_tiles;
+                    if (!(dbg & 16)) mbar_wait(t_empty(acc), acc_phase ^ 1u, 14);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                    uint32_t b_kb16 = b_base16 + n_tile * tile_b16;   // resident: weight block (n_tile, kb = ai)
+                    for (int ai = 0; ai < a_loads; ++ai, b_kb16 += b_blk16) {
+                        mbar_wait(a_full(a_stage), a_phase, 15);
+                        tc_fence_after();
+                        const uint32_t sa16 = a_base16 + a_stage * a_stage16;
+                        const uint32_t first = ai != 0;
+                        if (RES) {
+                            if (HALO) {
+                                uint32_t b16 = b_kb16;
 #pragma unroll
-                    for (int ti = 0; ti < 9; ++ti) {
-                        const int kb = ti * cblk + ai;
-                        uint32_t b16;
-                        if (p.b_resident) {
-                            b16 = b_tile16 + kb * b_blk16;
+                                for (int ti = 0; ti < 9; ++ti, b16 += tap_b16)   // kb = ti * cblk + ai
+                                    mma4(d_tmem, sa16 + tap_rows8[ti], b16, ti == 0 ? first : 1u);
+                            } else {
+                                mma4(d_tmem, sa16, b_kb16, first);
+                            }
                         } else {
-                            mbar_wait(b_full(b_stage), b_phase, 16);
-                            tc_fence_after();
-                            b16 = (b_base >> 4) + b_stage * b_blk16;
-                        }
-                        issue_tap(sa16 + tap_rows8[ti], b16);
-                        if (!p.b_resident) {
-                            if (leader) umma_commit(b_empty(b_stage));
-                            if (++b_stage == p.b_stages) {
-                                b_stage = 0;
-                                b_phase ^= 1u;
+#pragma unroll
+                            for (int ti = 0; ti < (HALO ? 9 : 1); ++ti) {
+                                mbar_wait(b_full(b_stage), b_phase, 16);
+                                tc_fence_after();
+                                mma4(d_tmem, sa16 + tap_rows8[ti], b_base16 + b_stage * b_blk16, ti == 0 ? first : 1u);
+                                umma_commit(b_empty(b_stage));
+                                if (++b_stage == n_b_stages) {
+                                    b_stage = 0;
+                                    b_phase ^= 1u;
+                                }
                             }
                         }
-                    }
-                } else {
-                    uint32_t b16;
-                    if (p.b_resident) {
-                        b16 = b_tile16 + ai * b_blk16;
-                    } else {
-                        mbar_wait(b_full(b_stage), b_phase, 16);
-                        tc_fence_after();
-                        b16 = (b_base >> 4) + b_stage * b_blk16;
-                    }
-                    issue_tap(sa16, b16);
-                    if (!p.b_resident) {
-                        if (leader) umma_commit(b_empty(b_stage));
-                        if (++b_stage == p.b_stages) {
-                            b_stage = 0;
-                            b_phase ^= 1u;
+                        umma_commit(a_empty(a_stage));
+                        if (++a_stage == n_a_stages) {
+                            a_stage = 0;
+                            a_phase ^= 1u;
                         }
                     }
+                    if (!(dbg & 16)) umma_commit(t_full(acc));
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1u;
+                    }
                 }
-                if (leader) umma_commit(a_empty(a_stage));
-                if (++a_stage == p.a_stages) {
-                    a_stage = 0;
-                    a_phase ^= 1u;
-                }
-            }
-            if (leader && !(p.dbg & 16)) umma_commit(t_full(acc));
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1u;
-            }
+            };
+            if (p.b_resident) run(std::true_type{});
+            else run(std::false_type{});
         }
+        __syncwarp();
     } else if (warp >= 3) {
         // ===== epilogue: two groups of four warps; group g takes the 64-column chunks with index % 2 == g =====
         // Staging: "warp-private" (p.epi_warp) when the 32 accumulator rows of a warp are one storable
@@ -377,11 +384,11 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                     cur_b = b;
                 }
             }
-            if (!(p.dbg & 16)) mbar_wait(t_full(acc), acc_phase, 17);
+            if (!(IGEMM2_DBG(p.dbg) & 16)) mbar_wait(t_full(acc), acc_phase, 17);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int cc = (BLOCK_N == 64 ? 0 : group * 64); cc < ((p.dbg & 2) ? 0 : BLOCK_N); cc += 128) {  // dbg 2: no epilogue
+            for (int cc = (BLOCK_N == 64 ? 0 : group * 64); cc < ((IGEMM2_DBG(p.dbg) & 2) ? 0 : BLOCK_N); cc += 128) {  // dbg 2: no epilogue
                 uint32_t v[64];
                 tmem_ld_32x64(taddr + cc, v);
                 // the store that last read this group's staging buffer must have drained
@@ -502,7 +509,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0 && !(p.dbg & 16)) mbar_arrive(t_empty(acc));
+            if (lane == 0 && !(IGEMM2_DBG(p.dbg) & 16)) mbar_arrive(t_empty(acc));
             if (BLOCK_N != 64 && ++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;

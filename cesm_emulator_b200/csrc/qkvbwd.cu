@@ -39,13 +39,19 @@ struct QkvBwdMaps {
     CUtensorMap x;    // [rows][64],   box {64 ci, 128 px}
     CUtensorMap w;    // [64 ci][cout] (W^T, K-major for the data gradient), box {64 co, 64 ci}
 };
+// bisection knobs only in -DCESM_QKVBWD_DEBUG builds (CESM_NVCC_EXTRA)
+#ifdef CESM_QKVBWD_DEBUG
+#define QKVBWD_DBG(x) (x)
+#else
+#define QKVBWD_DBG(x) 0
+#endif
 struct QkvBwdParams {
     long long rows;
     int tiles, chunks;          // row tiles; cout / 128
     h16* dx;          // [rows][64]
     float* dw;                  // dW[co * so + ci] (+=)
     long long so;
-    int dbg;   // CESM_QKVBWD_DBG bisection bits (0 in production): 1 = no data-gradient MMAs, 2 = no weight-gradient MMAs
+    int dbg;   // CESM_QKVBWD_DBG bisection bits (debug builds only): 1 = no data-gradient MMAs, 2 = no weight-gradient MMAs
 };
 
 __global__ void __launch_bounds__(QB_THREADS, 1)
@@ -121,60 +127,64 @@ qkv_bwd_kernel(const __grid_constant__ QkvBwdMaps maps, const QkvBwdParams p) {
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the loops, one elected lane issues =====
-        const bool leader = elect_one();
+        // ===== MMA issuer: one elected thread runs the loops =====
         constexpr uint32_t idesc_dg = make_idesc_f16(QB_TILE, QB_C, 0, 0);    // K-major A, B
         constexpr uint32_t idesc_wg = make_idesc_f16(QB_CHUNK, QB_C, 1, 1);   // MN-major A, B
-        const uint64_t dk = make_smem_desc_sw128(0, 0, 1024);                  // K-major SW128
-        const uint64_t dmn = make_smem_desc_sw128(0, QB_SUB, 1024);            // MN-major: 64-channel atoms QB_SUB apart
-        int st = 0, xs = 0, acc = 0, it = 0;
-        uint32_t ph = 0, xph = 0, accph = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-            mbar_wait(d1_empty(acc), accph ^ 1u, 33);
-            mbar_wait(x_full(xs), xph, 34);
-            tc_fence_after();
-            const uint32_t x16 = (x_base + xs * QB_SUB) >> 4;
-            const uint32_t d1 = tmem_d1 + acc * 64;
-            for (int c = 0; c < p.chunks; ++c) {
-                mbar_wait(s_full(st), ph, 35);
+        if (elect_one()) {
+            const uint64_t dk = make_smem_desc_sw128(0, 0, 1024);              // K-major SW128
+            const uint64_t dmn = make_smem_desc_sw128(0, QB_SUB, 1024);        // MN-major: 64-channel atoms QB_SUB apart
+            const int dbg = QKVBWD_DBG(p.dbg);
+            const int chunks = p.chunks;
+            int st = 0, xs = 0, acc = 0, it = 0;
+            uint32_t ph = 0, xph = 0, accph = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+                mbar_wait(d1_empty(acc), accph ^ 1u, 33);
+                mbar_wait(x_full(xs), xph, 34);
                 tc_fence_after();
-                const uint32_t a16 = (smem_base + st * QB_STAGE) >> 4;
-                const uint32_t w16 = a16 + ((2 * QB_SUB) >> 4);
-                // data gradient: K = 128 co = 8 steps of 16 (32 B inside a 128-byte row; second sub-tile after 4)
+                const uint32_t x16 = (x_base + xs * QB_SUB) >> 4;
+                const uint32_t d1 = tmem_d1 + acc * 64;
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(s_full(st), ph, 35);
+                    tc_fence_after();
+                    const uint32_t a16 = (smem_base + st * QB_STAGE) >> 4;
+                    const uint32_t w16 = a16 + ((2 * QB_SUB) >> 4);
+                    // data gradient: K = 128 co = 8 steps of 16 (32 B inside a 128-byte row; second sub-tile after 4)
+                    if (!(dbg & 1)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t ao = a16 + (k >> 2) * (QB_SUB >> 4) + (k & 3) * 2;
-                    const uint32_t bo = w16 + (k >> 2) * (QB_WSUB >> 4) + (k & 3) * 2;
-                    if (leader && !(p.dbg & 1)) umma_f16(d1, dk | (uint64_t)ao, dk | (uint64_t)bo, idesc_dg, (c > 0 || k > 0) ? 1u : 0u);
-                }
-                // weight gradient: K = 128 pixels = 8 steps of 16 pixels (2048 B)
-                const uint32_t d2 = tmem_d2 + c * 64;
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t ao = a16 + (k >> 2) * (QB_SUB >> 4) + (k & 3) * 2;
+                            const uint32_t bo = w16 + (k >> 2) * (QB_WSUB >> 4) + (k & 3) * 2;
+                            umma_f16(d1, dk | (uint64_t)ao, dk | (uint64_t)bo, idesc_dg, k == 0 ? (uint32_t)(c != 0) : 1u);
+                        }
+                    }
+                    // weight gradient: K = 128 pixels = 8 steps of 16 pixels (2048 B)
+                    const uint32_t d2 = tmem_d2 + c * 64;
+                    if (!(dbg & 2)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (leader && !(p.dbg & 2))
-                        umma_f16(d2, dmn | (uint64_t)(a16 + k * 128), dmn | (uint64_t)(x16 + k * 128), idesc_wg,
-                                  (it > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 8; ++k)
+                            umma_f16(d2, dmn | (uint64_t)(a16 + k * 128), dmn | (uint64_t)(x16 + k * 128), idesc_wg,
+                                     k == 0 ? (uint32_t)(it != 0) : 1u);
+                    }
+                    umma_commit(s_empty(st));
+                    if (++st == QB_STAGES) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
                 }
-                if (leader) umma_commit(s_empty(st));
-                if (++st == QB_STAGES) {
-                    st = 0;
-                    ph ^= 1u;
-                }
-            }
-            if (leader) {
                 umma_commit(x_empty(xs));
                 umma_commit(d1_full(acc));
+                if (++xs == QB_XSTAGES) {
+                    xs = 0;
+                    xph ^= 1u;
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    accph ^= 1u;
+                }
             }
-            if (++xs == QB_XSTAGES) {
-                xs = 0;
-                xph ^= 1u;
-            }
-            if (++acc == 2) {
-                acc = 0;
-                accph ^= 1u;
-            }
+            umma_commit(d2_full);
         }
-        if (leader) umma_commit(d2_full);
+        __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int q = warp & 3;

@@ -122,33 +122,33 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the loop (warp-uniform operands), one elected lane issues;
-        // the constant descriptor word is hoisted and only the start-address field advances =====
+        // ===== MMA issuer: one elected thread runs the loop (its instruction stream is the critical path: no
+        // per-MMA predicate, no re-convergence points); the constant descriptor word is hoisted and only the
+        // start-address field advances =====
         constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 1, 1);
-        const bool leader = elect_one();
-        const uint64_t desc_hi = make_smem_desc_sw128(0, kPix * 128, 1024);
-        int stage = 0;
-        uint32_t phase = 0, accum = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(full_bar(stage), phase, 22);
-            tc_fence_after();
-            const uint32_t sa16 = (smem_base + stage * S::kStageBytes) >> 4;
-            const uint32_t sb16 = sa16 + (S::kABytes >> 4);
+        if (elect_one()) {
+            const uint64_t desc_hi = make_smem_desc_sw128(0, kPix * 128, 1024);
+            const uint32_t base16 = smem_base >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase, 22);
+                tc_fence_after();
+                const uint32_t sa16 = base16 + stage * (S::kStageBytes >> 4);
+                const uint32_t sb16 = sa16 + (S::kABytes >> 4);
 #pragma unroll
-            for (int k = 0; k < kPix / 16; ++k) {
-                // 16 pixels = two 8-row groups = 2048 B further along K
-                if (leader)
+                for (int k = 0; k < kPix / 16; ++k)   // 16 pixels = two 8-row groups = 2048 B further along K
                     umma_f16(tmem_base, desc_hi | (uint64_t)(sa16 + k * 128), desc_hi | (uint64_t)(sb16 + k * 128), idesc,
-                              accum);
-                accum = 1;
-            }
-            if (leader) umma_commit(empty_bar(stage));
-            if (leader && kb == num_kb - 1) umma_commit(tmem_full_bar);
-            if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1u;
+                             k == 0 ? (uint32_t)(kb != 0) : 1u);
+                umma_commit(empty_bar(stage));
+                if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue: fp32 partial -> red.global.add into dW[co][tap][ci] =====
         const int q = warp & 3;

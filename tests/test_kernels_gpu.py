@@ -584,6 +584,7 @@ def test_device_data_path(cuda, K, crop):
 def test_device_data_path_matches_reference_dataset_class(cuda):
     """The gather kernel against windows produced by the REFERENCE's dataset class (dataset_single_member.py:
     168-196; fixture written by tests/golden/make_dataset_golden.py from the imported class)."""
+    import numpy as np
     from cesm_emulator_b200.synthetic import SyntheticEnsemble
     from test_host_logic import _ScriptedDraws, _dataset_fixture
     g, cond_np, tgt_np = _dataset_fixture()
