@@ -190,6 +190,7 @@ static int knob_int(const char* name) {
     return e ? atoi(e) : 0;
 }
 static int knob_pw() { static int v = knob_int("CESM_IGEMM_PW"); return v; }            // force halo row width
+static int knob_bn() { static int v = knob_int("CESM_IGEMM_BN"); return v; }            // force the column-tile width
 static int knob_astages() { static int v = knob_int("CESM_IGEMM_ASTAGES"); return v; }  // force A stages
 static int knob_dbg() {
     static int v = [] { const char* e = getenv("CESM_IGEMM_DBG"); return e ? atoi(e) : 0; }();
@@ -220,8 +221,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
     p.oh = a->oh;
     p.ow = a->ow;
     p.cout = a->cout;
-    const int block_n = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
-    p.n_tiles = a->cout / block_n;
+    int block_n = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
 
     // ---- HALO candidates: padded row width pw in {16, 32, 64, 128}, bw = pw - 2, bh = 128 / pw ----
     bool halo = false;
@@ -251,6 +251,26 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
     p.tiles_w = ceil_div(a->ow, p.bw);
     p.tiles_h = ceil_div(a->oh, p.bh);
     p.m_tiles = p.tiles_w * p.tiles_h * ceil_div(a->n, p.bn);
+
+    // ---- column-tile width of the tensor-bound (halo) shapes: MMA efficiency against wave quantisation ----
+    // A 128 x N x 16 MMA is bound by the shared-memory operand feed (4 KB of A + N/32 KB of B per MMA): measured
+    // ~75 / 90 / 165 clocks at N = 64 / 128 / 256 (tools/bench_igemm.py).  With few row tiles (48x72 x 6 frames = 216
+    // tiles on 148 SMs) a narrower N fills the last wave: 3 waves of N=128 tiles beat 2 waves of N=256 tiles.
+    if (halo) {
+        static const double clk[3] = {75.0, 90.0, 165.0};
+        double best = 1e30;
+        for (int n = 256, i = 2; n >= 64; n >>= 1, --i) {
+            if (a->cout % n) continue;
+            const long long tiles = (long long)p.m_tiles * (a->cout / n);
+            const double t = (double)((tiles + sm_count() - 1) / sm_count()) * clk[i];
+            if (t < best - 1e-9) {   // ties keep the wider tile
+                best = t;
+                block_n = n;
+            }
+        }
+    }
+    if (knob_bn() && a->cout % knob_bn() == 0) block_n = knob_bn();
+    p.n_tiles = a->cout / block_n;
 
     // ---- GroupNorm statistics: every tile must lie within one sample ----
     p.gn_sums = a->gn_sums;

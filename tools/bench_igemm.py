@@ -40,6 +40,9 @@ def main():
         ("L0 3x3 128->64 cat", 6, 192, 288, 64, 64, 64, 9, False),
         ("L1 3x3 128->128", 6, 96, 144, 128, 0, 128, 9, False),
         ("L2 3x3 256->256", 6, 48, 72, 256, 0, 256, 9, False),
+        ("L2 3x3 512->256 cat", 6, 48, 72, 256, 256, 256, 9, False),
+        ("L3 3x3 512->512", 6, 24, 36, 512, 0, 512, 9, False),
+        ("L1 3x3 256->128 cat", 6, 96, 144, 128, 128, 128, 9, False),
         ("L0 1x1 64->768", 6, 192, 288, 64, 0, 768, 1, False),
         ("L0 1x1 256->64", 6, 192, 288, 256, 0, 64, 1, False),
         ("L0 1x1 768->64", 6, 192, 288, 768, 0, 64, 1, False),
