@@ -191,6 +191,7 @@ static int knob_int(const char* name) {
 }
 static int knob_pw() { static int v = knob_int("CESM_IGEMM_PW"); return v; }            // force halo row width
 static int knob_bn() { static int v = knob_int("CESM_IGEMM_BN"); return v; }            // force the column-tile width
+static int knob_no_pair() { static int v = env_flag("CESM_IGEMM_NO_PAIR"); return v; }
 static int knob_astages() { static int v = knob_int("CESM_IGEMM_ASTAGES"); return v; }  // force A stages
 static int knob_dbg() {
     static int v = [] { const char* e = getenv("CESM_IGEMM_DBG"); return e ? atoi(e) : 0; }();
@@ -256,13 +257,19 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
     // A 128 x N x 16 MMA is bound by the shared-memory operand feed (4 KB of A + N/32 KB of B per MMA): measured
     // ~75 / 90 / 165 clocks at N = 64 / 128 / 256 (tools/bench_igemm.py).  With few row tiles (48x72 x 6 frames = 216
     // tiles on 148 SMs) a narrower N fills the last wave: 3 waves of N=128 tiles beat 2 waves of N=256 tiles.
+    // CTA pairs (cta_group::2, igemm2.cu): two row tiles per cluster share the weight rows, so a CTA reads
+    // N*16 B instead of N*32 B of B per MMA (~66 / 75 / 130 clocks).  CESM_IGEMM_NO_PAIR=1 keeps single CTAs.
+    const bool pair = halo && !knob_no_pair() && p.m_tiles >= 2 && sm_count() >= 2;
     if (halo) {
-        static const double clk[3] = {75.0, 90.0, 165.0};
+        static const double clk1[3] = {75.0, 90.0, 165.0}, clk2[3] = {66.0, 75.0, 130.0};
+        const double* clk = pair ? clk2 : clk1;
+        const int units = pair ? sm_count() / 2 : sm_count();
+        const long long m_units = pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
         double best = 1e30;
         for (int n = 256, i = 2; n >= 64; n >>= 1, --i) {
             if (a->cout % n) continue;
-            const long long tiles = (long long)p.m_tiles * (a->cout / n);
-            const double t = (double)((tiles + sm_count() - 1) / sm_count()) * clk[i];
+            const long long tiles = m_units * (a->cout / n);
+            const double t = (double)((tiles + units - 1) / units) * clk[i];
             if (t < best - 1e-9) {   // ties keep the wider tile
                 best = t;
                 block_n = n;
@@ -303,8 +310,8 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
         p.a_box_bytes = 128u * p.bw * p.bh * p.bn;
     }
     const long long budget = (long long)kIgemm2MaxSmem - 1024 /*align*/ - 1024 /*barriers*/ - 2 * 16384 /*out staging*/;
-    const long long b_total = (long long)a->cout * p.num_kb * 128;
-    const long long b_blk = (long long)block_n * 128;
+    const long long b_total = (long long)a->cout * p.num_kb * 128 / (pair ? 2 : 1);   // per CTA
+    const long long b_blk = (long long)block_n * 128 / (pair ? 2 : 1);
     const int a_min = 2;
     if (b_total + a_min * (long long)p.a_stage_bytes <= budget && !knob_no_bres()) {
         p.b_resident = 1;
@@ -383,7 +390,7 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
         const int ktot = p.num_kb * 64;
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)a->cout};
         const uint64_t str[1] = {(uint64_t)ktot * 2};
-        const uint32_t bbox[2] = {64u, (uint32_t)block_n};
+        const uint32_t bbox[2] = {64u, (uint32_t)(pair ? block_n / 2 : block_n)};
         int rc = get_tensor_map_h16(&maps.b, a->wt, 2, dims, str, bbox);
         if (rc) return rc;
     }
@@ -414,10 +421,16 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
     // go instead of in three passes over the 510 MB tensor; tools/bench_igemm.py)
     p.m_major = ((knob_mmajor == 1 && p.b_resident) || knob_mmajor == 2) && p.n_tiles > 1 ? 1 : 0;
     p.wt_stable = a->wt_stable ? 1 : 0;
-    const int total_tiles = p.m_tiles * p.n_tiles;
-    const int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    int grid;
+    if (pair) {
+        const int units = ((p.m_tiles + 1) / 2) * p.n_tiles, clusters = sm_count() / 2;
+        grid = 2 * (units < clusters ? units : clusters);
+    } else {
+        const int total_tiles = p.m_tiles * p.n_tiles;
+        grid = total_tiles < sm_count() ? total_tiles : sm_count();
+    }
     note_launch();
-    CESM_CHECK_CUDA(igemm2_launch(maps, p, block_n, halo, grid, smem, st));
+    CESM_CHECK_CUDA(igemm2_launch(maps, p, block_n, halo, pair, grid, smem, st));
     return CESM_OK;
 }
 

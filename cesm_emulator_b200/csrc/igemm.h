@@ -79,8 +79,9 @@ struct Igemm2Params {
     int32_t dbg;                       // CESM_IGEMM_DBG bisection bits (0 in production)
 };
 
-cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, int grid, size_t smem,
-                          cudaStream_t stream);
+// pair: launch as clusters of two CTAs working as one cta_group::2 unit (halo mode only; grid must be even)
+cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, bool pair, int grid,
+                          size_t smem, cudaStream_t stream);
 
 cudaError_t wgrad_launch(const CUtensorMap* xmaps, int n_xmaps, const CUtensorMap& ymap, const WgradParams& p,
                          int block_n, int ksplit, cudaStream_t stream);

@@ -84,9 +84,13 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&v)[64])
         : "memory");
 }
 
-template <int BLOCK_N, bool HALO, bool GN>
+// PAIR (HALO only): the two CTAs of a cluster work as one cta_group::2 unit on TWO row tiles (CTA r takes row tile
+// 2*pair + r) of the same column tile.  Each CTA loads its own activation halo and HALF of the weight rows, keeps
+// its own 128 accumulator rows in its own TMEM and runs its own epilogue; the even CTA issues the M = 256 MMAs.
+template <int BLOCK_N, bool HALO, bool GN, bool PAIR>
 __global__ void __launch_bounds__(kIgemm2Threads, 1)
 igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
+    static_assert(!PAIR || HALO, "CTA pairs are wired for the 3x3 halo mode only");
     pdl_trigger();  // pdl_wait() sits in the two TMA producers: everything else depends on their data
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -94,7 +98,11 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
 
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + p.a_stages * p.a_stage_bytes;
-    const uint32_t b_blk_bytes = BLOCK_N * kStageRowBytes;
+    constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;      // weight rows of a block held by THIS CTA
+    const uint32_t b_blk_bytes = kBRows * kStageRowBytes;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs, owns the full barriers)
+    const int work_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // persistent loop: first unit ...
+    const int work_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // ... and stride (CTAs or CTA pairs)
     const uint32_t b_bytes = p.b_resident ? (uint32_t)p.n_tiles * p.num_kb * b_blk_bytes : p.b_stages * b_blk_bytes;
     const uint32_t o_base = b_base + b_bytes;                 // 2 output staging buffers
     const uint32_t bar_base = o_base + 2 * kOutStageBytes;
@@ -118,7 +126,8 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
     const int a_loads = HALO ? cblk : p.num_kb;    // activation loads per tile
     const int taps_per_a = HALO ? 9 : 1;
     const int pw = HALO ? p.bw + 2 : p.bw;         // accumulator rows per tile row
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int m_units = PAIR ? (p.m_tiles + 1) >> 1 : p.m_tiles;   // row tiles, or pairs of row tiles
+    const int total_tiles = m_units * p.n_tiles;
     constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
 
     if (threadIdx.x == 0) {
@@ -135,15 +144,19 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(t_full(s), 1);
-            mbar_init(t_empty(s), BLOCK_N == 64 ? 4 : 8);
+            mbar_init(t_empty(s), (BLOCK_N == 64 ? 4 : 8) * (PAIR ? 2 : 1));   // PAIR: both CTAs' epilogues
         }
         mbar_init(b_all_bar, 1);
         fence_barrier_init();
     }
     if (threadIdx.x < 128) reinterpret_cast<float*>(smem_gen + (gn_base - smem_base))[threadIdx.x] = 0.f;
-    if (warp == 2) tmem_alloc(tmem_ptr_addr, kTmemCols);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair(tmem_ptr_addr, kTmemCols);
+        else tmem_alloc(tmem_ptr_addr, kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -156,9 +169,10 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             t = tile / p.n_tiles;
             n_tile = tile - t * p.n_tiles;
         } else {
-            n_tile = tile / p.m_tiles;
-            t = tile - n_tile * p.m_tiles;
+            n_tile = tile / m_units;
+            t = tile - n_tile * m_units;
         }
+        if (PAIR) t = 2 * t + (int)cta_rank;   // may be == m_tiles (odd count): a ghost tile, all out of bounds
         const int tw = t % p.tiles_w;
         t /= p.tiles_w;
         const int th = t % p.tiles_h;
@@ -173,12 +187,27 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         pdl_wait();  // the preceding kernel has completed: its outputs (our activations) are visible
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = work_id; tile < total_tiles; tile += work_stride) {
             int n_tile, n0, oh0, ow0;
             tile_coords(tile, n_tile, n0, oh0, ow0);
             for (int ai = 0; ai < a_loads; ++ai) {
                 mbar_wait(a_empty(stage), phase ^ 1u, 11);
                 const uint32_t dst = a_base + stage * p.a_stage_bytes;
+                if (PAIR) {
+                    // both halos report to the leader's barrier, which expects the bytes of both
+                    if (cta_rank == 0) mbar_arrive_expect_tx(a_full(stage), 2 * p.a_box_bytes);
+                    int midx = 0, c = ai << 6;
+                    if (ai >= cblk0) {
+                        midx = 1;
+                        c = (ai - cblk0) << 6;
+                    }
+                    tma_load_4d_pair(dst, &maps.a[midx], a_full(stage), c, ow0 - 1, oh0 - 1, n0);
+                    if (++stage == p.a_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                    continue;
+                }
                 if (IGEMM2_DBG(p.dbg) & 32) {  // bisection: no activation traffic at all
                     mbar_arrive(a_full(stage));
                     if (++stage == p.a_stages) {
@@ -215,22 +244,35 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         // ===== weight producer =====
         // weights re-packed at the top of the step are fetched while the preceding kernel still drains
         if (!p.wt_stable) pdl_wait();
+        const int row_off = (int)cta_rank * kBRows;   // PAIR: this CTA's half of a block's weight rows
         if (p.b_resident) {
             const uint32_t total_bytes = (uint32_t)p.n_tiles * p.num_kb * b_blk_bytes;
-            mbar_arrive_expect_tx(b_all_bar, total_bytes);
+            if (cta_rank == 0) mbar_arrive_expect_tx(b_all_bar, (PAIR ? 2u : 1u) * total_bytes);
             for (int nt = 0; nt < p.n_tiles; ++nt)
-                for (int kb = 0; kb < p.num_kb; ++kb)
-                    tma_load_2d(b_base + (nt * p.num_kb + kb) * b_blk_bytes, &maps.b, b_all_bar, kb * kKBlk,
-                                nt * BLOCK_N);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const uint32_t dst = b_base + (nt * p.num_kb + kb) * b_blk_bytes;
+                    if (PAIR) tma_load_2d_pair(dst, &maps.b, b_all_bar, kb * kKBlk, nt * BLOCK_N + row_off);
+                    else tma_load_2d(dst, &maps.b, b_all_bar, kb * kKBlk, nt * BLOCK_N);
+                }
         } else {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = p.m_major ? tile % p.n_tiles : tile / p.m_tiles;
+            for (int tile = work_id; tile < total_tiles; tile += work_stride) {
+                const int n_tile = p.m_major ? tile % p.n_tiles : tile / m_units;
                 for (int ai = 0; ai < a_loads; ++ai)
                     for (int ti = 0; ti < taps_per_a; ++ti) {
                         const int kb = HALO ? ti * cblk + ai : ai;
                         mbar_wait(b_empty(stage), phase ^ 1u, 12);
+                        if (PAIR) {
+                            if (cta_rank == 0) mbar_arrive_expect_tx(b_full(stage), 2 * b_blk_bytes);
+                            tma_load_2d_pair(b_base + stage * b_blk_bytes, &maps.b, b_full(stage), kb * kKBlk,
+                                             n_tile * BLOCK_N + row_off);
+                            if (++stage == p.b_stages) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(b_full(stage), b_blk_bytes);
                         tma_load_2d(b_base + stage * b_blk_bytes, &maps.b, b_full(stage), kb * kKBlk, n_tile * BLOCK_N);
                         if (++stage == p.b_stages) {
@@ -249,8 +291,8 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         // of one generic lambda, descriptors are a constant upper word OR a 14-bit start-address field advanced by
         // adds (+2 per 16-element K step = 32 B, +8 per 128-byte row for the halo tap views), and only the first
         // MMA of a tile carries a run-time accumulate flag.
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_f16(kTileM, BLOCK_N, 0, 0);
+        if (cta_rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, BLOCK_N, 0, 0);
             const uint64_t desc_hi = make_smem_desc_sw128(0, 0, 1024);   // start-address field = 0
             uint32_t tap_rows8[9];  // HALO: ((1+dh)*pw + (1+dw)) * 8 = row offset of the tap view in 16-byte units
 #pragma unroll
@@ -261,23 +303,33 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             const uint32_t a_base16 = a_base >> 4, b_base16 = b_base >> 4;
             const uint32_t tap_b16 = cblk * b_blk16;        // HALO, resident: weight-block stride between taps
             const uint32_t tile_b16 = p.num_kb * b_blk16;   // resident: stride between n tiles
-            const int n_a_stages = p.a_stages, n_b_stages = p.b_stages, n_tiles = p.n_tiles, m_tiles = p.m_tiles;
+            const int n_a_stages = p.a_stages, n_b_stages = p.b_stages, n_tiles = p.n_tiles;
             const bool m_major = p.m_major != 0;
             const int dbg = IGEMM2_DBG(p.dbg);
             auto mma4 = [&](uint32_t d_tmem, uint32_t a16, uint32_t b16, uint32_t first_accum) {
                 if (dbg & 4) return;  // bisection knob (debug builds only): no MMAs
+                // timing-only probes (results wrong): 64 = alternate between the two accumulator stages per MMA
+                // (is the chain of dependent accumulations the limit?), 128 = half-width MMAs (N/2: the operand
+                // bytes per MMA a CTA pair would read)
+                const uint32_t id = (dbg & 128) ? make_idesc_f16(kTileM, BLOCK_N / 2, 0, 0) : idesc;
 #pragma unroll
-                for (int k = 0; k < kKBlk / 16; ++k)
-                    umma_f16(d_tmem, desc_hi | (uint64_t)(a16 + 2 * k), desc_hi | (uint64_t)(b16 + 2 * k), idesc,
-                             k == 0 ? first_accum : 1u);
+                for (int k = 0; k < kKBlk / 16; ++k) {
+                    const uint64_t da = desc_hi | (uint64_t)(a16 + 2 * k), db = desc_hi | (uint64_t)(b16 + 2 * k);
+                    if (PAIR) umma_f16_pair(d_tmem, da, db, idesc, k == 0 ? first_accum : 1u);
+                    else umma_f16((dbg & 64) ? (tmem_base + (k & 1) * BLOCK_N) : d_tmem, da, db, id, k == 0 ? first_accum : 1u);
+                }
+            };
+            auto commit = [&](uint32_t bar) {
+                if (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
             };
             auto run = [&](auto resident_tag) {
                 constexpr bool RES = decltype(resident_tag)::value;
                 int a_stage = 0, b_stage = 0, acc = 0;
                 uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
                 if (RES) mbar_wait(b_all_bar, 0, 13);
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                    const int n_tile = m_major ? tile % n_tiles : tile / m_tiles;
+                for (int tile = work_id; tile < total_tiles; tile += work_stride) {
+                    const int n_tile = m_major ? tile % n_tiles : tile / m_units;
                     if (!(dbg & 16)) mbar_wait(t_empty(acc), acc_phase ^ 1u, 14);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -302,20 +354,20 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                                 mbar_wait(b_full(b_stage), b_phase, 16);
                                 tc_fence_after();
                                 mma4(d_tmem, sa16 + tap_rows8[ti], b_base16 + b_stage * b_blk16, ti == 0 ? first : 1u);
-                                umma_commit(b_empty(b_stage));
+                                commit(b_empty(b_stage));
                                 if (++b_stage == n_b_stages) {
                                     b_stage = 0;
                                     b_phase ^= 1u;
                                 }
                             }
                         }
-                        umma_commit(a_empty(a_stage));
+                        commit(a_empty(a_stage));
                         if (++a_stage == n_a_stages) {
                             a_stage = 0;
                             a_phase ^= 1u;
                         }
                     }
-                    if (!(dbg & 16)) umma_commit(t_full(acc));
+                    if (!(dbg & 16)) commit(t_full(acc));
                     if (++acc == 2) {
                         acc = 0;
                         acc_phase ^= 1u;
@@ -354,6 +406,63 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             }
             epi_bar_sync(group);
         };
+        // 16 values x 32 rows -> 16 totals with a halving butterfly (16 shuffles): after the step for lane bit b a
+        // lane keeps the half of its values selected by that bit; even lanes end up with total number
+        // idx = bit-reversed (lane >> 1) in v[0] ([0..7] octet sums, [8..15] octet sums of squares).
+        auto butterfly16 = [&](float (&v)[16]) -> int {
+            {
+                const bool up = lane & 16;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 8], 16);
+                    v[i] = (up ? v[i + 8] : v[i]) + recv;
+                }
+            }
+            {
+                const bool up = lane & 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 4], 8);
+                    v[i] = (up ? v[i + 4] : v[i]) + recv;
+                }
+            }
+            {
+                const bool up = lane & 4;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 2], 4);
+                    v[i] = (up ? v[i + 2] : v[i]) + recv;
+                }
+            }
+            {
+                const bool up = lane & 2;
+                const float recv = __shfl_xor_sync(0xffffffffu, up ? v[0] : v[1], 2);
+                v[0] = (up ? v[1] : v[0]) + recv;
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        };
+        // BLOCK_N <= 128: a thread meets ONE 64-column chunk per tile, always the same columns while the column
+        // tile stays the same, so the 16 per-row partial sums are simply kept in registers across tiles and reduced
+        // (butterfly + 16 global atomics per warp) only when the (sample, column tile) changes -- no shuffles, no
+        // shared-memory atomics and no barrier per tile (round 2: they cost 8 us of a 34 us L0 convolution).
+        constexpr bool kRunningStats = GN && BLOCK_N <= 128;
+        float racc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) racc[i] = 0.f;
+        int run_key = -1;   // b * n_tiles + n_tile
+        auto run_flush = [&]() {
+            if (run_key < 0) return;
+            const int b = run_key / p.n_tiles, nt = run_key - b * p.n_tiles;
+            const int col = nt * BLOCK_N + (BLOCK_N == 64 ? 0 : group * 64);
+            const int idx = butterfly16(racc);
+            if ((lane & 1) == 0) {
+                const int g = (col + 8 * (idx & 7)) / p.gn_cpg;
+                atomicAdd(p.gn_sums + ((size_t)b * p.gn_groups + g) * 2 + (idx >> 3), racc[0]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) racc[i] = 0.f;
+        };
         // per-tile constants of the row -> pixel map
         const int rw = r % pw;
         const int rh = (r / pw) % p.bh;
@@ -363,7 +472,7 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
         const int st_w = HALO ? 0 : r0 % p.bw, st_h = HALO ? q : (r0 / p.bw) % p.bh, st_n = HALO ? 0 : r0 / (p.bw * p.bh);
         const bool st_ok = HALO ? (q < p.bh) : (st_n < p.bn);
         int tile_it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+        for (int tile = work_id; tile < total_tiles; tile += work_stride, ++tile_it) {
             if (BLOCK_N == 64) {
                 // one 64-column chunk per tile: the groups alternate over tiles instead (stage == group),
                 // so each has two tile periods for its TMEM read-out, statistics and store
@@ -373,13 +482,32 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             }
             int n_tile, n0, oh0, ow0;
             tile_coords(tile, n_tile, n0, oh0, ow0);
+            if (PAIR && n0 >= p.n) {
+                // ghost tile of an odd row-tile count: nothing to store, but the accumulator hand-over still runs
+                mbar_wait(t_full(acc), acc_phase, 17);
+                tc_fence_after();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(t_empty(acc));
+                if (BLOCK_N != 64 && ++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+                continue;
+            }
             const int n = n0 + rn, oh = oh0 + rh, ow = ow0 + rw;
             const bool valid = (rw < p.bw) && (rn < p.bn) && (n < p.n) && (oh < p.oh) && (ow < p.ow);
             const long long pix = (static_cast<long long>(n) * p.out_h + (oh * p.o_sh + p.o_h0)) * p.out_w +
                                   (ow * p.o_sw + p.o_w0);
             if (GN) {
                 const int b = n0 / p.gn_frames;  // the tile lies within one sample (host guarantees)
-                if (b != cur_b) {
+                if (kRunningStats) {
+                    const int key = b * p.n_tiles + n_tile;
+                    if (key != run_key) {
+                        run_flush();
+                        run_key = key;
+                    }
+                } else if (b != cur_b) {
                     if (cur_b >= 0) gn_flush(cur_b);
                     cur_b = b;
                 }
@@ -387,6 +515,8 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
             if (!(IGEMM2_DBG(p.dbg) & 16)) mbar_wait(t_full(acc), acc_phase, 17);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+            const int last_cc = BLOCK_N == 64 ? 0 : group * 64 + (BLOCK_N > 128 ? 128 : 0);   // this group's last chunk
+            bool released = false;
 #pragma unroll 1
             for (int cc = (BLOCK_N == 64 ? 0 : group * 64); cc < ((IGEMM2_DBG(p.dbg) & 2) ? 0 : BLOCK_N); cc += 128) {  // dbg 2: no epilogue
                 uint32_t v[64];
@@ -405,6 +535,17 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                 const uint4* rp = reinterpret_cast<const uint4*>(
                     reinterpret_cast<const h16*>(p.residual) + (valid ? pix : 0) * p.ldr + col);
                 tmem_ld_wait();
+                if (cc == last_cc) {
+                    // the accumulator stage is in registers now: hand it back BEFORE the arithmetic, staging and
+                    // store of this chunk, so the MMAs of the tile after next never wait for the epilogue's tail
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0 && !(IGEMM2_DBG(p.dbg) & 16)) {
+                        if (PAIR) mbar_arrive_leader(t_empty(acc));   // the leader's MMA warp waits for both epilogues
+                        else mbar_arrive(t_empty(acc));
+                    }
+                    released = true;
+                }
                 float sv[16];  // GN: [0..7] per 8-column octet sums of this row, [8..15] sums of squares
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {  // 8 columns = one 16-byte unit
@@ -439,46 +580,18 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                         const float s = ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
                         const float qq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c2.x, c2.x,
                                          fmaf(c2.y, c2.y, fmaf(d.x, d.x, d.y * d.y)))))));
-                        sv[j] = valid ? s : 0.f;
-                        sv[8 + j] = valid ? qq : 0.f;
+                        if (kRunningStats) {
+                            racc[j] += valid ? s : 0.f;
+                            racc[8 + j] += valid ? qq : 0.f;
+                        } else {
+                            sv[j] = valid ? s : 0.f;
+                            sv[8 + j] = valid ? qq : 0.f;
+                        }
                     }
                 }
-                if (GN) {
-                    // 16 values x 32 rows -> 16 totals with a halving butterfly (16 shuffles): after the
-                    // step for lane bit b a lane keeps the half of its values selected by that bit.
-                    {
-                        const bool up = lane & 16;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[i] : sv[i + 8], 16);
-                            sv[i] = (up ? sv[i + 8] : sv[i]) + recv;
-                        }
-                    }
-                    {
-                        const bool up = lane & 8;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[i] : sv[i + 4], 8);
-                            sv[i] = (up ? sv[i + 4] : sv[i]) + recv;
-                        }
-                    }
-                    {
-                        const bool up = lane & 4;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[i] : sv[i + 2], 4);
-                            sv[i] = (up ? sv[i + 2] : sv[i]) + recv;
-                        }
-                    }
-                    {
-                        const bool up = lane & 2;
-                        const float recv = __shfl_xor_sync(0xffffffffu, up ? sv[0] : sv[1], 2);
-                        sv[0] = (up ? sv[1] : sv[0]) + recv;
-                    }
-                    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                if (GN && !kRunningStats) {
+                    const int idx = butterfly16(sv);
                     if ((lane & 1) == 0) {
-                        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
-                                        ((lane >> 1) & 1);
                         const int g = (col + 8 * (idx & 7)) / p.gn_cpg;
                         atomicAdd(gn_acc + 2 * g + (idx >> 3), sv[0]);
                     }
@@ -507,56 +620,69 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0 && !(IGEMM2_DBG(p.dbg) & 16)) mbar_arrive(t_empty(acc));
+            if (!released) {   // debug builds without an epilogue loop
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0 && !(IGEMM2_DBG(p.dbg) & 16)) {
+                    if (PAIR) mbar_arrive_leader(t_empty(acc));
+                    else mbar_arrive(t_empty(acc));
+                }
+            }
             if (BLOCK_N != 64 && ++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;
             }
         }
-        if (GN) gn_flush(cur_b);
+        if (kRunningStats) run_flush();
+        else if (GN) gn_flush(cur_b);
         if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) cluster_sync_all();   // neither CTA may free its half while the pair's MMAs / barriers are in use
+    else __syncthreads();
+    if (warp == 2) {
+        if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO, bool GN>
+template <int BLOCK_N, bool HALO, bool GN, bool PAIR>
 static cudaError_t launch_igemm2(const Igemm2Maps& maps, const Igemm2Params& p, int grid, size_t smem,
                                  cudaStream_t stream) {
     static bool configured = false;  // benign race: attribute set is idempotent
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BLOCK_N, HALO, GN>,
+        cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BLOCK_N, HALO, GN, PAIR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIgemm2MaxSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    launch_pdl(igemm2_kernel<BLOCK_N, HALO, GN>, grid, kIgemm2Threads, smem, stream, maps, p);
+    launch_pdl_cluster(igemm2_kernel<BLOCK_N, HALO, GN, PAIR>, grid, kIgemm2Threads, smem, stream, PAIR ? 2 : 1, maps, p);
     return cudaGetLastError();
 }
 
 template <int BLOCK_N>
-static cudaError_t launch_igemm2_n(const Igemm2Maps& maps, const Igemm2Params& p, bool halo, int grid, size_t smem,
-                                   cudaStream_t stream) {
+static cudaError_t launch_igemm2_n(const Igemm2Maps& maps, const Igemm2Params& p, bool halo, bool pair, int grid,
+                                   size_t smem, cudaStream_t stream) {
     const bool gn = p.gn_sums != nullptr;
-    if (halo) return gn ? launch_igemm2<BLOCK_N, true, true>(maps, p, grid, smem, stream)
-                        : launch_igemm2<BLOCK_N, true, false>(maps, p, grid, smem, stream);
-    return gn ? launch_igemm2<BLOCK_N, false, true>(maps, p, grid, smem, stream)
-              : launch_igemm2<BLOCK_N, false, false>(maps, p, grid, smem, stream);
+    if (halo && pair)
+        return gn ? launch_igemm2<BLOCK_N, true, true, true>(maps, p, grid, smem, stream)
+                  : launch_igemm2<BLOCK_N, true, false, true>(maps, p, grid, smem, stream);
+    if (halo) return gn ? launch_igemm2<BLOCK_N, true, true, false>(maps, p, grid, smem, stream)
+                        : launch_igemm2<BLOCK_N, true, false, false>(maps, p, grid, smem, stream);
+    return gn ? launch_igemm2<BLOCK_N, false, true, false>(maps, p, grid, smem, stream)
+              : launch_igemm2<BLOCK_N, false, false, false>(maps, p, grid, smem, stream);
 }
 
-cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, int grid, size_t smem,
-                          cudaStream_t stream) {
+cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, bool pair, int grid,
+                          size_t smem, cudaStream_t stream) {
     switch (block_n) {
-        case 64: return launch_igemm2_n<64>(maps, p, halo, grid, smem, stream);
-        case 128: return launch_igemm2_n<128>(maps, p, halo, grid, smem, stream);
-        case 256: return launch_igemm2_n<256>(maps, p, halo, grid, smem, stream);
+        case 64: return launch_igemm2_n<64>(maps, p, halo, pair, grid, smem, stream);
+        case 128: return launch_igemm2_n<128>(maps, p, halo, pair, grid, smem, stream);
+        case 256: return launch_igemm2_n<256>(maps, p, halo, pair, grid, smem, stream);
     }
     return cudaErrorInvalidValue;
 }
