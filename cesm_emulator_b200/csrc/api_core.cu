@@ -543,6 +543,102 @@ static void choose_tile64(int n, int oh, int ow, int* bw, int* bh, int* bn) {
         }
 }
 
+// 3x3 stride-1 weight gradients with <= 128 output channels go to wgrad3.cu (one halo fetch serves all nine taps).
+// Its accumulators are 64 columns wide, so at 256+ output channels the wider MMAs of wgrad.cu win again
+// (tools/bench_wgrad.py on B200: 64->64 38.8 -> 32.2 us, 128->64 66.6 -> 53.4, 128->128 43.1 -> 33.9, 256->256 33.5 -> 36.1).
+// Returns true when it handled the call (*rc = status).  CESM_WGRAD3=0 disables it, CESM_WGRAD3_MAXCOUT moves the bar.
+static bool wgrad3_try(const cesm_wgrad_args* a, cudaStream_t st, int* rc) {
+    static const int enabled = [] { const char* e = getenv("CESM_WGRAD3"); return e ? atoi(e) : 1; }();
+    static const int max_cout = [] { const char* e = getenv("CESM_WGRAD3_MAXCOUT"); return e ? atoi(e) : 128; }();
+    if (!enabled || a->stride != 1 || a->num_taps != 9 || a->cout > max_cout) return false;
+    if (a->oh != a->h || a->ow != a->w || a->y_h != a->oh || a->y_w != a->ow || a->y_sh != 1 || a->y_sw != 1 ||
+        a->y_h0 != 0 || a->y_w0 != 0)
+        return false;
+    bool seen[9] = {};
+    for (int t = 0; t < 9; ++t) {
+        const int dh = a->tap_dh[t], dw = a->tap_dw[t];
+        if (dh < -1 || dh > 1 || dw < -1 || dw > 1 || seen[(dh + 1) * 3 + dw + 1]) return false;
+        seen[(dh + 1) * 3 + dw + 1] = true;
+    }
+    auto run = [&]() -> int {
+        Wgrad3Params p{};
+        p.c0 = a->c0;
+        p.c1 = a->c1;
+        p.n = a->n;
+        p.cout = a->cout;
+        // pixel tile: 32 x 4 or 16 x 8, whichever wastes fewer out-of-range pixels
+        const long long waste32 = (long long)ceil_div(a->ow, 32) * 32 * ceil_div(a->oh, 4) * 4;
+        const long long waste16 = (long long)ceil_div(a->ow, 16) * 16 * ceil_div(a->oh, 8) * 8;
+        p.bw = waste16 < waste32 ? 16 : 32;
+        p.bh = 128 / p.bw;
+        p.tiles_w = ceil_div(a->ow, p.bw);
+        p.tiles_h = ceil_div(a->oh, p.bh);
+        const int pw = p.bw + 2;
+        p.halo_box_bytes = (uint32_t)(pw * (p.bh + 2) * 128);
+        p.halo_stage_bytes = (p.halo_box_bytes + 256u + 1023u) / 1024u * 1024u;   // + the ghost tap's extra rows
+        const int ctot = a->c0 + a->c1;
+        long long so, si;
+        int tap_off_in[9];
+        if (a->dw_so != 0) {
+            so = a->dw_so;
+            si = a->dw_si;
+            for (int t = 0; t < 9; ++t) tap_off_in[t] = a->dw_tap_off[t];
+        } else {
+            so = 9LL * ctot;
+            si = 1;
+            for (int t = 0; t < 9; ++t) tap_off_in[t] = t * ctot;
+            CESM_CHECK_CUDA(cudaMemsetAsync(a->dw, 0, sizeof(float) * (size_t)a->cout * 9 * ctot, st));
+        }
+        p.so = so;
+        p.si = si;
+        p.dw = a->dw;
+        // taps in ascending halo-row order (pairs are stacked through a positive leading-byte offset)
+        for (int k = 0; k < 9; ++k) {
+            const int dh = k / 3 - 1, dw = k % 3 - 1;
+            for (int t = 0; t < 9; ++t)
+                if (a->tap_dh[t] == dh && a->tap_dw[t] == dw) {
+                    p.tap_row[k] = (1 + dh) * pw + (1 + dw);
+                    p.tap_off[k] = tap_off_in[t];
+                }
+        }
+        p.tap_row[9] = p.tap_row[8] + 1;
+        p.tap_off[9] = p.tap_off[8];
+        Wgrad3Maps maps;
+        const uint32_t xbox[4] = {64u, (uint32_t)pw, (uint32_t)(p.bh + 2), 1u};
+        const void* src[2] = {a->x0, a->x1};
+        const int cs[2] = {a->c0, a->c1};
+        for (int s = 0; s < 2; ++s) {
+            if (!src[s]) {
+                maps.x[s] = maps.x[0];
+                continue;
+            }
+            const uint64_t dims[4] = {(uint64_t)cs[s], (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+            const uint64_t str[3] = {(uint64_t)cs[s] * 2, (uint64_t)a->w * cs[s] * 2, (uint64_t)a->h * a->w * cs[s] * 2};
+            int e = get_tensor_map_h16(&maps.x[s], src[s], 4, dims, str, xbox);
+            if (e) return e;
+        }
+        {
+            const int co = a->cout;
+            const uint32_t ybox[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, 1u};
+            const uint64_t dims[4] = {(uint64_t)co, (uint64_t)a->ow, (uint64_t)a->oh, (uint64_t)a->n};
+            const uint64_t str[3] = {(uint64_t)co * 2, (uint64_t)a->ow * co * 2, (uint64_t)a->oh * a->ow * co * 2};
+            int e = get_tensor_map_h16(&maps.y, a->dy, 4, dims, str, ybox);
+            if (e) return e;
+        }
+        const int cblk = ctot / 64;
+        const int groups = cblk * (a->cout / 64);
+        const int tiles = p.tiles_w * p.tiles_h * a->n;
+        int ksplit = sm_count() / groups;   // one CTA per SM (512 TMEM columns, 4 x 42 KB ring)
+        if (ksplit > tiles) ksplit = tiles;
+        if (ksplit < 1) ksplit = 1;
+        note_launch();
+        CESM_CHECK_CUDA(wgrad3_launch(maps, p, cblk, ksplit, st));
+        return CESM_OK;
+    };
+    *rc = run();
+    return true;
+}
+
 extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
     CESM_REQUIRE(a != nullptr, "args is NULL");
     CESM_REQUIRE(a->c0 > 0 && a->c0 % 64 == 0 && a->c1 >= 0 && a->c1 % 64 == 0,
@@ -554,6 +650,11 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
                  "stride 2 needs a single source with even h, w");
     CESM_REQUIRE((a->c1 == 0) == (a->x1 == nullptr), "x1 / c1 mismatch");
     cudaStream_t st = as_stream(stream);
+
+    {
+        int rc = 0;
+        if (wgrad3_try(a, st, &rc)) return rc;
+    }
 
     WgradParams p{};
     p.c0 = a->c0;

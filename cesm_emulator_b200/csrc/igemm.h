@@ -44,6 +44,25 @@ struct WgradParams {
     int32_t tap_off[16];
 };
 
+// ---- 3x3 weight gradient with halo reuse (wgrad3.cu) -------------------------------------------------
+struct Wgrad3Maps {
+    CUtensorMap x[2];   // box {64 ci, bw + 2, bh + 2, 1}
+    CUtensorMap y;      // box {64 co, bw, bh, 1}
+};
+struct Wgrad3Params {
+    int32_t c0, c1;
+    int32_t n, cout;
+    int32_t bw, bh;              // pixel tile: bw * bh == 128, bw in {16, 32}
+    int32_t tiles_w, tiles_h;
+    uint32_t halo_box_bytes;     // (bw + 2) * (bh + 2) * 128
+    uint32_t halo_stage_bytes;   // the same rounded up to 1024 (+ slack for the ghost tap's view)
+    int32_t tap_row[10];         // halo row of pixel (0, 0) for each tap, ascending; [9] = ghost of the last pair
+    int32_t tap_off[10];         // offset of that tap in dw
+    float* dw;                   // fp32, red.add at dw[co*so + ci*si + tap_off[tap]]
+    long long so, si;
+};
+cudaError_t wgrad3_launch(const Wgrad3Maps& maps, const Wgrad3Params& p, int cblk, int ksplit, cudaStream_t stream);
+
 // ---- second-generation persistent kernel (igemm2.cu) ------------------------------------------
 static constexpr size_t kIgemm2MaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
