@@ -258,10 +258,10 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
     // ~75 / 90 / 165 clocks at N = 64 / 128 / 256 (tools/bench_igemm.py).  With few row tiles (48x72 x 6 frames = 216
     // tiles on 148 SMs) a narrower N fills the last wave: 3 waves of N=128 tiles beat 2 waves of N=256 tiles.
     // CTA pairs (cta_group::2, igemm2.cu): two row tiles per cluster share the weight rows, so a CTA reads
-    // N*16 B instead of N*32 B of B per MMA (~66 / 75 / 130 clocks).  CESM_IGEMM_NO_PAIR=1 keeps single CTAs.
+    // N*16 B instead of N*32 B of B per MMA (measured ~62 / 84 / 135 clocks).  CESM_IGEMM_NO_PAIR=1 keeps single CTAs.
     const bool pair = halo && !knob_no_pair() && p.m_tiles >= 2 && sm_count() >= 2;
     if (halo) {
-        static const double clk1[3] = {75.0, 90.0, 165.0}, clk2[3] = {66.0, 75.0, 130.0};
+        static const double clk1[3] = {75.0, 90.0, 165.0}, clk2[3] = {62.0, 84.0, 135.0};
         const double* clk = pair ? clk2 : clk1;
         const int units = pair ? sm_count() / 2 : sm_count();
         const long long m_units = pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
