@@ -56,7 +56,11 @@ def traffic(path):
     ids = list(per)
     starts = [i for i, k in enumerate(ids) if "relayout_tiled_kernel<0>" in per[k]["name"]]
     ends = [i for i, k in enumerate(ids) if "adamw_clip_kernel" in per[k]["name"]]
-    lo, hi = (starts[-1], ends[-1] + 1) if starts and ends and ends[-1] > starts[-1] else (0, len(ids))
+    lo, hi = 0, len(ids)
+    if starts and ends:   # the last COMPLETE step (a capture cut short ends inside a step)
+        before = [i for i in starts if i < ends[-1]]
+        if before:
+            lo, hi = before[-1], ends[-1] + 1
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
     for k in ids[lo:hi]:
         d = per[k]
