@@ -728,7 +728,12 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
     }
     const int block_n = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
     const int units = a->num_taps * (ctot / 64);
-    const int base_ctas = ((units + 1) / 2) * (a->cout / block_n);
+    // CTA pairs where a launch has at least two 128-row blocks and is fed through L2 (multi-tap, or many input
+    // channels): CESM_WGRAD_PAIR=0 turns them off, =2 forces them wherever block_n >= 128
+    static const int wg_pair = [] { const char* e = getenv("CESM_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
+    const int m_tiles = (units + 1) / 2;
+    const bool pair = block_n >= 128 && m_tiles >= 2 && (wg_pair == 2 || (wg_pair == 1 && a->num_taps > 1));
+    const int base_ctas = (pair ? (m_tiles + 1) / 2 * 2 : m_tiles) * (a->cout / block_n);
     const int tiles = ceil_div(a->ow, p.bw) * ceil_div(a->oh, p.bh) * ceil_div(a->n, p.bn);
     // split-K so that the grid is ONE resident wave (two CTAs per SM; rounding up would leave a second
     // wave of a few CTAs that costs as much as the first)
@@ -738,6 +743,6 @@ extern "C" int cesm_wgrad(const cesm_wgrad_args* a, void* stream) {
     if (ksplit > tiles) ksplit = tiles;
     if (ksplit < 1) ksplit = 1;
     note_launch();
-    CESM_CHECK_CUDA(wgrad_launch(xmaps, n_xmaps, ymap, p, block_n, ksplit, st));
+    CESM_CHECK_CUDA(wgrad_launch(xmaps, n_xmaps, ymap, p, block_n, ksplit, pair, st));
     return CESM_OK;
 }

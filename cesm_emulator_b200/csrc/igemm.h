@@ -102,8 +102,9 @@ struct Igemm2Params {
 cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, bool pair, int grid,
                           size_t smem, cudaStream_t stream);
 
+// pair: clusters of two CTAs along the (tap, ci) blocks working as one cta_group::2 unit (block_n >= 128)
 cudaError_t wgrad_launch(const CUtensorMap* xmaps, int n_xmaps, const CUtensorMap& ymap, const WgradParams& p,
-                         int block_n, int ksplit, cudaStream_t stream);
+                         int block_n, int ksplit, bool pair, cudaStream_t stream);
 
 cudaError_t igemm_launch(const CUtensorMap* amaps, int n_amaps, const CUtensorMap& bmap, const IgemmParams& p,
                          int block_n, cudaStream_t stream);

@@ -35,9 +35,14 @@ struct WgradSmem {
     static constexpr int kTotal = kBarOffset + 1024 + 1024;
 };
 
-template <int BLOCK_N, int STAGES>
+// PAIR (BLOCK_N >= 128): the two CTAs of a cluster take two neighbouring 128-row (tap, ci) blocks of the SAME output
+// channels and pixel range and work as one cta_group::2 unit (M = 256): each loads its own activation tiles and HALF
+// of the dY channel atoms, so the L2 -> shared-memory feed that bounds these launches drops by a third at 256
+// columns (48 -> 32 KB per 64 pixels).  The even CTA issues; loads of both report to its barriers; commits multicast.
+template <int BLOCK_N, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
+    static_assert(!PAIR || BLOCK_N >= 128, "a CTA of a pair holds whole 64-channel atoms of dY");
     pdl_trigger();  // pdl_wait() sits in the TMA producer: MMA and epilogue depend on its data
     using S = WgradSmem<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -58,6 +63,8 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
     const int u0 = blockIdx.x * 2, u1 = u0 + 1;
     const bool has_u1 = u1 < units;
     const int col0 = blockIdx.y * BLOCK_N;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    constexpr int kBAtoms = PAIR ? BLOCK_N / 128 : BLOCK_N / 64;   // dY atoms THIS CTA loads
 
     const int tiles_w = (p.ow + p.bw - 1) / p.bw;
     const int tiles_h = (p.oh + p.bh - 1) / p.bh;
@@ -81,9 +88,13 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr_addr, BLOCK_N);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair(tmem_ptr_addr, BLOCK_N);
+        else tmem_alloc(tmem_ptr_addr, BLOCK_N);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -100,7 +111,9 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
             udh[i] = p.tap_dh[tap];
             udw[i] = p.tap_dw[tap];
         }
-        const uint32_t tx_bytes = p.box_bytes * ((has_u1 ? 2 : 1) + BLOCK_N / 64);
+        // PAIR: every CTA always loads two activation tiles (an out-of-range unit re-loads unit 0; its rows are
+        // dropped by the epilogue) so that the leader can expect a fixed byte count for both CTAs
+        const uint32_t tx_bytes = PAIR ? 2u * p.box_bytes * (2 + kBAtoms) : p.box_bytes * ((has_u1 ? 2 : 1) + BLOCK_N / 64);
         int stage = 0;
         uint32_t phase = 0;
         for (int t = t_begin; t < t_end; ++t) {
@@ -109,13 +122,23 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
             const int ow0 = tw * p.bw, oh0 = th * p.bh, n0 = tn * p.bn;
             const uint32_t sa = smem_base + stage * S::kStageBytes;
             const uint32_t sb = sa + S::kABytes;
-            mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_4d(sa, &maps.x[um[0]], full_bar(stage), uc[0], ow0 + udw[0], oh0 + udh[0], n0);
-            if (has_u1)
-                tma_load_4d(sa + kPix * 128, &maps.x[um[1]], full_bar(stage), uc[1], ow0 + udw[1], oh0 + udh[1], n0);
+            if (PAIR) {
+                if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+                tma_load_4d_pair(sa, &maps.x[um[0]], full_bar(stage), uc[0], ow0 + udw[0], oh0 + udh[0], n0);
+                tma_load_4d_pair(sa + kPix * 128, &maps.x[um[1]], full_bar(stage), uc[1], ow0 + udw[1], oh0 + udh[1], n0);
 #pragma unroll
-            for (int a = 0; a < BLOCK_N / 64; ++a)
-                tma_load_4d(sb + a * kPix * 128, &maps.y, full_bar(stage), col0 + a * 64, ow0, oh0, n0);
+                for (int a = 0; a < kBAtoms; ++a)
+                    tma_load_4d_pair(sb + a * kPix * 128, &maps.y, full_bar(stage),
+                                     col0 + ((int)cta_rank * kBAtoms + a) * 64, ow0, oh0, n0);
+            } else {
+                mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+                tma_load_4d(sa, &maps.x[um[0]], full_bar(stage), uc[0], ow0 + udw[0], oh0 + udh[0], n0);
+                if (has_u1)
+                    tma_load_4d(sa + kPix * 128, &maps.x[um[1]], full_bar(stage), uc[1], ow0 + udw[1], oh0 + udh[1], n0);
+#pragma unroll
+                for (int a = 0; a < BLOCK_N / 64; ++a)
+                    tma_load_4d(sb + a * kPix * 128, &maps.y, full_bar(stage), col0 + a * 64, ow0, oh0, n0);
+            }
             if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
@@ -125,8 +148,8 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         // ===== MMA issuer: one elected thread runs the loop (its instruction stream is the critical path: no
         // per-MMA predicate, no re-convergence points); the constant descriptor word is hoisted and only the
         // start-address field advances =====
-        constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 1, 1);
-        if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, BLOCK_N, 1, 1);
+        if (cta_rank == 0 && elect_one()) {
             const uint64_t desc_hi = make_smem_desc_sw128(0, kPix * 128, 1024);
             const uint32_t base16 = smem_base >> 4;
             int stage = 0;
@@ -137,11 +160,18 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                 const uint32_t sa16 = base16 + stage * (S::kStageBytes >> 4);
                 const uint32_t sb16 = sa16 + (S::kABytes >> 4);
 #pragma unroll
-                for (int k = 0; k < kPix / 16; ++k)   // 16 pixels = two 8-row groups = 2048 B further along K
-                    umma_f16(tmem_base, desc_hi | (uint64_t)(sa16 + k * 128), desc_hi | (uint64_t)(sb16 + k * 128), idesc,
-                             k == 0 ? (uint32_t)(kb != 0) : 1u);
-                umma_commit(empty_bar(stage));
-                if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+                for (int k = 0; k < kPix / 16; ++k) {   // 16 pixels = two 8-row groups = 2048 B further along K
+                    const uint64_t da = desc_hi | (uint64_t)(sa16 + k * 128), db = desc_hi | (uint64_t)(sb16 + k * 128);
+                    if (PAIR) umma_f16_pair(tmem_base, da, db, idesc, k == 0 ? (uint32_t)(kb != 0) : 1u);
+                    else umma_f16(tmem_base, da, db, idesc, k == 0 ? (uint32_t)(kb != 0) : 1u);
+                }
+                if (PAIR) {
+                    umma_commit_pair(empty_bar(stage));
+                    if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);
+                } else {
+                    umma_commit(empty_bar(stage));
+                    if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+                }
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1u;
@@ -174,37 +204,44 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N);
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 2) {
+        if (PAIR) tmem_dealloc_pair(tmem_base, BLOCK_N);
+        else tmem_dealloc(tmem_base, BLOCK_N);
+    }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool PAIR>
 static cudaError_t launch_wgrad(const WgradMaps& maps, const WgradParams& p, dim3 grid, cudaStream_t stream) {
     using S = WgradSmem<BLOCK_N, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             S::kTotal);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, STAGES, PAIR>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    launch_pdl(wgrad_kernel<BLOCK_N, STAGES>, grid, 256, S::kTotal, stream, maps, p);
+    launch_pdl_cluster(wgrad_kernel<BLOCK_N, STAGES, PAIR>, grid, 256, S::kTotal, stream, PAIR ? 2 : 1, maps, p);
     return cudaGetLastError();
 }
 
 cudaError_t wgrad_launch(const CUtensorMap* xmaps, int n_xmaps, const CUtensorMap& ymap, const WgradParams& p,
-                         int block_n, int ksplit, cudaStream_t stream) {
+                         int block_n, int ksplit, bool pair, cudaStream_t stream) {
     WgradMaps maps;
     for (int i = 0; i < 4; ++i) maps.x[i] = xmaps[i < n_xmaps ? i : 0];
     maps.y = ymap;
     const int units = p.num_taps * ((p.c0 + p.c1) >> 6);
-    dim3 grid((units + 1) / 2, p.cout / block_n, ksplit);
+    const int m_tiles = (units + 1) / 2;
+    dim3 grid(pair ? (m_tiles + 1) / 2 * 2 : m_tiles, p.cout / block_n, ksplit);
     switch (block_n) {
-        case 64: return launch_wgrad<64, 4>(maps, p, grid, stream);
-        case 128: return launch_wgrad<128, 3>(maps, p, grid, stream);
+        case 64: return launch_wgrad<64, 4, false>(maps, p, grid, stream);
+        case 128: return pair ? launch_wgrad<128, 3, true>(maps, p, grid, stream)
+                              : launch_wgrad<128, 3, false>(maps, p, grid, stream);
         // 256 columns: one CTA per SM with a 4-deep 48 KB ring beats two CTAs with 2 stages each
         // (64->768 projection gradient at 192x288: 104 -> 87 us, 6.3 TB/s; tools/bench_wgrad.py)
-        case 256: return launch_wgrad<256, 4>(maps, p, grid, stream);
+        case 256: return pair ? launch_wgrad<256, 4, true>(maps, p, grid, stream)
+                              : launch_wgrad<256, 4, false>(maps, p, grid, stream);
         default: return cudaErrorInvalidValue;
     }
 }
