@@ -37,7 +37,9 @@ def test_plain_gemm(cuda, m, k, n):
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 128, 128, 64, 64), (3, 64, 64, 128, 128), (2, 32, 32, 256, 256),
                                              (6, 8, 8, 512, 512), (2, 48, 72, 64, 128), (1, 24, 36, 128, 64),
-                                             (2, 192, 288, 64, 64)])
+                                             (2, 192, 288, 64, 64),
+                                             # CTA pairs: odd row-tile counts (one ghost tile) and a single tile (no pair)
+                                             (3, 8, 14, 64, 64), (1, 8, 14, 128, 128), (5, 16, 30, 64, 256)])
 def test_conv3x3(cuda, n, h, w, cin, cout):
     from cesm_emulator_b200 import kernels as K
     torch.manual_seed(1)
@@ -103,7 +105,8 @@ def test_upsample_convT4x4s2(cuda, n, h, w, c):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,frames", [(6, 64, 64, 64, 64, 3), (6, 48, 72, 128, 128, 3), (4, 16, 24, 64, 256, 2),
-                                                    (2, 192, 288, 64, 64, 1), (6, 8, 8, 128, 128, 3)])
+                                                    (2, 192, 288, 64, 64, 1), (6, 8, 8, 128, 128, 3),
+                                                    (3, 8, 14, 64, 64, 1), (1, 8, 14, 64, 128, 1), (9, 16, 30, 128, 64, 3)])
 def test_conv3x3_fused_groupnorm_stats_and_flipped_taps(cuda, n, h, w, cin, cout, frames):
     """Persistent kernel extras: (a) the per-sample per-group (sum, sum of squares) of the fp16
     outputs from the epilogue equal those of the stored tensor; (b) the data-gradient form
