@@ -16,10 +16,20 @@
 //     stays in shared memory across the persistent tile loop; otherwise it is streamed through its
 //     own mbarrier ring, decoupled from the activation ring.
 //   * persistent CTAs (one per SM) with two TMEM accumulator stages: the epilogue of tile i overlaps
-//     the MMAs of tile i+1.
+//     the MMAs of tile i+1; a stage is handed back as soon as tcgen05.ld has it in registers.
 //   * the epilogue goes TMEM -> registers -> swizzled shared memory -> TMA store (full 128-byte
 //     lines), fusing bias, residual add and -- for the convs that feed a GroupNorm -- the per-sample
-//     per-group sum / sum-of-squares of the fp16-rounded outputs (video_net.py:216).
+//     per-group sum / sum-of-squares of the fp16-rounded outputs (video_net.py:216), kept in registers
+//     across tiles and reduced once per (sample, column tile).
+//   * (round 2) ONE elected thread runs the MMA issue loop: its instruction stream is the critical path
+//     (a 128x64x16 MMA is 32 tensor clocks), so the loop carries no per-MMA predicate, no per-tap branch
+//     and no debug knob (those exist only under -DCESM_IGEMM_DEBUG).
+//   * (round 2) PAIR mode for the 3x3 convolutions: the two CTAs of a cluster work as one cta_group::2
+//     unit on two row tiles of the same column tile (M = 256).  What bounds a 128 x N x 16 SS-mode MMA is
+//     the shared-memory operand feed (~77-90 B/clk measured: 4 KB of A + N*32 B of B per MMA); in a pair
+//     each CTA supplies its own A rows and HALF of the B rows.  Only the even CTA issues; TMA loads of
+//     both CTAs report to its barriers (peer bit of the barrier address cleared), commits are multicast,
+//     the epilogues of both return the accumulator stage to the leader's barrier.
 //
 // Warp roles (352 threads): 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer
 // (+ TMEM allocation), 3..10 = epilogue: two groups of four warps (warp w reads TMEM lanes
