@@ -34,6 +34,7 @@ class IgemmArgs(Structure):
         ("o_sh", c_int32), ("o_sw", c_int32), ("o_h0", c_int32), ("o_w0", c_int32),
         ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int32),
         ("gn_sums", c_void_p), ("gn_groups", c_int32), ("gn_frames", c_int32), ("wt_stable", c_int32),
+        ("ln_colsum", c_void_p), ("ln_eps", ctypes.c_float), ("reserved_", c_int32),
     ]
 
 

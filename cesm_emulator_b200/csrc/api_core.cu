@@ -346,6 +346,13 @@ static int igemm2_run(const cesm_igemm_args* a, cudaStream_t st) {
     p.residual = a->residual;
     p.ldr = a->ldr;
     p.dbg = knob_dbg();
+    if (a->ln_colsum) {
+        CESM_REQUIRE(a->cout == 64 && a->c0 == 64 && a->c1 == 0 && a->num_taps == 1 && a->stride == 1 && !a->gn_sums &&
+                         a->residual == a->a0 && a->ldr == 64 && !a->out_fp32,
+                     "the LayerNorm fold needs a 64 -> 64 one-tap projection whose residual is its own input");
+        p.ln_colsum = a->ln_colsum;
+        p.ln_eps = a->ln_eps;
+    }
 
     // ---- tensor maps ----
     Igemm2Maps maps;
@@ -446,8 +453,9 @@ extern "C" int cesm_igemm(const cesm_igemm_args* a, void* stream) {
     CESM_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0 && a->oh > 0 && a->ow > 0, "empty geometry");
     CESM_REQUIRE((a->c1 == 0) == (a->a1 == nullptr), "a1 / c1 mismatch");
     CESM_REQUIRE(a->ldo % 8 == 0 && (a->residual == nullptr || a->ldr % 8 == 0), "row pitches must be multiples of 8");
-    if (!a->out_fp32 && !(knob_v1() && a->gn_sums == nullptr))
+    if (!a->out_fp32 && !(knob_v1() && a->gn_sums == nullptr && a->ln_colsum == nullptr))
         return igemm2_run(a, as_stream(stream));  // persistent kernel (igemm2.cu)
+    CESM_REQUIRE(a->ln_colsum == nullptr, "the LayerNorm fold exists in the fp16 persistent kernel only");
     CESM_REQUIRE(a->gn_sums == nullptr, "fused GroupNorm statistics need fp16 output");
 
     IgemmParams p{};

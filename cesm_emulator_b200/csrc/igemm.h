@@ -96,11 +96,13 @@ struct Igemm2Params {
     int32_t m_major;                   // 1: consecutive tiles are the column tiles of ONE row tile (resident weights)
     int32_t wt_stable;                 // 1: weights predate the preceding kernel: their loads need not wait for it
     int32_t dbg;                       // CESM_IGEMM_DBG bisection bits (0 in production)
+    const float* ln_colsum;            // LayerNorm folded into a 64 -> 64 projection (see cesm_igemm_args) or null
+    float ln_eps;
 };
 
 // pair: launch as clusters of two CTAs working as one cta_group::2 unit (halo mode only; grid must be even)
 cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, bool pair, int grid,
-                          size_t smem, cudaStream_t stream);
+                          size_t smem, cudaStream_t stream);   // p.ln_colsum != null: the LayerNorm-fold epilogue (block_n 64)
 
 // pair: clusters of two CTAs along the (tap, ci) blocks working as one cta_group::2 unit (block_n >= 128)
 cudaError_t wgrad_launch(const CUtensorMap* xmaps, int n_xmaps, const CUtensorMap& ymap, const WgradParams& p,

@@ -97,10 +97,14 @@ __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&v)[64])
 // PAIR (HALO only): the two CTAs of a cluster work as one cta_group::2 unit on TWO row tiles (CTA r takes row tile
 // 2*pair + r) of the same column tile.  Each CTA loads its own activation halo and HALF of the weight rows, keeps
 // its own 128 accumulator rows in its own TMEM and runs its own epilogue; the even CTA issues the M = 256 MMAs.
-template <int BLOCK_N, bool HALO, bool GN, bool PAIR>
+// LNF (64 -> 64, one tap, residual = the GEMM input x): the channel LayerNorm of x is folded into the epilogue,
+// out = x + rstd(x) * (x W'^T - mean(x) * colsum(W')) -- a thread holds a whole 64-channel row of x as its
+// residual, so the row statistics cost no extra pass (the temporal-attention block at one frame is this ONE kernel).
+template <int BLOCK_N, bool HALO, bool GN, bool PAIR, bool LNF = false>
 __global__ void __launch_bounds__(kIgemm2Threads, 1)
 igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
     static_assert(!PAIR || HALO, "CTA pairs are wired for the 3x3 halo mode only");
+    static_assert(!LNF || (BLOCK_N == 64 && !HALO && !GN && !PAIR), "the LayerNorm fold is a 64-column plain GEMM epilogue");
     pdl_trigger();  // pdl_wait() sits in the two TMA producers: everything else depends on their data
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -557,18 +561,41 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                     released = true;
                 }
                 float sv[16];  // GN: [0..7] per 8-column octet sums of this row, [8..15] sums of squares
+                uint4 xrow[LNF ? 8 : 1];   // LNF: the row of x (= the residual) whose LayerNorm is folded in
+                float ln_mean = 0.f, ln_rstd = 0.f;
+                if (LNF) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        xrow[j] = valid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u);
+                        const float2 a = unpack_h2(xrow[j].x), b = unpack_h2(xrow[j].y), c2 = unpack_h2(xrow[j].z),
+                                     d = unpack_h2(xrow[j].w);
+                        s1 += ((a.x + a.y) + (b.x + b.y)) + ((c2.x + c2.y) + (d.x + d.y));
+                        s2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(c2.x, c2.x,
+                             fmaf(c2.y, c2.y, fmaf(d.x, d.x, fmaf(d.y, d.y, s2))))))));
+                    }
+                    ln_mean = s1 * (1.f / 64.f);
+                    ln_rstd = rsqrtf(fmaxf(s2 * (1.f / 64.f) - ln_mean * ln_mean, 0.f) + p.ln_eps);
+                }
+                const float4* cp = reinterpret_cast<const float4*>(p.ln_colsum + (LNF ? col : 0));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {  // 8 columns = one 16-byte unit
                     float f[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[8 * j + i]);
+                    if (LNF) {
+                        const float4 c0 = __ldg(cp + 2 * j), c1 = __ldg(cp + 2 * j + 1);
+                        const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = ln_rstd * fmaf(-ln_mean, cs[i], f[i]);
+                    }
                     if (p.bias) {
                         const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
                         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                         f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                     }
                     if (has_res && valid) {
-                        const uint4 rr = __ldg(rp + j);
+                        const uint4 rr = LNF ? xrow[j] : __ldg(rp + j);
                         const float2 a = unpack_h2(rr.x), b = unpack_h2(rr.y),
                                      c2 = unpack_h2(rr.z), d = unpack_h2(rr.w);
                         f[0] += a.x; f[1] += a.y; f[2] += b.x; f[3] += b.y;
@@ -660,17 +687,18 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HALO, bool GN, bool PAIR>
+template <int BLOCK_N, bool HALO, bool GN, bool PAIR, bool LNF = false>
 static cudaError_t launch_igemm2(const Igemm2Maps& maps, const Igemm2Params& p, int grid, size_t smem,
                                  cudaStream_t stream) {
     static bool configured = false;  // benign race: attribute set is idempotent
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BLOCK_N, HALO, GN, PAIR>,
+        cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BLOCK_N, HALO, GN, PAIR, LNF>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIgemm2MaxSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    launch_pdl_cluster(igemm2_kernel<BLOCK_N, HALO, GN, PAIR>, grid, kIgemm2Threads, smem, stream, PAIR ? 2 : 1, maps, p);
+    launch_pdl_cluster(igemm2_kernel<BLOCK_N, HALO, GN, PAIR, LNF>, grid, kIgemm2Threads, smem, stream, PAIR ? 2 : 1, maps,
+                       p);
     return cudaGetLastError();
 }
 
@@ -689,6 +717,10 @@ static cudaError_t launch_igemm2_n(const Igemm2Maps& maps, const Igemm2Params& p
 
 cudaError_t igemm2_launch(const Igemm2Maps& maps, const Igemm2Params& p, int block_n, bool halo, bool pair, int grid,
                           size_t smem, cudaStream_t stream) {
+    if (p.ln_colsum != nullptr) {
+        if (block_n != 64 || halo || pair || p.gn_sums != nullptr) return cudaErrorInvalidValue;
+        return launch_igemm2<64, false, false, false, true>(maps, p, grid, smem, stream);
+    }
     switch (block_n) {
         case 64: return launch_igemm2_n<64>(maps, p, halo, pair, grid, smem, stream);
         case 128: return launch_igemm2_n<128>(maps, p, halo, pair, grid, smem, stream);

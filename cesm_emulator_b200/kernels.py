@@ -108,12 +108,17 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
           out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None,
           out_place: Tuple[int, int, int, int] = (1, 1, 0, 0),
           bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-          out_dtype: torch.dtype = H16, gn_sums: Optional[torch.Tensor] = None, gn_frames: int = 1):
+          out_dtype: torch.dtype = H16, gn_sums: Optional[torch.Tensor] = None, gn_frames: int = 1,
+          ln_fold: Optional[Tuple[torch.Tensor, float]] = None):
     """out[n,oh,ow,:] = sum_t A[n, oh*stride+dh_t, ow*stride+dw_t, :] @ wt[:, t, :]^T (+bias)(+residual).
 
     a0/a1: fp16 [N,H,W,C]; wt: fp16 [cout, len(taps)*(C0+C1)].  `out_hw` is the iterated output
     grid (defaults to H//stride, W//stride); `out_place` = (o_sh, o_sw, o_h0, o_w0) scatters the
     grid into a larger `out` tensor (transposed-conv phases).
+
+    `ln_fold=(colsum, eps)`: a0 is x [.., 64], residual must be the same x, wt = W * gamma (per input channel) and
+    colsum[co] = sum_ci wt[co, ci] (fp32, of the fp16 values): returns x + LayerNorm_channels(x) W^T with the row
+    statistics computed in the epilogue (no LayerNorm kernel, no normalised tensor in HBM).
     """
     _req_cuda(a0, a1, wt, out, bias, residual)
     assert a0.dtype == H16 and wt.dtype == H16 and a0.dim() == 4
@@ -145,6 +150,11 @@ def igemm(a0: torch.Tensor, wt: torch.Tensor, *, taps: Sequence[Tuple[int, int]]
         # fused GroupNorm statistics: gn_sums fp32 [n / gn_frames, groups, 2] (zeroed by the call)
         assert gn_sums.dtype == torch.float32 and gn_sums.dim() == 3 and gn_sums.shape[0] * gn_frames == n
         args.gn_sums, args.gn_groups, args.gn_frames = _ptr(gn_sums), gn_sums.shape[1], gn_frames
+    if ln_fold is not None:
+        cs, eps = ln_fold
+        assert residual is not None and residual.data_ptr() == a0.data_ptr() and c0 == 64 and cout == 64 and a1 is None
+        assert cs.dtype == torch.float32 and cs.numel() == cout and cs.is_cuda
+        args.ln_colsum, args.ln_eps = _ptr(cs), float(eps)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == cout
     if residual is not None:

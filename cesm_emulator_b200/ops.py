@@ -163,30 +163,46 @@ def prepack_all() -> int:
 _FOLDS: list = []
 
 
-def _fold_f1(meta, wqkv, wout, hidden: int, C: int) -> torch.Tensor:
-    key = (_key(wqkv), _key(wout))
+def _fold_compute(ent, wqkv, wout, gamma) -> None:
+    """Rebuild the tensors of a fold entry IN PLACE (their addresses are baked into captured graphs)."""
+    C, hidden = ent[1].shape[0], ent[4]
+    wv = wqkv.detach().reshape(3 * hidden, C)[2 * hidden:].float()
+    wo = wout.detach().reshape(C, hidden).float()
+    w = wo @ wv                                  # [C out, C in]: the implicit-GEMM operand layout
+    ent[1].copy_(w)
+    if gamma is not None:                        # LayerNorm folded into the GEMM epilogue (kernels.igemm ln_fold)
+        ent[6].copy_(w * gamma.detach().reshape(1, C).float())
+        ent[7].copy_(ent[6].float().sum(dim=1))  # of the fp16 values the tensor core multiplies
+
+
+def _fold_f1(meta, wqkv, wout, hidden: int, C: int, gamma=None):
+    """W_out W_v of a temporal-attention block for the one-frame path.  Returns the fp16 [C, C] matrix, or -- with
+    `gamma` (C == 64) -- the pair (W * gamma, its row sums) that `kernels.igemm(..., ln_fold=)` takes."""
+    key = (_key(wqkv), _key(wout), None if gamma is None else _key(gamma))
     ent = meta.__dict__.get("fold_f1")
-    if ent is None or ent[1].device != wqkv.device:
-        ent = [None, torch.empty((C, C), dtype=H16, device=wqkv.device), weakref.ref(wqkv), weakref.ref(wout), hidden]
+    if ent is None or ent[1].device != wqkv.device or (gamma is not None and ent[5] is None):
+        dev = wqkv.device
+        ent = [None, torch.empty((C, C), dtype=H16, device=dev), weakref.ref(wqkv), weakref.ref(wout), hidden,
+               None if gamma is None else weakref.ref(gamma),
+               None if gamma is None else torch.empty((C, C), dtype=H16, device=dev),
+               None if gamma is None else torch.empty((C,), dtype=torch.float32, device=dev)]
         meta.__dict__["fold_f1"] = ent
         _FOLDS.append(ent)
     if ent[0] != key:
-        wv = wqkv.detach().reshape(3 * hidden, C)[2 * hidden:].float()
-        wo = wout.detach().reshape(C, hidden).float()
-        ent[1].copy_(wo @ wv)   # [C out, C in]: the implicit-GEMM operand layout
+        _fold_compute(ent, wqkv, wout, gamma)
         ent[0] = key
-    return ent[1]
+    return ent[1] if gamma is None else (ent[6], ent[7])
 
 
 def refresh_folds() -> None:
-    live = [e for e in _FOLDS if e[2]() is not None and e[3]() is not None]
+    live = [e for e in _FOLDS if e[2]() is not None and e[3]() is not None and (e[5] is None or e[5]() is not None)]
     _FOLDS[:] = live
     for e in live:
         wqkv, wout = e[2](), e[3]()
-        key = (_key(wqkv), _key(wout))
+        gamma = None if e[5] is None else e[5]()
+        key = (_key(wqkv), _key(wout), None if gamma is None else _key(gamma))
         if e[0] != key:
-            C, hidden = e[1].shape[0], e[4]
-            e[1].copy_(wout.detach().reshape(C, hidden).float() @ wqkv.detach().reshape(3 * hidden, C)[2 * hidden:].float())
+            _fold_compute(e, wqkv, wout, gamma)
             e[0] = key
 
 
@@ -692,6 +708,11 @@ class TemporalAttnBlockFn(_Fn):
         g = gamma.reshape(-1)
         pos_bias = pos_bias.contiguous().float()
         train = _train(ctx)
+        if F == 1 and not train and C == 64:
+            # (see below) ... and at 64 channels the LayerNorm goes into the same kernel: a thread of the GEMM
+            # epilogue holds the whole row of x as its residual, so  y = x + rstd (x (W gamma)^T - mean colsum)
+            wln, colsum = _fold_f1(meta, wqkv, wout, hidden, C, gamma=gamma)
+            return K.igemm(x, wln, residual=x, ln_fold=(colsum, eps))
         xn = K.ln_fwd(x, g, eps)
         if F == 1 and not train:
             # one frame (every step of the sampling chain): the softmax over a single key is exactly 1, so the

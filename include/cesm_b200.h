@@ -90,6 +90,15 @@ typedef struct cesm_igemm_args {
      * engine re-packs every weight once at the top of a step), so the weight tiles may be fetched while
      * that kernel is still draining (programmatic dependent launch).  0 is always safe. */
     int32_t wt_stable;
+    /* Optional channel-LayerNorm folded into a 64 -> 64 projection with a residual -- the whole temporal-attention
+     * block at ONE frame without gradients (video_net.py:78-87 + :380-453: the softmax over a single key is 1, so
+     * y = x + LN(x) (W_out W_v)^T).  If ln_colsum != NULL, `a0` and `residual` must both be the [rows, 64] tensor x,
+     * `wt` = W * gamma (scaled per INPUT channel) and ln_colsum[co] = sum_ci wt[co][ci] (of the fp16 values); the
+     * call returns   out = x + rstd(x) * (x wt^T - mean(x) * ln_colsum) (+ bias)   with the row statistics taken
+     * over the 64 channels (biased variance, + ln_eps).  Needs cout == c0 == 64, c1 == 0, one tap, stride 1. */
+    const float* ln_colsum;
+    float ln_eps;
+    int32_t reserved_;
 } cesm_igemm_args;
 
 int cesm_igemm(const cesm_igemm_args* args, void* stream);

@@ -630,6 +630,30 @@ def test_device_data_path_survives_host_run_ahead(cuda):
         assert torch.equal(conds[i].cpu(), refs[i][0]) and torch.equal(x0s[i].cpu(), refs[i][1]), i
 
 
+@pytest.mark.parametrize("rows_shape", [(2, 16, 24), (1, 5, 7), (16, 48, 72)])
+def test_layernorm_folded_into_projection(cuda, rows_shape):
+    """kernels.igemm(ln_fold=): x + LN(x) W^T from ONE GEMM whose epilogue takes the row statistics from its residual
+    (the one-frame temporal-attention block, video_net.py:78-87 + :380-453), against the two-kernel form and fp32 torch."""
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(11)
+    C, eps = 64, 1e-5
+    x = (rnd((*rows_shape, C), cuda) * 1.5 + 0.7).contiguous()          # rows with a non-zero mean
+    gamma = 1.0 + 0.2 * torch.randn(C, device=cuda)
+    w = torch.randn(C, C, device=cuda) * 0.1
+    wln = (w * gamma[None, :]).to(K.H16)
+    colsum = wln.float().sum(dim=1)
+    y = K.igemm(x, wln, residual=x, ln_fold=(colsum, eps))
+    xf = x.float()
+    mu = xf.mean(-1, keepdim=True)
+    var = xf.var(-1, unbiased=False, keepdim=True)
+    ref = xf + ((xf - mu) / (var + eps).sqrt() * gamma) @ w.t()
+    assert err(y, ref) < 2e-3
+    two = K.igemm(K.ln_fwd(x, gamma, eps), w.to(K.H16), residual=x)
+    assert err(y, two.float()) < 2e-3
+    with pytest.raises(AssertionError):
+        K.igemm(x, wln, residual=x.clone(), ln_fold=(colsum, eps))       # the residual must be the GEMM input itself
+
+
 def test_film_projections_batched(cuda):
     """ops.FilmAllFn (all FiLM linears of a pass in one launch, one fused backward) against torch."""
     from cesm_emulator_b200 import ops
