@@ -254,6 +254,17 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                 }
             }
         }
+        if (PAIR) {
+            // producer tail: the leader's multicast commits arrive on THIS CTA's empty barriers asynchronously; do
+            // not leave (and let the shared memory be handed to another CTA) before the last of them has landed
+            for (int k = 0; k < p.a_stages; ++k) {
+                mbar_wait(a_empty(stage), phase ^ 1u, 18);
+                if (++stage == p.a_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
     } else if (warp == 1 && lane == 0) {
         // ===== weight producer =====
         // weights re-packed at the top of the step are fetched while the preceding kernel still drains
@@ -294,6 +305,15 @@ igemm2_kernel(const __grid_constant__ Igemm2Maps maps, const Igemm2Params p) {
                             phase ^= 1u;
                         }
                     }
+            }
+            if (PAIR) {   // producer tail (see the activation producer)
+                for (int k = 0; k < p.b_stages; ++k) {
+                    mbar_wait(b_empty(stage), phase ^ 1u, 19);
+                    if (++stage == p.b_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
             }
         }
     } else if (warp == 2) {

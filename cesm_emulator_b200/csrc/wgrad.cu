@@ -144,6 +144,17 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                 phase ^= 1u;
             }
         }
+        if (PAIR) {
+            // producer tail: the leader's multicast commits land on THIS CTA's empty barriers asynchronously; stay
+            // until the last one has arrived (the shared memory must not change hands under an in-flight arrive)
+            for (int k = 0; k < STAGES; ++k) {
+                mbar_wait(empty_bar(stage), phase ^ 1u, 24);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
     } else if (warp == 1) {
         // ===== MMA issuer: one elected thread runs the loop (its instruction stream is the critical path: no
         // per-MMA predicate, no re-convergence points); the constant descriptor word is hoisted and only the

@@ -286,9 +286,10 @@ def test_weights_stay_fresh_across_train_eval_train(cuda):
         with torch.no_grad():
             got = d.model(x, c, t)
         ref = fresh_eps()
-        # run-to-run noise (atomics order -> flipped fp16 roundings) is ~3e-4; a stale operand after 4 steps at
-        # lr = 1e-2 moves the output by O(1)
-        assert rel_err(got, ref) < 2e-3, (rnd, rel_err(got, ref))
+        # run-to-run noise (atomics order -> flipped fp16 roundings) is ~3e-4 at initialisation and up to 3e-3
+        # after eight steps at lr = 1e-2 (2.9e-3 seen once in ~25 runs: the kicked network amplifies it); a stale
+        # operand moves the output by >= 5e-2 (asserted at the end), so 1e-2 separates the two cleanly
+        assert rel_err(got, ref) < 1e-2, (rnd, rel_err(got, ref))
         outs.append(got)
         # the graph captured in round 0 must see round 1's weights: one replayed reverse step against the module's
         # own p_sample (eager, fresh operands) with the noise the replay drew
@@ -300,7 +301,7 @@ def test_weights_stay_fresh_across_train_eval_train(cuda):
         samp.step()
         with torch.no_grad():
             y_ref = d.p_sample(x, c, t, noise=samp.z)
-        assert rel_err(samp.x, y_ref) < 2e-3, (rnd, rel_err(samp.x, y_ref))
+        assert rel_err(samp.x, y_ref) < 1e-2, (rnd, rel_err(samp.x, y_ref))
     assert rel_err(outs[1], outs[0]) > 5e-2   # training really changed the network between the two evals
     ops.set_grad_sink(None)
 
