@@ -88,7 +88,8 @@ def test_parity_is_reproducible_run_to_run(cuda, baseline):
     runs = [module_loss_and_grads(baseline, x0, cond, t, noise) for _ in range(3)]
     for eps, loss, grads in runs[1:]:
         assert rel_err(eps, runs[0][0]) < 2e-3
-        assert max(rel_err(grads[k], runs[0][2][k]) for k in grads) < 6e-3
+        # worst tensor measured 3-3.6e-3; the bar is the parity bar itself (a race shows as an outlier >> 1e-2)
+        assert max(rel_err(grads[k], runs[0][2][k]) for k in grads) < 1e-2
 
 
 def test_p_sample_step_matches_oracle(cuda, baseline):
