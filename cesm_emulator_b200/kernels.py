@@ -100,6 +100,10 @@ def zero_scratch(shape, device) -> torch.Tensor:
 # engine fills this after its once-per-step re-pack, the sampling engine after its warm-up step): igemm may
 # then fetch them before the preceding kernel has finished (cesm_igemm_args.wt_stable).
 STABLE_WEIGHT_PTRS: set = set()
+# linattn_fwd_out (apply + to_out + residual in one mma.sync kernel) is correct and removes ~1 GB of traffic per
+# full-resolution block of the sampling step, but it is issue-bound (softmax + 192 MMAs per 16 pixels on CUDA-core
+# rates): 6.19 ms per reverse step against 6.10 ms with the split kernels on B200.  Opt-in: CESM_LINATTN_OUT=1.
+_NO_LINATTN_OUT = not bool(int(__import__("os").environ.get("CESM_LINATTN_OUT", "0")))
 _NO_WT_STABLE = not bool(int(__import__("os").environ.get("CESM_WT_STABLE", "0")))  # opt-in (CESM_WT_STABLE=1): -0.03 ms per step
 
 
@@ -455,6 +459,26 @@ def linattn_fwd(qkv, NI: int, n: int, H: int, D: int, scale: float):
     _lib.call("cesm_linattn_fwd", _ptr(qkv), _ptr(ws), _ptr(out), NI, n, H, D, scale, _stream(),
               _meta=_bytes_meta(qkv, out))
     return out, ws
+
+
+def linattn_out_ok(H: int, D: int, C: int) -> bool:
+    """Shapes the fused apply + to_out + residual kernel covers (csrc/linattn.cu la_apply_out_kernel)."""
+    return H in (4, 8) and D == 32 and C in (64, 128) and not _NO_LINATTN_OUT
+
+
+def linattn_fwd_out(qkv, wout, bout, x, NI: int, n: int, H: int, D: int, scale: float):
+    """No-grad forward of the whole tail of the block: y = x + bout + W_out * linear_attention(qkv), fp16 [NI*n, C];
+    the H*D-wide attention output stays in registers.  wout: fp32 [C, H*D] (Conv2d weight), bout: fp32 [C] or None."""
+    _req_cuda(qkv, wout, bout, x)
+    C = x.shape[-1]
+    assert wout.dtype == torch.float32 and wout.numel() == C * H * D and wout.is_contiguous()
+    assert x.dtype == H16 and x.is_contiguous() and x.numel() == NI * n * C
+    dev = qkv.device
+    ws = zero_scratch((_lib.load().cesm_linattn_ws_floats(NI, H),), dev)
+    y = torch.empty_like(x)
+    _lib.call("cesm_linattn_fwd_out", _ptr(qkv), _ptr(ws), _ptr(wout), _ptr(bout), _ptr(x), _ptr(y), NI, n, H, D, C,
+              scale, _stream(), _meta=_bytes_meta(qkv, x, y))
+    return y
 
 
 def linattn_bwd(qkv, ws, dout, NI: int, n: int, H: int, D: int, scale: float):

@@ -790,6 +790,12 @@ class SpatialAttnBlockFn(_Fn):
         train = _train(ctx)
         xn = K.ln_fwd(x, g, eps)
         qkv = K.igemm(xn, _conv_fwd_weight(meta.cq, wqkv, 3 * hidden, C, 1, train))
+        if not train and K.linattn_out_ok(heads, D, C):
+            # no gradients (sampling): apply + to_out + bias + residual in one kernel; the hidden-wide attention
+            # output is never written (kernels.linattn_fwd_out).  to_out's fp32 weight is read directly.
+            y = K.linattn_fwd_out(qkv.view(-1, 3 * hidden), wout.detach().reshape(C, hidden), bout.detach(),
+                                  x.view(-1, C), NI, H_ * W_, heads, D, D ** -0.5)
+            return y.view(NI, H_, W_, C)
         o, ws = K.linattn_fwd(qkv.view(-1, 3 * hidden), NI, H_ * W_, heads, D, D ** -0.5)
         y = K.igemm(o.view(NI, H_, W_, hidden), _conv_fwd_weight(meta.co, wout, C, hidden, 1, train), bias=bout,
                     residual=x)

@@ -273,6 +273,12 @@ int cesm_tattn_long_bwd(const void* qkv, const float* bias_diag, const float* cs
 size_t cesm_linattn_ws_floats(int NI, int H);
 int cesm_linattn_fwd(const void* qkv, float* ws, void* out, int NI, int n, int H, int dim_head, float scale,
                      void* stream);
+/* Forward without gradients: the same core followed, in the SAME kernel, by to_out (1x1 conv with bias,
+ * video_net.py:323/347) and the block's residual add (:69): y = x + bias + W_out * out.  The H*32-wide attention
+ * output never reaches HBM.  wout: fp32 [C][H*32] (the Conv2d weight), bias: fp32 [C] or NULL, x / y: fp16
+ * [NI*n][C].  H in {4, 8}, dim_head == 32, C in {64, 128}. */
+int cesm_linattn_fwd_out(const void* qkv, float* ws, const float* wout, const float* bias, const void* x, void* y, int NI,
+                         int n, int H, int dim_head, int C, float scale, void* stream);
 int cesm_linattn_bwd(const void* qkv, float* ws, const void* dout, float* scratch, void* dqkv, int NI, int n, int H,
                      int dim_head, float scale, void* stream);
 

@@ -654,6 +654,33 @@ def test_layernorm_folded_into_projection(cuda, rows_shape):
         K.igemm(x, wln, residual=x.clone(), ln_fold=(colsum, eps))       # the residual must be the GEMM input itself
 
 
+@pytest.mark.parametrize("NI,n,C,H", [(2, 16 * 24, 64, 8), (3, 100, 64, 4), (2, 36 * 18, 128, 8), (1, 17, 128, 4),
+                                      (16, 48 * 72, 64, 8)])
+def test_linear_attention_apply_fused_with_output_projection(cuda, NI, n, C, H):
+    """cesm_linattn_fwd_out (apply + to_out + bias + residual in one kernel, no-grad forward) against the two-step
+    path it replaces (cesm_linattn_fwd, then the 1x1 projection GEMM with bias and residual) and fp32 torch."""
+    from cesm_emulator_b200 import kernels as K
+    torch.manual_seed(13)
+    D = 32
+    hid = H * D
+    qkv = rnd((NI * n, 3 * hid), cuda)
+    x = rnd((NI * n, C), cuda)
+    wout = torch.randn(C, hid, device=cuda) * 0.1
+    bout = torch.randn(C, device=cuda)
+    y = K.linattn_fwd_out(qkv, wout, bout, x, NI, n, H, D, D ** -0.5)
+    o, _ = K.linattn_fwd(qkv, NI, n, H, D, D ** -0.5)
+    two = K.igemm(o.view(NI, 1, n, hid), wout.to(K.H16), bias=bout, residual=x.view(NI, 1, n, C)).view(-1, C)
+    assert err(y, two) < 3e-3
+    # fp32 restatement (video_net.py:338-347)
+    q, k, v = qkv.float().view(NI, n, 3, H, D).unbind(2)
+    qs = q.softmax(-1) * D ** -0.5
+    ks = k.softmax(1)
+    ctx = torch.einsum("bnhd,bnhe->bhde", ks, v)
+    out = torch.einsum("bhde,bnhd->bnhe", ctx, qs).reshape(NI * n, hid)
+    ref = x.float() + out @ wout.t() + bout
+    assert err(y, ref) < 3e-3
+
+
 def test_film_projections_batched(cuda):
     """ops.FilmAllFn (all FiLM linears of a pass in one launch, one fused backward) against torch."""
     from cesm_emulator_b200 import ops
