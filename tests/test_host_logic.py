@@ -220,3 +220,38 @@ def test_prediction_netcdf_product(tmp_path):
         assert list(f.variables["member_id"][:]) == [0, 1] and f.variables["lon"].shape == (6,)
     with pytest.raises(ValueError):
         write_prediction_netcdf(path, pred, lat=[0.0, 1.0])
+
+
+def test_layernorm_fold_algebra_and_in_place_refresh():
+    """ops._fold_f1(gamma=...) builds the operands of the one-kernel one-frame temporal block (cesm_igemm ln_colsum):
+    x + LN(x) (W_out W_v)^T  ==  x + rstd (x (W gamma)^T - mean colsum).  The tensors are rebuilt IN PLACE when the
+    weights change (their addresses are baked into captured graphs)."""
+    import types
+    from cesm_emulator_b200 import ops
+    torch.manual_seed(0)
+    C, hidden, eps = 64, 256, 1e-5
+    wqkv = torch.nn.Parameter(torch.randn(3 * hidden, C) * 0.05)
+    wout = torch.nn.Parameter(torch.randn(C, hidden) * 0.05)
+    gamma = torch.nn.Parameter(1.0 + 0.1 * torch.randn(1, C, 1, 1, 1))
+    meta = types.SimpleNamespace()
+    wln, colsum = ops._fold_f1(meta, wqkv, wout, hidden, C, gamma=gamma)
+    x = torch.randn(50, C) * 1.3 + 0.4
+
+    def want():
+        mu, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
+        ln = (x - mu) / (var + eps).sqrt() * gamma.detach().reshape(1, C)
+        return x + ln @ (wout.detach() @ wqkv.detach()[2 * hidden:]).t()
+
+    def got():
+        mu, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
+        return x + (var + eps).rsqrt() * (x @ wln.float().t() - mu * colsum[None, :])
+
+    assert (got() - want()).abs().max() < 5e-3 * want().abs().max()          # fp16 rounding of W gamma
+    assert torch.allclose(colsum, wln.float().sum(1))
+    ptrs = (wln.data_ptr(), colsum.data_ptr())
+    with torch.no_grad():
+        wout.mul_(1.5)                     # in-place update bumps the version -> the fold key changes
+    ops.refresh_folds()
+    wln2, colsum2 = ops._fold_f1(meta, wqkv, wout, hidden, C, gamma=gamma)
+    assert (wln2.data_ptr(), colsum2.data_ptr()) == ptrs
+    assert (got() - want()).abs().max() < 5e-3 * want().abs().max()
